@@ -1,0 +1,113 @@
+"""ctypes binding of libdiffmm_b200.so (the C ABI declared in include/diffmm_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing, or a call
+returns a non-zero status, this module raises.  PyTorch is used only for device memory, streams
+and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffmm_b200.so")
+
+c_i64, c_i32, c_f32, c_vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
+
+
+class GemmEpilogue(C.Structure):
+    """Mirror of struct dmm_gemm_epilogue."""
+    _fields_ = [
+        ("bias", c_vp), ("act", c_i32), ("alpha", c_f32), ("beta", c_f32),
+        ("residual", c_vp), ("ld_res", c_i64),
+        ("out_f32", c_vp), ("ld_out", c_i64),
+        ("out_hi", c_vp), ("out_lo", c_vp), ("ld_out16", c_i64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol of include/diffmm_b200.h must appear here
+PROTOTYPES = {
+    "dmm_version": (C.c_int, []),
+    "dmm_last_error": (C.c_char_p, []),
+    "dmm_init": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
+    "dmm_destroy": (None, [c_vp]),
+    "dmm_num_sms": (C.c_int, [c_vp]),
+    "dmm_pack_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp]),
+    "dmm_csr_rows_to_dense": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmm_time_embedding": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "dmm_q_sample": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, C.c_int,
+                               c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "dmm_gemm_bf16_tn": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
+                                   C.POINTER(GemmEpilogue), c_vp]),
+    "dmm_gemm_f32_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp]),
+    "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "dmm_spmm_csr": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_f32, c_f32,
+                               c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmm_sign_noise_": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
+    "dmm_bpr_fwd_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_infonce_fwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_f32,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_infonce_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_f32,
+                                  c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_scatter_add_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}          # device index -> dmm_ctx*
+launch_count = 0   # kernels-launching C-ABI calls made by this process (bench.py's gpu_launches evidence)
+
+
+class DiffMMError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (no CUDA call is made). Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise DiffMMError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(diffmm_b200 has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def last_error() -> str:
+    return (load().dmm_last_error() or b"").decode()
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise DiffMMError(f"{what} failed with status {status}: {last_error()}")
+
+
+def ctx(device_index: int):
+    """Per-device context handle (created on first use)."""
+    lib = load()
+    h = _ctx.get(device_index)
+    if h is None:
+        out = c_vp()
+        check(lib.dmm_init(int(device_index), C.byref(out)), "dmm_init")
+        h = out
+        _ctx[device_index] = h
+    return h
+
+
+def call(name: str, *args):
+    global launch_count
+    lib = load()
+    launch_count += 1
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,434 @@
+// Dense contraction for the Denoise MLP on the Blackwell tensor pipe (sm_100a).
+//
+//   C[M,N] = epilogue( sum_pass A_pass[M,K] . B_pass[N,K]^T )      bf16 operands, fp32 accum in TMEM
+//
+// Replaces cuBLAS SGEMM behind nn.Linear / torch.mm in the reference (Model.py:205,208,212,215,
+// 416-417).  Design (one CTA per SM, persistent over output tiles, warp specialised):
+//   warp 0  : TMA producer   — cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) into a STAGES-deep ring
+//   warp 1  : MMA issuer     — one lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
+//   warp 2  : TMEM allocator — 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
+//   warps 4-7: epilogue      — tcgen05.ld 32 lanes x 32 columns, bias/tanh/posterior-mean, fp32 and
+//                              split-bf16 stores (the bf16 pair is the next contraction's operand)
+// The optional lo operands add the passes A_lo.B_hi and A_hi.B_lo into the same accumulator
+// ("bf16x3"), which restores fp32-level accuracy without leaving the bf16 tensor pipe.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int n_pass;
+  int pass_a[3];  // 0 = hi, 1 = lo
+  int pass_b[3];
+  dmm_gemm_epilogue ep;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must fault the launch (reported through cudaGetLastError) instead
+// of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("diffmm_b200 gemm: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+//   [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128 B = 1024)
+//   [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ epilogue math
+__device__ __forceinline__ float epi_value(float acc, float bias, int act) {
+  float v = acc + bias;
+  if (act == 1) v = tanhf(v);
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int k_iters = p.n_pass * p.num_k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+          const CUtensorMap* ma = p.pass_a[ps] ? &tm_a_lo : &tm_a_hi;
+          const CUtensorMap* mb = p.pass_b[ps] ? &tm_b_lo : &tm_b_hi;
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, n_blk * BN);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int j = 0; j < k_iters; ++j) {
+          mbar_wait(full_bar(stage), phase, 3);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // +32 B per UMMA_K step inside the 128 B swizzle row => +2 in the (addr >> 4) field
+            tcgen05_mma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));  // smem slot is free once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tcgen05_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    const dmm_gemm_epilogue& ep = p.ep;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tcgen05_fence_after();
+      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
+        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), r);
+        float v[32];
+        const bool full = (n0 + 32 <= p.N);
+        if (!row_ok) {
+          // rows past M were zero-filled by TMA; nothing to store
+        } else if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = epi_value(__uint_as_float(r[j]), ep.bias ? __ldg(ep.bias + n0 + j) : 0.f, ep.act);
+          if (ep.residual) {
+            const float4* rp = reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ld_res + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(rp + q);
+              v[4 * q + 0] = ep.alpha * v[4 * q + 0] + ep.beta * t.x;
+              v[4 * q + 1] = ep.alpha * v[4 * q + 1] + ep.beta * t.y;
+              v[4 * q + 2] = ep.alpha * v[4 * q + 2] + ep.beta * t.z;
+              v[4 * q + 3] = ep.alpha * v[4 * q + 3] + ep.beta * t.w;
+            }
+          } else if (ep.alpha != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          }
+          if (ep.out_f32) {
+            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ld_out + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (ep.out_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              uint16_t h0, l0, h1, l1;
+              dmm_split_bf16(v[2 * q], h0, l0);
+              dmm_split_bf16(v[2 * q + 1], h1, l1);
+              hi[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            uint4* hp = reinterpret_cast<uint4*>(ep.out_hi + (int64_t)row * ep.ld_out16 + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hp[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            if (ep.out_lo) {
+              uint4* lp = reinterpret_cast<uint4*>(ep.out_lo + (int64_t)row * ep.ld_out16 + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) lp[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+          }
+        } else {
+          // ragged last column block: scalar, guarded
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            if (n >= p.N) break;
+            float x = epi_value(__uint_as_float(r[j]), ep.bias ? __ldg(ep.bias + n) : 0.f, ep.act);
+            if (ep.residual)
+              x = ep.alpha * x + ep.beta * __ldg(ep.residual + (int64_t)row * ep.ld_res + n);
+            else
+              x *= ep.alpha;
+            if (ep.out_f32) ep.out_f32[(int64_t)row * ep.ld_out + n] = x;
+            if (ep.out_hi) {
+              uint16_t h, l;
+              dmm_split_bf16(x, h, l);
+              ep.out_hi[(int64_t)row * ep.ld_out16 + n] = h;
+              if (ep.out_lo) ep.out_lo[(int64_t)row * ep.ld_out16 + n] = l;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(dmm_ctx* ctx, CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box,
+                                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dmm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld", (int)r, (long long)rows, (long long)k,
+                  (long long)ld);
+    return DMM_ERR_CUDA;
+  }
+  return DMM_OK;
+}
+
+template <int BN>
+int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
+           const uint16_t* b_lo, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
+  if ((rc = make_map(ctx, &ma_lo, a_lo ? a_lo : a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
+  if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, BN))) return rc;
+  if ((rc = make_map(ctx, &mb_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, BN))) return rc;
+  p.num_n_blocks = (int)dmm_ceil_div(p.N, BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+}  // namespace
+
+extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
+                                const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t M, int64_t N,
+                                int64_t K, const dmm_gemm_epilogue* ep, void* stream) {
+  DMM_CHECK_ARG(ctx && a_hi && b_hi && ep, "dmm_gemm_bf16_tn: null argument");
+  DMM_CHECK_ARG(ctx->encode_tiled, "dmm_gemm_bf16_tn: cuTensorMapEncodeTiled unavailable");
+  DMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "dmm_gemm_bf16_tn: empty problem M=%lld N=%lld K=%lld", (long long)M,
+                (long long)N, (long long)K);
+  DMM_CHECK_ARG(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "dmm_gemm_bf16_tn: dimension too large");
+  DMM_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
+                "dmm_gemm_bf16_tn: lda/ldb must be >= K and multiples of 8 (got %lld, %lld, K=%lld)", (long long)lda,
+                (long long)ldb, (long long)K);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(a_hi) && al16(a_lo) && al16(b_hi) && al16(b_lo), "dmm_gemm_bf16_tn: operands must be 16-byte aligned");
+  DMM_CHECK_ARG(al16(ep->residual) && al16(ep->out_f32) && al16(ep->out_hi) && al16(ep->out_lo),
+                "dmm_gemm_bf16_tn: epilogue buffers must be 16-byte aligned");
+  DMM_CHECK_ARG(!ep->residual || (ep->ld_res >= N && ep->ld_res % 4 == 0), "dmm_gemm_bf16_tn: ld_res must be >= N and %%4");
+  DMM_CHECK_ARG(!ep->out_f32 || (ep->ld_out >= N && ep->ld_out % 4 == 0), "dmm_gemm_bf16_tn: ld_out must be >= N and %%4");
+  DMM_CHECK_ARG(!ep->out_hi || (ep->ld_out16 >= N && ep->ld_out16 % 8 == 0), "dmm_gemm_bf16_tn: ld_out16 must be >= N and %%8");
+  DMM_CHECK_ARG(!ep->out_lo || ep->out_hi, "dmm_gemm_bf16_tn: out_lo requires out_hi");
+  DMM_CHECK_ARG(ep->act == 0 || ep->act == 1, "dmm_gemm_bf16_tn: unknown activation %d", ep->act);
+
+  GemmParams p;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.num_m_blocks = (int)dmm_ceil_div(M, BLOCK_M);
+  p.num_k_blocks = (int)dmm_ceil_div(K, BLOCK_K);
+  p.n_pass = 0;
+  // small correction passes first, the dominant hi.hi product last
+  if (a_lo) { p.pass_a[p.n_pass] = 1; p.pass_b[p.n_pass] = 0; ++p.n_pass; }
+  if (b_lo) { p.pass_a[p.n_pass] = 0; p.pass_b[p.n_pass] = 1; ++p.n_pass; }
+  p.pass_a[p.n_pass] = 0; p.pass_b[p.n_pass] = 0; ++p.n_pass;
+  for (int i = p.n_pass; i < 3; ++i) p.pass_a[i] = p.pass_b[i] = 0;
+  p.ep = *ep;
+
+  int bn;
+  if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else bn = (p.num_m_blocks * dmm_ceil_div(N, 256) >= ctx->num_sms) ? 256 : 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 64: return launch<64>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case 128: return launch<128>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    default: return launch<256>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+  }
+}

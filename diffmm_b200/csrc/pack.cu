@@ -1,0 +1,235 @@
+// Operand staging kernels for the Denoise path: fp32 -> split-bf16 packing (optionally transposed),
+// CSR user rows -> dense operand tiles, time-embedding columns, q_sample.  All HBM-bound,
+// vectorised where alignment allows; grids are sized from the data, block = 256 threads.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ fp32 -> bf16 hi/lo (no transpose)
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                                        int64_t ld_src, uint16_t* __restrict__ hi,
+                                                        uint16_t* __restrict__ lo, int64_t ld_dst) {
+  // one block row-slab: blockIdx.y = row, threads stride over ld_dst (zero pad beyond cols)
+  const int64_t r = blockIdx.y;
+  if (r >= rows) return;
+  const float* s = src + r * ld_src;
+  uint16_t* h = hi + r * ld_dst;
+  uint16_t* l = lo ? lo + r * ld_dst : nullptr;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ld_dst; c += (int64_t)gridDim.x * blockDim.x) {
+    uint16_t vh = 0, vl = 0;
+    if (c < cols) dmm_split_bf16(__ldg(s + c), vh, vl);
+    h[c] = vh;
+    if (l) l[c] = vl;
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 hi/lo, transposed (32x32 smem tile)
+__global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                                             int64_t ld_src, uint16_t* __restrict__ hi,
+                                                             uint16_t* __restrict__ lo, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + r * ld_src + c) : 0.f;
+  }
+  __syncthreads();
+  // dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (c < cols && r < ld_dst) {
+      uint16_t vh, vl;
+      dmm_split_bf16(tile[tx][i], vh, vl);
+      hi[c * ld_dst + r] = vh;
+      if (lo) lo[c * ld_dst + r] = vl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CSR rows -> dense 0/1 tiles
+__global__ void __launch_bounds__(256) csr_rows_zero_kernel(int64_t n_rows, int64_t n_cols, float* __restrict__ x,
+                                                            int64_t ld_x, uint16_t* __restrict__ a, int64_t ld_a) {
+  const int64_t r = blockIdx.y;
+  if (r >= n_rows) return;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
+    if (x) x[r * ld_x + c] = 0.f;
+    if (a) a[r * ld_a + c] = 0;
+  }
+}
+__global__ void __launch_bounds__(256) csr_rows_scatter_kernel(const int64_t* __restrict__ indptr,
+                                                               const int32_t* __restrict__ indices,
+                                                               const int64_t* __restrict__ row_ids, int64_t row0,
+                                                               int64_t n_rows, int64_t n_cols, float* __restrict__ x,
+                                                               int64_t ld_x, uint16_t* __restrict__ a, int64_t ld_a) {
+  // one warp per output row
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t u = row_ids ? row_ids[r] : row0 + r;
+  const int64_t b = indptr[u], e = indptr[u + 1];
+  for (int64_t j = b + lane; j < e; j += 32) {
+    const int32_t c = indices[j];
+    if (c >= 0 && c < n_cols) {
+      if (x) x[r * ld_x + c] = 1.f;
+      if (a) a[r * ld_a + c] = 0x3F80;  // bf16(1.0)
+    }
+  }
+}
+
+// ------------------------------------------------------------------ time embedding columns
+__global__ void __launch_bounds__(256) time_embedding_kernel(const int64_t* __restrict__ t, int64_t t_all,
+                                                             int64_t n_rows, int d, const float* __restrict__ w,
+                                                             const float* __restrict__ b, uint16_t* __restrict__ a_hi,
+                                                             uint16_t* __restrict__ a_lo, int64_t ld_a, int64_t col0,
+                                                             float* __restrict__ temb) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const float ts = (float)(t ? t[r] : t_all);
+  const int half = d / 2;
+  float e[64];
+  // Model.py:196-201: freqs = exp(-ln(1e4) * j / half); [cos, sin]; zero pad if d is odd
+  for (int j = 0; j < half; ++j) {
+    const float f = expf(-logf(10000.f) * (float)j / (float)half);
+    const float ang = ts * f;
+    e[j] = cosf(ang);
+    e[half + j] = sinf(ang);
+  }
+  if (d & 1) e[d - 1] = 0.f;
+  for (int o = 0; o < d; ++o) {
+    float acc = b[o];
+    for (int j = 0; j < d; ++j) acc = fmaf(e[j], w[o * d + j], acc);
+    if (temb) temb[r * d + o] = acc;
+    if (a_hi) {
+      uint16_t h, l;
+      dmm_split_bf16(acc, h, l);
+      a_hi[r * ld_a + col0 + o] = h;
+      if (a_lo) a_lo[r * ld_a + col0 + o] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ q_sample
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0, int64_t ld_x0,
+                                                       const float* __restrict__ noise, int64_t ld_n,
+                                                       const float* __restrict__ ca, const float* __restrict__ cb,
+                                                       int64_t n_cols, int mode, float* __restrict__ xt, int64_t ld_x,
+                                                       uint16_t* __restrict__ a_hi, uint16_t* __restrict__ a_lo,
+                                                       int64_t ld_a) {
+  // one block per row
+  const int64_t r = blockIdx.x;
+  const float* x = x0 + r * ld_x0;
+  const float* g = noise + r * ld_n;
+  __shared__ float red[8];
+  __shared__ float s_inv;
+  float inv = 1.f;
+  if (mode == 1) {
+    float ss = 0.f;
+    for (int64_t c = threadIdx.x; c < n_cols; c += blockDim.x) {
+      const float v = __ldg(g + c);
+      ss = fmaf(v, v, ss);
+    }
+    ss = dmm_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+      s_inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    }
+    __syncthreads();
+    inv = s_inv;
+  }
+  const float a = ca[r], b = cb[r];
+  for (int64_t c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    const float xv = __ldg(x + c);
+    float nv = __ldg(g + c);
+    if (mode == 1) {
+      const float sg = (xv > 0.f) ? 1.f : ((xv < 0.f) ? -1.f : 0.f);
+      nv = sg * (nv * inv);
+    }
+    const float v = a * xv + b * nv;
+    if (xt) xt[r * ld_x + c] = v;
+    if (a_hi) {
+      uint16_t h, l;
+      dmm_split_bf16(v, h, l);
+      a_hi[r * ld_a + c] = h;
+      if (a_lo) a_lo[r * ld_a + c] = l;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                             uint16_t* dst_hi, uint16_t* dst_lo, int64_t ld_dst, int transpose, void* stream) {
+  DMM_CHECK_ARG(ctx && src && dst_hi, "dmm_pack_bf16: null argument");
+  DMM_CHECK_ARG(rows > 0 && cols > 0 && ld_src >= cols, "dmm_pack_bf16: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!transpose) {
+    DMM_CHECK_ARG(ld_dst >= cols, "dmm_pack_bf16: ld_dst < cols");
+    DMM_CHECK_ARG(rows < 65536LL * 32768LL, "dmm_pack_bf16: too many rows");
+    // grid.y is limited to 65535: fold rows into chunks
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+      const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+      dim3 grid((unsigned)(dmm_ceil_div(ld_dst, 256) < 64 ? dmm_ceil_div(ld_dst, 256) : 64), (unsigned)nr);
+      pack_rows_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, nr, cols, ld_src, dst_hi + r0 * ld_dst,
+                                             dst_lo ? dst_lo + r0 * ld_dst : nullptr, ld_dst);
+    }
+  } else {
+    DMM_CHECK_ARG(ld_dst >= rows, "dmm_pack_bf16: ld_dst < rows (transposed)");
+    const int64_t gy = dmm_ceil_div(ld_dst, 32);
+    DMM_CHECK_ARG(gy < 65536, "dmm_pack_bf16: too many rows for the transposed path");
+    dim3 grid((unsigned)dmm_ceil_div(cols, 32), (unsigned)gy);
+    pack_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+  }
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_csr_rows_to_dense(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices,
+                                     const int64_t* row_ids, int64_t row0, int64_t n_rows, int64_t n_cols,
+                                     float* x_f32, int64_t ld_x, uint16_t* a_bf16, int64_t ld_a, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && indices, "dmm_csr_rows_to_dense: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0, "dmm_csr_rows_to_dense: bad shape");
+  DMM_CHECK_ARG((!x_f32 || ld_x >= n_cols) && (!a_bf16 || ld_a >= n_cols), "dmm_csr_rows_to_dense: ld too small");
+  if (n_rows == 0) return DMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+    const int64_t nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
+    dim3 grid((unsigned)(dmm_ceil_div(n_cols, 256) < 32 ? dmm_ceil_div(n_cols, 256) : 32), (unsigned)nr);
+    csr_rows_zero_kernel<<<grid, 256, 0, st>>>(nr, n_cols, x_f32 ? x_f32 + r0 * ld_x : nullptr, ld_x,
+                                               a_bf16 ? a_bf16 + r0 * ld_a : nullptr, ld_a);
+  }
+  DMM_LAUNCH_CHECK();
+  csr_rows_scatter_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, st>>>(indptr, indices, row_ids, row0, n_rows,
+                                                                                   n_cols, x_f32, ld_x, a_bf16, ld_a);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_time_embedding(dmm_ctx* ctx, const int64_t* t, int64_t t_all, int64_t n_rows, int d_emb,
+                                  const float* emb_w, const float* emb_b, uint16_t* a_hi, uint16_t* a_lo,
+                                  int64_t ld_a, int64_t col0, float* temb_f32, void* stream) {
+  DMM_CHECK_ARG(ctx && emb_w && emb_b, "dmm_time_embedding: null argument");
+  DMM_CHECK_ARG(d_emb >= 2 && d_emb <= 64, "dmm_time_embedding: d_emb must be in [2, 64]");
+  DMM_CHECK_ARG(!a_hi || ld_a >= col0 + d_emb, "dmm_time_embedding: ld_a too small");
+  if (n_rows <= 0) return DMM_OK;
+  time_embedding_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+      t, t_all, n_rows, d_emb, emb_w, emb_b, a_hi, a_lo, ld_a, col0, temb_f32);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_q_sample(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const float* noise, int64_t ld_noise,
+                            const float* coef_a, const float* coef_b, int64_t n_rows, int64_t n_cols, int mode,
+                            float* x_t, int64_t ld_x, uint16_t* a_hi, uint16_t* a_lo, int64_t ld_a, void* stream) {
+  DMM_CHECK_ARG(ctx && x0 && noise && coef_a && coef_b, "dmm_q_sample: null argument");
+  DMM_CHECK_ARG(mode == 0 || mode == 1, "dmm_q_sample: mode must be 0 or 1");
+  DMM_CHECK_ARG(n_cols > 0 && ld_x0 >= n_cols && ld_noise >= n_cols, "dmm_q_sample: bad shape");
+  if (n_rows <= 0) return DMM_OK;
+  q_sample_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(x0, ld_x0, noise, ld_noise, coef_a, coef_b, n_cols,
+                                                                      mode, x_t, ld_x, a_hi, a_lo, ld_a);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}

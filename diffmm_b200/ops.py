@@ -1,0 +1,235 @@
+"""Tensor-level wrappers over the C ABI (include/diffmm_b200.h).
+
+Every function takes CUDA torch tensors (memory + stream plumbing only), validates layout, and
+calls exactly one C-ABI entry point on the current stream.  No arithmetic happens in PyTorch here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmEpilogue
+
+
+def pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ctx(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.DiffMMError("diffmm_b200 operators need CUDA tensors (there is no CPU fallback)")
+    return _lib.ctx(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _row_major(t: torch.Tensor, name: str) -> int:
+    """Returns the leading dimension (elements) of a 2-D row-major (possibly padded) tensor."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# ----------------------------------------------------------------------------------------- packing
+def pack_bf16(src: torch.Tensor, ld_dst: Optional[int] = None, transpose: bool = False, split: bool = True):
+    """fp32 [R, C] -> (hi, lo) bf16 [R, ld] (or [C, ld] transposed); lo is None when split=False."""
+    assert src.dtype == torch.float32
+    ld_src = _row_major(src, "src")
+    R, Cc = src.shape
+    out_rows, inner = (Cc, R) if transpose else (R, Cc)
+    ld = pad_to(inner, 64) if ld_dst is None else ld_dst
+    hi = torch.empty((out_rows, ld), dtype=torch.bfloat16, device=src.device)
+    lo = torch.empty_like(hi) if split else None
+    _lib.call("dmm_pack_bf16", _ctx(src), _p(src), R, Cc, ld_src, _p(hi), _p(lo), ld, int(transpose), _stream())
+    return hi, lo
+
+
+def pack_bf16_into(src: torch.Tensor, hi: torch.Tensor, lo: Optional[torch.Tensor], transpose: bool = False):
+    ld_src = _row_major(src, "src")
+    ld = _row_major(hi, "hi")
+    R, Cc = src.shape
+    _lib.call("dmm_pack_bf16", _ctx(src), _p(src), R, Cc, ld_src, _p(hi), _p(lo), ld, int(transpose), _stream())
+
+
+def csr_rows_to_dense(indptr, indices, n_rows, n_cols, *, row_ids=None, row0=0, x_f32=None, a_bf16=None):
+    """Binary CSR rows -> dense fp32 tile and/or bf16 operand tile (zero filled to n_cols)."""
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+    ld_x = _row_major(x_f32, "x_f32") if x_f32 is not None else 0
+    ld_a = _row_major(a_bf16, "a_bf16") if a_bf16 is not None else 0
+    _lib.call("dmm_csr_rows_to_dense", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows),
+              int(n_cols), _p(x_f32), ld_x, _p(a_bf16), ld_a, _stream())
+
+
+def time_embedding(emb_w, emb_b, n_rows, *, t=None, t_all=0, a_hi=None, a_lo=None, col0=0, temb_f32=None):
+    d = emb_w.shape[0]
+    ld_a = _row_major(a_hi, "a_hi") if a_hi is not None else 0
+    _lib.call("dmm_time_embedding", _ctx(emb_w), _p(t), int(t_all), int(n_rows), int(d), _p(emb_w), _p(emb_b),
+              _p(a_hi), _p(a_lo), ld_a, int(col0), _p(temb_f32), _stream())
+
+
+def q_sample(x0, noise, coef_a, coef_b, mode, *, x_t=None, a_hi=None, a_lo=None):
+    """x_t = a[r] x0 + b[r] noise (mode 0) or the default sign(x0)*normalize(noise) (mode 1)."""
+    n_rows, n_cols = x0.shape
+    _lib.call("dmm_q_sample", _ctx(x0), _p(x0), _row_major(x0, "x0"), _p(noise), _row_major(noise, "noise"),
+              _p(coef_a), _p(coef_b), n_rows, n_cols, int(mode), _p(x_t),
+              _row_major(x_t, "x_t") if x_t is not None else 0, _p(a_hi), _p(a_lo),
+              _row_major(a_hi, "a_hi") if a_hi is not None else 0, _stream())
+
+
+# ----------------------------------------------------------------------------------------- GEMM
+def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo):
+    ep = GemmEpilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.act = int(act)
+    ep.alpha = float(alpha)
+    ep.beta = float(beta)
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.ld_res = _row_major(residual, "residual") if residual is not None else 0
+    ep.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    ep.ld_out = _row_major(out_f32, "out_f32") if out_f32 is not None else 0
+    ep.out_hi = out_hi.data_ptr() if out_hi is not None else None
+    ep.out_lo = out_lo.data_ptr() if out_lo is not None else None
+    ep.ld_out16 = _row_major(out_hi, "out_hi") if out_hi is not None else 0
+    return ep
+
+
+def gemm_bf16_tn(a_hi, a_lo, b_hi, b_lo, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None,
+                 out_f32=None, out_hi=None, out_lo=None):
+    """C[M,N] = epi(A[M,K] . B[N,K]^T) on tcgen05; lo operands add the split-bf16 correction passes."""
+    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo)
+    _lib.call("dmm_gemm_bf16_tn", _ctx(a_hi), _p(a_hi), _p(a_lo), _row_major(a_hi, "a_hi"), _p(b_hi), _p(b_lo),
+              _row_major(b_hi, "b_hi"), int(M), int(N), int(K), C.byref(ep), _stream())
+
+
+def gemm_f32_tn(a, b, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None, out_f32=None,
+                out_hi=None, out_lo=None):
+    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo)
+    _lib.call("dmm_gemm_f32_tn", _ctx(a), _p(a), _row_major(a, "a"), _p(b), _row_major(b, "b"), int(M), int(N), int(K),
+              C.byref(ep), _stream())
+
+
+# ----------------------------------------------------------------------------------------- top-k
+def topk_edges(scores, n_cols, out_ptr, row_base, out_users, out_items, status=None):
+    """Emits, for each row r, the (out_ptr[r+1]-out_ptr[r]) largest columns (ascending) at out_ptr[r]."""
+    assert scores.dtype == torch.float32 and out_ptr.dtype == torch.int64 and out_items.dtype == torch.int32
+    n_rows = scores.shape[0]
+    assert out_ptr.numel() >= n_rows + 1
+    _lib.call("dmm_topk_edges", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(out_ptr),
+              int(row_base), _p(out_users), _p(out_items), _p(status), _stream())
+
+
+# ----------------------------------------------------------------------------------------- adjacency
+@dataclass
+class CsrAdj:
+    """Normalised bipartite adjacency D^-1/2 ([[0,R],[R^T,0]] + I) D^-1/2 in CSR over N = U + I nodes."""
+    ptr: torch.Tensor      # int64 [N+1]
+    idx: torch.Tensor      # int32 [2E+N], ascending inside each row
+    val: torch.Tensor      # fp32  [2E+N]
+    n_users: int
+    n_items: int
+
+    @property
+    def n_nodes(self):
+        return self.n_users + self.n_items
+
+    @property
+    def nnz(self):
+        return self.idx.numel()
+
+    def to_torch_coo(self):
+        """Torch sparse COO view (int64 indices) for callers that still use torch.sparse.mm."""
+        counts = (self.ptr[1:] - self.ptr[:-1])
+        rows = torch.repeat_interleave(torch.arange(self.n_nodes, device=self.ptr.device), counts)
+        return torch.sparse_coo_tensor(torch.stack([rows, self.idx.long()]), self.val, (self.n_nodes, self.n_nodes))
+
+
+def build_norm_adj(row_ptr: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int) -> CsrAdj:
+    assert row_ptr.dtype == torch.int64 and items.dtype == torch.int32
+    E = int(items.numel())
+    N = n_users + n_items
+    dev = row_ptr.device
+    lib = _lib.load()
+    ws_bytes = int(lib.dmm_build_adj_workspace_bytes(n_users, n_items, E))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    idx = torch.empty(2 * E + N, dtype=torch.int32, device=dev)
+    val = torch.empty(2 * E + N, dtype=torch.float32, device=dev)
+    _lib.call("dmm_build_norm_adj_csr", _ctx(row_ptr), _p(row_ptr), _p(items), n_users, n_items, E, _p(ptr), _p(idx),
+              _p(val), _p(ws), ws_bytes, _stream())
+    return CsrAdj(ptr, idx, val, n_users, n_items)
+
+
+# ----------------------------------------------------------------------------------------- SpMM
+def spmm(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None, row0=0, row1=None):
+    """out[row0:row1] = alpha * A[row0:row1] . x (+ beta * z[row0:row1]); rows outside the block untouched."""
+    assert x.dtype == torch.float32 and x.shape[0] == adj.n_nodes
+    D = x.shape[1]
+    if out is None:
+        out = torch.empty((adj.n_nodes, D), dtype=torch.float32, device=x.device)
+    row1 = adj.n_nodes if row1 is None else row1
+    _lib.call("dmm_spmm_csr", _ctx(x), _p(adj.ptr), _p(adj.idx), _p(adj.val), int(row0), int(row1), _p(x),
+              _row_major(x, "x"), D, float(alpha), float(beta), _p(z), _row_major(z, "z") if z is not None else 0,
+              _p(out), _row_major(out, "out"), _stream())
+    return out
+
+
+def sign_noise_(e: torch.Tensor, rnd: torch.Tensor, noise_degree: float):
+    """In place e += sign(e) * normalize_rows(rnd) * noise_degree (Main.py:320-321)."""
+    _lib.call("dmm_sign_noise_", _ctx(e), _p(e), _row_major(e, "e"), _p(rnd), _row_major(rnd, "rnd"), e.shape[0],
+              e.shape[1], float(noise_degree), _stream())
+    return e
+
+
+# ----------------------------------------------------------------------------------------- losses
+def bpr_fwd_bwd(u_emb, i_emb, users, pos, neg, grad_scale=1.0, want_grad=True):
+    B, D = users.numel(), u_emb.shape[1]
+    dev = u_emb.device
+    row_loss = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    g = [torch.empty((B, D), dtype=torch.float32, device=dev) for _ in range(3)] if want_grad else [None] * 3
+    _lib.call("dmm_bpr_fwd_bwd", _ctx(u_emb), _p(u_emb), _row_major(u_emb, "u_emb"), _p(i_emb), _row_major(i_emb, "i_emb"),
+              _p(users), _p(pos), _p(neg), B, D, float(grad_scale), _p(row_loss), _p(loss), _p(g[0]), _p(g[1]), _p(g[2]),
+              _stream())
+    return loss, g
+
+
+def infonce_fwd(v1, v2, idx, temperature):
+    B, D = idx.numel(), v1.shape[1]
+    dev = v1.device
+    ws = torch.empty(2 * B * D, dtype=torch.float32, device=dev)
+    row_loss = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    lse = torch.empty(B, dtype=torch.float32, device=dev)
+    inv1 = torch.empty(B, dtype=torch.float32, device=dev)
+    inv2 = torch.empty(B, dtype=torch.float32, device=dev)
+    _lib.call("dmm_infonce_fwd", _ctx(v1), _p(v1), _row_major(v1, "v1"), _p(v2), _row_major(v2, "v2"), _p(idx), B, D,
+              float(temperature), _p(ws), _p(row_loss), _p(loss), _p(lse), _p(inv1), _p(inv2), _stream())
+    return loss, (lse, inv1, inv2)
+
+
+def infonce_bwd(v1, v2, idx, temperature, saved, grad_scale=1.0):
+    B, D = idx.numel(), v1.shape[1]
+    dev = v1.device
+    lse, inv1, inv2 = saved
+    ws = torch.empty(2 * B * D, dtype=torch.float32, device=dev)
+    g1 = torch.empty((B, D), dtype=torch.float32, device=dev)
+    g2 = torch.empty((B, D), dtype=torch.float32, device=dev)
+    _lib.call("dmm_infonce_bwd", _ctx(v1), _p(v1), _row_major(v1, "v1"), _p(v2), _row_major(v2, "v2"), _p(idx), B, D,
+              float(temperature), _p(lse), _p(inv1), _p(inv2), float(grad_scale), _p(ws), _p(g1), _p(g2), _stream())
+    return g1, g2
+
+
+def scatter_add_rows(src, idx, dst):
+    _lib.call("dmm_scatter_add_rows", _ctx(src), _p(src), _row_major(src, "src"), _p(idx), idx.numel(), src.shape[1],
+              _p(dst), _row_major(dst, "dst"), _stream())
+    return dst

@@ -1,0 +1,170 @@
+/* diffmm_b200 — C ABI of the B200 (sm_100a) DiffMM hot-path library.
+ *
+ * The reference (sun2ot/DiffMM) is pure Python/PyTorch and has no FFI layer; its hot path is
+ * the set of ATen/cuBLAS/cuSPARSE calls listed in SURVEY.md §2.1.  Each entry point below
+ * replaces one of those call sites (cited as reference file:line) and is what a maintainer
+ * binds from Python with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - nothing is allocated inside: the caller passes outputs and workspaces
+ *     (dmm_*_workspace_bytes tells how much);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), touches only
+ *     the current device of `ctx`, and returns 0 or a negative dmm_status; the message of the
+ *     last failure on the calling thread is dmm_last_error();
+ *   - "bf16" buffers are raw uint16_t bit patterns (round-to-nearest-even);
+ *   - leading dimensions (ld*) are in ELEMENTS.
+ */
+#ifndef DIFFMM_B200_H_
+#define DIFFMM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmm_ctx dmm_ctx;
+
+enum dmm_status {
+  DMM_OK = 0,
+  DMM_ERR_INVALID = -1,   /* bad argument (shape, alignment, null)   */
+  DMM_ERR_CUDA = -2,      /* CUDA runtime / driver error             */
+  DMM_ERR_UNSUPPORTED = -3,
+  DMM_ERR_WORKSPACE = -4  /* workspace too small                     */
+};
+
+/* ---- library / context ------------------------------------------------------------------ */
+int dmm_version(void);
+const char* dmm_last_error(void);
+/* Binds to CUDA device `device` (must be sm_100); resolves cuTensorMapEncodeTiled. */
+int dmm_init(int device, dmm_ctx** out);
+void dmm_destroy(dmm_ctx* ctx);
+int dmm_num_sms(const dmm_ctx* ctx);
+
+/* ---- operand packing --------------------------------------------------------------------
+ * fp32 [rows, cols] (ld_src) -> bf16 hi (and optionally lo = bf16(x - hi)) [rows, ld_dst].
+ * With transpose != 0 the destination is [cols, ld_dst] (dst[c, r] = src[r, c]).
+ * Replaces the implicit fp32 operand read of F.linear (Model.py:212,215).                  */
+int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                  uint16_t* dst_hi, uint16_t* dst_lo, int64_t ld_dst, int transpose, void* stream);
+
+/* Binary CSR user rows -> dense GEMM operand.  For r in [0, n_rows): row_ids[r] (or row0 + r
+ * when row_ids == NULL) selects the CSR row; writes x_f32[r, :] (ld_x, fp32 0/1, optional) and
+ * a_bf16[r, :] (ld_a, bf16 0/1, optional), zero filling both up to n_cols.
+ * Replaces DiffusionData.__getitem__ + default collate (DataHandler.py:217-225) over the dense
+ * U x I matrix (DataHandler.py:128).                                                        */
+int dmm_csr_rows_to_dense(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices,
+                          const int64_t* row_ids, int64_t row0, int64_t n_rows, int64_t n_cols,
+                          float* x_f32, int64_t ld_x, uint16_t* a_bf16, int64_t ld_a, void* stream);
+
+/* Time embedding columns (Model.py:196-202): temb = [cos(t f), sin(t f)] W_e^T + b_e written as
+ * bf16 hi/lo into columns [col0, col0+d) of a_hi/a_lo (ld_a) and optionally fp32 into temb_f32
+ * [n_rows, d].  `t` int64 per row, or NULL with `t_all` for every row (Model.py:319).        */
+int dmm_time_embedding(dmm_ctx* ctx, const int64_t* t, int64_t t_all, int64_t n_rows, int d_emb,
+                       const float* emb_w, const float* emb_b, uint16_t* a_hi, uint16_t* a_lo,
+                       int64_t ld_a, int64_t col0, float* temb_f32, void* stream);
+
+/* q_sample (Model.py:324-341): x_t = a[r] x0 + b[r] noise with fp32 per-row coefficients
+ * (the fp64->fp32 cast of Model.py:352 is done by the caller).  mode 0: `noise` is used as is.
+ * mode 1: the default noise sign(x0) * normalize_row(noise) (Model.py:337, eps 1e-12).
+ * Writes x_t fp32 (ld_x) and optionally bf16 hi/lo (ld_a).                                   */
+int dmm_q_sample(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const float* noise, int64_t ld_noise,
+                 const float* coef_a, const float* coef_b, int64_t n_rows, int64_t n_cols, int mode,
+                 float* x_t, int64_t ld_x, uint16_t* a_hi, uint16_t* a_lo, int64_t ld_a, void* stream);
+
+/* ---- dense contraction on tcgen05 / TMEM / TMA -------------------------------------------
+ * C[M,N] = epilogue( A[M,K] . B[N,K]^T ), both operands K-major bf16, fp32 accumulation in TMEM.
+ * a_lo / b_lo (nullable) add the split-bf16 correction passes A_lo.B_hi and A_hi.B_lo, which
+ * make the product fp32-faithful (rel ~1e-5) on the bf16 tensor pipe.
+ * Replaces cuBLAS SGEMM behind nn.Linear / torch.mm (Model.py:205,208,212,215,416-417).      */
+typedef struct dmm_gemm_epilogue {
+  const float* bias;      /* [N] added per column, or NULL                                   */
+  int32_t act;            /* 0 none, 1 tanh (Model.py:213)                                   */
+  float alpha;            /* v = alpha * v (+ beta * residual)  — posterior mean, Model.py:375 */
+  float beta;
+  const float* residual;  /* fp32 [M,N] ld_res, or NULL                                      */
+  int64_t ld_res;
+  float* out_f32;         /* optional fp32 [M,N]                                             */
+  int64_t ld_out;
+  uint16_t* out_hi;       /* optional bf16 [M,N] (operand of the next contraction)           */
+  uint16_t* out_lo;       /* optional bf16 residual part                                     */
+  int64_t ld_out16;
+} dmm_gemm_epilogue;
+
+int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
+                     const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb,
+                     int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, void* stream);
+
+/* Same contract on the fp32 CUDA-core pipe from fp32 operands (verification mode; no tensor cores). */
+int dmm_gemm_f32_tn(dmm_ctx* ctx, const float* a, int64_t lda, const float* b, int64_t ldb,
+                    int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, void* stream);
+
+/* ---- per-user variable-k top-k -> edge list ------------------------------------------------
+ * For row r of scores [n_rows, n_cols] (ld) emits the k_r = out_ptr[r+1]-out_ptr[r] largest
+ * entries' column indices into out_items[out_ptr[r] .. out_ptr[r+1]) sorted ascending by column,
+ * and row_base + r into out_users.  Tie-break: value descending, then column ascending.
+ * k_r > n_cols is an error flagged in *status (device int, optional).
+ * Replaces the per-user torch.topk loop + int(indices[j]) syncs of Main.py:224-230.          */
+int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
+                   const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
+                   int32_t* status, void* stream);
+
+/* ---- normalised bipartite adjacency ---------------------------------------------------------
+ * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and
+ * unique within a row) builds A = D^-1/2 ([[0,R],[R^T,0]] + I) D^-1/2 as CSR over N = U + I nodes:
+ * adj_ptr int64 [N+1], adj_idx int32 [2E+N] (sorted within rows), adj_val fp32 with the
+ * reference's fp64 arithmetic (d_r^-1/2 * 1) * d_c^-1/2 rounded to fp32.
+ * Replaces Coach.makeTorchAdj (Main.py:113-116) -> DataHandler.makeTorchAdj / normalizeAdj
+ * (DataHandler.py:53-93), which run on the host in scipy.                                    */
+int64_t dmm_build_adj_workspace_bytes(int64_t n_users, int64_t n_items, int64_t n_edges);
+int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* items,
+                           int64_t n_users, int64_t n_items, int64_t n_edges,
+                           int64_t* adj_ptr, int32_t* adj_idx, float* adj_val,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- CSR SpMM ------------------------------------------------------------------------------
+ * Y[r0:r1, :] = alpha * A[r0:r1, :] . X (+ beta * Z[r0:r1, :]),  X fp32 [N_cols, D] (ld_x).
+ * `row0,row1` select a row block (row-partitioned propagation); Y/Z are indexed by absolute row.
+ * D must be a multiple of 4 and <= 256.  A symmetric => the backward is the same call.
+ * Replaces torch.sparse.mm (Model.py:90,93,105,111,114,123,130; Main.py:319).                */
+int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
+                 int64_t row0, int64_t row1, const float* x, int64_t ld_x, int64_t D,
+                 float alpha, float beta, const float* z, int64_t ld_z,
+                 float* y, int64_t ld_y, void* stream);
+
+/* Cross-layer CL perturbation (Main.py:320-321) fused with nothing else:
+ * e[r,:] += sign(e[r,:]) * rnd[r,:] / max(||rnd[r,:]||, 1e-12) * noise_degree, in place. */
+int dmm_sign_noise_(dmm_ctx* ctx, float* e, int64_t ld_e, const float* rnd, int64_t ld_r,
+                    int64_t n_rows, int64_t D, float noise_degree, void* stream);
+
+/* ---- fused losses ---------------------------------------------------------------------------
+ * BPR (Utils/Utils.py:78-98): loss = mean_b -log(1e-5 + sigmoid(u.p - u.n)) over gathered rows
+ * users[b] of U_emb and pos[b]/neg[b] of I_emb; also writes d(loss)/d(rows) scaled by
+ * `grad_scale` into g_u/g_p/g_n [B, D] (optional).                                           */
+int dmm_bpr_fwd_bwd(dmm_ctx* ctx, const float* u_emb, int64_t ld_u, const float* i_emb, int64_t ld_i,
+                    const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t B, int64_t D,
+                    float grad_scale, float* row_loss /* [B] scratch */, float* loss,
+                    float* g_u, float* g_p, float* g_n, void* stream);
+
+/* InfoNCE (Utils/Utils.py:57-75) on gathered rows idx[b] of v1/v2: row-L2 normalise, logits/temp,
+ * -mean diag log-softmax, never materialising the B x B matrix in HBM.  Forward writes loss and
+ * saves per-row log-sum-exp (lse, [B]) and inverse norms (inv1, inv2, [B]); backward writes
+ * d(loss)/d(gathered rows) [B, D] for both views (caller scatter-adds by idx).               */
+int dmm_infonce_fwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2, int64_t ld2,
+                    const int64_t* idx, int64_t B, int64_t D, float temperature,
+                    float* workspace /* 2*B*D floats */, float* row_loss /* [B] scratch */, float* loss,
+                    float* lse, float* inv1, float* inv2, void* stream);
+int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2, int64_t ld2,
+                    const int64_t* idx, int64_t B, int64_t D, float temperature,
+                    const float* lse, const float* inv1, const float* inv2, float grad_scale,
+                    float* workspace /* 2*B*D floats */, float* g1, float* g2, void* stream);
+
+/* Scatter-add of per-batch row gradients into a table gradient: dst[idx[b], :] += src[b, :]. */
+int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,
+                         int64_t D, float* dst, int64_t ld_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFMM_B200_H_ */

@@ -1,0 +1,120 @@
+"""GPU parity tests of the tcgen05 contraction (dmm_gemm_bf16_tn) and the fp32 verification
+kernel against numpy.  bf16 single pass is compared on bf16-rounded operands (exact products,
+fp32 accumulation => tight tolerance); the split-bf16 ("bf16x3") mode against fp64 numpy at the
+north-star fp32 tolerance (rel 1e-5 of the row scale)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffmm_b200 import ops as o
+    return o
+
+
+def _bf16_round(x):
+    return torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+
+
+def _ref(a, b, bias, act, alpha, beta, res):
+    v = a.astype(np.float64) @ b.astype(np.float64).T
+    if bias is not None:
+        v = v + bias
+    if act:
+        v = np.tanh(v)
+    v = alpha * v
+    if res is not None:
+        v = v + beta * res
+    return v
+
+
+SHAPES = [(128, 256, 64), (128, 64, 64), (128, 128, 128), (200, 300, 210), (1024, 1024, 1000), (300, 7050, 1024),
+          (2048, 1024, 7060), (1024, 64, 6710), (77, 40, 50)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_simt_fp32(ops, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = torch.empty((M, N), device=DEV)
+    ops.gemm_f32_tn(T(a), T(b), M, N, K, bias=T(bias), act=1, out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), _ref(a, b, bias, 1, 1.0, 0.0, None), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_tcgen05(ops, M, N, K, mode):
+    rng = np.random.default_rng(M * 3 + N * 5 + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    a_hi, a_lo = ops.pack_bf16(T(a))
+    b_hi, b_lo = ops.pack_bf16(T(b))
+    ldn = ops.pad_to(N, 8)
+    res_t = torch.zeros((M, ldn), device=DEV)
+    res_t[:, :N] = T(res)
+    out = torch.full((M, ldn), float("nan"), device=DEV)
+    out_hi = torch.zeros((M, ldn), dtype=torch.bfloat16, device=DEV)
+    out_lo = torch.zeros((M, ldn), dtype=torch.bfloat16, device=DEV)
+    split = mode == "bf16x3"
+    ops.gemm_bf16_tn(a_hi, a_lo if split else None, b_hi, b_lo if split else None, M, N, K, bias=T(bias), act=1,
+                     alpha=0.75, beta=0.5, residual=res_t[:, :N], out_f32=out[:, :N], out_hi=out_hi[:, :N],
+                     out_lo=out_lo[:, :N])
+    torch.cuda.synchronize()
+    got = out[:, :N].cpu().numpy()
+    if split:
+        want = _ref(a, b, bias, 1, 0.75, 0.5, res)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-5)
+    else:
+        want = _ref(_bf16_round(a), _bf16_round(b), bias, 1, 0.75, 0.5, res)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-5)
+    rec = (out_hi.float() + out_lo.float())[:, :N].cpu().numpy()
+    np.testing.assert_allclose(rec, got, rtol=2 ** -15, atol=1e-30)
+    if ldn > N:
+        assert torch.isnan(out[:, N:]).all()          # padding columns are never written
+
+
+def test_tcgen05_no_epilogue_extras(ops):
+    rng = np.random.default_rng(9)
+    M, N, K = 256, 512, 192
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K)).astype(np.float32)
+    a_hi, _ = ops.pack_bf16(T(a), split=False)
+    b_hi, _ = ops.pack_bf16(T(b), split=False)
+    out = torch.empty((M, N), device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, out_f32=out)
+    want = _bf16_round(a).astype(np.float64) @ _bf16_round(b).astype(np.float64).T
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_tcgen05_many_tiles_persistent(ops):
+    # more tiles than SMs: exercises the TMEM double buffering and the smem ring phase wrap
+    rng = np.random.default_rng(10)
+    M, N, K = 128 * 40, 256 * 9, 320
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K)).astype(np.float32)
+    a_hi, _ = ops.pack_bf16(T(a), split=False)
+    b_hi, _ = ops.pack_bf16(T(b), split=False)
+    out = torch.empty((M, N), device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, out_f32=out)
+    want = torch.from_numpy(_bf16_round(a)).to(DEV).double() @ torch.from_numpy(_bf16_round(b)).to(DEV).double().T
+    assert torch.allclose(out.double(), want, rtol=1e-5, atol=1e-3)
+
+
+def test_bad_arguments_raise(ops):
+    from diffmm_b200._lib import DiffMMError
+    a = torch.zeros((128, 60), dtype=torch.bfloat16, device=DEV)       # ld 60 is not a multiple of 8
+    out = torch.empty((128, 128), device=DEV)
+    with pytest.raises(DiffMMError):
+        ops.gemm_bf16_tn(a, None, a, None, 128, 128, 60, out_f32=out)
