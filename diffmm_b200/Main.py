@@ -1,0 +1,395 @@
+"""Trainer with the reference's CLI, ``Coach`` method names, phases, RNG order and log lines
+(reference Main.py:18-487), driving the B200 kernels:
+
+  phase 1 (Main.py:145-192)  diffusion training       — Denoise fwd/bwd on tcgen05 GEMMs
+  phase 2 (Main.py:195-253)  modality graph rebuild   — rebuild.rebuild_modal_adj (no host sync per edge)
+  phase 3 (Main.py:292-377)  joint training           — CSR SpMM + fused BPR / InfoNCE kernels
+  eval    (Main.py:390-448)  scores + masked top-20 on device, the reference's metric arithmetic on host
+
+Usage: ``python -m diffmm_b200.Main -c conf/tiktok.toml`` (or put diffmm_b200/dropin first on sys.path and
+run the reference's own Main.py unchanged: it then binds to these Model/DataHandler/Utils symbols).
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+from torch.optim.adam import Adam
+from torch.optim.lr_scheduler import CosineAnnealingLR
+
+from . import ops, rng
+from .autograd import linear_tn, spmm
+from .Conf import Config, load_config
+from .DataHandler import DataHandler
+from .Model import Denoise, GaussianDiffusion, Model, _as_csr
+from .rebuild import rebuild_modal_adj
+from .Utils.Log import Log
+from .Utils.Utils import InfoNCE, bpr_loss, l2_reg_loss
+
+main_log = None      # module global like the reference (Main.py:471)
+config = None
+
+
+class _NullLog:
+    def info(self, *_a, **_k):
+        pass
+
+
+def _log():
+    return main_log if main_log is not None else _NullLog()
+
+
+class Coach:
+    def __init__(self, handler: DataHandler, config: Config, group=None):
+        self.handler = handler
+        self.config = config
+        self.group = group
+        self.device = torch.device(f"cuda:{self.config.base.gpu}" if torch.cuda.is_available() else "cpu")
+        self.phase_seconds = {}
+        _log().info(f"USER: {self.config.data.user_num}, ITEM: {self.config.data.item_num}")
+        _log().info(f"NUM OF INTERACTIONS: {len(self.handler.trainData)}")
+
+    @property
+    def has_audio(self):
+        return getattr(self.handler, "has_audio", self.config.data.name == "tiktok")
+
+    def makePrint(self, name, epoch, results: dict):
+        result_str = f"Epoch {epoch}/{self.config.train.epoch}, {name}: "
+        for metric in results:
+            result_str += f"{metric}={results[metric]:.5f}, "
+        return result_str[:-2] + "  "
+
+    def save_max(self, new: list, old: list) -> list:
+        return [i if i > j else j for i, j in zip(new, old)]
+
+    def run(self):
+        self.prepareModel()
+        _log().info("Model Initialized ✅")
+        recallMax, ndcgMax, precisionMax = 0, 0, 0
+        his_max = [0, 0, 0]
+        bestEpoch = 0
+        self.history = []
+        _log().info("Start training 🚀")
+        try:
+            for epoch in range(0, self.config.train.epoch):
+                tstFlag = (epoch % self.config.train.tstEpoch == 0)
+                result = self.trainEpoch()
+                if self.config.train.use_lr_scheduler:
+                    self.model_scheduler.step()
+                    self.image_scheduler.step()
+                    self.text_scheduler.step()
+                    if self.has_audio:
+                        self.audio_scheduler.step()
+                _log().info(self.makePrint("⏩ Train", epoch, result))
+                rec = dict(epoch=epoch, train=result)
+                if tstFlag:
+                    result = self.testEpoch()
+                    rec["test"] = result
+                    his_max = self.save_max([result["Recall"], result["NDCG"], result["Precision"]], his_max)
+                    if result["Recall"] > recallMax:
+                        recallMax, ndcgMax, precisionMax = result["Recall"], result["NDCG"], result["Precision"]
+                        bestEpoch = epoch
+                    _log().info(self.makePrint("🧪 Test", epoch, result))
+                self.history.append(rec)
+                _log().info(f"💡 Current best: Epoch: {bestEpoch}, Recall: {recallMax:.5f}({his_max[0]:.5f}), NDCG: {ndcgMax:.5f}({his_max[1]:.5f}), Precision: {precisionMax:.5f}({his_max[2]:.5f})")
+            _log().info(f"Best epoch: {bestEpoch}, Recall: {recallMax:.5f}({his_max[0]:.5f}), NDCG: {ndcgMax:.5f}({his_max[1]:.5f}), Precision: {precisionMax:.5f}({his_max[2]:.5f})")
+        except KeyboardInterrupt:
+            _log().info("🈲 Training interrupted by user!")
+
+    def prepareModel(self):
+        """Main.py:85-110 — same construction order (parameter init consumes the torch RNG)."""
+        h = self.handler
+        if self.has_audio:
+            self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach(), h.audio_feats.detach()).cuda(self.device)
+        else:
+            self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach()).cuda(self.device)
+        self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
+        self.diffusion_model = GaussianDiffusion(self.config).cuda(self.device)
+
+        out_dims = ast.literal_eval(self.config.base.denoise_dim) + [self.config.data.item_num]
+        in_dims = out_dims[::-1]
+        self.image_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
+        self.image_denoise_opt = Adam(self.image_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        self.image_scheduler = CosineAnnealingLR(self.image_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
+        self.text_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
+        self.text_denoise_opt = Adam(self.text_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        self.text_scheduler = CosineAnnealingLR(self.text_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
+        if self.has_audio:
+            self.audio_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
+            self.audio_denoise_opt = Adam(self.audio_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+            self.audio_scheduler = CosineAnnealingLR(self.audio_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
+
+    def makeTorchAdj(self, u_list, i_list, edge_list):
+        """Main.py:113-116 (kept for callers that still build edge lists on the host)."""
+        from scipy.sparse import coo_matrix
+        mat = coo_matrix((edge_list, (u_list, i_list)), shape=(self.config.data.user_num, self.config.data.item_num), dtype=np.float32)
+        return DataHandler.makeTorchAdj(mat, self.config.data.user_num, self.config.data.item_num, self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _denoise_dict(self):
+        d = {"image": self.image_denoise_model, "text": self.text_denoise_model}
+        if self.has_audio:
+            d["audio"] = self.audio_denoise_model
+        return d
+
+    def _tick(self, name, t0):
+        torch.cuda.synchronize()
+        self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + (time.perf_counter() - t0)
+
+    def trainDiffusion(self):
+        """Phase 1 (Main.py:145-192)."""
+        image_diff_loss, text_diff_loss, audio_diff_loss = 0, 0, 0
+        for i, batch_data in enumerate(self.handler.diffusionLoader):
+            batch_u_items = batch_data[0]
+            i_embs = self.model.getItemEmbs()
+            image_feats = self.model.getImageFeats().detach()
+            text_feats = self.model.getTextFeats().detach()
+
+            batch_image_loss = self.diffusion_model.training_losses(self.image_denoise_model, batch_u_items, i_embs, image_feats)
+            loss_image = batch_image_loss.mean()
+            image_diff_loss += loss_image.item()
+            batch_text_loss = self.diffusion_model.training_losses(self.text_denoise_model, batch_u_items, i_embs, text_feats)
+            loss_text = batch_text_loss.mean()
+            text_diff_loss += loss_text.item()
+
+            self.image_denoise_opt.zero_grad()
+            self.text_denoise_opt.zero_grad()
+            if self.has_audio:
+                audio_feats = self.model.getAudioFeats().detach()
+                self.audio_denoise_opt.zero_grad()
+                batch_audio_loss = self.diffusion_model.training_losses(self.audio_denoise_model, batch_u_items, i_embs, audio_feats)
+                loss_audio = batch_audio_loss.mean()
+                audio_diff_loss += loss_audio.item()
+                total_loss = loss_image.item() + loss_text.item() + loss_audio.item()
+                batch_diff_loss = (loss_image + loss_text + loss_audio) / total_loss
+                image_diff_loss /= total_loss
+                text_diff_loss /= total_loss
+                audio_diff_loss /= total_loss
+            else:
+                total_loss = loss_image.item() + loss_text.item()
+                batch_diff_loss = (loss_image + loss_text) / total_loss
+                image_diff_loss /= total_loss
+                text_diff_loss /= total_loss
+            batch_diff_loss.backward()
+            self.image_denoise_opt.step()
+            self.text_denoise_opt.step()
+            if self.has_audio:
+                self.audio_denoise_opt.step()
+        return image_diff_loss, text_diff_loss, audio_diff_loss
+
+    def rebuildGraphs(self):
+        """Phase 2 (Main.py:195-253) on device.  The shuffled loader of the reference only permutes users,
+        which cannot change the adjacency; its RNG draws are replayed so later phases see the same stream."""
+        h = self.handler
+        it = iter(h.diffusionLoader.index_batches())
+        next(it, None)                                   # base-seed + sampler-seed + randperm draws
+        adjs = rebuild_modal_adj(self.diffusion_model, self._denoise_dict(), h.train_indptr, h.train_indices,
+                                 self.config.data.user_num, self.config.data.item_num,
+                                 self.config.hyper.sampling_step, getattr(self.config.base, "precision", "bf16"),
+                                 group=self.group)
+        self.image_adj, self.text_adj = adjs["image"], adjs["text"]
+        if self.has_audio:
+            self.audio_adj = adjs["audio"]
+
+    def trainJoint(self):
+        """Phase 3 (Main.py:292-377)."""
+        cfg = self.config
+        U = cfg.data.user_num
+        ep_loss = ep_rec_loss = ep_reg_loss = ep_cl_loss = 0
+        biadj = _as_csr(self.handler.torchBiAdj)
+        for i, batch_data in enumerate(self.handler.trainLoader):
+            users, pos_items, neg_items = batch_data
+            users = users.long().cuda(self.device)
+            pos_items = pos_items.long().cuda(self.device)
+            neg_items = neg_items.long().cuda(self.device)
+
+            if self.has_audio:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj, self.audio_adj)
+            else:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
+            final_user_embs, final_item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
+
+            rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
+            reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
+            ep_rec_loss += rec_loss.item()
+            ep_reg_loss += reg_loss.item()
+
+            # cross-layer CL (Main.py:315-330)
+            joint_embs = torch.cat([self.model.u_embs, self.model.i_embs], dim=0)
+            all_embs = []
+            all_embs_cl = joint_embs
+            for k in range(3):
+                joint_embs = spmm(biadj, joint_embs)
+                random_noise = rng.rand_like(joint_embs)
+                joint_embs = _SignNoise.apply(joint_embs, random_noise, cfg.hyper.noise_degree)
+                all_embs.append(joint_embs)
+                if k == 0:
+                    all_embs_cl = joint_embs
+            final_embs = torch.mean(torch.stack(all_embs), dim=0)
+            cl1_user_embs, cl1_item_embs = final_embs[:U], final_embs[U:]
+            cl2_user_embs, cl2_item_embs = all_embs_cl[:U], all_embs_cl[U:]
+            cl_loss = (InfoNCE(cl1_user_embs, cl2_user_embs, users, cfg.hyper.cross_cl_temp)
+                       + InfoNCE(cl1_item_embs, cl2_item_embs, pos_items, cfg.hyper.cross_cl_temp)) * cfg.hyper.cross_cl_rate
+
+            T, R = cfg.hyper.modal_cl_temp, cfg.hyper.modal_cl_rate
+            views = [(gcn_output.u_image_embs, gcn_output.i_image_embs), (gcn_output.u_text_embs, gcn_output.i_text_embs)]
+            if self.has_audio:
+                views.append((gcn_output.u_audio_embs, gcn_output.i_audio_embs))
+            if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
+                pairs = [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else [])
+                for a, b in pairs:
+                    cl_loss = cl_loss + (InfoNCE(views[a][0], views[b][0], users, T) + InfoNCE(views[a][1], views[b][1], pos_items, T)) * R
+            else:                            # main view as the anchor (Main.py:351-356,363-367)
+                for vu, vi in views:
+                    cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
+
+            ep_cl_loss += cl_loss.item()
+            batch_joint_loss = rec_loss + reg_loss + cl_loss
+            ep_loss += batch_joint_loss.item()
+            self.opt.zero_grad()
+            batch_joint_loss.backward()
+            self.opt.step()
+        return ep_loss, ep_rec_loss, ep_reg_loss, ep_cl_loss
+
+    def trainEpoch(self):
+        t0 = time.perf_counter()
+        self.handler.trainData.negSampling()
+        self.phase_seconds["neg_sampling"] = self.phase_seconds.get("neg_sampling", 0.0) + (time.perf_counter() - t0)
+        train_steps = len(self.handler.trainData) // self.config.train.batch
+        diffusion_steps = len(self.handler.diffusionData) // self.config.train.batch
+
+        _log().info("Diffusion model training")
+        t0 = time.perf_counter()
+        image_diff_loss, text_diff_loss, audio_diff_loss = self.trainDiffusion()
+        self._tick("diffusion_train", t0)
+
+        _log().info("Re-build multimodal UI matrix")
+        t0 = time.perf_counter()
+        self.rebuildGraphs()
+        self._tick("rebuild", t0)
+
+        _log().info("Joint training 🤝")
+        t0 = time.perf_counter()
+        ep_loss, ep_rec_loss, ep_reg_loss, ep_cl_loss = self.trainJoint()
+        self._tick("joint_train", t0)
+
+        result = dict()
+        result["Loss"] = ep_loss / train_steps
+        result["BPR Loss"] = ep_rec_loss / train_steps
+        result["reg loss"] = ep_reg_loss / train_steps
+        result["CL loss"] = ep_cl_loss / train_steps
+        result["image loss"] = image_diff_loss / diffusion_steps
+        result["text loss"] = text_diff_loss / diffusion_steps
+        if self.has_audio:
+            result["audio loss"] = audio_diff_loss / diffusion_steps
+        return result
+
+    def testEpoch(self):
+        """Main.py:390-420 with the train mask applied from the device CSR instead of dense host rows."""
+        t0 = time.perf_counter()
+        testData = self.handler.testData
+        iter(self.handler.testLoader)        # the reference's loop draws one DataLoader base seed here (RNG parity)
+        epRecall = epNdcg = epPrecision = 0
+        with torch.no_grad():
+            if self.has_audio:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj, self.audio_adj)
+            else:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
+            user_embs, item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
+            users_all = torch.from_numpy(np.asarray(testData.test_users)).long()
+            tb = self.config.train.test_batch
+            I = self.config.data.item_num
+            for s in range(0, len(users_all), tb):
+                usr = users_all[s:s + tb].cuda(self.device)
+                trainMask = self.handler.diffusionData.rows(usr)
+                predict = linear_tn(user_embs[usr], item_embs, None, 0, "bf16x3")[:, :I] * (1 - trainMask) - trainMask * 1e8
+                _, top_idxs = torch.topk(predict, self.config.base.topk)
+                recall, ndcg, precision = self.calcRes(top_idxs.cpu().numpy(), testData.test_user_its, usr.cpu())
+                epRecall += recall
+                epNdcg += ndcg
+                epPrecision += precision
+        n = len(testData)
+        self._tick("eval", t0)
+        return {"Recall": epRecall / n, "NDCG": epNdcg / n, "Precision": epPrecision / n}
+
+    def calcRes(self, top_idxs: np.ndarray, test_u_its: list, users: Tensor):
+        """Main.py:422-448 (same arithmetic)."""
+        assert top_idxs.shape[0] == len(users)
+        topk = self.config.base.topk
+        allRecall = allNdcg = allPrecision = 0
+        users = users.tolist() if hasattr(users, "tolist") else list(users)
+        for i in range(len(users)):
+            u_rec_list = list(top_idxs[i])
+            u_its = test_u_its[users[i]]
+            tstNum = len(u_its)
+            maxDcg = np.sum([np.reciprocal(np.log2(loc + 2)) for loc in range(min(tstNum, topk))])
+            recall_hits = dcg = 0
+            for item in u_its:
+                if item in u_rec_list:
+                    recall_hits += 1
+                    dcg += np.reciprocal(np.log2(u_rec_list.index(item) + 2))
+            allRecall += recall_hits / tstNum
+            allNdcg += dcg / maxDcg
+            allPrecision += recall_hits / topk
+        return allRecall, allNdcg, allPrecision
+
+
+class _SignNoise(torch.autograd.Function):
+    """e + sign(e) * normalize(rnd) * noise_degree (Main.py:320-321); d/de = identity (sign has zero grad)."""
+
+    @staticmethod
+    def forward(ctx, e, rnd, noise_degree):
+        out = e.detach().clone()
+        ops.sign_noise_(out, rnd, float(noise_degree))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+def seed_it(seed):
+    """Main.py:450-456."""
+    random.seed(seed)
+    os.environ["PYTHONSEED"] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+def main(argv=None):
+    global main_log, config
+    parser = argparse.ArgumentParser(description="Model Configs")
+    parser.add_argument("--config", "-c", default="conf/test.toml", type=str, help="config file path")
+    args = parser.parse_args(argv)
+    try:
+        config = load_config(args.config)
+        print(f"Load configuration ({config.data.name}) file successfully👌")
+    except Exception as e:
+        print(f"Error loading configuration file: {e}")
+        raise SystemExit(1)
+    seed_it(config.base.seed)
+    main_log = Log("main", config.data.name)
+    main_log.info("Start")
+    main_log.info("Configuration Details:")
+    for section, options in config.__dict__.items():
+        main_log.info(f"{section}: {options}")
+    data_handler = DataHandler(config)
+    main_log.info("Load Data")
+    data_handler.LoadData()
+    coach = Coach(data_handler, config)
+    coach.run()
+    return coach
+
+
+if __name__ == "__main__":
+    main()

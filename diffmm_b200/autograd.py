@@ -1,0 +1,173 @@
+"""torch.autograd.Function wrappers that give the C-ABI kernels forward + backward semantics.
+
+PyTorch only provides the tape here; every contraction, SpMM and loss below runs in
+libdiffmm_b200.so.  Backward formulas are stated next to each Function.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+_PRECISIONS = ("bf16", "bf16x3")
+
+
+def check_precision(p: str) -> str:
+    if p not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}, got {p!r}")
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# packed-weight cache: weights change once per optimiser step (tensor._version bumps), while the
+# reverse-diffusion chain reuses them 5 x (#batches) times.
+# ------------------------------------------------------------------------------------------------
+_PACK_CACHE: dict = {}
+
+
+def packed_weight(w: torch.Tensor, transpose: bool, split: bool):
+    key = (w.data_ptr(), tuple(w.shape), transpose)
+    ent = _PACK_CACHE.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver and (ent[2] is not None or not split):
+        return ent[1], (ent[2] if split else None)
+    src = w.detach()
+    hi, lo = ops.pack_bf16(src, transpose=transpose, split=True)
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (ver, hi, lo)
+    return hi, (lo if split else None)
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """Row-major view/copy with unit inner stride (padded leading dimensions are fine)."""
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
+def _new_out(M: int, N: int, device) -> torch.Tensor:
+    ld = ops.pad_to(N, 4)
+    buf = torch.empty((M, ld), dtype=torch.float32, device=device)
+    return buf[:, :N] if ld != N else buf
+
+
+class LinearTN(torch.autograd.Function):
+    """y = act(x W^T + b) with x [M,K], W [N,K] (nn.Linear layout), on dmm_gemm_bf16_tn.
+
+    backward (g = dL/dy, g' = g * (1 - y^2) for tanh):
+        dx = g' W          -> gemm_tn(A = g' [M,N],   B = W^T [K,N])
+        dW = g'^T x        -> gemm_tn(A = g'^T [N,M], B = x^T [K,M])
+        db = sum_rows g'
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int, precision: str):
+        split = precision == "bf16x3"
+        x = _rows(x.detach())
+        M, K = x.shape
+        N = weight.shape[0]
+        x_hi, x_lo = ops.pack_bf16(x, split=split)
+        w_hi, w_lo = packed_weight(weight, False, split)
+        y = _new_out(M, N, x.device)
+        ops.gemm_bf16_tn(x_hi, x_lo, w_hi, w_lo, M, N, K, bias=bias.detach() if bias is not None else None, act=act,
+                         out_f32=y)
+        ctx.act, ctx.split, ctx.has_bias = act, split, bias is not None
+        ctx.save_for_backward(x, weight, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        split = ctx.split
+        g = _rows(g)
+        if ctx.act == 1:
+            g = g * (1.0 - y * y)
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            g_hi, g_lo = ops.pack_bf16(g, split=split)
+            wt_hi, wt_lo = packed_weight(weight, True, split)
+            dx = _new_out(M, K, g.device)
+            ops.gemm_bf16_tn(g_hi, g_lo, wt_hi, wt_lo, M, K, N, out_f32=dx)
+        if ctx.needs_input_grad[1]:
+            gt_hi, gt_lo = ops.pack_bf16(g, transpose=True, split=split)
+            xt_hi, xt_lo = ops.pack_bf16(x, transpose=True, split=split)
+            dw = _new_out(N, K, g.device)
+            ops.gemm_bf16_tn(gt_hi, gt_lo, xt_hi, xt_lo, N, K, M, out_f32=dw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(0)
+        return dx, dw, db, None, None
+
+
+def linear_tn(x, weight, bias=None, act: int = 0, precision: str = "bf16"):
+    return LinearTN.apply(x, weight, bias, act, check_precision(precision))
+
+
+class SpMM(torch.autograd.Function):
+    """y = A x for the symmetric normalised adjacency; dL/dx = A^T g = A g (same kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, adj: ops.CsrAdj):
+        ctx.adj = adj
+        return ops.spmm(adj, _rows(x.detach()))
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.spmm(ctx.adj, _rows(g)), None
+
+
+def spmm(adj: ops.CsrAdj, x: torch.Tensor) -> torch.Tensor:
+    return SpMM.apply(x, adj)
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """-mean_b log softmax_b(<n1_b, n2_.>/T)_b on gathered, L2-normalised rows (Utils/Utils.py:57-75).
+
+    backward: with p = softmax rows, dL/dn1_i = sum_j (p_ij - d_ij) n2_j / (B T),
+    dL/dn2_j = sum_i (p_ij - d_ij) n1_i / (B T), then the normalisation Jacobian
+    (I - n n^T)/|x|, and a scatter-add over the (repeating) gather indices.
+    """
+
+    @staticmethod
+    def forward(ctx, v1, v2, idx, temperature: float):
+        v1d, v2d = _rows(v1.detach()), _rows(v2.detach())
+        loss, saved = ops.infonce_fwd(v1d, v2d, idx, temperature)
+        ctx.temperature = temperature
+        ctx.save_for_backward(v1d, v2d, idx, *saved)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        v1, v2, idx, lse, inv1, inv2 = ctx.saved_tensors
+        g1, g2 = ops.infonce_bwd(v1, v2, idx, ctx.temperature, (lse, inv1, inv2), 1.0)
+        d1 = d2 = None
+        if ctx.needs_input_grad[0]:
+            d1 = ops.scatter_add_rows(g1 * g, idx, torch.zeros_like(v1))
+        if ctx.needs_input_grad[1]:
+            d2 = ops.scatter_add_rows(g2 * g, idx, torch.zeros_like(v2))
+        return d1, d2, None, None
+
+
+class BPRFn(torch.autograd.Function):
+    """mean_b -log(1e-5 + sigmoid(u_b.p_b - u_b.n_b)) on rows already gathered by the caller's
+    indices (Utils/Utils.py:78-98); gradients come back per batch row."""
+
+    @staticmethod
+    def forward(ctx, u, p, n):
+        B = u.shape[0]
+        ar = torch.arange(B, device=u.device)
+        ud, pd, nd = _rows(u.detach()), _rows(p.detach()), _rows(n.detach())
+        # item table = [p; n]: pos rows 0..B-1, neg rows B..2B-1
+        tab = torch.cat([pd, nd], 0)
+        loss, grads = ops.bpr_fwd_bwd(ud, tab, ar, ar, ar + B, 1.0, True)
+        ctx.save_for_backward(*grads)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gu, gp, gn = ctx.saved_tensors
+        return gu * g, gp * g, gn * g

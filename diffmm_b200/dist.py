@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the B200 box,
+gloo in the CPU tests).  The path shards in two places:
+
+  * rebuild (denoise chain + top-k): users are independent -> contiguous user blocks per rank, Denoise
+    weights replicated, NO data-path collective; one all-gather of the emitted edge lists at the end
+    (offsets are the train-CSR indptr, known a priori because k_u = deg(u));
+  * propagation: rows of the symmetric adjacency and of X are block-partitioned, one all-gather of the
+    X blocks per SpMM layer, local SpMM on the local row block (dmm_spmm_csr row0/row1).
+
+The reference has no distributed code at all (single process, single device).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as td
+
+
+def world_size(group=None) -> int:
+    return td.get_world_size(group) if td.is_available() and td.is_initialized() else 1
+
+
+def rank(group=None) -> int:
+    return td.get_rank(group) if td.is_available() and td.is_initialized() else 0
+
+
+def row_blocks(n_rows: int, world: int, weights: Optional[torch.Tensor] = None) -> List[Tuple[int, int]]:
+    """Contiguous row blocks, one per rank.  With ``weights`` (e.g. CSR indptr, i.e. cumulative nnz) the cut
+    points balance the cumulative weight instead of the row count; blocks stay contiguous and cover [0, n)."""
+    if weights is None:
+        cuts = [(n_rows * r) // world for r in range(world + 1)]
+    else:
+        cum = weights.detach().to("cpu", torch.float64)
+        # cum has n_rows + 1 entries (indptr); add the row index so that zero-degree rows still cost something
+        cost = cum + torch.arange(n_rows + 1, dtype=torch.float64)
+        total = float(cost[-1])
+        targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64)
+        inner = torch.searchsorted(cost, targets).clamp_(0, n_rows).tolist() if world > 1 else []
+        cuts = [0] + [int(c) for c in inner] + [n_rows]
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_rows(n_rows: int, world: int, rk: int, indptr: Optional[torch.Tensor] = None) -> Tuple[int, int]:
+    """User block of rank ``rk`` for the rebuild.  Rows cost the same GEMM work regardless of degree, so the
+    split is by row count (indptr is accepted for API symmetry and ignored)."""
+    return row_blocks(n_rows, world)[rk]
+
+
+def allgather_edges(items_local: torch.Tensor, indptr: torch.Tensor, n_users: int, group=None) -> torch.Tensor:
+    """Every rank filled items[indptr[r0]:indptr[r1]) for its user block; returns the complete edge list on
+    every rank.  all-gather-v over padded equal-size segments (one collective per modality)."""
+    world, rk = world_size(group), rank(group)
+    if world == 1:
+        return items_local
+    blocks = row_blocks(n_users, world)
+    ptr_cpu = indptr.detach().to("cpu")
+    offs = [(int(ptr_cpu[a]), int(ptr_cpu[b])) for a, b in blocks]
+    seg = max(1, max(e - s for s, e in offs))
+    send = torch.zeros(seg, dtype=items_local.dtype, device=items_local.device)
+    s, e = offs[rk]
+    send[: e - s] = items_local[s:e]
+    recv = torch.empty(seg * world, dtype=items_local.dtype, device=items_local.device)
+    td.all_gather_into_tensor(recv, send, group=group)
+    out = torch.empty_like(items_local)
+    for r, (s, e) in enumerate(offs):
+        out[s:e] = recv[r * seg: r * seg + (e - s)]
+    return out
+
+
+def allgather_rows(x_local: torch.Tensor, blocks: List[Tuple[int, int]], group=None) -> torch.Tensor:
+    """All-gather of row-partitioned X blocks (N x D) before a row-partitioned SpMM layer."""
+    world, rk = world_size(group), rank(group)
+    if world == 1:
+        return x_local
+    D = x_local.shape[1]
+    seg = max(1, max(b - a for a, b in blocks))
+    send = torch.zeros((seg, D), dtype=x_local.dtype, device=x_local.device)
+    a, b = blocks[rk]
+    send[: b - a] = x_local
+    recv = torch.empty((seg * world, D), dtype=x_local.dtype, device=x_local.device)
+    td.all_gather_into_tensor(recv, send, group=group)
+    return torch.cat([recv[r * seg: r * seg + (b - a)] for r, (a, b) in enumerate(blocks)], 0)

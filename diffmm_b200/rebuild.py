@@ -1,0 +1,180 @@
+"""Reverse-diffusion chain + per-user top-k graph rebuild, entirely on device.
+
+Replaces, for the rebuild phase of Coach.trainEpoch (reference Main.py:195-253):
+  GaussianDiffusion.generate_view / p_mean_variance (Model.py:300-322,357-378) — S x (cat, 2 cuBLAS
+  SGEMMs, tanh, axpby), the Python double loop of per-user torch.topk + int(tensor) syncs
+  (Main.py:224-230), and the scipy adjacency build + H2D (Main.py:113-116, DataHandler.py:53-93).
+
+Per user block the data flow is
+  CSR rows -> bf16 0/1 operand tile (+ fp32 x_t)                       dmm_csr_rows_to_dense
+  for i = S-1..0:  temb columns                                        dmm_time_embedding
+                   h = tanh([x_t, temb] W1^T + b1)   (bf16 hi/lo)      dmm_gemm_bf16_tn  (tcgen05)
+                   x_t = c1[i] (h W2^T + b2) + c2[i] x_t  (fp32 + bf16 operand for the next step)
+  top-k_u (k_u = deg(u)) -> item ids at the train-CSR offsets          dmm_topk_edges
+and once per modality
+  edges -> normalised CSR adjacency                                    dmm_build_norm_adj_csr
+Users are independent, so blocks can be any size (results do not depend on it) and shard across
+ranks with no data-path collective except the final edge all-gather (dist.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops, rng
+from .autograd import check_precision, packed_weight
+
+
+class ChainWorkspace:
+    """Device buffers of one user block, reused across steps, modalities and blocks."""
+
+    def __init__(self, rows: int, n_items: int, hidden: int, d_emb: int, split: bool, device):
+        self.rows, self.n_items, self.hidden, self.d_emb, self.split = rows, n_items, hidden, d_emb, split
+        self.ld_a = ops.pad_to(n_items + d_emb, 64)
+        self.ld_x = ops.pad_to(n_items, 32)
+        self.ld_h = ops.pad_to(hidden, 64)
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.a_hi = torch.empty((rows, self.ld_a), **bf)
+        self.a_lo = torch.empty((rows, self.ld_a), **bf) if split else None
+        self.h_hi = torch.empty((rows, self.ld_h), **bf)
+        self.h_lo = torch.empty((rows, self.ld_h), **bf) if split else None
+        self.x = torch.empty((rows, self.ld_x), dtype=torch.float32, device=device)
+
+    def fits(self, rows, n_items, hidden, d_emb, split):
+        return (rows <= self.rows and n_items == self.n_items and hidden == self.hidden and d_emb == self.d_emb
+                and split == self.split)
+
+
+def _single_layer(den):
+    if len(den.in_layers) != 1 or len(den.out_layers) != 1:
+        raise NotImplementedError("the fused chain supports denoise_dim with one hidden layer (all shipped configs)")
+    return den.in_layers[0], den.out_layers[0]
+
+
+def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
+                  csr: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, row_ids: Optional[torch.Tensor] = None,
+                  row0: int = 0, n_rows: Optional[int] = None, sampling_step: int = 0,
+                  precision: Optional[str] = None, ws: Optional[ChainWorkspace] = None,
+                  noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """generate_view (Model.py:300-322) for a block of users given as dense rows or CSR rows.
+    Returns the fp32 [n_rows, I] scores (a view of the workspace: consume before the next call)."""
+    lin1, lin2 = _single_layer(den)
+    W1, b1, W2, b2 = lin1.weight, lin1.bias, lin2.weight, lin2.bias
+    H, K1 = W1.shape
+    I = W2.shape[0]
+    d = den.time_emb_dim
+    assert K1 == I + d
+    precision = check_precision(precision or den.precision)
+    split = precision == "bf16x3"
+    dev = W1.device
+    if x_dense is not None:
+        n_rows = x_dense.shape[0]
+        assert x_dense.shape[1] == I
+    assert n_rows is not None and n_rows > 0
+    if ws is None or not ws.fits(n_rows, I, H, d, split):
+        ws = ChainWorkspace(n_rows, I, H, d, split, dev)
+    M = n_rows
+    a_hi, h_hi, x = ws.a_hi[:M], ws.h_hi[:M], ws.x[:M]
+    a_lo = ws.a_lo[:M] if split else None
+    h_lo = ws.h_lo[:M] if split else None
+    xv = x[:, :I]
+
+    exact_input = False                       # True when bf16(x) == x, so the A_lo pass is identically zero
+    if sampling_step == 0:
+        if csr is not None:
+            ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, x_f32=x, a_bf16=a_hi)
+            exact_input = True
+        else:
+            xd = x_dense if (x_dense.stride(1) == 1 and x_dense.dtype == torch.float32) else x_dense.float().contiguous()
+            xv.copy_(xd)
+            ops.pack_bf16_into(xd, a_hi, a_lo)
+    else:
+        if csr is not None:
+            x0 = torch.empty((M, ws.ld_x), dtype=torch.float32, device=dev)
+            ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, x_f32=x0)
+            x0 = x0[:, :I]
+        else:
+            x0 = x_dense if x_dense.stride(1) == 1 else x_dense.contiguous()
+        if noise is None:
+            noise = rng.randn_like(x0)                                       # Model.py:337 draw
+        ta, tb = diff._tables_f32(dev)
+        t = sampling_step - 1
+        ca = ta[t].expand(M).contiguous()
+        cb = tb[t].expand(M).contiguous()
+        ops.q_sample(x0, noise, ca, cb, 1, x_t=xv, a_hi=a_hi, a_lo=a_lo)
+
+    w1_hi, w1_lo = packed_weight(W1, False, split)
+    w2_hi, w2_lo = packed_weight(W2, False, split)
+    emb_w, emb_b = den.emb_layer.weight.detach(), den.emb_layer.bias.detach()
+    b1d, b2d = b1.detach(), b2.detach()
+    S = diff.steps
+    for i in range(S - 1, -1, -1):
+        ops.time_embedding(emb_w, emb_b, M, t_all=i, a_hi=a_hi, a_lo=a_lo, col0=I)
+        first = i == S - 1
+        ops.gemm_bf16_tn(a_hi, None if (first and exact_input) else a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1,
+                         out_hi=h_hi, out_lo=h_lo)
+        c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
+        c2 = float(np.float32(diff._h_coef2[i]))
+        last = i == 0
+        ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
+                         residual=xv if c2 != 0.0 else None, out_f32=xv,
+                         out_hi=None if last else a_hi[:, :I], out_lo=None if (last or not split) else a_lo[:, :I])
+    return xv
+
+
+def default_block_rows(n_users: int, n_items: int, hidden: int, split: bool, budget_bytes: int = 12 << 30) -> int:
+    """Largest user block whose workspace stays under ``budget_bytes`` (multiple of 128 rows)."""
+    per_row = ops.pad_to(n_items + 16, 64) * 2 * (2 if split else 1) + ops.pad_to(n_items, 32) * 4 \
+        + ops.pad_to(hidden, 64) * 2 * (2 if split else 1)
+    rows = max(128, (budget_bytes // per_row) // 128 * 128)
+    return int(min(n_users, rows))
+
+
+def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torch.Tensor, indices: torch.Tensor,
+                  n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
+                  row_range: Optional[Tuple[int, int]] = None, block_rows: Optional[int] = None,
+                  out_items: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """Top-k item ids per modality for users in ``row_range`` (default all), written at the train-CSR
+    offsets (k_u = deg(u), Main.py:215-216,226).  Returns {modality: int32 [E]} (only this range filled)."""
+    r0, r1 = row_range if row_range is not None else (0, n_users)
+    any_den = next(iter(denoise_models.values()))
+    precision = check_precision(precision or any_den.precision)
+    split = precision == "bf16x3"
+    H = any_den.in_layers[0].weight.shape[0]
+    if block_rows is None:
+        block_rows = default_block_rows(r1 - r0, n_items, H, split)
+    E = int(indices.numel())
+    dev = indptr.device
+    if out_items is None:
+        out_items = {m: torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E] for m in denoise_models}
+    ws = None
+    with torch.no_grad():
+        for b0 in range(r0, r1, block_rows):
+            b1 = min(b0 + block_rows, r1)
+            for m, den in denoise_models.items():
+                if ws is None or not ws.fits(b1 - b0, n_items, H, den.time_emb_dim, split):
+                    ws = ChainWorkspace(b1 - b0, n_items, H, den.time_emb_dim, split, dev)
+                scores = denoise_chain(diff, den, csr=(indptr, indices), row0=b0, n_rows=b1 - b0,
+                                       sampling_step=sampling_step, precision=precision, ws=ws)
+                ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m])
+    return out_items
+
+
+def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torch.Tensor, indices: torch.Tensor,
+                      n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
+                      block_rows: Optional[int] = None, group=None) -> Dict[str, ops.CsrAdj]:
+    """The whole rebuild phase (Main.py:195-253): {modality: normalised CSR adjacency}.
+    With a torch.distributed ``group`` of more than one rank, users are row-sharded and the edge lists
+    all-gathered (dist.py); every rank then builds the same adjacency."""
+    from . import dist as ddist
+    if group is not None and ddist.world_size(group) > 1:
+        r0, r1 = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr)
+        items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
+                              row_range=(r0, r1), block_rows=block_rows)
+        items = {m: ddist.allgather_edges(v, indptr, n_users, group) for m, v in items.items()}
+    else:
+        items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
+                              block_rows=block_rows)
+    return {m: ops.build_norm_adj(indptr, v, n_users, n_items) for m, v in items.items()}

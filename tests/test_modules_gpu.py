@@ -1,0 +1,214 @@
+"""GPU parity of the reference-facing classes (Denoise / GaussianDiffusion / Model / losses / rebuild)
+against golden vectors produced by the unmodified reference and against the numpy oracle.
+
+Tolerances (written here, per north_star): "bf16x3" (split-bf16, fp32-faithful) rel 1e-4 of the tensor
+scale on forward values and 1e-3 on gradients; "bf16" rel 2e-2 of the tensor scale.  Index work
+(top-k, adjacency structure) is bit-exact given identical scores."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, params_of
+from oracle import diffmm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+U, I, H, D = 40, 120, 32, 64
+TOL = {"bf16x3": 1e-4, "bf16": 2e-2}
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def close(got, want, rel, what=""):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    scale = np.abs(want).max() + 1e-30
+    err = np.abs(got - want).max() / scale
+    assert err <= rel, f"{what}: max err {err:.3e} of scale {scale:.3e} > {rel}"
+
+
+def make_cfg(precision, **over):
+    from diffmm_b200.Conf import Config
+    cfg = Config()
+    cfg.base.denoise_dim = f"[{H}]"
+    cfg.base.precision = precision
+    cfg.hyper.noise_scale, cfg.hyper.sim_weight, cfg.train.reg = 0.5, 0.01, 1e-4
+    cfg.hyper.noise_degree, cfg.hyper.residual_weight, cfg.hyper.modal_adj_weight = 1.5, 0.5, 0.2
+    cfg.data.user_num, cfg.data.item_num = U, I
+    cfg.data.image_feat_dim, cfg.data.text_feat_dim, cfg.data.audio_feat_dim = 16, 24, 8
+    for k, v in over.items():
+        sec, key = k.split(".")
+        setattr(getattr(cfg, sec), key, v)
+    return cfg
+
+
+def make_denoise(cfg, p):
+    from diffmm_b200.Model import Denoise
+    den = Denoise([I, H], [H, I], cfg).to(DEV)
+    sd = {"emb_layer.weight": p["emb_w"], "emb_layer.bias": p["emb_b"], "in_layers.0.weight": p["w1"],
+          "in_layers.0.bias": p["b1"], "out_layers.0.weight": p["w2"], "out_layers.0.bias": p["b2"],
+          "gate_layer.weight": p["gate_w"], "gate_layer.bias": p["gate_b"]}
+    den.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})   # reference parameter names
+    return den
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_denoise_forward(precision):
+    g = load_golden("denoise_forward")
+    den = make_denoise(make_cfg(precision), params_of(g))
+    with torch.no_grad():
+        close(den(T(g["x_t"]), T(g["t"])), g["out_nogate"], TOL[precision], "no gate")
+        close(den(T(g["x_t"]), T(g["t"]), modal_feat=T(g["feat"])), g["out_gate"], TOL[precision], "gate")
+
+
+def test_schedule_and_snr():
+    from diffmm_b200.Model import GaussianDiffusion
+    g = load_golden("schedule")
+    gd = GaussianDiffusion(make_cfg("bf16")).to(DEV)
+    for k in ("betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_alphas_cumprod"):
+        np.testing.assert_allclose(getattr(gd, k).cpu().numpy(), g[f"tiktok.{k}"], rtol=1e-14)
+    np.testing.assert_allclose(gd.SNR(torch.arange(5, device=DEV)).cpu().numpy(), g["tiktok.snr"], rtol=1e-13)
+
+
+def test_q_sample_methods():
+    from diffmm_b200.Model import GaussianDiffusion
+    q = load_golden("q_sample")
+    gd = GaussianDiffusion(make_cfg("bf16")).to(DEV)
+    np.testing.assert_allclose(gd.forward_cal_xt(T(q["x0"]), T(q["t"]), T(q["noise"])).cpu().numpy(), q["xt_explicit"],
+                               rtol=1e-6, atol=1e-7)
+    assert gd.q_sample.__func__ is gd.forward_cal_xt.__func__
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_training_losses_value_and_grads(precision):
+    from diffmm_b200.Model import GaussianDiffusion
+    g = load_golden("training_losses")
+    cfg = make_cfg(precision)
+    den = make_denoise(cfg, params_of(g))
+    gd = GaussianDiffusion(cfg).to(DEV)
+    i_embs = T(g["i_embs"]).requires_grad_(True)
+    losses = gd.training_losses(den, T(g["x0"]), i_embs, T(g["feat"]), timesteps=T(g["t"]), noise=T(g["noise"]))
+    assert losses.dtype == torch.float64 and losses.shape == (g["x0"].shape[0],)
+    close(losses, g["losses"], TOL[precision] * (1 if precision == "bf16x3" else 5), "loss rows")
+    losses.mean().backward()
+    gt = 1e-3 if precision == "bf16x3" else 1e-1
+    got = {"w1": den.in_layers[0].weight.grad, "b1": den.in_layers[0].bias.grad, "w2": den.out_layers[0].weight.grad,
+           "b2": den.out_layers[0].bias.grad, "emb_w": den.emb_layer.weight.grad, "emb_b": den.emb_layer.bias.grad,
+           "gate_w": den.gate_layer.weight.grad, "gate_b": den.gate_layer.bias.grad}
+    for k, v in got.items():
+        close(v, g[f"g.{k}"], gt, f"grad {k}")
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_generate_view(precision):
+    from diffmm_b200.Model import GaussianDiffusion
+    from diffmm_b200.rebuild import denoise_chain
+    g = load_golden("generate_view")
+    cfg = make_cfg(precision)
+    den = make_denoise(cfg, params_of(load_golden("training_losses")))
+    gd = GaussianDiffusion(cfg).to(DEV)
+    v0 = gd.generate_view(den, T(g["x0"]), 0)
+    assert tuple(v0.shape) == g["view0"].shape
+    close(v0, g["view0"], TOL[precision], "view0 dense")
+    v0c = denoise_chain(gd, den, csr=(T(g["indptr"]), T(g["indices"], torch.int32)), row0=0, n_rows=U)
+    close(v0c, g["view0"], TOL[precision], "view0 csr")
+    v2 = denoise_chain(gd, den, x_dense=T(g["x0"]), sampling_step=2, noise=T(g["randn"]))
+    close(v2, g["view2"], TOL[precision], "view2")
+    assert gd.p_sample.__func__ is gd.generate_view.__func__
+
+
+@pytest.mark.parametrize("tag,mods", [("3", ["image", "text", "audio"]), ("2", ["image", "text"])])
+def test_gcn_mm_value_and_grads(tag, mods):
+    from diffmm_b200.DataHandler import DataHandler
+    from diffmm_b200.Model import Model
+    from scipy.sparse import coo_matrix
+    g = load_golden(f"gcn_mm_{tag}")
+    cfg = make_cfg("bf16x3")
+    feats = [T(g[f"feat.{m}"]) for m in mods]
+    model = Model(cfg, feats[0], feats[1], feats[2] if tag == "3" else None).to(DEV)
+    with torch.no_grad():
+        model.u_embs.copy_(T(g["u_embs"]))
+        model.i_embs.copy_(T(g["i_embs"]))
+        model.modal_weight.copy_(T(g["modal_weight"]))
+        for m in mods:
+            getattr(model, f"{m}_layer").weight.copy_(T(g[f"lin_w.{m}"]))
+            getattr(model, f"{m}_layer").bias.copy_(T(g[f"lin_b.{m}"]))
+
+    def adj_of(u, i):
+        mat = coo_matrix((np.ones(len(u)), (u, i)), shape=(U, I), dtype=np.float32)
+        return DataHandler.makeTorchAdj(mat, U, I, torch.device(DEV))
+
+    bi = adj_of(g["trn_u"], g["trn_i"])
+    assert bi.is_sparse and hasattr(bi, "_dmm_csr")
+    madj = [adj_of(g[f"adj_u.{m}"], g[f"adj_i.{m}"]) for m in mods]
+    out = model.gcn_MM(bi, *madj)
+    final = torch.cat([out.u_final_embs, out.i_final_embs])
+    close(final, g["final"], 1e-4, "final")
+    zs = [torch.cat([out.u_image_embs, out.i_image_embs]), torch.cat([out.u_text_embs, out.i_text_embs])]
+    if tag == "3":
+        zs.append(torch.cat([out.u_audio_embs, out.i_audio_embs]))
+    probe = T(g["probe"])
+    scal = (final * probe).sum()
+    for k, (m, z) in enumerate(zip(mods, zs)):
+        close(z, g[f"z.{m}"], 1e-4, f"z {m}")
+        scal = scal + (z * probe * (0.5 + k)).sum()
+    scal.backward()
+    close(model.u_embs.grad, g["g_u"], 1e-3, "g_u")
+    close(model.i_embs.grad, g["g_i"], 1e-3, "g_i")
+    close(model.modal_weight.grad, g["g_mw"], 1e-3, "g_modal_weight")
+    for m in mods:
+        close(getattr(model, f"{m}_layer").weight.grad, g[f"g_lin_w.{m}"], 1e-3, f"g_lin_w {m}")
+        close(getattr(model, f"{m}_layer").bias.grad, g[f"g_lin_b.{m}"], 1e-3, f"g_lin_b {m}")
+
+
+def test_losses_autograd_surface():
+    from diffmm_b200.Utils.Utils import InfoNCE, bpr_loss, l2_reg_loss
+    g = load_golden("losses")
+    v1, v2 = T(g["v1"]).requires_grad_(True), T(g["v2"]).requires_grad_(True)
+    l = InfoNCE(v1, v2, T(g["idx"]), float(g["temp"]))
+    (3.0 * l).backward()
+    np.testing.assert_allclose(l.item(), g["infonce"], rtol=1e-5)
+    np.testing.assert_allclose(v1.grad.cpu().numpy(), 3.0 * g["g_v1"], rtol=1e-4, atol=5e-7)
+    np.testing.assert_allclose(v2.grad.cpu().numpy(), 3.0 * g["g_v2"], rtol=1e-4, atol=5e-7)
+    u, p, n = (T(g[k]).requires_grad_(True) for k in ("u", "p", "n"))
+    b = bpr_loss(u, p, n)
+    b.backward()
+    np.testing.assert_allclose(b.item(), g["bpr"], rtol=1e-5)
+    np.testing.assert_allclose(u.grad.cpu().numpy(), g["g_u"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(n.grad.cpu().numpy(), g["g_n"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(l2_reg_loss(1e-4, [T(g["v1"]), T(g["v2"])], DEV).item(), g["l2"], rtol=1e-5)
+    with pytest.raises(ValueError):
+        InfoNCE(v1, v2[:, :32], T(g["idx"]), 0.2)
+
+
+@pytest.mark.parametrize("precision,min_overlap", [("bf16x3", 0.995), ("bf16", 0.9)])
+def test_rebuild_modal_adj_end_to_end(precision, min_overlap):
+    """Whole phase 2 on device vs the oracle chain (generate_view -> top-k -> adjacency)."""
+    from diffmm_b200.Model import GaussianDiffusion
+    from diffmm_b200.rebuild import rebuild_edges, rebuild_modal_adj
+    g = load_golden("generate_view")
+    r = load_golden("rebuild")
+    cfg = make_cfg(precision)
+    den = make_denoise(cfg, params_of(load_golden("training_losses")))
+    gd = GaussianDiffusion(cfg).to(DEV)
+    indptr, indices = T(g["indptr"]), T(g["indices"], torch.int32)
+    items = rebuild_edges(gd, {"image": den}, indptr, indices, U, I, block_rows=16)["image"].cpu().numpy()
+    ptr = g["indptr"]
+    hit = tot = 0
+    for u in range(U):
+        want = set(r["edge_i"][r["edge_u"] == u].tolist())       # the reference's own torch.topk loop output
+        got = set(items[ptr[u]:ptr[u + 1]].tolist())
+        assert len(got) == len(want) == ptr[u + 1] - ptr[u]
+        hit += len(got & want)
+        tot += len(want)
+    assert hit / tot >= min_overlap, f"edge overlap {hit / tot:.4f}"
+    adj = rebuild_modal_adj(gd, {"image": den}, indptr, indices, U, I)["image"]
+    users = np.repeat(np.arange(U), np.diff(ptr))
+    wp, wi, wv = O.normalized_adj_csr(users, items, U, I)        # adjacency of OUR edges: structure must be exact
+    if precision == "bf16x3" and hit == tot:
+        np.testing.assert_array_equal(adj.idx.cpu().numpy(), wi)
+        np.testing.assert_array_equal(adj.ptr.cpu().numpy(), wp)
