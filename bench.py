@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffMM hot path on B200: denoise/top-k graph rebuild users per second.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (1 process per GPU under torchrun for N > 1)
+    python bench.py --impl reference ...                   # the reference's CPU path (numpy oracle port) on host cores
+
+A "step" is one full pass of phase 2 (reference Main.py:195-253) over the workload's users: for every
+modality the S-step reverse-diffusion chain (2 tcgen05 GEMMs per step), the per-user top-k (k = deg(u)),
+and the normalised-adjacency build.  Workload (N = 1): conf/baby.toml shape (19445 users x 7050 items,
+2 modalities, hidden 1024, 5 steps), synthetic interactions + random-init weights of that architecture.
+For N > 1 every rank owns a shard of the same size (weak scaling: N x 19445 users), no data-path
+collective except the final edge all-gather.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: users, items, modalities, hidden, steps, hyper (noise_scale, noise_min, noise_max)
+    "tiktok": dict(users=9308, items=6710, modalities=["image", "text", "audio"], hidden=1024, steps=5, noise=(0.5, 1e-4, 0.02)),
+    "baby": dict(users=19445, items=7050, modalities=["image", "text"], hidden=1024, steps=5, noise=(0.1, 1e-4, 0.02)),
+    "sports": dict(users=35598, items=18357, modalities=["image", "text"], hidden=1024, steps=5, noise=(0.1, 1e-4, 0.02)),
+}
+METRIC = "denoise_topk_rebuild_users_per_sec"
+UNIT = "users/s"
+KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sort kernels are not counted)
+    "dmm_pack_bf16": 1, "dmm_csr_rows_to_dense": 2, "dmm_time_embedding": 1, "dmm_q_sample": 1, "dmm_gemm_bf16_tn": 1,
+    "dmm_gemm_f32_tn": 1, "dmm_topk_edges": 1, "dmm_build_norm_adj_csr": 3, "dmm_spmm_csr": 1, "dmm_sign_noise_": 1,
+    "dmm_bpr_fwd_bwd": 2, "dmm_infonce_fwd": 3, "dmm_infonce_bwd": 3, "dmm_scatter_add_rows": 1,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(name, device, seed, precision):
+    import torch
+    from diffmm_b200 import synth
+    from diffmm_b200.Conf import Config
+    from diffmm_b200.Model import Denoise, GaussianDiffusion
+    w = WORKLOADS[name]
+    cfg = Config()
+    cfg.base.precision = precision
+    cfg.base.denoise_dim = f"[{w['hidden']}]"
+    cfg.hyper.steps = w["steps"]
+    cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = w["noise"]
+    cfg.data.user_num, cfg.data.item_num = w["users"], w["items"]
+    inter = synth.interactions(w["users"], w["items"], seed=seed)
+    torch.manual_seed(seed)
+    diff = GaussianDiffusion(cfg).to(device)
+    dens = {m: Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg).to(device) for m in w["modalities"]}
+    return cfg, inter, diff, dens
+
+
+def oracle_params(den):
+    f = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    return dict(emb_w=f(den.emb_layer.weight), emb_b=f(den.emb_layer.bias), w1=f(den.in_layers[0].weight),
+                b1=f(den.in_layers[0].bias), w2=f(den.out_layers[0].weight), b2=f(den.out_layers[0].bias),
+                gate_w=f(den.gate_layer.weight), gate_b=f(den.gate_layer.bias))
+
+
+def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, seed=0):
+    """The reference's phase 2 restated in numpy (oracle/diffmm_oracle.py) on `n_sample` users; returns seconds."""
+    from oracle import diffmm_oracle as O
+    sched = O.make_schedule(*w["noise"], w["steps"])
+    users = np.arange(min(n_sample, w["users"]))
+    ptr, idx = inter.indptr, inter.indices
+    t0 = time.perf_counter()
+    x = np.zeros((len(users), w["items"]), dtype=np.float32)
+    for r, u in enumerate(users):
+        x[r, idx[ptr[u]:ptr[u + 1]]] = 1.0
+    deg = np.diff(ptr)[users]
+    edges = 0
+    for m, p in params_by_mod.items():
+        for b0 in range(0, len(users), 1024):                       # the reference's batch of 1024 (Main.py:211)
+            view = O.generate_view(sched, p, x[b0:b0 + 1024], 0)
+            edges += sum(len(e) for e in O.topk_edges(view, deg[b0:b0 + 1024]))
+    dt = time.perf_counter() - t0
+    return dt, len(users), edges
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    from diffmm_b200 import synth
+    inter = synth.interactions(w["users"], w["items"], seed=args.seed)
+    rng = np.random.default_rng(args.seed)
+    I, H, d = w["items"], w["hidden"], 10
+
+    def rand_params():
+        s1, s2 = np.sqrt(2.0 / (I + d + H)), np.sqrt(2.0 / (I + H))
+        return dict(emb_w=rng.standard_normal((d, d), dtype=np.float32) * 0.3, emb_b=np.zeros(d, np.float32),
+                    w1=(rng.standard_normal((H, I + d), dtype=np.float32) * s1), b1=np.zeros(H, np.float32),
+                    w2=(rng.standard_normal((I, H), dtype=np.float32) * s2), b2=np.zeros(I, np.float32),
+                    gate_w=np.zeros((64, 64), np.float32), gate_b=np.zeros(64, np.float32))
+    params = {m: rand_params() for m in w["modalities"]}
+    n_sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_rebuild_sample(inter, w, params, min(n_sample, 256))
+    total = 0.0
+    users = 0
+    for _ in range(args.steps):
+        dt, n, _ = cpu_rebuild_sample(inter, w, params, n_sample)
+        total += dt
+        users += n
+    val = users / total
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shape rebuild phase (Main.py:195-253), numpy oracle port of the "
+                                   f"reference CPU path, sample of {n_sample} users x {len(w['modalities'])} modalities per step",
+                       "users": w["users"], "items": w["items"], "modalities": len(w["modalities"]), "hidden": w["hidden"],
+                       "diffusion_steps": w["steps"]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} users x {len(w['modalities'])} modalities x {args.steps} steps"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as td
+    from diffmm_b200 import _lib, ops, rebuild
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    w = WORKLOADS[args.workload]
+    U, I, H, S, mods = w["users"], w["items"], w["hidden"], w["steps"], w["modalities"]
+    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed + rank, args.precision)
+    E = int(inter.indices.size)
+    h_indptr = torch.from_numpy(inter.indptr).pin_memory()
+    h_indices = torch.from_numpy(inter.indices).pin_memory()
+    d_indptr, d_indices = h_indptr.to(dev), h_indices.to(dev)
+    h_edges = {m: torch.empty(E, dtype=torch.int32).pin_memory() for m in mods}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # per-launch instrumentation of the dominant kernel (events on the launching stream)
+    gemm_events = []
+    orig_gemm = ops.gemm_bf16_tn
+
+    def timed_gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, **kw):
+        if not timed_gemm.on:
+            return orig_gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, **kw)
+        e1.record()
+        gemm_events.append((2.0 * M * N * K, e0, e1))
+    timed_gemm.on = False
+    ops.gemm_bf16_tn = timed_gemm
+    rebuild.ops.gemm_bf16_tn = timed_gemm
+
+    counts = {}
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        counts[name] = counts.get(name, 0) + 1
+        return orig_call(name, *a)
+    _lib.call = counting_call
+    ops._lib.call = counting_call
+
+    def step_device():
+        items = rebuild.rebuild_edges(diff, dens, d_indptr, d_indices, U, I, 0, args.precision)
+        return {m: ops.build_norm_adj(d_indptr, v, U, I) for m, v in items.items()}, items
+
+    def step_e2e():
+        ip = h_indptr.to(dev, non_blocking=True)
+        ix = h_indices.to(dev, non_blocking=True)
+        items = rebuild.rebuild_edges(diff, dens, ip, ix, U, I, 0, args.precision)
+        adjs = {m: ops.build_norm_adj(ip, v, U, I) for m, v in items.items()}
+        for m, v in items.items():
+            h_edges[m].copy_(v, non_blocking=True)
+        return adjs
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    counts.clear()
+    timed_gemm.on = True
+    ev = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                                    # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    timed_gemm.on = False
+    launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in counts.items())
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events)
+    gemm_flops = sum(f for f, _, _ in gemm_events)
+
+    # end-to-end: host CSR in pinned memory -> device, rebuild, edge lists back to pinned host memory
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ev2 = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_e2e()
+        e1.record()
+        ev2.append((e0, e1))
+    barrier()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    pk = peaks()
+    n_gemm = max(len(gemm_events), 1)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    value = world * U * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shape rebuild phase (Main.py:195-253): {U} users x {I} items per GPU, "
+                               f"{len(mods)} modalities, hidden {H}, {S} reverse steps, top-k k=deg(u), adjacency build",
+                   "users_per_gpu": U, "items": I, "modalities": len(mods), "hidden": H, "diffusion_steps": S, "edges": E,
+                   "precision": args.precision, "l2": "256 MiB flush write between timed steps; per-step working set > L2",
+                   "parallelism": f"user-sharded x{world}" if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "gemm_bf16_tn_kernel (tcgen05)",
+                     "launches": len(gemm_events), "avg_launch_ms": gemm_ms / n_gemm, "share_of_step": gemm_ms / ms,
+                     "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside the step); burst {pk['tf_burst']}",
+                     "frac_of_burst": achieved / pk["tf_burst"]},
+        "e2e": {"value": world * U * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(h_indptr.numel() * 8 + h_indices.numel() * 4),
+                "d2h_bytes_per_step": int(len(mods) * E * 4)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu_baseline:
+        params = {m: oracle_params(d) for m, d in dens.items()}
+        dt, n, _ = cpu_rebuild_sample(inter, w, params, args.cpu_sample)
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"first {n} users x {len(mods)} modalities, numpy oracle of Main.py:195-253 "
+                                          f"(generate_view + per-user top-k), {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="baby", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

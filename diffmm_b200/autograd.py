@@ -5,6 +5,7 @@ libdiffmm_b200.so.  Backward formulas are stated next to each Function.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -24,20 +25,35 @@ def check_precision(p: str) -> str:
 # packed-weight cache: weights change once per optimiser step (tensor._version bumps), while the
 # reverse-diffusion chain reuses them 5 x (#batches) times.
 # ------------------------------------------------------------------------------------------------
-_PACK_CACHE: dict = {}
+_PACK_CACHE: dict = {}     # id(param) -> (weakref(param), version, {transpose: (hi, lo)})
+
+
+def pack_any(src: torch.Tensor, transpose: bool, split: bool):
+    """dmm_pack_bf16 of a 2-D fp32 tensor in either memory order: a column-major view (e.g. ``w.t()``)
+    is packed by reading its row-major base with the opposite transpose flag."""
+    if src.stride(1) == 1 and src.stride(0) >= src.shape[1]:
+        return ops.pack_bf16(src, transpose=transpose, split=split)
+    if src.stride(0) == 1 and src.stride(1) >= src.shape[0]:
+        return ops.pack_bf16(src.t(), transpose=not transpose, split=split)
+    return ops.pack_bf16(src.contiguous(), transpose=transpose, split=split)
 
 
 def packed_weight(w: torch.Tensor, transpose: bool, split: bool):
-    key = (w.data_ptr(), tuple(w.shape), transpose)
-    ent = _PACK_CACHE.get(key)
-    ver = w._version
-    if ent is not None and ent[0] == ver and (ent[2] is not None or not split):
-        return ent[1], (ent[2] if split else None)
-    src = w.detach()
-    hi, lo = ops.pack_bf16(src, transpose=transpose, split=True)
-    if len(_PACK_CACHE) > 64:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (ver, hi, lo)
+    """bf16 hi/lo operand copy of ``w`` (or of w^T).  Only nn.Parameters are cached (stable storage,
+    in-place updates bump ``_version``); the entry is validated by object identity, never by address."""
+    if not isinstance(w, torch.nn.Parameter):
+        return pack_any(w.detach(), transpose, split)
+    ent = _PACK_CACHE.get(id(w))
+    if ent is None or ent[0]() is not w or ent[1] != w._version:
+        if len(_PACK_CACHE) > 256:
+            for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
+                del _PACK_CACHE[k]
+        ent = (weakref.ref(w), w._version, {})
+        _PACK_CACHE[id(w)] = ent
+    packs = ent[2]
+    if transpose not in packs:
+        packs[transpose] = pack_any(w.detach(), transpose, True)
+    hi, lo = packs[transpose]
     return hi, (lo if split else None)
 
 
@@ -95,7 +111,7 @@ class LinearTN(torch.autograd.Function):
             ops.gemm_bf16_tn(g_hi, g_lo, wt_hi, wt_lo, M, K, N, out_f32=dx)
         if ctx.needs_input_grad[1]:
             gt_hi, gt_lo = ops.pack_bf16(g, transpose=True, split=split)
-            xt_hi, xt_lo = ops.pack_bf16(x, transpose=True, split=split)
+            xt_hi, xt_lo = pack_any(x, True, split)
             dw = _new_out(N, K, g.device)
             ops.gemm_bf16_tn(gt_hi, gt_lo, xt_hi, xt_lo, N, K, M, out_f32=dw)
         if ctx.has_bias and ctx.needs_input_grad[2]:

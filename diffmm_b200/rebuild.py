@@ -81,11 +81,11 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     h_lo = ws.h_lo[:M] if split else None
     xv = x[:, :I]
 
-    exact_input = False                       # True when bf16(x) == x, so the A_lo pass is identically zero
     if sampling_step == 0:
         if csr is not None:
             ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, x_f32=x, a_bf16=a_hi)
-            exact_input = True
+            if split:
+                a_lo[:, :I].zero_()           # 0/1 rows are exact in bf16; the temb columns still carry a lo part
         else:
             xd = x_dense if (x_dense.stride(1) == 1 and x_dense.dtype == torch.float32) else x_dense.float().contiguous()
             xv.copy_(xd)
@@ -112,8 +112,7 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     S = diff.steps
     for i in range(S - 1, -1, -1):
         ops.time_embedding(emb_w, emb_b, M, t_all=i, a_hi=a_hi, a_lo=a_lo, col0=I)
-        first = i == S - 1
-        ops.gemm_bf16_tn(a_hi, None if (first and exact_input) else a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1,
+        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1,
                          out_hi=h_hi, out_lo=h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))

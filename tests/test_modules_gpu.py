@@ -14,7 +14,7 @@ from oracle import diffmm_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 U, I, H, D = 40, 120, 32, 64
-TOL = {"bf16x3": 1e-4, "bf16": 2e-2}
+TOL = {"bf16x3": 2e-4, "bf16": 2e-2}
 
 
 def T(a, dtype=None):
