@@ -67,12 +67,22 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
   if (threadIdx.x == 0) ptr[n] = carry;
 }
 
-__device__ __forceinline__ double dinv_of(int64_t deg) { return deg > 0 ? 1.0 / sqrt((double)deg) : 0.0; }
+// d^-1/2 per node in fp64 (degree counts the self loop), computed once per node instead of per entry
+__global__ void __launch_bounds__(256) node_dinv_kernel(const int64_t* __restrict__ row_ptr,
+                                                        const int64_t* __restrict__ item_ptr, int64_t n_users,
+                                                        int64_t n_items, double* __restrict__ dinv) {
+  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_users + n_items) return;
+  const int64_t deg = node < n_users ? row_ptr[node + 1] - row_ptr[node] + 1
+                                     : item_ptr[node - n_users + 1] - item_ptr[node - n_users] + 1;
+  dinv[node] = deg > 0 ? 1.0 / sqrt((double)deg) : 0.0;
+}
 
 __global__ void __launch_bounds__(256) fill_adj_kernel(const int64_t* __restrict__ row_ptr,
                                                        const int32_t* __restrict__ items,
                                                        const int64_t* __restrict__ item_ptr,
-                                                       const int32_t* __restrict__ users_by_item, int64_t n_users,
+                                                       const int32_t* __restrict__ users_by_item,
+                                                       const double* __restrict__ dinv, int64_t n_users,
                                                        int64_t n_items, int64_t n_edges, int64_t* __restrict__ adj_ptr,
                                                        int32_t* __restrict__ adj_idx, float* __restrict__ adj_val) {
   const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(256) fill_adj_kernel(const int64_t* __restrict
     const int64_t u = node;
     const int64_t b = row_ptr[u], e = row_ptr[u + 1];
     const int64_t o = b + u;  // one self loop per preceding user row
-    const double du = dinv_of(e - b + 1);
+    const double du = dinv[u];
     if (lane == 0) {
       adj_ptr[u] = o;
       adj_idx[o] = (int32_t)u;
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(256) fill_adj_kernel(const int64_t* __restrict
     }
     for (int64_t j = b + lane; j < e; j += 32) {
       const int32_t it = items[j];
-      const double di = dinv_of(item_ptr[it + 1] - item_ptr[it] + 1);
+      const double di = dinv[n_users + it];
       adj_idx[o + 1 + (j - b)] = (int32_t)(n_users + it);
       adj_val[o + 1 + (j - b)] = (float)((du * 1.0) * di);
     }
@@ -99,10 +109,10 @@ __global__ void __launch_bounds__(256) fill_adj_kernel(const int64_t* __restrict
     const int64_t it = node - n_users;
     const int64_t b = item_ptr[it], e = item_ptr[it + 1];
     const int64_t o = n_edges + n_users + b + it;
-    const double di = dinv_of(e - b + 1);
+    const double di = dinv[node];
     for (int64_t j = b + lane; j < e; j += 32) {
       const int32_t u = users_by_item[j];
-      const double du = dinv_of(row_ptr[u + 1] - row_ptr[u] + 1);
+      const double du = dinv[u];
       adj_idx[o + (j - b)] = u;
       adj_val[o + (j - b)] = (float)((di * 1.0) * du);
     }
@@ -121,13 +131,14 @@ struct Workspace {
   int32_t* users_by_item;  // [E]
   int32_t* item_count;     // [I] (+1 status word)
   int64_t* item_ptr;       // [I+1]
+  double* dinv;            // [U+I]
   void* cub_tmp;
   size_t cub_bytes;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-inline size_t carve(Workspace& w, void* base, int64_t I, int64_t E) {
+inline size_t carve(Workspace& w, void* base, int64_t U, int64_t I, int64_t E) {
   uint8_t* p = (uint8_t*)base;
   size_t off = 0;
   const size_t e4 = align256((size_t)(E > 0 ? E : 1) * 4);
@@ -136,6 +147,7 @@ inline size_t carve(Workspace& w, void* base, int64_t I, int64_t E) {
   w.users_by_item = (int32_t*)(p + off); off += e4;
   w.item_count = (int32_t*)(p + off); off += align256((size_t)(I + 1) * 4);
   w.item_ptr = (int64_t*)(p + off); off += align256((size_t)(I + 1) * 8);
+  w.dinv = (double*)(p + off); off += align256((size_t)(U + I) * 8);
   w.cub_tmp = p + off;
   return off;
 }
@@ -143,9 +155,8 @@ inline size_t carve(Workspace& w, void* base, int64_t I, int64_t E) {
 }  // namespace
 
 extern "C" int64_t dmm_build_adj_workspace_bytes(int64_t n_users, int64_t n_items, int64_t n_edges) {
-  (void)n_users;
   Workspace w;
-  const size_t fixed = carve(w, nullptr, n_items, n_edges);
+  const size_t fixed = carve(w, nullptr, n_users, n_items, n_edges);
   // CUB radix-sort temporary storage is O(#tiles) histograms; bound it generously
   return (int64_t)(fixed + (size_t)(32u << 20) + (size_t)(n_edges > 0 ? n_edges : 0));
 }
@@ -159,7 +170,7 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
   DMM_CHECK_ARG(n_edges == 0 || items, "dmm_build_norm_adj_csr: null items");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
-  const size_t fixed = carve(w, workspace, n_items, n_edges);
+  const size_t fixed = carve(w, workspace, n_users, n_items, n_edges);
   DMM_CHECK_ARG((size_t)workspace_bytes > fixed, "dmm_build_norm_adj_csr: workspace too small");
   w.cub_bytes = (size_t)workspace_bytes - fixed;
 
@@ -184,7 +195,9 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
                                              (int)n_edges, 0, end_bit, st));
   }
   const int64_t N = n_users + n_items;
-  fill_adj_kernel<<<(unsigned)dmm_ceil_div(N * 32, 256), 256, 0, st>>>(row_ptr, items, w.item_ptr, w.users_by_item,
+  node_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.item_ptr, n_users, n_items, w.dinv);
+  DMM_LAUNCH_CHECK();
+  fill_adj_kernel<<<(unsigned)dmm_ceil_div(N * 32, 256), 256, 0, st>>>(row_ptr, items, w.item_ptr, w.users_by_item, w.dinv,
                                                                       n_users, n_items, n_edges, adj_ptr, adj_idx, adj_val);
   DMM_LAUNCH_CHECK();
   return DMM_OK;

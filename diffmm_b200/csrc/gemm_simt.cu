@@ -44,10 +44,15 @@ __global__ void __launch_bounds__(256) gemm_f32_tn_kernel(const float* __restric
       if (n >= N) continue;
       float v = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
       if (ep.act == 1) v = tanhf(v);
-      if (ep.residual)
+      if (ep.residual) {
         v = ep.alpha * v + ep.beta * ep.residual[(int64_t)m * ep.ld_res + n];
-      else
+      } else if (ep.res_hi) {
+        float r = dmm_bf16_to_f32(ep.res_hi[(int64_t)m * ep.ld_res16 + n]);
+        if (ep.res_lo) r += dmm_bf16_to_f32(ep.res_lo[(int64_t)m * ep.ld_res16 + n]);
+        v = ep.alpha * v + ep.beta * r;
+      } else {
         v *= ep.alpha;
+      }
       if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ld_out + n] = v;
       if (ep.out_hi) {
         uint16_t h, l;

@@ -7,7 +7,7 @@
 //   warp 0  : TMA producer   — cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) into a STAGES-deep ring
 //   warp 1  : MMA issuer     — one lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2  : TMEM allocator — 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
-//   warps 4-7: epilogue      — tcgen05.ld 32 lanes x 32 columns, bias/tanh/posterior-mean, fp32 and
+//   warps 4-11: epilogue     — tcgen05.ld 32 lanes x 32 columns, bias/tanh/posterior-mean, fp32 and
 //                              split-bf16 stores (the bf16 pair is the next contraction's operand)
 // The optional lo operands add the passes A_lo.B_hi and A_hi.B_lo into the same accumulator
 // ("bf16x3"), which restores fp32-level accuracy without leaving the bf16 tensor pipe.
@@ -18,8 +18,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 
 template <int BN>
 struct Cfg {
@@ -129,10 +130,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 }
 
 // ------------------------------------------------------------------------------------------ epilogue math
-__device__ __forceinline__ float epi_value(float acc, float bias, int act) {
-  float v = acc + bias;
-  if (act == 1) v = tanhf(v);
-  return v;
+// tanh(x) = 1 - 2 / (exp(2x) + 1): absolute error ~1e-7 (the outputs are compared at the scale of 1),
+// saturates correctly for |x| large (exp -> inf / 0)
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, t + 1.f);
 }
 
 template <int BN>
@@ -163,7 +165,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -187,8 +189,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
+        // n fastest: the CTAs running together cover every column block of a few row blocks, so each A
+        // tile is fetched from HBM once and re-read from L2 by its neighbours
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile % p.num_n_blocks;
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap* ma = p.pass_a[ps] ? &tm_a_lo : &tm_a_hi;
           const CUtensorMap* mb = p.pass_b[ps] ? &tm_b_lo : &tm_b_hi;
@@ -241,12 +245,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), (warp - 4) / 4 the
+    // parity of the 32-column chunks this warp drains, so two warps per SM sub-partition overlap
+    // their global loads/stores.
+    const int ew = (warp - EPI_WARP0) & 3;
+    const int chalf = (warp - EPI_WARP0) >> 2;
     const dmm_gemm_epilogue& ep = p.ep;
+    const bool has_res = ep.residual != nullptr || ep.res_hi != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile % p.num_n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 4);
@@ -255,29 +264,78 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf; c < BN / 32; c += EPI_WARPS / 4) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
-        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), r);
-        float v[32];
         const bool full = (n0 + 32 <= p.N);
-        if (!row_ok) {
-          // rows past M were zero-filled by TMA; nothing to store
-        } else if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = epi_value(__uint_as_float(r[j]), ep.bias ? __ldg(ep.bias + n0 + j) : 0.f, ep.act);
+        // residual loads are issued before the TMEM load so their latency overlaps it
+        float res[32];
+        if (row_ok && full && has_res) {
           if (ep.residual) {
             const float4* rp = reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ld_res + n0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(rp + q);
-              v[4 * q + 0] = ep.alpha * v[4 * q + 0] + ep.beta * t.x;
-              v[4 * q + 1] = ep.alpha * v[4 * q + 1] + ep.beta * t.y;
-              v[4 * q + 2] = ep.alpha * v[4 * q + 2] + ep.beta * t.z;
-              v[4 * q + 3] = ep.alpha * v[4 * q + 3] + ep.beta * t.w;
+              const float4 t = rp[q];
+              res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
             }
+          } else {
+            const uint4* hp = reinterpret_cast<const uint4*>(ep.res_hi + (int64_t)row * ep.ld_res16 + n0);
+            uint4 h[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = hp[q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t w[4] = {h[q].x, h[q].y, h[q].z, h[q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                res[8 * q + 2 * e] = __uint_as_float(w[e] << 16);
+                res[8 * q + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+              }
+            }
+            if (ep.res_lo) {
+              const uint4* lp = reinterpret_cast<const uint4*>(ep.res_lo + (int64_t)row * ep.ld_res16 + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = lp[q];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t w[4] = {h[q].x, h[q].y, h[q].z, h[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  res[8 * q + 2 * e] += __uint_as_float(w[e] << 16);
+                  res[8 * q + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                }
+              }
+            }
+          }
+        }
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
+        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), r);
+        float v[32];
+        if (!row_ok) {
+          // rows past M were zero-filled by TMA; nothing to store
+        } else if (full) {
+          if (ep.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(bp + q);
+              v[4 * q] = __uint_as_float(r[4 * q]) + t.x;
+              v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + t.y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + t.z;
+              v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ep.alpha * v[j] + ep.beta * res[j];
           } else if (ep.alpha != 1.f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
@@ -311,11 +369,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
             if (n >= p.N) break;
-            float x = epi_value(__uint_as_float(r[j]), ep.bias ? __ldg(ep.bias + n) : 0.f, ep.act);
-            if (ep.residual)
-              x = ep.alpha * x + ep.beta * __ldg(ep.residual + (int64_t)row * ep.ld_res + n);
-            else
+            float x = __uint_as_float(r[j]) + (ep.bias ? __ldg(ep.bias + n) : 0.f);
+            if (ep.act == 1) x = fast_tanh(x);
+            if (ep.residual) {
+              x = ep.alpha * x + ep.beta * ep.residual[(int64_t)row * ep.ld_res + n];
+            } else if (ep.res_hi) {
+              float rr = dmm_bf16_to_f32(ep.res_hi[(int64_t)row * ep.ld_res16 + n]);
+              if (ep.res_lo) rr += dmm_bf16_to_f32(ep.res_lo[(int64_t)row * ep.ld_res16 + n]);
+              x = ep.alpha * x + ep.beta * rr;
+            } else {
               x *= ep.alpha;
+            }
             if (ep.out_f32) ep.out_f32[(int64_t)row * ep.ld_out + n] = x;
             if (ep.out_hi) {
               uint16_t h, l;
@@ -402,6 +466,10 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   DMM_CHECK_ARG(al16(ep->residual) && al16(ep->out_f32) && al16(ep->out_hi) && al16(ep->out_lo),
                 "dmm_gemm_bf16_tn: epilogue buffers must be 16-byte aligned");
   DMM_CHECK_ARG(!ep->residual || (ep->ld_res >= N && ep->ld_res % 4 == 0), "dmm_gemm_bf16_tn: ld_res must be >= N and %%4");
+  DMM_CHECK_ARG(!(ep->residual && ep->res_hi), "dmm_gemm_bf16_tn: residual and res_hi are mutually exclusive");
+  DMM_CHECK_ARG(!ep->res_hi || (ep->ld_res16 >= N && ep->ld_res16 % 8 == 0), "dmm_gemm_bf16_tn: ld_res16 must be >= N and %%8");
+  DMM_CHECK_ARG(!ep->res_lo || ep->res_hi, "dmm_gemm_bf16_tn: res_lo requires res_hi");
+  DMM_CHECK_ARG(al16(ep->bias) && al16(ep->res_hi) && al16(ep->res_lo), "dmm_gemm_bf16_tn: bias/res_hi/res_lo must be 16-byte aligned");
   DMM_CHECK_ARG(!ep->out_f32 || (ep->ld_out >= N && ep->ld_out % 4 == 0), "dmm_gemm_bf16_tn: ld_out must be >= N and %%4");
   DMM_CHECK_ARG(!ep->out_hi || (ep->ld_out16 >= N && ep->ld_out16 % 8 == 0), "dmm_gemm_bf16_tn: ld_out16 must be >= N and %%8");
   DMM_CHECK_ARG(!ep->out_lo || ep->out_hi, "dmm_gemm_bf16_tn: out_lo requires out_hi");

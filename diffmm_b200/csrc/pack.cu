@@ -48,32 +48,41 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------ CSR rows -> dense 0/1 tiles
-__global__ void __launch_bounds__(256) csr_rows_zero_kernel(int64_t n_rows, int64_t n_cols, float* __restrict__ x,
-                                                            int64_t ld_x, uint16_t* __restrict__ a, int64_t ld_a) {
-  const int64_t r = blockIdx.y;
-  if (r >= n_rows) return;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
-    if (x) x[r * ld_x + c] = 0.f;
-    if (a) a[r * ld_a + c] = 0;
-  }
+// One CTA per output row: zero fill with 16-byte stores (scalar head/tail where the row is not
+// 16-byte aligned), then the row's interactions are scattered as 1.0.  HBM-bound: one write of the tile.
+template <typename T>
+__device__ __forceinline__ void zero_row(T* __restrict__ p, int64_t n) {
+  constexpr int PER = 16 / (int)sizeof(T);
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  int64_t head = ((16 - (addr & 15)) & 15) / (int64_t)sizeof(T);
+  if (head > n) head = n;
+  for (int64_t c = threadIdx.x; c < head; c += blockDim.x) p[c] = T(0);
+  const int64_t nvec = (n - head) / PER;
+  uint4* v = reinterpret_cast<uint4*>(p + head);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t c = threadIdx.x; c < nvec; c += blockDim.x) v[c] = z;
+  for (int64_t c = head + nvec * PER + threadIdx.x; c < n; c += blockDim.x) p[c] = T(0);
 }
-__global__ void __launch_bounds__(256) csr_rows_scatter_kernel(const int64_t* __restrict__ indptr,
-                                                               const int32_t* __restrict__ indices,
-                                                               const int64_t* __restrict__ row_ids, int64_t row0,
-                                                               int64_t n_rows, int64_t n_cols, float* __restrict__ x,
-                                                               int64_t ld_x, uint16_t* __restrict__ a, int64_t ld_a) {
-  // one warp per output row
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= n_rows) return;
-  const int64_t u = row_ids ? row_ids[r] : row0 + r;
-  const int64_t b = indptr[u], e = indptr[u + 1];
-  for (int64_t j = b + lane; j < e; j += 32) {
-    const int32_t c = indices[j];
-    if (c >= 0 && c < n_cols) {
-      if (x) x[r * ld_x + c] = 1.f;
-      if (a) a[r * ld_a + c] = 0x3F80;  // bf16(1.0)
+
+__global__ void __launch_bounds__(256) csr_rows_dense_kernel(const int64_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ indices,
+                                                             const int64_t* __restrict__ row_ids, int64_t row0,
+                                                             int64_t n_rows, int64_t n_cols, float* __restrict__ x,
+                                                             int64_t ld_x, uint16_t* __restrict__ a, int64_t ld_a) {
+  for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    if (x) zero_row<float>(x + r * ld_x, n_cols);
+    if (a) zero_row<uint16_t>(a + r * ld_a, n_cols);
+    __syncthreads();   // the scatter below must land after this CTA's zero stores
+    const int64_t u = row_ids ? row_ids[r] : row0 + r;
+    const int64_t b = indptr[u], e = indptr[u + 1];
+    for (int64_t j = b + threadIdx.x; j < e; j += blockDim.x) {
+      const int32_t c = indices[j];
+      if (c >= 0 && c < n_cols) {
+        if (x) x[r * ld_x + c] = 1.f;
+        if (a) a[r * ld_a + c] = 0x3F80;  // bf16(1.0)
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -194,16 +203,9 @@ extern "C" int dmm_csr_rows_to_dense(dmm_ctx* ctx, const int64_t* indptr, const 
   DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0, "dmm_csr_rows_to_dense: bad shape");
   DMM_CHECK_ARG((!x_f32 || ld_x >= n_cols) && (!a_bf16 || ld_a >= n_cols), "dmm_csr_rows_to_dense: ld too small");
   if (n_rows == 0) return DMM_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
-    const int64_t nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
-    dim3 grid((unsigned)(dmm_ceil_div(n_cols, 256) < 32 ? dmm_ceil_div(n_cols, 256) : 32), (unsigned)nr);
-    csr_rows_zero_kernel<<<grid, 256, 0, st>>>(nr, n_cols, x_f32 ? x_f32 + r0 * ld_x : nullptr, ld_x,
-                                               a_bf16 ? a_bf16 + r0 * ld_a : nullptr, ld_a);
-  }
-  DMM_LAUNCH_CHECK();
-  csr_rows_scatter_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, st>>>(indptr, indices, row_ids, row0, n_rows,
-                                                                                   n_cols, x_f32, ld_x, a_bf16, ld_a);
+  const unsigned grid = (unsigned)(n_rows < (int64_t)ctx->num_sms * 64 ? n_rows : (int64_t)ctx->num_sms * 64);
+  csr_rows_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, x_f32, ld_x,
+                                                               a_bf16, ld_a);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

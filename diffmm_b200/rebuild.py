@@ -83,12 +83,11 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
 
     if sampling_step == 0:
         if csr is not None:
-            ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, x_f32=x, a_bf16=a_hi)
+            ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, a_bf16=a_hi)
             if split:
                 a_lo[:, :I].zero_()           # 0/1 rows are exact in bf16; the temb columns still carry a lo part
         else:
             xd = x_dense if (x_dense.stride(1) == 1 and x_dense.dtype == torch.float32) else x_dense.float().contiguous()
-            xv.copy_(xd)
             ops.pack_bf16_into(xd, a_hi, a_lo)
     else:
         if csr is not None:
@@ -103,23 +102,31 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
         t = sampling_step - 1
         ca = ta[t].expand(M).contiguous()
         cb = tb[t].expand(M).contiguous()
-        ops.q_sample(x0, noise, ca, cb, 1, x_t=xv, a_hi=a_hi, a_lo=a_lo)
+        ops.q_sample(x0, noise, ca, cb, 1, a_hi=a_hi, a_lo=a_lo)
 
     w1_hi, w1_lo = packed_weight(W1, False, split)
     w2_hi, w2_lo = packed_weight(W2, False, split)
     emb_w, emb_b = den.emb_layer.weight.detach(), den.emb_layer.bias.detach()
     b1d, b2d = b1.detach(), b2.detach()
     S = diff.steps
+    ax_hi = a_hi[:, :I]
+    ax_lo = a_lo[:, :I] if split else None
     for i in range(S - 1, -1, -1):
         ops.time_embedding(emb_w, emb_b, M, t_all=i, a_hi=a_hi, a_lo=a_lo, col0=I)
-        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1,
-                         out_hi=h_hi, out_lo=h_lo)
+        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1, out_hi=h_hi, out_lo=h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))
-        last = i == 0
-        ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
-                         residual=xv if c2 != 0.0 else None, out_f32=xv,
-                         out_hi=None if last else a_hi[:, :I], out_lo=None if (last or not split) else a_lo[:, :I])
+        # x_t lives only as the bf16 operand (hi, and lo in bf16x3 mode: hi + lo carries 16 mantissa bits):
+        # the posterior mean c1 * pred + c2 * x_t reads it as the residual and overwrites it in place, so
+        # an intermediate step moves 2 (4) bytes per element each way instead of 4 + 4 + 2.  The last step
+        # (c2 == 0 for beta_fixed schedules) writes the fp32 scores the top-k consumes.
+        if i == 0:
+            ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
+                             res_hi=ax_hi if c2 != 0.0 else None, res_lo=ax_lo if c2 != 0.0 else None, out_f32=xv)
+        else:
+            ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
+                             res_hi=ax_hi if c2 != 0.0 else None, res_lo=ax_lo if c2 != 0.0 else None,
+                             out_hi=ax_hi, out_lo=ax_lo)
     return xv
 
 

@@ -90,6 +90,9 @@ typedef struct dmm_gemm_epilogue {
   uint16_t* out_hi;       /* optional bf16 [M,N] (operand of the next contraction)           */
   uint16_t* out_lo;       /* optional bf16 residual part                                     */
   int64_t ld_out16;
+  const uint16_t* res_hi; /* residual given as bf16 hi (+ lo) instead of fp32 (exclusive with */
+  const uint16_t* res_lo; /* `residual`); may alias out_hi/out_lo: each element is read, then  */
+  int64_t ld_res16;       /* written, by the same thread                                      */
 } dmm_gemm_epilogue;
 
 int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
