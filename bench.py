@@ -333,6 +333,31 @@ def run_ours(args):
         ev2.append((e0, e1))
     barrier()
     ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+
+    # per-entry-point device time inside a step (separate untimed pass; events around every C-ABI call)
+    per_call = []
+
+    def timing_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        per_call.append((name, e0, e1))
+    _lib.call = timing_call
+    ops._lib.call = timing_call
+    n_bd = 2
+    for _ in range(n_bd):
+        flush.fill_(1)
+        step_device()
+    barrier()
+    _lib.call = orig_call
+    ops._lib.call = orig_call
+    breakdown = {}
+    for name, a, b in per_call:
+        d = breakdown.setdefault(name, [0, 0.0])
+        d[0] += 1
+        d[1] += a.elapsed_time(b)
+    breakdown = {k: {"calls_per_step": v[0] // n_bd, "ms_per_step": round(v[1] / n_bd, 4)} for k, v in breakdown.items()}
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -369,6 +394,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "wall_s_timed_region": t_wall,
+        "breakdown_ms_per_step": breakdown,
     }
     if not args.no_cpu_baseline:
         params = {m: oracle_params(d) for m, d in dens.items()}

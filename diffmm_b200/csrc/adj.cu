@@ -8,7 +8,7 @@
 //      users ascending inside every item row  (CUB DeviceRadixSort: CCCL library plumbing, the only
 //      non-hand-written device code of the library; candidate for a hand-written counting sort);
 //   2. item row offsets by a histogram + single-block scan;
-//   3. one warp per node writes its row [self loop | neighbours] in ascending column order with
+//   3. one thread per stored entry writes [self loop | neighbours] rows in ascending column order with
 //      val = (d_r^-1/2 * 1) * d_c^-1/2 evaluated in fp64 and rounded to fp32 like the reference.
 // HBM-bound: ~8E bytes in, 8(2E+N) + 8(N+1) bytes out.
 #include "common.cuh"
@@ -78,50 +78,52 @@ __global__ void __launch_bounds__(256) node_dinv_kernel(const int64_t* __restric
   dinv[node] = deg > 0 ? 1.0 / sqrt((double)deg) : 0.0;
 }
 
+// Entry-parallel fill (no per-row walks, so popular items with thousands of users cost the same per
+// entry as everything else).  Thread j < E writes the user-side entry of edge j (CSR by user) and the
+// item-side entry of the j-th (item, user) pair of the transposed list; thread j < N writes node j's
+// self loop and row pointer.  Row layout: users [self | items ascending], items [users ascending | self].
 __global__ void __launch_bounds__(256) fill_adj_kernel(const int64_t* __restrict__ row_ptr,
                                                        const int32_t* __restrict__ items,
+                                                       const int32_t* __restrict__ edge_user,
                                                        const int64_t* __restrict__ item_ptr,
+                                                       const int32_t* __restrict__ items_sorted,
                                                        const int32_t* __restrict__ users_by_item,
                                                        const double* __restrict__ dinv, int64_t n_users,
                                                        int64_t n_items, int64_t n_edges, int64_t* __restrict__ adj_ptr,
                                                        int32_t* __restrict__ adj_idx, float* __restrict__ adj_val) {
-  const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t N = n_users + n_items;
-  if (node >= N) return;
-  if (node < n_users) {
-    const int64_t u = node;
-    const int64_t b = row_ptr[u], e = row_ptr[u + 1];
-    const int64_t o = b + u;  // one self loop per preceding user row
-    const double du = dinv[u];
-    if (lane == 0) {
-      adj_ptr[u] = o;
-      adj_idx[o] = (int32_t)u;
-      adj_val[o] = (float)((du * 1.0) * du);
-    }
-    for (int64_t j = b + lane; j < e; j += 32) {
+  if (j < n_edges) {
+    {
+      const int64_t u = edge_user[j];
       const int32_t it = items[j];
-      const double di = dinv[n_users + it];
-      adj_idx[o + 1 + (j - b)] = (int32_t)(n_users + it);
-      adj_val[o + 1 + (j - b)] = (float)((du * 1.0) * di);
+      const int64_t o = j + u + 1;  // one self loop per user row up to and including u
+      adj_idx[o] = (int32_t)(n_users + it);
+      adj_val[o] = (float)((dinv[u] * 1.0) * dinv[n_users + it]);
     }
-  } else {
-    const int64_t it = node - n_users;
-    const int64_t b = item_ptr[it], e = item_ptr[it + 1];
-    const int64_t o = n_edges + n_users + b + it;
-    const double di = dinv[node];
-    for (int64_t j = b + lane; j < e; j += 32) {
+    {
+      const int64_t it = items_sorted[j];
       const int32_t u = users_by_item[j];
-      const double du = dinv[u];
-      adj_idx[o + (j - b)] = u;
-      adj_val[o + (j - b)] = (float)((di * 1.0) * du);
+      const int64_t o = n_edges + n_users + j + it;  // user block, then one self loop per preceding item row
+      adj_idx[o] = u;
+      adj_val[o] = (float)((dinv[n_users + it] * 1.0) * dinv[u]);
     }
-    if (lane == 0) {
-      adj_ptr[node] = o;
-      adj_idx[o + (e - b)] = (int32_t)node;
-      adj_val[o + (e - b)] = (float)((di * 1.0) * di);
-      if (node == N - 1) adj_ptr[N] = 2 * n_edges + N;
+  }
+  if (j < N) {
+    const double d = dinv[j];
+    int64_t start, self;
+    if (j < n_users) {
+      start = row_ptr[j] + j;
+      self = start;
+    } else {
+      const int64_t it = j - n_users;
+      start = n_edges + n_users + item_ptr[it] + it;
+      self = n_edges + n_users + item_ptr[it + 1] + it;
     }
+    adj_ptr[j] = start;
+    adj_idx[self] = (int32_t)j;
+    adj_val[self] = (float)((d * 1.0) * d);
+    if (j == N - 1) adj_ptr[N] = 2 * n_edges + N;
   }
 }
 
@@ -197,8 +199,10 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
   const int64_t N = n_users + n_items;
   node_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.item_ptr, n_users, n_items, w.dinv);
   DMM_LAUNCH_CHECK();
-  fill_adj_kernel<<<(unsigned)dmm_ceil_div(N * 32, 256), 256, 0, st>>>(row_ptr, items, w.item_ptr, w.users_by_item, w.dinv,
-                                                                      n_users, n_items, n_edges, adj_ptr, adj_idx, adj_val);
+  const int64_t work = n_edges > N ? n_edges : N;
+  fill_adj_kernel<<<(unsigned)dmm_ceil_div(work, 256), 256, 0, st>>>(row_ptr, items, w.edge_user, w.item_ptr, w.items_sorted,
+                                                                    w.users_by_item, w.dinv, n_users, n_items, n_edges,
+                                                                    adj_ptr, adj_idx, adj_val);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

@@ -7,8 +7,10 @@
 //   warp 0  : TMA producer   — cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) into a STAGES-deep ring
 //   warp 1  : MMA issuer     — one lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2  : TMEM allocator — 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
-//   warps 4-11: epilogue     — tcgen05.ld 32 lanes x 32 columns, bias/tanh/posterior-mean, fp32 and
-//                              split-bf16 stores (the bf16 pair is the next contraction's operand)
+//   warps 3-10: epilogue     — tcgen05.ld 32 lanes x 32 columns, bias/tanh/posterior-mean, fp32 and
+//                              split-bf16 stores (the bf16 pair is the next contraction's operand);
+//                              the bf16 residual of chunk c+1 is prefetched into registers while chunk c
+//                              is drained, and the first chunk's before the accumulator barrier
 // The optional lo operands add the passes A_lo.B_hi and A_hi.B_lo into the same accumulator
 // ("bf16x3"), which restores fp32-level accuracy without leaving the bf16 tensor pipe.
 #include "common.cuh"
@@ -18,9 +20,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARP0 = 4;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 3;   // warps 0-2: TMA producer, MMA issuer, TMEM allocator
+constexpr int EPI_WARPS = 8;   // any 8 consecutive warps cover each TMEM lane quarter (warp % 4) twice
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: one 32 x 32 fp32 chunk, or bf16 hi + lo chunks
 
 template <int BN>
 struct Cfg {
@@ -30,12 +33,17 @@ struct Cfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 };
 
 struct GemmParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  // Work items: the first `full_items` are whole BLOCK_M x BN tiles (a whole number of waves over the
+  // grid); the tiles of the last, partly filled wave are cut into `split` column slices of `sub_bn`
+  // columns each so that the tail keeps (almost) every SM busy for 1/split of a tile time.
+  int full_items, total_items, split, sub_bn;
   int n_pass;
   int pass_a[3];  // 0 = hi, 1 = lo
   int pass_b[3];
@@ -137,10 +145,35 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.f - __fdividef(2.f, t + 1.f);
 }
 
+struct WorkItem {
+  int m_blk;   // row block
+  int col0;    // first output column
+  int bn;      // columns of this item (BN, or sub_bn for a tail slice)
+};
+// n fastest: the CTAs running together cover every column block of a few row blocks, so each A tile is
+// fetched from HBM once and re-read from L2 by its neighbours
+template <int BN>
+__device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
+  WorkItem it;
+  if (w < p.full_items) {
+    it.m_blk = w / p.num_n_blocks;
+    it.col0 = (w % p.num_n_blocks) * BN;
+    it.bn = BN;
+  } else {
+    const int r = w - p.full_items;
+    const int tile = p.full_items + r / p.split;
+    it.m_blk = tile / p.num_n_blocks;
+    it.col0 = (tile % p.num_n_blocks) * BN + (r % p.split) * p.sub_bn;
+    it.bn = p.sub_bn;
+  }
+  return it;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ CUtensorMap tm_bs_hi, const __grid_constant__ CUtensorMap tm_bs_lo,
                     const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -181,27 +214,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int k_iters = p.n_pass * p.num_k_blocks;
+  // items whose first column lies beyond N (slices of a ragged last column block) are skipped by all roles
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // n fastest: the CTAs running together cover every column block of a few row blocks, so each A
-        // tile is fetched from HBM once and re-read from L2 by its neighbours
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile % p.num_n_blocks;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        const WorkItem wi = decode_work<BN>(w, p);
+        if (wi.col0 >= p.N) continue;
+        const bool sub = wi.bn != BN;
+        const uint32_t tx_bytes = (uint32_t)(C::A_BYTES + wi.bn * BLOCK_K * 2);
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap* ma = p.pass_a[ps] ? &tm_a_lo : &tm_a_hi;
-          const CUtensorMap* mb = p.pass_b[ps] ? &tm_b_lo : &tm_b_hi;
+          const CUtensorMap* mb = p.pass_b[ps] ? (sub ? &tm_bs_lo : &tm_b_lo) : (sub ? &tm_bs_hi : &tm_b_hi);
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            mbar_expect_tx(full_bar(stage), tx_bytes);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-            tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, n_blk * BN);
+            tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, wi.m_blk * BLOCK_M);
+            tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, wi.col0);
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -213,11 +246,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        const WorkItem wi = decode_work<BN>(w, p);
+        if (wi.col0 >= p.N) continue;
+        const uint32_t idesc = make_idesc(wi.bn);
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
@@ -241,153 +276,220 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
         tcgen05_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        ++it;
       }
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), (warp - 4) / 4 the
-    // parity of the 32-column chunks this warp drains, so two warps per SM sub-partition overlap
-    // their global loads/stores.
-    const int ew = (warp - EPI_WARP0) & 3;
+    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), (warp - EPI_WARP0) / 4
+    // the parity of the 32-column chunks this warp drains.
+    //
+    // tcgen05.ld hands every thread one ROW of the chunk, and a row-per-thread global access touches 32
+    // different 128-byte lines per instruction (the L1 tag stage, not DRAM, then bounds the epilogue).
+    // So every global access goes through a per-warp 4 KB shared-memory staging tile, swizzled so that
+    // both views are bank-conflict free: the row view (thread = row) used with the accumulator, and the
+    // coalesced view (4 or 8 consecutive lanes cover one row segment) used against global memory.
+    // The bf16 residual of the NEXT chunk is fetched (coalesced) into registers while this one is drained.
+    const int ew = warp & 3;
     const int chalf = (warp - EPI_WARP0) >> 2;
     const dmm_gemm_epilogue& ep = p.ep;
-    const bool has_res = ep.residual != nullptr || ep.res_hi != nullptr;
+    const bool res16 = ep.res_hi != nullptr;
+    const bool res16lo = ep.res_lo != nullptr;
+    uint8_t* const stg = smem_raw + (smem_base - smem_u32(smem_raw)) + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES +
+                         (warp - EPI_WARP0) * EPI_STAGE_BYTES;
+    // bf16 chunk: 32 rows x 64 B; 16-byte piece p of row r lives at r*64 + ((p ^ ((r >> 1) & 3)) << 4)
+    auto at16 = [&](int sub, int r, int pc) -> uint4* {
+      return reinterpret_cast<uint4*>(stg + sub * 2048 + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+    };
+    // fp32 chunk: 32 rows x 128 B; piece p of row r lives at r*128 + ((p ^ (r & 7)) << 4)
+    auto at32 = [&](int r, int pc) -> uint4* { return reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)); };
+    const int cr16 = lane >> 2, cp16 = lane & 3;  // coalesced view, bf16: rows cr16 + 8 i, piece cp16
+    const int cr32 = lane >> 3, cp32 = lane & 7;  // coalesced view, fp32: rows cr32 + 4 i, piece cp32
+
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile % p.num_n_blocks;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const WorkItem wi = decode_work<BN>(w, p);
+      if (wi.col0 >= p.N) continue;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      ++it;
+      const int rbase = wi.m_blk * BLOCK_M + ew * 32;
+      const int row = rbase + lane;
+      // coalesced fetch of the raw bf16 residual chunk starting at column n0 (rows/pieces out of range skipped;
+      // a piece that starts below N always lies inside the padded row because ld % 8 == 0)
+      auto fetch_res16 = [&](int n0, uint4 (&h)[4], uint4 (&l)[4]) {
+        const int col = n0 + 8 * cp16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rbase + cr16 + 8 * i;
+          if (r < p.M && col < p.N) {
+            h[i] = *reinterpret_cast<const uint4*>(ep.res_hi + (int64_t)r * ep.ld_res16 + col);
+            if (res16lo) l[i] = *reinterpret_cast<const uint4*>(ep.res_lo + (int64_t)r * ep.ld_res16 + col);
+          }
+        }
+      };
+      uint4 nh[4], nl[4];
+      if (res16 && chalf * 32 < wi.bn && wi.col0 + chalf * 32 < p.N) fetch_res16(wi.col0 + chalf * 32, nh, nl);
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + ew * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = chalf; c < BN / 32; c += EPI_WARPS / 4) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        const bool full = (n0 + 32 <= p.N);
-        // residual loads are issued before the TMEM load so their latency overlaps it
+        const int n0 = wi.col0 + c * 32;
+        if (c * 32 >= wi.bn || n0 >= p.N) break;  // warp-uniform
         float res[32];
-        if (row_ok && full && has_res) {
-          if (ep.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ld_res + n0);
+        if (res16) {
+          // registers (coalesced view) -> staging tile -> this thread's row
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = rp[q];
-              res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+          for (int i = 0; i < 4; ++i) {
+            *at16(0, cr16 + 8 * i, cp16) = nh[i];
+            if (res16lo) *at16(1, cr16 + 8 * i, cp16) = nl[i];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 h = *at16(0, lane, q);
+            const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              res[8 * q + 2 * e] = __uint_as_float(wv[e] << 16);
+              res[8 * q + 2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u);
             }
-          } else {
-            const uint4* hp = reinterpret_cast<const uint4*>(ep.res_hi + (int64_t)row * ep.ld_res16 + n0);
-            uint4 h[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) h[q] = hp[q];
+          }
+          if (res16lo) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint32_t w[4] = {h[q].x, h[q].y, h[q].z, h[q].w};
+              const uint4 h = *at16(1, lane, q);
+              const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                res[8 * q + 2 * e] = __uint_as_float(w[e] << 16);
-                res[8 * q + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-              }
-            }
-            if (ep.res_lo) {
-              const uint4* lp = reinterpret_cast<const uint4*>(ep.res_lo + (int64_t)row * ep.ld_res16 + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = lp[q];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t w[4] = {h[q].x, h[q].y, h[q].z, h[q].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  res[8 * q + 2 * e] += __uint_as_float(w[e] << 16);
-                  res[8 * q + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                }
+                res[8 * q + 2 * e] += __uint_as_float(wv[e] << 16);
+                res[8 * q + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
               }
             }
           }
+          __syncwarp();
+          const int c1 = c + EPI_WARPS / 4;
+          if (c1 * 32 < wi.bn && wi.col0 + c1 * 32 < p.N) fetch_res16(wi.col0 + c1 * 32, nh, nl);
+        } else if (ep.residual) {
+          // fp32 residual: coalesced global -> staging tile -> row
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rbase + cr32 + 4 * i, col = n0 + 4 * cp32;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < p.M && col < p.N) t = *reinterpret_cast<const float4*>(ep.residual + (int64_t)r * ep.ld_res + col);
+            *reinterpret_cast<float4*>(at32(cr32 + 4 * i, cp32)) = t;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(at32(lane, q));
+            res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+          }
+          __syncwarp();
         }
+        const bool has_res = res16 || ep.residual != nullptr;
+
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
         tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), r);
         float v[32];
-        if (!row_ok) {
-          // rows past M were zero-filled by TMA; nothing to store
-        } else if (full) {
-          if (ep.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+        if (ep.bias) {
+          // columns past N read the bias row's padding only when it exists: clamp by whole float4 pieces
+          const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(bp + q);
-              v[4 * q] = __uint_as_float(r[4 * q]) + t.x;
-              v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + t.y;
-              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + t.z;
-              v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + t.w;
+          for (int q = 0; q < 8; ++q) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + 4 * q + 4 <= p.N) {
+              t = __ldg(bp + q);
+            } else {
+              if (n0 + 4 * q + 0 < p.N) t.x = __ldg(ep.bias + n0 + 4 * q + 0);
+              if (n0 + 4 * q + 1 < p.N) t.y = __ldg(ep.bias + n0 + 4 * q + 1);
+              if (n0 + 4 * q + 2 < p.N) t.z = __ldg(ep.bias + n0 + 4 * q + 2);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          }
-          if (ep.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
-          }
-          if (has_res) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ep.alpha * v[j] + ep.beta * res[j];
-          } else if (ep.alpha != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-          }
-          if (ep.out_f32) {
-            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ld_out + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-          if (ep.out_hi) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              uint16_t h0, l0, h1, l1;
-              dmm_split_bf16(v[2 * q], h0, l0);
-              dmm_split_bf16(v[2 * q + 1], h1, l1);
-              hi[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-            uint4* hp = reinterpret_cast<uint4*>(ep.out_hi + (int64_t)row * ep.ld_out16 + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hp[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (ep.out_lo) {
-              uint4* lp = reinterpret_cast<uint4*>(ep.out_lo + (int64_t)row * ep.ld_out16 + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) lp[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-            }
+            v[4 * q] = __uint_as_float(r[4 * q]) + t.x;
+            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + t.y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + t.z;
+            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + t.w;
           }
         } else {
-          // ragged last column block: scalar, guarded
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            if (n >= p.N) break;
-            float x = __uint_as_float(r[j]) + (ep.bias ? __ldg(ep.bias + n) : 0.f);
-            if (ep.act == 1) x = fast_tanh(x);
-            if (ep.residual) {
-              x = ep.alpha * x + ep.beta * ep.residual[(int64_t)row * ep.ld_res + n];
-            } else if (ep.res_hi) {
-              float rr = dmm_bf16_to_f32(ep.res_hi[(int64_t)row * ep.ld_res16 + n]);
-              if (ep.res_lo) rr += dmm_bf16_to_f32(ep.res_lo[(int64_t)row * ep.ld_res16 + n]);
-              x = ep.alpha * x + ep.beta * rr;
-            } else {
-              x *= ep.alpha;
-            }
-            if (ep.out_f32) ep.out_f32[(int64_t)row * ep.ld_out + n] = x;
-            if (ep.out_hi) {
-              uint16_t h, l;
-              dmm_split_bf16(x, h, l);
-              ep.out_hi[(int64_t)row * ep.ld_out16 + n] = h;
-              if (ep.out_lo) ep.out_lo[(int64_t)row * ep.ld_out16 + n] = l;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ep.alpha * v[j] + ep.beta * res[j];
+        } else if (ep.alpha != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        }
+
+        if (ep.out_f32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(at32(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const int col = n0 + 4 * cp32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = rbase + cr32 + 4 * i;
+            const float4 t = *reinterpret_cast<const float4*>(at32(cr32 + 4 * i, cp32));
+            if (rr < p.M) {
+              float* op = ep.out_f32 + (int64_t)rr * ep.ld_out + col;
+              if (col + 4 <= p.N) {
+                *reinterpret_cast<float4*>(op) = t;
+              } else {
+                if (col + 0 < p.N) op[0] = t.x;
+                if (col + 1 < p.N) op[1] = t.y;
+                if (col + 2 < p.N) op[2] = t.z;
+              }
             }
           }
+          __syncwarp();
+        }
+        if (ep.out_hi) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            uint16_t h0, l0, h1, l1;
+            dmm_split_bf16(v[2 * q], h0, l0);
+            dmm_split_bf16(v[2 * q + 1], h1, l1);
+            hi[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *at16(0, lane, q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            if (ep.out_lo) *at16(1, lane, q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+          __syncwarp();
+          const int col = n0 + 8 * cp16;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint16_t* const base = sub ? ep.out_lo : ep.out_hi;
+            if (base == nullptr) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = rbase + cr16 + 8 * i;
+              const uint4 t = *at16(sub, cr16 + 8 * i, cp16);
+              if (rr < p.M) {
+                uint16_t* op = base + (int64_t)rr * ep.ld_out16 + col;
+                if (col + 8 <= p.N) {
+                  *reinterpret_cast<uint4*>(op) = t;
+                } else {
+                  const uint32_t wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col + e < p.N) op[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tcgen05_fence_before();
@@ -395,6 +497,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
+
 
   tcgen05_fence_before();
   __syncthreads();
@@ -429,21 +532,32 @@ template <int BN>
 int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
            const uint16_t* b_lo, int64_t ldb, GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo;
   int rc;
+  p.num_n_blocks = (int)dmm_ceil_div(p.N, BN);
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  // tail wave: when the last wave would fill at most half of the grid, cut its tiles into column slices
+  const int rem = tiles % grid;
+  p.split = 1;
+  if (rem > 0 && tiles > grid) {
+    while (p.split * 2 <= BN / 64 && rem * p.split * 2 <= grid) p.split *= 2;
+  }
+  p.sub_bn = BN / p.split;
+  p.full_items = p.split > 1 ? tiles - rem : tiles;
+  p.total_items = p.full_items + (p.split > 1 ? rem * p.split : 0);
   if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
   if ((rc = make_map(ctx, &ma_lo, a_lo ? a_lo : a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
   if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, BN))) return rc;
   if ((rc = make_map(ctx, &mb_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, BN))) return rc;
-  p.num_n_blocks = (int)dmm_ceil_div(p.N, BN);
+  if ((rc = make_map(ctx, &mbs_hi, b_hi, p.N, p.K, ldb, p.sub_bn))) return rc;
+  if ((rc = make_map(ctx, &mbs_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, p.sub_bn))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

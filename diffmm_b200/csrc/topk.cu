@@ -16,6 +16,9 @@
 namespace {
 
 constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_NB_LOG2 = 11;
+constexpr int TOPK_NB = 1 << TOPK_NB_LOG2;   // range-adapted buckets of the first pass
+constexpr int TOPK_CAND = 1024;              // threshold-bucket keys selected exactly in shared memory
 
 __device__ __forceinline__ uint32_t order_key(float f) {
   uint32_t u = __float_as_uint(f);
@@ -46,6 +49,76 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
   return base + incl - v;
 }
 
+// MSB-first radix select (4 passes x 8 bits, warp-aggregated shared-memory histograms) of the
+// `want`-th largest of `count` keys read through `key_at`.  Returns the threshold key and, in
+// *need_eq, how many keys equal to it belong to the top `want`.  Uniform across the block.
+template <typename KeyAt>
+__device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int count, int want, int* hist, uint32_t* s_prefix,
+                                                 int* s_kk, int* need_eq) {
+  const int tid = threadIdx.x;
+  uint32_t prefix = 0u, mask = 0u;
+  int kk = want;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < count; i0 += TOPK_THREADS) {
+      const int i = i0 + tid;
+      const bool in = i < count;
+      const uint32_t key = in ? key_at(i) : 0u;
+      const bool cand = in && ((key & mask) == prefix);
+      const uint32_t digit = (key >> shift) & 0xFFu;
+      // one shared-memory atomic per distinct digit per warp
+      const uint32_t active = __ballot_sync(0xffffffffu, cand);
+      if (cand) {
+        const uint32_t peers = __match_any_sync(active, digit);
+        if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[digit], __popc(peers));
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // descending scan: lane l owns bins 255-8l .. 248-8l
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[255 - 8 * tid - j];
+        sum += loc[j];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += t;
+      }
+      const int excl = incl - sum;
+      if (excl < kk && kk <= incl) {
+        int cum = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (cum < kk && kk <= cum + loc[j]) {
+            *s_prefix = prefix | ((uint32_t)(255 - 8 * tid - j) << shift);
+            *s_kk = kk - cum;
+          }
+          cum += loc[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix = *s_prefix;
+    kk = *s_kk;
+    mask |= 0xFFu << shift;
+  }
+  *need_eq = kk;
+  return prefix;
+}
+
+// Selection strategy.  The leading radix digits of fp32 scores (sign + exponent) barely discriminate, so
+// a plain 4-pass radix select walks the whole row four times with almost every key a candidate.
+// Instead ONE histogram pass over range-adapted buckets ((key - kmin) >> sh, NB buckets, monotone in
+// the key) isolates the bucket holding the k-th largest key; only that bucket's keys (a handful for
+// continuous scores) go through the exact radix select in shared memory.  Rows whose threshold bucket
+// is crowded (heavy ties) fall back to the exact select over the whole row.  Either way the result is
+// the exact (value desc, column asc) top-k.
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* __restrict__ scores, int64_t ld,
                                                                   int64_t n_rows, int n_cols,
@@ -54,10 +127,13 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* _
                                                                   int32_t* __restrict__ out_items,
                                                                   int32_t* __restrict__ status) {
   extern __shared__ uint32_t s_keys[];  // n_cols keys when IN_SMEM
+  __shared__ int bucket[TOPK_NB];
+  __shared__ uint32_t cand[TOPK_CAND];
   __shared__ int hist[256];
   __shared__ int warp_sums[TOPK_THREADS / 32];
+  __shared__ uint32_t s_red[2 * (TOPK_THREADS / 32)];
   __shared__ uint32_t s_prefix;
-  __shared__ int s_kk;
+  __shared__ int s_kk, s_bin, s_above, s_ncand;
 
   const int64_t r = blockIdx.x;
   if (r >= n_rows) return;
@@ -70,7 +146,13 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* _
   }
   const float* row = scores + r * ld;
   const int tid = threadIdx.x;
+  const bool take_all = !(k < n_cols);
 
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+  auto track = [&](uint32_t key) {
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  };
   if (IN_SMEM) {
     // single HBM read of the row; float4 when the row start is 16 B aligned
     const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
@@ -79,84 +161,94 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* _
       const float4* row4 = reinterpret_cast<const float4*>(row);
       for (int i = tid; i < n4; i += TOPK_THREADS) {
         const float4 v = __ldcs(row4 + i);
-        s_keys[4 * i + 0] = order_key(v.x);
-        s_keys[4 * i + 1] = order_key(v.y);
-        s_keys[4 * i + 2] = order_key(v.z);
-        s_keys[4 * i + 3] = order_key(v.w);
+        const uint4 q = make_uint4(order_key(v.x), order_key(v.y), order_key(v.z), order_key(v.w));
+        reinterpret_cast<uint4*>(s_keys)[i] = q;
+        track(q.x); track(q.y); track(q.z); track(q.w);
       }
-      for (int i = (n4 << 2) + tid; i < n_cols; i += TOPK_THREADS) s_keys[i] = order_key(__ldcs(row + i));
+      for (int i = (n4 << 2) + tid; i < n_cols; i += TOPK_THREADS) {
+        const uint32_t q = order_key(__ldcs(row + i));
+        s_keys[i] = q;
+        track(q);
+      }
     } else {
-      for (int i = tid; i < n_cols; i += TOPK_THREADS) s_keys[i] = order_key(__ldcs(row + i));
+      for (int i = tid; i < n_cols; i += TOPK_THREADS) {
+        const uint32_t q = order_key(__ldcs(row + i));
+        s_keys[i] = q;
+        track(q);
+      }
     }
+  } else if (!take_all) {
+    for (int i = tid; i < n_cols; i += TOPK_THREADS) track(order_key(__ldg(row + i)));
   }
-  if (tid == 0) {
-    s_prefix = 0u;
-    s_kk = k;
-  }
-  __syncthreads();
-
   auto key_at = [&](int i) -> uint32_t { return IN_SMEM ? s_keys[i] : order_key(__ldg(row + i)); };
 
-  uint32_t prefix = 0u, mask = 0u;
-  int kk = k;
-  if (k < n_cols) {
-#pragma unroll 1
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[tid] = 0;
-      __syncthreads();
-      for (int i0 = 0; i0 < n_cols; i0 += TOPK_THREADS) {
-        const int i = i0 + tid;
-        const bool in = i < n_cols;
-        const uint32_t key = in ? key_at(i) : 0u;
-        const bool cand = in && ((key & mask) == prefix);
-        const uint32_t digit = (key >> shift) & 0xFFu;
-        // warp-aggregated histogram: one shared-memory atomic per distinct digit per warp
-        const uint32_t active = __ballot_sync(0xffffffffu, cand);
-        if (cand) {
-          const uint32_t peers = __match_any_sync(active, digit);
-          if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[digit], __popc(peers));
-        }
+  uint32_t T = 0u;
+  int need_eq = 0;
+  if (!take_all) {
+#pragma unroll
+    for (int j = 0; j < TOPK_NB / TOPK_THREADS; ++j) bucket[tid + j * TOPK_THREADS] = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((tid & 31) == 0) {
+      s_red[tid >> 5] = kmin;
+      s_red[TOPK_THREADS / 32 + (tid >> 5)] = kmax;
+    }
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TOPK_THREADS / 32; ++i) {
+      kmin = min(kmin, s_red[i]);
+      kmax = max(kmax, s_red[TOPK_THREADS / 32 + i]);
+    }
+    // (kmax - kmin) >> sh < TOPK_NB
+    const uint32_t range = kmax - kmin;
+    const int bits = 32 - __clz(range);               // range == 0 -> 0
+    const int sh = bits > TOPK_NB_LOG2 ? bits - TOPK_NB_LOG2 : 0;
+    for (int i = tid; i < n_cols; i += TOPK_THREADS) atomicAdd(&bucket[(key_at(i) - kmin) >> sh], 1);
+    __syncthreads();
+    {
+      // descending scan over the buckets: thread t owns buckets NB-1-PER*t .. NB-PER*(t+1)
+      constexpr int PER = TOPK_NB / TOPK_THREADS;
+      int loc[PER], sum = 0;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        loc[j] = bucket[TOPK_NB - 1 - PER * tid - j];
+        sum += loc[j];
       }
-      __syncthreads();
-      if (tid < 32) {
-        // descending scan: lane l owns bins 255-8l .. 248-8l
-        int loc[8], sum = 0;
+      int tot;
+      const int excl = block_excl_scan(sum, warp_sums, &tot);
+      if (excl < k && k <= excl + sum) {
+        int cum = excl;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          loc[j] = hist[255 - 8 * tid - j];
-          sum += loc[j];
-        }
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (tid >= o) incl += t;
-        }
-        const int excl = incl - sum;
-        const int want = kk;  // == s_kk, kept in a register by every thread
-        if (excl < want && want <= incl) {
-          int cum = excl;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (cum < want && want <= cum + loc[j]) {
-              s_prefix = prefix | ((uint32_t)(255 - 8 * tid - j) << shift);
-              s_kk = want - cum;
-            }
-            cum += loc[j];
+        for (int j = 0; j < PER; ++j) {
+          if (cum < k && k <= cum + loc[j]) {
+            s_bin = TOPK_NB - 1 - PER * tid - j;
+            s_above = cum;
           }
+          cum += loc[j];
         }
       }
+    }
+    __syncthreads();
+    const int bin = s_bin;
+    const int want = k - s_above;          // >= 1: rank of the threshold inside its bucket
+    const int m = bucket[bin];
+    if (m <= TOPK_CAND) {
+      for (int i = tid; i < n_cols; i += TOPK_THREADS) {
+        const uint32_t key = key_at(i);
+        if ((int)((key - kmin) >> sh) == bin) cand[atomicAdd(&s_ncand, 1)] = key;
+      }
       __syncthreads();
-      prefix = s_prefix;
-      kk = s_kk;
-      mask |= 0xFFu << shift;
+      T = radix_select([&](int i) -> uint32_t { return cand[i]; }, m, want, hist, &s_prefix, &s_kk, &need_eq);
+    } else {
+      T = radix_select(key_at, n_cols, k, hist, &s_prefix, &s_kk, &need_eq);
     }
   }
-  // threshold key T = prefix; take every key > T and the first kk keys == T (ascending column)
-  const uint32_t T = (k < n_cols) ? prefix : 0u;
-  const int need_eq = (k < n_cols) ? kk : 0;
-  const bool take_all = !(k < n_cols);
 
+  // take every key > T and the first need_eq keys == T (ascending column)
   // contiguous segment per thread, odd length => conflict-free strided shared-memory reads
   int seg = (n_cols + TOPK_THREADS - 1) / TOPK_THREADS;
   seg |= 1;
@@ -172,6 +264,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* _
   int eq_take = need_eq - eq_before;
   eq_take = eq_take < 0 ? 0 : (eq_take > c_eq ? c_eq : eq_take);
   const int pos0 = block_excl_scan(c_gt + eq_take, warp_sums, &tot);
+  if (c_gt + eq_take == 0) return;        // no barrier follows
   int64_t w = o0 + pos0;
   const int32_t user = (int32_t)(row_base + r);
   for (int i = b; i < e; ++i) {
@@ -201,7 +294,8 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
   if (n_rows == 0) return DMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)n_cols * sizeof(uint32_t);
-  const size_t cap = (size_t)ctx->max_smem_optin > 8192 ? (size_t)ctx->max_smem_optin - 4096 : 0;
+  // static shared memory of the kernel (buckets, candidates, scratch) is ~14 KB
+  const size_t cap = (size_t)ctx->max_smem_optin > 32768 ? (size_t)ctx->max_smem_optin - 16384 : 0;
   if (smem <= cap) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
