@@ -23,7 +23,7 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARP0 = 3;   // warps 0-2: TMA producer, MMA issuer, TMEM allocator
 constexpr int EPI_WARPS = 8;   // any 8 consecutive warps cover each TMEM lane quarter (warp % 4) twice
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
-constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: one 32 x 32 fp32 chunk, or bf16 hi + lo chunks
+constexpr int EPI_STAGE_BYTES = 4096 + 128;  // per epilogue warp: one 32 x 32 fp32 chunk (or bf16 hi + lo chunks) + 32 bias values
 
 template <int BN>
 struct Cfg {
@@ -169,7 +169,216 @@ __device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
   return it;
 }
 
-template <int BN>
+// ------------------------------------------------------------------------------------------ epilogue
+// One work item drained by one epilogue warp (TMEM lane quarter `ew`, chunk parity `chalf`).
+//
+// tcgen05.ld hands every thread one ROW of a 32-column chunk, and a row-per-thread global access touches
+// 32 different 128-byte lines per instruction (the L1 tag stage, not DRAM, would bound the epilogue).  So
+// every global access goes through a per-warp shared-memory staging tile, swizzled so that both views are
+// bank-conflict free: the row view (thread = row) used with the accumulator, and the coalesced view (4 or
+// 8 consecutive lanes cover one row segment) used against global memory.  The bf16 residual and the bias
+// of the NEXT chunk are fetched (coalesced) into registers while this chunk is drained; the first chunk's
+// before the accumulator barrier.  X3: lo (split-bf16) residual/output parts may be present.  INTERIOR:
+// the item lies fully inside [0,M) x [0,N), no bounds predicates.
+template <int BN, bool X3, bool INTERIOR>
+__device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkItem wi, uint8_t* const stg,
+                                              const uint32_t taddr, const uint32_t tfull, const uint32_t tphase,
+                                              const int ew, const int chalf, const int lane) {
+  const dmm_gemm_epilogue& ep = p.ep;
+  const bool res16 = ep.res_hi != nullptr;
+  const bool res16lo = X3 && ep.res_lo != nullptr;
+  const bool out_lo = X3 && ep.out_lo != nullptr;
+  const bool has_res = res16 || ep.residual != nullptr;
+  const int rbase = wi.m_blk * BLOCK_M + ew * 32;
+  const int nchunks = wi.bn >> 5;
+  // bf16 chunk: 32 rows x 64 B; 16-byte piece pc of row r lives at r*64 + ((pc ^ ((r >> 1) & 3)) << 4)
+  auto at16 = [&](int sub, int r, int pc) -> uint4* {
+    return reinterpret_cast<uint4*>(stg + sub * 2048 + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+  };
+  // fp32 chunk: 32 rows x 128 B; piece pc of row r lives at r*128 + ((pc ^ (r & 7)) << 4)
+  auto at32 = [&](int r, int pc) -> uint4* { return reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)); };
+  float* const stg_bias = reinterpret_cast<float*>(stg + 4096);
+  const int cr16 = lane >> 2, cp16 = lane & 3;  // coalesced view, bf16: rows cr16 + 8 i, piece cp16
+  const int cr32 = lane >> 3, cp32 = lane & 7;  // coalesced view, fp32: rows cr32 + 4 i, piece cp32
+  auto chunk_ok = [&](int c) -> bool { return c < nchunks && (INTERIOR || wi.col0 + c * 32 < p.N); };
+
+  uint4 nh[4], nl[4];
+  float nb = 0.f;
+  // coalesced fetch of chunk c's raw bf16 residual and bias (a 16-byte piece that starts below N always lies
+  // inside the padded row because the leading dimension is a multiple of 8)
+  auto fetch = [&](int c) {
+    const int n0 = wi.col0 + c * 32;
+    if (ep.bias) nb = (INTERIOR || n0 + lane < p.N) ? __ldg(ep.bias + n0 + lane) : 0.f;
+    if (res16) {
+      const int col = n0 + 8 * cp16;
+      const int64_t off = (int64_t)(rbase + cr16) * ep.ld_res16 + col;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (INTERIOR || (rbase + cr16 + 8 * i < p.M && col < p.N)) {
+          nh[i] = *reinterpret_cast<const uint4*>(ep.res_hi + off + (int64_t)(8 * i) * ep.ld_res16);
+          if (res16lo) nl[i] = *reinterpret_cast<const uint4*>(ep.res_lo + off + (int64_t)(8 * i) * ep.ld_res16);
+        }
+      }
+    }
+  };
+  if (chunk_ok(chalf)) fetch(chalf);
+  mbar_wait(tfull, tphase, 4);
+  tcgen05_fence_after();
+
+#pragma unroll 1
+  for (int c = chalf; chunk_ok(c); c += EPI_WARPS / 4) {
+    const int n0 = wi.col0 + c * 32;
+    // ---- residual + bias: registers (coalesced view) -> staging tile; read back per row below
+    if (ep.bias) stg_bias[lane] = nb;
+    if (res16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        *at16(0, cr16 + 8 * i, cp16) = nh[i];
+        if (res16lo) *at16(1, cr16 + 8 * i, cp16) = nl[i];
+      }
+    } else if (ep.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rbase + cr32 + 4 * i, col = n0 + 4 * cp32;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (INTERIOR || (r < p.M && col < p.N)) t = *reinterpret_cast<const float4*>(ep.residual + (int64_t)r * ep.ld_res + col);
+        *reinterpret_cast<float4*>(at32(cr32 + 4 * i, cp32)) = t;
+      }
+    }
+    // next chunk's residual / bias: in flight while this chunk is combined and stored (it may alias only the
+    // output of the NEXT chunk, which this warp writes later)
+    if (chunk_ok(c + EPI_WARPS / 4)) fetch(c + EPI_WARPS / 4);
+    // ---- accumulator chunk
+    uint32_t r[32];
+    __syncwarp();  // tcgen05.ld is .sync.aligned; also publishes the staging tile to the row view
+    tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 8 columns per step
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = __uint_as_float(r[8 * q + j]);
+      if (ep.bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(stg_bias + 8 * q);
+        const float4 b1 = *reinterpret_cast<const float4*>(stg_bias + 8 * q + 4);
+        t[0] += b0.x; t[1] += b0.y; t[2] += b0.z; t[3] += b0.w;
+        t[4] += b1.x; t[5] += b1.y; t[6] += b1.z; t[7] += b1.w;
+      }
+      if (ep.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fast_tanh(t[j]);
+      }
+      if (has_res) {
+        float rs[8];
+        if (res16) {
+          const uint4 h = *at16(0, lane, q);
+          const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            rs[2 * e] = __uint_as_float(wv[e] << 16);
+            rs[2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u);
+          }
+          if (res16lo) {
+            const uint4 l = *at16(1, lane, q);
+            const uint32_t lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              rs[2 * e] += __uint_as_float(lv[e] << 16);
+              rs[2 * e + 1] += __uint_as_float(lv[e] & 0xFFFF0000u);
+            }
+          }
+        } else {
+          const float4 r0 = *reinterpret_cast<const float4*>(at32(lane, 2 * q));
+          const float4 r1 = *reinterpret_cast<const float4*>(at32(lane, 2 * q + 1));
+          rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
+          rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fmaf(ep.alpha, t[j], ep.beta * rs[j]);
+      } else if (ep.alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] *= ep.alpha;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * q + j] = t[j];
+    }
+    __syncwarp();  // every row has consumed the staged residual / bias: the tile is reused for the outputs
+
+    // ---- outputs: row view -> staging tile -> coalesced global stores
+    if (ep.out_f32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(at32(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      const int col = n0 + 4 * cp32;
+      float* const op0 = ep.out_f32 + (int64_t)(rbase + cr32) * ep.ld_out + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(at32(cr32 + 4 * i, cp32));
+        float* const op = op0 + (int64_t)(4 * i) * ep.ld_out;
+        if (INTERIOR) {
+          *reinterpret_cast<float4*>(op) = t;
+        } else if (rbase + cr32 + 4 * i < p.M) {
+          if (col + 4 <= p.N) {
+            *reinterpret_cast<float4*>(op) = t;
+          } else {
+            if (col + 0 < p.N) op[0] = t.x;
+            if (col + 1 < p.N) op[1] = t.y;
+            if (col + 2 < p.N) op[2] = t.z;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (ep.out_hi) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = v[8 * q + 2 * e], x1 = v[8 * q + 2 * e + 1];
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          if (out_lo) {
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(hi[e] << 16),
+                                                           x1 - __uint_as_float(hi[e] & 0xFFFF0000u));
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+        }
+        *at16(0, lane, q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (out_lo) *at16(1, lane, q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      __syncwarp();
+      const int col = n0 + 8 * cp16;
+      const int64_t off = (int64_t)(rbase + cr16) * ep.ld_out16 + col;
+#pragma unroll
+      for (int sub = 0; sub < (X3 ? 2 : 1); ++sub) {
+        if (sub == 1 && !out_lo) break;
+        uint16_t* const base = (sub ? ep.out_lo : ep.out_hi) + off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t = *at16(sub, cr16 + 8 * i, cp16);
+          uint16_t* const op = base + (int64_t)(8 * i) * ep.ld_out16;
+          if (INTERIOR) {
+            *reinterpret_cast<uint4*>(op) = t;
+          } else if (rbase + cr16 + 8 * i < p.M) {
+            if (col + 8 <= p.N) {
+              *reinterpret_cast<uint4*>(op) = t;
+            } else {
+              const uint32_t wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (col + e < p.N) op[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int BN, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -283,29 +492,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp >= EPI_WARP0) {
     // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), (warp - EPI_WARP0) / 4
     // the parity of the 32-column chunks this warp drains.
-    //
-    // tcgen05.ld hands every thread one ROW of the chunk, and a row-per-thread global access touches 32
-    // different 128-byte lines per instruction (the L1 tag stage, not DRAM, then bounds the epilogue).
-    // So every global access goes through a per-warp 4 KB shared-memory staging tile, swizzled so that
-    // both views are bank-conflict free: the row view (thread = row) used with the accumulator, and the
-    // coalesced view (4 or 8 consecutive lanes cover one row segment) used against global memory.
-    // The bf16 residual of the NEXT chunk is fetched (coalesced) into registers while this one is drained.
     const int ew = warp & 3;
     const int chalf = (warp - EPI_WARP0) >> 2;
-    const dmm_gemm_epilogue& ep = p.ep;
-    const bool res16 = ep.res_hi != nullptr;
-    const bool res16lo = ep.res_lo != nullptr;
     uint8_t* const stg = smem_raw + (smem_base - smem_u32(smem_raw)) + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES +
                          (warp - EPI_WARP0) * EPI_STAGE_BYTES;
-    // bf16 chunk: 32 rows x 64 B; 16-byte piece p of row r lives at r*64 + ((p ^ ((r >> 1) & 3)) << 4)
-    auto at16 = [&](int sub, int r, int pc) -> uint4* {
-      return reinterpret_cast<uint4*>(stg + sub * 2048 + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
-    };
-    // fp32 chunk: 32 rows x 128 B; piece p of row r lives at r*128 + ((p ^ (r & 7)) << 4)
-    auto at32 = [&](int r, int pc) -> uint4* { return reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)); };
-    const int cr16 = lane >> 2, cp16 = lane & 3;  // coalesced view, bf16: rows cr16 + 8 i, piece cp16
-    const int cr32 = lane >> 3, cp32 = lane & 7;  // coalesced view, fp32: rows cr32 + 4 i, piece cp32
-
     int it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
       const WorkItem wi = decode_work<BN>(w, p);
@@ -313,191 +503,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       ++it;
-      const int rbase = wi.m_blk * BLOCK_M + ew * 32;
-      const int row = rbase + lane;
-      // coalesced fetch of the raw bf16 residual chunk starting at column n0 (rows/pieces out of range skipped;
-      // a piece that starts below N always lies inside the padded row because ld % 8 == 0)
-      auto fetch_res16 = [&](int n0, uint4 (&h)[4], uint4 (&l)[4]) {
-        const int col = n0 + 8 * cp16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rbase + cr16 + 8 * i;
-          if (r < p.M && col < p.N) {
-            h[i] = *reinterpret_cast<const uint4*>(ep.res_hi + (int64_t)r * ep.ld_res16 + col);
-            if (res16lo) l[i] = *reinterpret_cast<const uint4*>(ep.res_lo + (int64_t)r * ep.ld_res16 + col);
-          }
-        }
-      };
-      uint4 nh[4], nl[4];
-      if (res16 && chalf * 32 < wi.bn && wi.col0 + chalf * 32 < p.N) fetch_res16(wi.col0 + chalf * 32, nh, nl);
-      mbar_wait(tfull_bar(acc), acc_phase, 4);
-      tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = chalf; c < BN / 32; c += EPI_WARPS / 4) {
-        const int n0 = wi.col0 + c * 32;
-        if (c * 32 >= wi.bn || n0 >= p.N) break;  // warp-uniform
-        float res[32];
-        if (res16) {
-          // registers (coalesced view) -> staging tile -> this thread's row
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            *at16(0, cr16 + 8 * i, cp16) = nh[i];
-            if (res16lo) *at16(1, cr16 + 8 * i, cp16) = nl[i];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 h = *at16(0, lane, q);
-            const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              res[8 * q + 2 * e] = __uint_as_float(wv[e] << 16);
-              res[8 * q + 2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u);
-            }
-          }
-          if (res16lo) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 h = *at16(1, lane, q);
-              const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                res[8 * q + 2 * e] += __uint_as_float(wv[e] << 16);
-                res[8 * q + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
-              }
-            }
-          }
-          __syncwarp();
-          const int c1 = c + EPI_WARPS / 4;
-          if (c1 * 32 < wi.bn && wi.col0 + c1 * 32 < p.N) fetch_res16(wi.col0 + c1 * 32, nh, nl);
-        } else if (ep.residual) {
-          // fp32 residual: coalesced global -> staging tile -> row
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rbase + cr32 + 4 * i, col = n0 + 4 * cp32;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < p.M && col < p.N) t = *reinterpret_cast<const float4*>(ep.residual + (int64_t)r * ep.ld_res + col);
-            *reinterpret_cast<float4*>(at32(cr32 + 4 * i, cp32)) = t;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(at32(lane, q));
-            res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
-          }
-          __syncwarp();
-        }
-        const bool has_res = res16 || ep.residual != nullptr;
-
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
-        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), r);
-        float v[32];
-        if (ep.bias) {
-          // columns past N read the bias row's padding only when it exists: clamp by whole float4 pieces
-          const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + 4 * q + 4 <= p.N) {
-              t = __ldg(bp + q);
-            } else {
-              if (n0 + 4 * q + 0 < p.N) t.x = __ldg(ep.bias + n0 + 4 * q + 0);
-              if (n0 + 4 * q + 1 < p.N) t.y = __ldg(ep.bias + n0 + 4 * q + 1);
-              if (n0 + 4 * q + 2 < p.N) t.z = __ldg(ep.bias + n0 + 4 * q + 2);
-            }
-            v[4 * q] = __uint_as_float(r[4 * q]) + t.x;
-            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + t.y;
-            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + t.z;
-            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        if (ep.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
-        }
-        if (has_res) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ep.alpha * v[j] + ep.beta * res[j];
-        } else if (ep.alpha != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-        }
-
-        if (ep.out_f32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(at32(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          __syncwarp();
-          const int col = n0 + 4 * cp32;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = rbase + cr32 + 4 * i;
-            const float4 t = *reinterpret_cast<const float4*>(at32(cr32 + 4 * i, cp32));
-            if (rr < p.M) {
-              float* op = ep.out_f32 + (int64_t)rr * ep.ld_out + col;
-              if (col + 4 <= p.N) {
-                *reinterpret_cast<float4*>(op) = t;
-              } else {
-                if (col + 0 < p.N) op[0] = t.x;
-                if (col + 1 < p.N) op[1] = t.y;
-                if (col + 2 < p.N) op[2] = t.z;
-              }
-            }
-          }
-          __syncwarp();
-        }
-        if (ep.out_hi) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            uint16_t h0, l0, h1, l1;
-            dmm_split_bf16(v[2 * q], h0, l0);
-            dmm_split_bf16(v[2 * q + 1], h1, l1);
-            hi[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            lo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            *at16(0, lane, q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (ep.out_lo) *at16(1, lane, q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-          __syncwarp();
-          const int col = n0 + 8 * cp16;
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            uint16_t* const base = sub ? ep.out_lo : ep.out_hi;
-            if (base == nullptr) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = rbase + cr16 + 8 * i;
-              const uint4 t = *at16(sub, cr16 + 8 * i, cp16);
-              if (rr < p.M) {
-                uint16_t* op = base + (int64_t)rr * ep.ld_out16 + col;
-                if (col + 8 <= p.N) {
-                  *reinterpret_cast<uint4*>(op) = t;
-                } else {
-                  const uint32_t wv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col + e < p.N) op[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const bool interior = (wi.m_blk + 1) * BLOCK_M <= p.M && wi.col0 + wi.bn <= p.N;
+      if (interior) {
+        epilogue_item<BN, X3, true>(p, wi, stg, taddr, tfull_bar(acc), acc_phase, ew, chalf, lane);
+      } else {
+        epilogue_item<BN, X3, false>(p, wi, stg, taddr, tfull_bar(acc), acc_phase, ew, chalf, lane);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
-
 
   tcgen05_fence_before();
   __syncthreads();
@@ -554,10 +571,15 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   if ((rc = make_map(ctx, &mbs_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, p.sub_bn))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
+  if (p.ep.res_lo != nullptr || p.ep.out_lo != nullptr) {
+    gemm_bf16_tn_kernel<BN, true><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
+  } else {
+    gemm_bf16_tn_kernel<BN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
+  }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
