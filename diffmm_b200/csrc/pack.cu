@@ -168,6 +168,137 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ time embedding folded into the bias
+// In the reverse chain every row of a step shares the timestep (Model.py:319), so the 10 time-embedding
+// columns of cat([x_t, temb]) (Model.py:202-203,212) contribute the same vector to every row:
+//   bias_eff[h] = b[h] + sum_j W[h, col0 + j] * temb_j(t)          (fp32, exact weights)
+__global__ void __launch_bounds__(256) time_bias_kernel(int64_t t_all, int d, const float* __restrict__ emb_w,
+                                                        const float* __restrict__ emb_b, const float* __restrict__ w,
+                                                        int64_t ld_w, int64_t col0, const float* __restrict__ b,
+                                                        int64_t n_out, float* __restrict__ bias_eff) {
+  __shared__ float temb[64];
+  if (threadIdx.x < d) {
+    const int o = threadIdx.x;
+    const int half = d / 2;
+    const float ts = (float)t_all;
+    float acc = emb_b[o];
+    for (int j = 0; j < d; ++j) {
+      float e = 0.f;
+      if (j < half) {
+        e = cosf(ts * expf(-logf(10000.f) * (float)j / (float)half));
+      } else if (j < 2 * half) {
+        e = sinf(ts * expf(-logf(10000.f) * (float)(j - half) / (float)half));
+      }
+      acc = fmaf(e, emb_w[o * d + j], acc);
+    }
+    temb[o] = acc;
+  }
+  __syncthreads();
+  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_out) return;
+  float acc = b ? b[h] : 0.f;
+  const float* wr = w + h * ld_w + col0;
+  for (int j = 0; j < d; ++j) acc = fmaf(wr[j], temb[j], acc);
+  bias_eff[h] = acc;
+}
+
+// ------------------------------------------------------------------ first layer on binary CSR rows
+// h[r, :] = act(bias + sum_{c in row r} Wt[c, :]) for 0/1 rows (x0 of the reverse chain, Model.py:300-304 with
+// sampling_step 0): the dense [B, I] x [I, H] contraction of Model.py:212 degenerates to a gather-sum of the
+// rows of W^T.  One warp per user row; lane l owns the 16-byte pieces l, l+32, ... of the H columns, so every
+// gathered weight row is read with full 512-byte warp transactions (the packed W^T is L2 resident).
+template <bool LO>
+__global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ indices,
+                                                             const int64_t* __restrict__ row_ids, int64_t row0,
+                                                             int64_t n_rows, int64_t n_cols,
+                                                             const uint16_t* __restrict__ wt_hi,
+                                                             const uint16_t* __restrict__ wt_lo, int64_t ld_w,
+                                                             const float* __restrict__ bias, int act, int64_t n_out,
+                                                             uint16_t* __restrict__ h_hi, uint16_t* __restrict__ h_lo,
+                                                             int64_t ld_h) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t u = row_ids ? row_ids[r] : row0 + r;
+  const int64_t b = indptr[u], e = indptr[u + 1];
+  for (int64_t c0 = 8 * lane; c0 < n_out; c0 += 256) {   // 8 output columns per lane per pass
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (bias && c0 + j < n_out) ? bias[c0 + j] : 0.f;
+    for (int64_t k = b; k < e; ++k) {
+      const int32_t c = indices[k];
+      if (c < 0 || c >= n_cols) continue;
+      const uint4 q = *reinterpret_cast<const uint4*>(wt_hi + (int64_t)c * ld_w + c0);
+      const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(wv[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      }
+      if (LO) {
+        const uint4 ql = *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c * ld_w + c0);
+        const uint32_t lv[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(lv[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(lv[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+      if (act == 1) {
+        x0 = 1.f - __fdividef(2.f, __expf(2.f * x0) + 1.f);
+        x1 = 1.f - __fdividef(2.f, __expf(2.f * x1) + 1.f);
+      }
+      uint16_t a0, a1, l0, l1;
+      dmm_split_bf16(x0, a0, l0);
+      dmm_split_bf16(x1, a1, l1);
+      ph[j] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+      pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    if (c0 + 8 <= n_out) {
+      *reinterpret_cast<uint4*>(h_hi + r * ld_h + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (h_lo) *reinterpret_cast<uint4*>(h_lo + r * ld_h + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    } else {
+      for (int j = 0; j < 8 && c0 + j < n_out; ++j) {
+        h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
+        if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ x[r, c] += beta at the CSR positions
+// Posterior mean of the first reverse step: x_{t-1} = c1 * pred + c2 * x0 with binary x0 (Model.py:375);
+// the GEMM epilogue writes c1 * pred, this adds c2 where x0 is 1.  One warp per row.
+__global__ void __launch_bounds__(256) csr_axpy_bf16_kernel(const int64_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices,
+                                                            const int64_t* __restrict__ row_ids, int64_t row0,
+                                                            int64_t n_rows, int64_t n_cols, float beta,
+                                                            uint16_t* __restrict__ x_hi, uint16_t* __restrict__ x_lo,
+                                                            int64_t ld_x) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t u = row_ids ? row_ids[r] : row0 + r;
+  const int64_t b = indptr[u], e = indptr[u + 1];
+  for (int64_t k = b + lane; k < e; k += 32) {
+    const int32_t c = indices[k];
+    if (c < 0 || c >= n_cols) continue;
+    float v = dmm_bf16_to_f32(x_hi[r * ld_x + c]);
+    if (x_lo) v += dmm_bf16_to_f32(x_lo[r * ld_x + c]);
+    v += beta;
+    uint16_t h, l;
+    dmm_split_bf16(v, h, l);
+    x_hi[r * ld_x + c] = h;
+    if (x_lo) x_lo[r * ld_x + c] = l;
+  }
+}
+
 }  // namespace
 
 extern "C" int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
@@ -232,6 +363,55 @@ extern "C" int dmm_q_sample(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const 
   if (n_rows <= 0) return DMM_OK;
   q_sample_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(x0, ld_x0, noise, ld_noise, coef_a, coef_b, n_cols,
                                                                       mode, x_t, ld_x, a_hi, a_lo, ld_a);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t_all, int d_emb, const float* emb_w, const float* emb_b,
+                             const float* w, int64_t ld_w, int64_t col0, const float* b, int64_t n_out,
+                             float* bias_eff, void* stream) {
+  DMM_CHECK_ARG(ctx && emb_w && emb_b && w && bias_eff, "dmm_time_bias: null argument");
+  DMM_CHECK_ARG(d_emb >= 2 && d_emb <= 64, "dmm_time_bias: d_emb must be in [2, 64]");
+  DMM_CHECK_ARG(n_out > 0 && col0 >= 0 && ld_w >= col0 + d_emb, "dmm_time_bias: bad shape");
+  time_bias_kernel<<<(unsigned)dmm_ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(t_all, d_emb, emb_w, emb_b, w, ld_w,
+                                                                                       col0, b, n_out, bias_eff);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                                  int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
+                                  const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
+                                  uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && indices && wt_hi && h_hi, "dmm_csr_gather_act: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0 && n_out > 0, "dmm_csr_gather_act: bad shape");
+  DMM_CHECK_ARG(ld_w % 8 == 0 && ld_h % 8 == 0 && ld_w >= dmm_ceil_div(n_out, 8) * 8 && ld_h >= n_out,
+                "dmm_csr_gather_act: ld_w / ld_h must be multiples of 8 covering n_out (got %lld, %lld)", (long long)ld_w,
+                (long long)ld_h);
+  DMM_CHECK_ARG(act == 0 || act == 1, "dmm_csr_gather_act: unknown activation %d", act);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(wt_hi) && al16(wt_lo) && al16(h_hi) && al16(h_lo), "dmm_csr_gather_act: buffers must be 16-byte aligned");
+  if (n_rows == 0) return DMM_OK;
+  const unsigned grid = (unsigned)dmm_ceil_div(n_rows * 32, 256);
+  if (wt_lo) {
+    csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
+                                                                       wt_lo, ld_w, bias, act, n_out, h_hi, h_lo, ld_h);
+  } else {
+    csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
+                                                                        wt_lo, ld_w, bias, act, n_out, h_hi, h_lo, ld_h);
+  }
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_csr_axpy_bf16(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                                 int64_t row0, int64_t n_rows, int64_t n_cols, float beta, uint16_t* x_hi,
+                                 uint16_t* x_lo, int64_t ld_x, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && indices && x_hi, "dmm_csr_axpy_bf16: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0 && ld_x >= n_cols, "dmm_csr_axpy_bf16: bad shape");
+  if (n_rows == 0) return DMM_OK;
+  csr_axpy_bf16_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, indices, row_ids, row0, n_rows, n_cols, beta, x_hi, x_lo, ld_x);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

@@ -184,7 +184,38 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_edges_kernel(const float* _
 
   uint32_t T = 0u;
   int need_eq = 0;
-  if (!take_all) {
+  if (!take_all && k <= TOPK_THREADS) {
+    // Small k (almost every user): the k-th largest of the per-thread maxima is a lower bound L of the k-th
+    // largest key (the k largest maxima are k distinct keys >= L).  Keys >= L are compacted (a few more than
+    // k for continuous scores) and selected exactly in shared memory; no per-key atomics anywhere.
+    uint32_t* const tmax = reinterpret_cast<uint32_t*>(bucket);
+    tmax[tid] = kmax;   // threads that own no key publish 0, the smallest key
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+    int dummy;
+    const uint32_t L = radix_select([&](int i) -> uint32_t { return tmax[i]; }, TOPK_THREADS, k, hist, &s_prefix, &s_kk,
+                                    &dummy);
+    for (int i0 = 0; i0 < n_cols; i0 += TOPK_THREADS) {
+      const int i = i0 + tid;
+      const uint32_t key = i < n_cols ? key_at(i) : 0u;
+      const bool c = i < n_cols && key >= L;
+      const uint32_t bal = __ballot_sync(0xffffffffu, c);
+      if (bal) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&s_ncand, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+        if (c && pos < TOPK_CAND) cand[pos] = key;
+      }
+    }
+    __syncthreads();
+    const int m = s_ncand;   // >= k
+    if (m <= TOPK_CAND) {
+      T = radix_select([&](int i) -> uint32_t { return cand[i]; }, m, k, hist, &s_prefix, &s_kk, &need_eq);
+    } else {
+      T = radix_select(key_at, n_cols, k, hist, &s_prefix, &s_kk, &need_eq);
+    }
+  } else if (!take_all) {
 #pragma unroll
     for (int j = 0; j < TOPK_NB / TOPK_THREADS; ++j) bucket[tid + j * TOPK_THREADS] = 0;
 #pragma unroll

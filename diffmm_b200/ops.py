@@ -77,6 +77,31 @@ def time_embedding(emb_w, emb_b, n_rows, *, t=None, t_all=0, a_hi=None, a_lo=Non
               _p(a_hi), _p(a_lo), ld_a, int(col0), _p(temb_f32), _stream())
 
 
+def time_bias(emb_w, emb_b, weight, col0, bias, t_all, out=None):
+    """bias_eff = bias + weight[:, col0:col0+d] @ temb(t_all) (fp32 [H]); weight is the fp32 [H, K] Linear weight."""
+    d = emb_w.shape[0]
+    H = weight.shape[0]
+    if out is None:
+        out = torch.empty(H, dtype=torch.float32, device=weight.device)
+    _lib.call("dmm_time_bias", _ctx(weight), int(t_all), int(d), _p(emb_w), _p(emb_b), _p(weight), _row_major(weight, "weight"),
+              int(col0), _p(bias), H, _p(out), _stream())
+    return out
+
+
+def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0):
+    """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo)."""
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+    _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows), int(n_cols),
+              _p(wt_hi), _p(wt_lo), _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo),
+              _row_major(h_hi, "h_hi"), _stream())
+
+
+def csr_axpy_bf16(indptr, indices, n_rows, n_cols, beta, x_hi, x_lo, *, row_ids=None, row0=0):
+    """x[r, c] += beta at the CSR positions (x as bf16 hi (+ lo))."""
+    _lib.call("dmm_csr_axpy_bf16", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows), int(n_cols),
+              float(beta), _p(x_hi), _p(x_lo), _row_major(x_hi, "x_hi"), _stream())
+
+
 def q_sample(x0, noise, coef_a, coef_b, mode, *, x_t=None, a_hi=None, a_lo=None):
     """x_t = a[r] x0 + b[r] noise (mode 0) or the default sign(x0)*normalize(noise) (mode 1)."""
     n_rows, n_cols = x0.shape

@@ -6,10 +6,12 @@ Replaces, for the rebuild phase of Coach.trainEpoch (reference Main.py:195-253):
   (Main.py:224-230), and the scipy adjacency build + H2D (Main.py:113-116, DataHandler.py:53-93).
 
 Per user block the data flow is
-  CSR rows -> bf16 0/1 operand tile (+ fp32 x_t)                       dmm_csr_rows_to_dense
-  for i = S-1..0:  temb columns                                        dmm_time_embedding
-                   h = tanh([x_t, temb] W1^T + b1)   (bf16 hi/lo)      dmm_gemm_bf16_tn  (tcgen05)
-                   x_t = c1[i] (h W2^T + b2) + c2[i] x_t  (fp32 + bf16 operand for the next step)
+  [dense x_start / sampling_step > 0 only: rows -> bf16 operand tile   dmm_pack_bf16 / dmm_q_sample]
+  for i = S-1..0:  b1' = b1 + W1[:, I:] temb(i)                        dmm_time_bias
+                   h = tanh(x_t W1[:, :I]^T + b1')   (bf16 hi/lo)      dmm_gemm_bf16_tn  (tcgen05)
+                     (first step, binary CSR rows: gather-sum of W1^T  dmm_csr_gather_act)
+                   x_t = c1[i] (h W2^T + b2) + c2[i] x_t  (bf16 operand in place; fp32 scores at i = 0)
+                     (first step: c2 x0 added at the CSR positions     dmm_csr_axpy_bf16)
   top-k_u (k_u = deg(u)) -> item ids at the train-CSR offsets          dmm_topk_edges
 and once per modality
   edges -> normalised CSR adjacency                                    dmm_build_norm_adj_csr
@@ -32,7 +34,7 @@ class ChainWorkspace:
 
     def __init__(self, rows: int, n_items: int, hidden: int, d_emb: int, split: bool, device):
         self.rows, self.n_items, self.hidden, self.d_emb, self.split = rows, n_items, hidden, d_emb, split
-        self.ld_a = ops.pad_to(n_items + d_emb, 64)
+        self.ld_a = ops.pad_to(n_items, 64)
         self.ld_x = ops.pad_to(n_items, 32)
         self.ld_h = ops.pad_to(hidden, 64)
         bf = dict(dtype=torch.bfloat16, device=device)
@@ -41,6 +43,7 @@ class ChainWorkspace:
         self.h_hi = torch.empty((rows, self.ld_h), **bf)
         self.h_lo = torch.empty((rows, self.ld_h), **bf) if split else None
         self.x = torch.empty((rows, self.ld_x), dtype=torch.float32, device=device)
+        self.bias_eff = torch.empty(hidden, dtype=torch.float32, device=device)
 
     def fits(self, rows, n_items, hidden, d_emb, split):
         return (rows <= self.rows and n_items == self.n_items and hidden == self.hidden and d_emb == self.d_emb
@@ -81,11 +84,17 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     h_lo = ws.h_lo[:M] if split else None
     xv = x[:, :I]
 
-    if sampling_step == 0:
+    S = diff.steps
+    # Binary CSR rows at the head of the chain (sampling_step == 0): the first layer of the first reverse step
+    # is a gather-sum over W1^T and x0 is never densified (dmm_csr_gather_act / dmm_csr_axpy_bf16).
+    sparse_first = sampling_step == 0 and csr is not None and S >= 2
+    if sparse_first:
+        pass
+    elif sampling_step == 0:
         if csr is not None:
             ops.csr_rows_to_dense(csr[0], csr[1], M, I, row_ids=row_ids, row0=row0, a_bf16=a_hi)
             if split:
-                a_lo[:, :I].zero_()           # 0/1 rows are exact in bf16; the temb columns still carry a lo part
+                a_lo[:, :I].zero_()           # 0/1 rows are exact in bf16
         else:
             xd = x_dense if (x_dense.stride(1) == 1 and x_dense.dtype == torch.float32) else x_dense.float().contiguous()
             ops.pack_bf16_into(xd, a_hi, a_lo)
@@ -106,27 +115,38 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
 
     w1_hi, w1_lo = packed_weight(W1, False, split)
     w2_hi, w2_lo = packed_weight(W2, False, split)
+    if sparse_first:
+        w1t_hi, w1t_lo = packed_weight(W1, True, split)            # W1^T [I + d, pad(H)]: gathered by item id
     emb_w, emb_b = den.emb_layer.weight.detach(), den.emb_layer.bias.detach()
-    b1d, b2d = b1.detach(), b2.detach()
-    S = diff.steps
+    W1d, b1d, b2d = W1.detach(), b1.detach(), b2.detach()
     ax_hi = a_hi[:, :I]
     ax_lo = a_lo[:, :I] if split else None
     for i in range(S - 1, -1, -1):
-        ops.time_embedding(emb_w, emb_b, M, t_all=i, a_hi=a_hi, a_lo=a_lo, col0=I)
-        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, K1, bias=b1d, act=1, out_hi=h_hi, out_lo=h_lo)
+        # every row of a step shares the timestep (Model.py:319): the time-embedding columns of
+        # cat([x_t, temb]) (Model.py:203) fold into the bias, b1 + W1[:, I:] temb(i), in fp32
+        ops.time_bias(emb_w, emb_b, W1d, I, b1d, i, out=ws.bias_eff)
+        first_sparse = sparse_first and i == S - 1
+        if first_sparse:
+            ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, ws.bias_eff, 1, H, h_hi, h_lo,
+                               row_ids=row_ids, row0=row0)
+        else:
+            ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias=ws.bias_eff, act=1, out_hi=h_hi, out_lo=h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))
         # x_t lives only as the bf16 operand (hi, and lo in bf16x3 mode: hi + lo carries 16 mantissa bits):
         # the posterior mean c1 * pred + c2 * x_t reads it as the residual and overwrites it in place, so
         # an intermediate step moves 2 (4) bytes per element each way instead of 4 + 4 + 2.  The last step
         # (c2 == 0 for beta_fixed schedules) writes the fp32 scores the top-k consumes.
+        use_res = c2 != 0.0 and not first_sparse
         if i == 0:
             ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
-                             res_hi=ax_hi if c2 != 0.0 else None, res_lo=ax_lo if c2 != 0.0 else None, out_f32=xv)
+                             res_hi=ax_hi if use_res else None, res_lo=ax_lo if use_res else None, out_f32=xv)
         else:
             ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
-                             res_hi=ax_hi if c2 != 0.0 else None, res_lo=ax_lo if c2 != 0.0 else None,
+                             res_hi=ax_hi if use_res else None, res_lo=ax_lo if use_res else None,
                              out_hi=ax_hi, out_lo=ax_lo)
+            if first_sparse and c2 != 0.0:
+                ops.csr_axpy_bf16(csr[0], csr[1], M, I, c2, ax_hi, ax_lo, row_ids=row_ids, row0=row0)
     return xv
 
 

@@ -65,6 +65,28 @@ int dmm_time_embedding(dmm_ctx* ctx, const int64_t* t, int64_t t_all, int64_t n_
                        const float* emb_w, const float* emb_b, uint16_t* a_hi, uint16_t* a_lo,
                        int64_t ld_a, int64_t col0, float* temb_f32, void* stream);
 
+/* Time embedding folded into a bias (reverse chain: every row of a step shares t, Model.py:319):
+ * bias_eff[h] = b[h] + sum_j w[h, col0 + j] * temb_j(t_all), temb as in dmm_time_embedding, fp32.
+ * Replaces the 10 extra operand columns of cat([x_t, temb]) (Model.py:202-203,212) for constant t. */
+int dmm_time_bias(dmm_ctx* ctx, int64_t t_all, int d_emb, const float* emb_w, const float* emb_b,
+                  const float* w, int64_t ld_w, int64_t col0, const float* b, int64_t n_out,
+                  float* bias_eff, void* stream);
+
+/* First Denoise layer on binary CSR rows (x_t = x0 at the start of the reverse chain, Model.py:300-304):
+ * h[r, :] = act(bias + sum_{c in row r} wt[c, :]), wt = W^T packed bf16 hi (+ lo) [n_cols, ld_w],
+ * written as bf16 hi (+ lo) [n_rows, ld_h].  The dense contraction of Model.py:212 degenerates to a
+ * gather-sum for 0/1 rows; rows are selected like in dmm_csr_rows_to_dense.                   */
+int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                       int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
+                       const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
+                       uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream);
+
+/* x[r, c] += beta for every CSR entry (r, c) of the selected rows, x given as bf16 hi (+ lo):
+ * the c2 * x0 term of the posterior mean (Model.py:375) for binary x0.                        */
+int dmm_csr_axpy_bf16(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                      int64_t row0, int64_t n_rows, int64_t n_cols, float beta, uint16_t* x_hi,
+                      uint16_t* x_lo, int64_t ld_x, void* stream);
+
 /* q_sample (Model.py:324-341): x_t = a[r] x0 + b[r] noise with fp32 per-row coefficients
  * (the fp64->fp32 cast of Model.py:352 is done by the caller).  mode 0: `noise` is used as is.
  * mode 1: the default noise sign(x0) * normalize_row(noise) (Model.py:337, eps 1e-12).
