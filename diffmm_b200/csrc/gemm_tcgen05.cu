@@ -605,7 +605,7 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   DMM_CHECK_ARG(!(ep->residual && ep->res_hi), "dmm_gemm_bf16_tn: residual and res_hi are mutually exclusive");
   DMM_CHECK_ARG(!ep->res_hi || (ep->ld_res16 >= N && ep->ld_res16 % 8 == 0), "dmm_gemm_bf16_tn: ld_res16 must be >= N and %%8");
   DMM_CHECK_ARG(!ep->res_lo || ep->res_hi, "dmm_gemm_bf16_tn: res_lo requires res_hi");
-  DMM_CHECK_ARG(al16(ep->bias) && al16(ep->res_hi) && al16(ep->res_lo), "dmm_gemm_bf16_tn: bias/res_hi/res_lo must be 16-byte aligned");
+  DMM_CHECK_ARG(al16(ep->res_hi) && al16(ep->res_lo), "dmm_gemm_bf16_tn: res_hi/res_lo must be 16-byte aligned");
   DMM_CHECK_ARG(!ep->out_f32 || (ep->ld_out >= N && ep->ld_out % 4 == 0), "dmm_gemm_bf16_tn: ld_out must be >= N and %%4");
   DMM_CHECK_ARG(!ep->out_hi || (ep->ld_out16 >= N && ep->ld_out16 % 8 == 0), "dmm_gemm_bf16_tn: ld_out16 must be >= N and %%8");
   DMM_CHECK_ARG(!ep->out_lo || ep->out_hi, "dmm_gemm_bf16_tn: out_lo requires out_hi");

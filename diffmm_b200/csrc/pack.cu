@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
 // In the reverse chain every row of a step shares the timestep (Model.py:319), so the 10 time-embedding
 // columns of cat([x_t, temb]) (Model.py:202-203,212) contribute the same vector to every row:
 //   bias_eff[h] = b[h] + sum_j W[h, col0 + j] * temb_j(t)          (fp32, exact weights)
-__global__ void __launch_bounds__(256) time_bias_kernel(int64_t t_all, int d, const float* __restrict__ emb_w,
+__global__ void __launch_bounds__(256) time_bias_kernel(int64_t t0, int d, const float* __restrict__ emb_w,
                                                         const float* __restrict__ emb_b, const float* __restrict__ w,
                                                         int64_t ld_w, int64_t col0, const float* __restrict__ b,
                                                         int64_t n_out, float* __restrict__ bias_eff) {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) time_bias_kernel(int64_t t_all, int d, co
   if (threadIdx.x < d) {
     const int o = threadIdx.x;
     const int half = d / 2;
-    const float ts = (float)t_all;
+    const float ts = (float)(t0 + blockIdx.y);   // one timestep per grid row
     float acc = emb_b[o];
     for (int j = 0; j < d; ++j) {
       float e = 0.f;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) time_bias_kernel(int64_t t_all, int d, co
   float acc = b ? b[h] : 0.f;
   const float* wr = w + h * ld_w + col0;
   for (int j = 0; j < d; ++j) acc = fmaf(wr[j], temb[j], acc);
-  bias_eff[h] = acc;
+  bias_eff[(int64_t)blockIdx.y * n_out + h] = acc;
 }
 
 // ------------------------------------------------------------------ first layer on binary CSR rows
@@ -215,59 +215,74 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
                                                              const uint16_t* __restrict__ wt_hi,
                                                              const uint16_t* __restrict__ wt_lo, int64_t ld_w,
                                                              const float* __restrict__ bias, int act, int64_t n_out,
-                                                             uint16_t* __restrict__ h_hi, uint16_t* __restrict__ h_lo,
-                                                             int64_t ld_h) {
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                             int slices, uint16_t* __restrict__ h_hi,
+                                                             uint16_t* __restrict__ h_lo, int64_t ld_h) {
+  // one warp per (row, 256-column slice); lane l owns the 8 columns c0 .. c0+7 of the slice
+  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  const int64_t r = wg / slices;
   if (r >= n_rows) return;
+  const int64_t c0 = (wg % slices) * 256 + 8 * lane;
+  const bool col_ok = c0 < n_out;             // a piece that starts below n_out lies inside the padded row
   const int64_t u = row_ids ? row_ids[r] : row0 + r;
   const int64_t b = indptr[u], e = indptr[u + 1];
-  for (int64_t c0 = 8 * lane; c0 < n_out; c0 += 256) {   // 8 output columns per lane per pass
-    float acc[8];
+  float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (bias && c0 + j < n_out) ? bias[c0 + j] : 0.f;
-    for (int64_t k = b; k < e; ++k) {
-      const int32_t c = indices[k];
-      if (c < 0 || c >= n_cols) continue;
-      const uint4 q = *reinterpret_cast<const uint4*>(wt_hi + (int64_t)c * ld_w + c0);
-      const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[2 * j] += __uint_as_float(wv[j] << 16);
-        acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
-      }
-      if (LO) {
-        const uint4 ql = *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c * ld_w + c0);
-        const uint32_t lv[4] = {ql.x, ql.y, ql.z, ql.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[2 * j] += __uint_as_float(lv[j] << 16);
-          acc[2 * j + 1] += __uint_as_float(lv[j] & 0xFFFF0000u);
-        }
-      }
-    }
-    uint32_t ph[4], pl[4];
+  for (int j = 0; j < 8; ++j) acc[j] = (bias && c0 + j < n_out) ? bias[c0 + j] : 0.f;
+  auto add = [&](const uint4& q) {
+    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float x0 = acc[2 * j], x1 = acc[2 * j + 1];
-      if (act == 1) {
-        x0 = 1.f - __fdividef(2.f, __expf(2.f * x0) + 1.f);
-        x1 = 1.f - __fdividef(2.f, __expf(2.f * x1) + 1.f);
-      }
-      uint16_t a0, a1, l0, l1;
-      dmm_split_bf16(x0, a0, l0);
-      dmm_split_bf16(x1, a1, l1);
-      ph[j] = (uint32_t)a0 | ((uint32_t)a1 << 16);
-      pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      acc[2 * j] += __uint_as_float(wv[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
     }
-    if (c0 + 8 <= n_out) {
-      *reinterpret_cast<uint4*>(h_hi + r * ld_h + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-      if (h_lo) *reinterpret_cast<uint4*>(h_lo + r * ld_h + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-    } else {
-      for (int j = 0; j < 8 && c0 + j < n_out; ++j) {
-        h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
-        if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+  };
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t k = b; k < e; k += 32) {
+    // the row's item ids: one coalesced load per 32 items, broadcast by shuffle; 4 gathers in flight per lane
+    int32_t mine = (k + lane < e) ? indices[k + lane] : -1;
+    if (mine >= n_cols) mine = -1;
+    const int cnt = (int)((e - k) < 32 ? (e - k) : 32);
+    for (int j = 0; j < cnt; j += 4) {
+      int32_t c[4];
+      uint4 qh[4], ql[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const bool ok = col_ok && j + t < cnt && c[t] >= 0;
+        qh[t] = ok ? *reinterpret_cast<const uint4*>(wt_hi + (int64_t)c[t] * ld_w + c0) : zero;
+        if (LO) ql[t] = ok ? *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c[t] * ld_w + c0) : zero;
       }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        add(qh[t]);
+        if (LO) add(ql[t]);
+      }
+    }
+  }
+  if (!col_ok) return;
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+    if (act == 1) {
+      x0 = 1.f - __fdividef(2.f, __expf(2.f * x0) + 1.f);
+      x1 = 1.f - __fdividef(2.f, __expf(2.f * x1) + 1.f);
+    }
+    uint16_t a0, a1, l0, l1;
+    dmm_split_bf16(x0, a0, l0);
+    dmm_split_bf16(x1, a1, l1);
+    ph[j] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+    pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  }
+  if (c0 + 8 <= n_out) {
+    *reinterpret_cast<uint4*>(h_hi + r * ld_h + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (h_lo) *reinterpret_cast<uint4*>(h_lo + r * ld_h + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  } else {
+    for (int j = 0; j < 8 && c0 + j < n_out; ++j) {
+      h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
+      if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
     }
   }
 }
@@ -367,14 +382,15 @@ extern "C" int dmm_q_sample(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const 
   return DMM_OK;
 }
 
-extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t_all, int d_emb, const float* emb_w, const float* emb_b,
+extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, const float* emb_w, const float* emb_b,
                              const float* w, int64_t ld_w, int64_t col0, const float* b, int64_t n_out,
                              float* bias_eff, void* stream) {
   DMM_CHECK_ARG(ctx && emb_w && emb_b && w && bias_eff, "dmm_time_bias: null argument");
   DMM_CHECK_ARG(d_emb >= 2 && d_emb <= 64, "dmm_time_bias: d_emb must be in [2, 64]");
   DMM_CHECK_ARG(n_out > 0 && col0 >= 0 && ld_w >= col0 + d_emb, "dmm_time_bias: bad shape");
-  time_bias_kernel<<<(unsigned)dmm_ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(t_all, d_emb, emb_w, emb_b, w, ld_w,
-                                                                                       col0, b, n_out, bias_eff);
+  DMM_CHECK_ARG(n_t > 0 && n_t < 65536, "dmm_time_bias: n_t must be in [1, 65535]");
+  dim3 grid((unsigned)dmm_ceil_div(n_out, 256), (unsigned)n_t);
+  time_bias_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t0, d_emb, emb_w, emb_b, w, ld_w, col0, b, n_out, bias_eff);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
@@ -392,13 +408,16 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   DMM_CHECK_ARG(al16(wt_hi) && al16(wt_lo) && al16(h_hi) && al16(h_lo), "dmm_csr_gather_act: buffers must be 16-byte aligned");
   if (n_rows == 0) return DMM_OK;
-  const unsigned grid = (unsigned)dmm_ceil_div(n_rows * 32, 256);
+  const int slices = (int)dmm_ceil_div(n_out, 256);
+  const int64_t blocks = dmm_ceil_div(n_rows * slices * 32, 256);
+  DMM_CHECK_ARG(blocks < (1LL << 31), "dmm_csr_gather_act: too many rows");
+  const unsigned grid = (unsigned)blocks;
   if (wt_lo) {
     csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
-                                                                       wt_lo, ld_w, bias, act, n_out, h_hi, h_lo, ld_h);
+                                                                       wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h);
   } else {
     csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
-                                                                        wt_lo, ld_w, bias, act, n_out, h_hi, h_lo, ld_h);
+                                                                        wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h);
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;

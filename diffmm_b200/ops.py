@@ -77,14 +77,16 @@ def time_embedding(emb_w, emb_b, n_rows, *, t=None, t_all=0, a_hi=None, a_lo=Non
               _p(a_hi), _p(a_lo), ld_a, int(col0), _p(temb_f32), _stream())
 
 
-def time_bias(emb_w, emb_b, weight, col0, bias, t_all, out=None):
-    """bias_eff = bias + weight[:, col0:col0+d] @ temb(t_all) (fp32 [H]); weight is the fp32 [H, K] Linear weight."""
+def time_bias(emb_w, emb_b, weight, col0, bias, t0, n_t=1, out=None):
+    """bias_eff[i] = bias + weight[:, col0:col0+d] @ temb(t0 + i), i < n_t (fp32 [n_t, H]); weight is the fp32
+    [H, K] Linear weight."""
     d = emb_w.shape[0]
     H = weight.shape[0]
     if out is None:
-        out = torch.empty(H, dtype=torch.float32, device=weight.device)
-    _lib.call("dmm_time_bias", _ctx(weight), int(t_all), int(d), _p(emb_w), _p(emb_b), _p(weight), _row_major(weight, "weight"),
-              int(col0), _p(bias), H, _p(out), _stream())
+        out = torch.empty((n_t, H), dtype=torch.float32, device=weight.device)
+    assert out.is_contiguous() and out.numel() >= n_t * H
+    _lib.call("dmm_time_bias", _ctx(weight), int(t0), int(n_t), int(d), _p(emb_w), _p(emb_b), _p(weight),
+              _row_major(weight, "weight"), int(col0), _p(bias), H, _p(out), _stream())
     return out
 
 

@@ -7,7 +7,8 @@ Replaces, for the rebuild phase of Coach.trainEpoch (reference Main.py:195-253):
 
 Per user block the data flow is
   [dense x_start / sampling_step > 0 only: rows -> bf16 operand tile   dmm_pack_bf16 / dmm_q_sample]
-  for i = S-1..0:  b1' = b1 + W1[:, I:] temb(i)                        dmm_time_bias
+  b1'[i] = b1 + W1[:, I:] temb(i), all i at once                       dmm_time_bias
+  for i = S-1..0:
                    h = tanh(x_t W1[:, :I]^T + b1')   (bf16 hi/lo)      dmm_gemm_bf16_tn  (tcgen05)
                      (first step, binary CSR rows: gather-sum of W1^T  dmm_csr_gather_act)
                    x_t = c1[i] (h W2^T + b2) + c2[i] x_t  (bf16 operand in place; fp32 scores at i = 0)
@@ -43,7 +44,7 @@ class ChainWorkspace:
         self.h_hi = torch.empty((rows, self.ld_h), **bf)
         self.h_lo = torch.empty((rows, self.ld_h), **bf) if split else None
         self.x = torch.empty((rows, self.ld_x), dtype=torch.float32, device=device)
-        self.bias_eff = torch.empty(hidden, dtype=torch.float32, device=device)
+        self.bias_eff = None      # [S, hidden] fp32, sized on first use
 
     def fits(self, rows, n_items, hidden, d_emb, split):
         return (rows <= self.rows and n_items == self.n_items and hidden == self.hidden and d_emb == self.d_emb
@@ -121,16 +122,19 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     W1d, b1d, b2d = W1.detach(), b1.detach(), b2.detach()
     ax_hi = a_hi[:, :I]
     ax_lo = a_lo[:, :I] if split else None
+    # every row of a step shares the timestep (Model.py:319): the time-embedding columns of
+    # cat([x_t, temb]) (Model.py:203) fold into the bias, b1 + W1[:, I:] temb(i), in fp32 (all steps at once)
+    if ws.bias_eff is None or ws.bias_eff.shape[0] != S:
+        ws.bias_eff = torch.empty((S, H), dtype=torch.float32, device=dev)
+    ops.time_bias(emb_w, emb_b, W1d, I, b1d, 0, S, out=ws.bias_eff)
     for i in range(S - 1, -1, -1):
-        # every row of a step shares the timestep (Model.py:319): the time-embedding columns of
-        # cat([x_t, temb]) (Model.py:203) fold into the bias, b1 + W1[:, I:] temb(i), in fp32
-        ops.time_bias(emb_w, emb_b, W1d, I, b1d, i, out=ws.bias_eff)
+        bias1 = ws.bias_eff[i]
         first_sparse = sparse_first and i == S - 1
         if first_sparse:
-            ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, ws.bias_eff, 1, H, h_hi, h_lo,
+            ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, bias1, 1, H, h_hi, h_lo,
                                row_ids=row_ids, row0=row0)
         else:
-            ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias=ws.bias_eff, act=1, out_hi=h_hi, out_lo=h_lo)
+            ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias=bias1, act=1, out_hi=h_hi, out_lo=h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))
         # x_t lives only as the bf16 operand (hi, and lo in bf16x3 mode: hi + lo carries 16 mantissa bits):

@@ -66,9 +66,10 @@ int dmm_time_embedding(dmm_ctx* ctx, const int64_t* t, int64_t t_all, int64_t n_
                        int64_t ld_a, int64_t col0, float* temb_f32, void* stream);
 
 /* Time embedding folded into a bias (reverse chain: every row of a step shares t, Model.py:319):
- * bias_eff[h] = b[h] + sum_j w[h, col0 + j] * temb_j(t_all), temb as in dmm_time_embedding, fp32.
+ * bias_eff[i, h] = b[h] + sum_j w[h, col0 + j] * temb_j(t0 + i) for i in [0, n_t), temb as in
+ * dmm_time_embedding, fp32 [n_t, n_out] (all steps of the chain in one launch).
  * Replaces the 10 extra operand columns of cat([x_t, temb]) (Model.py:202-203,212) for constant t. */
-int dmm_time_bias(dmm_ctx* ctx, int64_t t_all, int d_emb, const float* emb_w, const float* emb_b,
+int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, const float* emb_w, const float* emb_b,
                   const float* w, int64_t ld_w, int64_t col0, const float* b, int64_t n_out,
                   float* bias_eff, void* stream);
 

@@ -1,5 +1,7 @@
 """GPU parity tests of the non-GEMM kernels against the numpy oracle and the golden vectors
 (bit-exact for index work, stated tolerances for fp32).  Everything goes through the C ABI."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -9,6 +11,7 @@ from oracle import diffmm_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def T(a, dtype=None):
@@ -70,6 +73,20 @@ def test_topk_random_vs_oracle(ops, n_cols, ld):
     want = O.topk_edges(scores, k)
     for r, w in enumerate(want):
         np.testing.assert_array_equal(items[ptr[r]:ptr[r + 1]], w, err_msg=f"row {r} k={k[r]}")
+
+
+def test_topk_generic_kernels_forced():
+    """The register path covers every shipped row width, so the generic kernels (bucket histogram + radix
+    select; rows wider than 32768 columns) are also forced onto small and mid-sized rows in a subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, DMM_TOPK_GENERIC="1")
+    args = ["500:500:0", "7050:7104:1", "33:36:1", "40000:40000:1"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dbg_topk.py"), *args], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == len(args) and all(ln.endswith("OK") for ln in lines), r.stdout + r.stderr
 
 
 def test_topk_ties_and_signed_zero(ops):
