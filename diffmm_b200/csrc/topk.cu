@@ -311,6 +311,26 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   constexpr int NW = NT / 32;
   const int64_t r = blockIdx.x;
   if (r >= n_rows) return;
+  const float* row = scores + r * ld;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
+
+  // 1. the row -> registers, issued before anything depends on out_ptr so that both latencies overlap.
+  //    Thread t owns the float4 pieces t, t + NT, ... (all TOPK_V4 loads in flight at once); the <= 3 columns
+  //    past the last whole piece are one extra key each on threads 0..2.
+  const int n4 = aligned ? (n_cols >> 2) : 0;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  float4 v[TOPK_V4];
+#pragma unroll
+  for (int j = 0; j < TOPK_V4; ++j) {
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid + NT * j < n4) v[j] = __ldcs(row4 + tid + NT * j);
+  }
+  const int tail_col = (n4 << 2) + tid;
+  const bool has_tail = aligned && tid < (n_cols & 3);
+  float tail_v = 0.f;
+  if (has_tail) tail_v = __ldcs(row + tail_col);
+
   const int64_t o0 = out_ptr[r], o1 = out_ptr[r + 1];
   int k = (int)(o1 - o0);
   if (k <= 0) return;
@@ -318,35 +338,22 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
     if (status && threadIdx.x == 0) atomicExch(status, 1);
     k = n_cols;
   }
-  const float* row = scores + r * ld;
   const int32_t user = (int32_t)(row_base + r);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (k > NT || k >= n_cols || (reinterpret_cast<uintptr_t>(row) & 15u) != 0) {  // block-uniform
+  if (k > NT || k >= n_cols || !aligned) {  // block-uniform
     topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
     return;
   }
 
-  // 1. the row -> registers.  Thread t owns the float4 pieces t, t + NT, ...; columns past n_cols get key 0
-  //    (the smallest key) and are excluded by their column index wherever it matters.
   uint32_t key[4 * TOPK_V4];
-  uint32_t tmax = 0u;
-  const float4* row4 = reinterpret_cast<const float4*>(row);
+  uint32_t tmax = has_tail ? order_key(tail_v) : 0u;
+  const uint32_t tail_key = tmax;
 #pragma unroll
   for (int j = 0; j < TOPK_V4; ++j) {
-    const int c0 = 4 * (tid + NT * j);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool ok[4] = {c0 < n_cols, c0 + 1 < n_cols, c0 + 2 < n_cols, c0 + 3 < n_cols};
-    if (ok[3]) {
-      v = __ldcs(row4 + tid + NT * j);
-    } else {
-      if (ok[0]) v.x = __ldcs(row + c0);
-      if (ok[1]) v.y = __ldcs(row + c0 + 1);
-      if (ok[2]) v.z = __ldcs(row + c0 + 2);
-    }
-    key[4 * j + 0] = ok[0] ? order_key(v.x) : 0u;
-    key[4 * j + 1] = ok[1] ? order_key(v.y) : 0u;
-    key[4 * j + 2] = ok[2] ? order_key(v.z) : 0u;
-    key[4 * j + 3] = ok[3] ? order_key(v.w) : 0u;
+    const bool ok = tid + NT * j < n4;       // pieces past the row hold key 0 and are never candidates
+    key[4 * j + 0] = ok ? order_key(v[j].x) : 0u;
+    key[4 * j + 1] = ok ? order_key(v[j].y) : 0u;
+    key[4 * j + 2] = ok ? order_key(v[j].z) : 0u;
+    key[4 * j + 3] = ok ? order_key(v[j].w) : 0u;
     tmax = max(max(tmax, key[4 * j]), max(key[4 * j + 1], max(key[4 * j + 2], key[4 * j + 3])));
   }
 
@@ -371,25 +378,26 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   for (int i = 0; i < NW; ++i) L = min(L, sm.red[i]);
 
   // 3. compact the keys >= L (value, column) into shared memory: one atomic per warp per hit group
-#pragma unroll
-  for (int j = 0; j < TOPK_V4; ++j) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int col = 4 * (tid + NT * j) + e;
-      const bool c = key[4 * j + e] >= L && col < n_cols;
-      const uint32_t bal = __ballot_sync(0xffffffffu, c);
-      if (bal) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sm.ncand, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const int pos = base + __popc(bal & ((1u << lane) - 1u));
-        if (c && pos < TOPK_CAND) {
-          sm.cand[pos] = key[4 * j + e];
-          sm.cand_col[pos] = col;
-        }
+  auto push = [&](bool c, uint32_t kv, int col) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, c);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.ncand, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (c && pos < TOPK_CAND) {
+        sm.cand[pos] = kv;
+        sm.cand_col[pos] = col;
       }
     }
+  };
+#pragma unroll
+  for (int j = 0; j < TOPK_V4; ++j) {
+    const bool ok = tid + NT * j < n4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) push(ok && key[4 * j + e] >= L, key[4 * j + e], 4 * (tid + NT * j) + e);
   }
+  if (n_cols & 3) push(has_tail && tail_key >= L, tail_key, tail_col);   // block-uniform condition
   __syncthreads();
   const int m = sm.ncand;                      // >= k by construction of L
   if (m > NT) {                                // crowded threshold (ties) or loose bound: exact generic path
