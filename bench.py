@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(name, device, seed, precision):
+def build_workload(name, device, seed, precision, world=1):
     import torch
     from diffmm_b200 import synth
     from diffmm_b200.Conf import Config
@@ -100,8 +100,8 @@ def build_workload(name, device, seed, precision):
     cfg.base.denoise_dim = f"[{w['hidden']}]"
     cfg.hyper.steps = w["steps"]
     cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = w["noise"]
-    cfg.data.user_num, cfg.data.item_num = w["users"], w["items"]
-    inter = synth.interactions(w["users"], w["items"], seed=seed)
+    cfg.data.user_num, cfg.data.item_num = w["users"] * world, w["items"]
+    inter = synth.interactions(w["users"] * world, w["items"], seed=seed)      # same global dataset on every rank
     torch.manual_seed(seed)
     diff = GaussianDiffusion(cfg).to(device)
     dens = {m: Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg).to(device) for m in w["modalities"]}
@@ -184,6 +184,13 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     from diffmm_b200 import synth
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can (numpy's BLAS pool)
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     inter = synth.interactions(w["users"], w["items"], seed=args.seed)
     rng = np.random.default_rng(args.seed)
     I, H, d = w["items"], w["hidden"], 10
@@ -205,7 +212,6 @@ def run_reference(args):
         total += dt
         users += n
     val = users / total
-    cores = os.cpu_count()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -234,7 +240,14 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     w = WORKLOADS[args.workload]
     U, I, H, S, mods = w["users"], w["items"], w["hidden"], w["steps"], w["modalities"]
-    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed + rank, args.precision)
+    # weak scaling: the job is world x U users; every rank holds the (small) global CSR and replicated Denoise
+    # weights (same seed), runs the chain + top-k on its own user block, then the edge lists are all-gathered
+    # (NCCL, one collective per modality) and every rank builds the normalised adjacency of the whole graph
+    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed, args.precision, world)
+    U_tot = U * world
+    r0, r1 = rank * U, (rank + 1) * U
+    from diffmm_b200 import dist as ddist
+    plan = ddist.EdgeGatherPlan(torch.from_numpy(inter.indptr), U_tot, world) if world > 1 else None
     E = int(inter.indices.size)
     h_indptr = torch.from_numpy(inter.indptr).pin_memory()
     h_indices = torch.from_numpy(inter.indices).pin_memory()
@@ -268,15 +281,19 @@ def run_ours(args):
     _lib.call = counting_call
     ops._lib.call = counting_call
 
+    def rebuild_step(ip, ix):
+        items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1))
+        if world > 1:
+            items = {m: ddist.allgather_edges(v, ip, U_tot, None, plan) for m, v in items.items()}
+        return {m: ops.build_norm_adj(ip, v, U_tot, I) for m, v in items.items()}, items
+
     def step_device():
-        items = rebuild.rebuild_edges(diff, dens, d_indptr, d_indices, U, I, 0, args.precision)
-        return {m: ops.build_norm_adj(d_indptr, v, U, I) for m, v in items.items()}, items
+        return rebuild_step(d_indptr, d_indices)
 
     def step_e2e():
         ip = h_indptr.to(dev, non_blocking=True)
         ix = h_indices.to(dev, non_blocking=True)
-        items = rebuild.rebuild_edges(diff, dens, ip, ix, U, I, 0, args.precision)
-        adjs = {m: ops.build_norm_adj(ip, v, U, I) for m, v in items.items()}
+        adjs, items = rebuild_step(ip, ix)
         for m, v in items.items():
             h_edges[m].copy_(v, non_blocking=True)
         return adjs
@@ -382,15 +399,16 @@ def run_ours(args):
                                f"{len(mods)} modalities, hidden {H}, {S} reverse steps, top-k k=deg(u), adjacency build",
                    "users_per_gpu": U, "items": I, "modalities": len(mods), "hidden": H, "diffusion_steps": S, "edges": E,
                    "precision": args.precision, "l2": "256 MiB flush write between timed steps; per-step working set > L2",
-                   "parallelism": f"user-sharded x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"user-sharded x{world}: {U_tot} users in total, edge lists all-gathered over NCCL, "
+                                   f"adjacency of the whole graph built on every rank") if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "gemm_bf16_tn_kernel (tcgen05)",
                      "launches": len(gemm_events), "avg_launch_ms": gemm_ms / n_gemm, "share_of_step": gemm_ms / ms,
                      "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside the step); burst {pk['tf_burst']}",
                      "frac_of_burst": achieved / pk["tf_burst"], "by_shape_MxNxK": by_shape},
         "e2e": {"value": world * U * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(h_indptr.numel() * 8 + h_indices.numel() * 4),
-                "d2h_bytes_per_step": int(len(mods) * E * 4)},
+                "h2d_bytes_per_step": int(world * (h_indptr.numel() * 8 + h_indices.numel() * 4)),
+                "d2h_bytes_per_step": int(world * len(mods) * E * 4)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "wall_s_timed_region": t_wall,

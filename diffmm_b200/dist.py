@@ -49,16 +49,28 @@ def shard_rows(n_rows: int, world: int, rk: int, indptr: Optional[torch.Tensor] 
     return row_blocks(n_rows, world)[rk]
 
 
-def allgather_edges(items_local: torch.Tensor, indptr: torch.Tensor, n_users: int, group=None) -> torch.Tensor:
+class EdgeGatherPlan:
+    """Host-side layout of the edge all-gather that follows the user-sharded rebuild, computed once per dataset
+    (the offsets are the train-CSR indptr at the block boundaries, so no device sync is needed per call)."""
+
+    def __init__(self, indptr: torch.Tensor, n_users: int, world: int):
+        self.blocks = row_blocks(n_users, world)
+        ptr_cpu = indptr.detach().to("cpu")
+        self.offs = [(int(ptr_cpu[a]), int(ptr_cpu[b])) for a, b in self.blocks]
+        self.seg = max(1, max(e - s for s, e in self.offs))
+        self.world = world
+
+
+def allgather_edges(items_local: torch.Tensor, indptr: torch.Tensor, n_users: int, group=None,
+                    plan: Optional[EdgeGatherPlan] = None) -> torch.Tensor:
     """Every rank filled items[indptr[r0]:indptr[r1]) for its user block; returns the complete edge list on
     every rank.  all-gather-v over padded equal-size segments (one collective per modality)."""
     world, rk = world_size(group), rank(group)
     if world == 1:
         return items_local
-    blocks = row_blocks(n_users, world)
-    ptr_cpu = indptr.detach().to("cpu")
-    offs = [(int(ptr_cpu[a]), int(ptr_cpu[b])) for a, b in blocks]
-    seg = max(1, max(e - s for s, e in offs))
+    if plan is None or plan.world != world:
+        plan = EdgeGatherPlan(indptr, n_users, world)
+    offs, seg = plan.offs, plan.seg
     send = torch.zeros(seg, dtype=items_local.dtype, device=items_local.device)
     s, e = offs[rk]
     send[: e - s] = items_local[s:e]

@@ -194,7 +194,7 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
 
 def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torch.Tensor, indices: torch.Tensor,
                       n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
-                      block_rows: Optional[int] = None, group=None) -> Dict[str, ops.CsrAdj]:
+                      block_rows: Optional[int] = None, group=None, plan=None) -> Dict[str, ops.CsrAdj]:
     """The whole rebuild phase (Main.py:195-253): {modality: normalised CSR adjacency}.
     With a torch.distributed ``group`` of more than one rank, users are row-sharded and the edge lists
     all-gathered (dist.py); every rank then builds the same adjacency."""
@@ -203,7 +203,7 @@ def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: 
         r0, r1 = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr)
         items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
                               row_range=(r0, r1), block_rows=block_rows)
-        items = {m: ddist.allgather_edges(v, indptr, n_users, group) for m, v in items.items()}
+        items = {m: ddist.allgather_edges(v, indptr, n_users, group, plan) for m, v in items.items()}
     else:
         items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
                               block_rows=block_rows)
