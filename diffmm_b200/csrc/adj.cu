@@ -7,7 +7,7 @@
 //   1. expand user ids per edge; stable LSD radix sort of (item, user) pairs by item gives R^T with
 //      users ascending inside every item row  (CUB DeviceRadixSort: CCCL library plumbing, the only
 //      non-hand-written device code of the library; candidate for a hand-written counting sort);
-//   2. item row offsets by a histogram + single-block scan;
+//   2. item row offsets from the boundaries of the sorted list (no atomics, no scan);
 //   3. one thread per stored entry writes [self loop | neighbours] rows in ascending column order with
 //      val = (d_r^-1/2 * 1) * d_c^-1/2 evaluated in fp64 and rounded to fp32 like the reference.
 // HBM-bound: ~8E bytes in, 8(2E+N) + 8(N+1) bytes out.
@@ -19,7 +19,6 @@ namespace {
 
 __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __restrict__ row_ptr, int64_t n_users,
                                                            int32_t* __restrict__ edge_user,
-                                                           int32_t* __restrict__ item_count,
                                                            const int32_t* __restrict__ items, int64_t n_items,
                                                            int32_t* __restrict__ bad) {
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -29,42 +28,22 @@ __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __rest
   for (int64_t j = b + lane; j < e; j += 32) {
     edge_user[j] = (int32_t)u;
     const int32_t it = items[j];
-    if (it < 0 || it >= n_items) {
-      atomicExch(bad, 1);
-    } else {
-      atomicAdd(&item_count[it], 1);
-    }
+    if (it < 0 || it >= n_items) atomicExch(bad, 1);
   }
 }
 
-// single-block exclusive scan of int32 counts into int64 offsets (n up to a few million: microseconds)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int64_t n,
-                                                           int64_t* __restrict__ ptr) {
-  __shared__ int64_t warp_sums[32];
-  __shared__ int64_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t base = 0; base < n; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int64_t v = i < n ? (int64_t)cnt[i] : 0;
-    int64_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[w] = incl;
-    __syncthreads();
-    int64_t wbase = 0;
-    for (int k = 0; k < w; ++k) wbase += warp_sums[k];
-    const int64_t c = carry;
-    if (i < n) ptr[i] = c + wbase + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c + wbase + incl;
-    __syncthreads();
+// Item row offsets from the item-sorted edge list: item_ptr[it] = first position whose item is >= it
+// (lower bound by binary search, one thread per item; no atomics: a popular item would serialise 10^5 of them).
+__global__ void __launch_bounds__(256) item_offsets_kernel(const int32_t* __restrict__ items_sorted, int64_t n_edges,
+                                                           int64_t n_items, int64_t* __restrict__ item_ptr) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it > n_items) return;
+  int64_t lo = 0, hi = n_edges;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(items_sorted + mid) < it) lo = mid + 1; else hi = mid;
   }
-  if (threadIdx.x == 0) ptr[n] = carry;
+  item_ptr[it] = lo;
 }
 
 // d^-1/2 per node in fp64 (degree counts the self loop), computed once per node instead of per entry
@@ -176,12 +155,10 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
   DMM_CHECK_ARG((size_t)workspace_bytes > fixed, "dmm_build_norm_adj_csr: workspace too small");
   w.cub_bytes = (size_t)workspace_bytes - fixed;
 
-  DMM_CUDA(cudaMemsetAsync(w.item_count, 0, (size_t)(n_items + 1) * 4, st));
   int32_t* bad = w.item_count + n_items;
-  expand_users_kernel<<<(unsigned)dmm_ceil_div(n_users * 32, 256), 256, 0, st>>>(row_ptr, n_users, w.edge_user,
-                                                                                w.item_count, items, n_items, bad);
-  DMM_LAUNCH_CHECK();
-  scan_counts_kernel<<<1, 1024, 0, st>>>(w.item_count, n_items, w.item_ptr);
+  DMM_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+  expand_users_kernel<<<(unsigned)dmm_ceil_div(n_users * 32, 256), 256, 0, st>>>(row_ptr, n_users, w.edge_user, items, n_items,
+                                                                                bad);
   DMM_LAUNCH_CHECK();
   if (n_edges > 0) {
     int end_bit = 1;
@@ -196,6 +173,8 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
     DMM_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, need, items, w.items_sorted, w.edge_user, w.users_by_item,
                                              (int)n_edges, 0, end_bit, st));
   }
+  item_offsets_kernel<<<(unsigned)dmm_ceil_div(n_items + 1, 256), 256, 0, st>>>(w.items_sorted, n_edges, n_items, w.item_ptr);
+  DMM_LAUNCH_CHECK();
   const int64_t N = n_users + n_items;
   node_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.item_ptr, n_users, n_items, w.dinv);
   DMM_LAUNCH_CHECK();

@@ -6,9 +6,12 @@
 //
 // Layout: one warp per output row.  For D = 64 a row of X is 256 B = 16 float4: the two half warps
 // gather two neighbours at a time with 128-bit loads (fully coalesced 256 B segments), 4 neighbours
-// per half warp in flight; rows longer than LONG_ROW are finished by the whole CTA with a fixed-order
-// shared-memory reduction (deterministic, no atomics).  HBM-bound: 8*nnz + 8*(N+1) + 2*N*D*4 bytes
-// per product when X is not L2 resident.
+// per half warp in flight.  Item popularity is heavy tailed (a popular item's row has 10^4..10^5
+// neighbours), so rows longer than PLAN_LONG_ROW are listed once per adjacency in a "plan"
+// (dmm_spmm_plan) and cut into PLAN_CHUNK-neighbour chunks: one warp per chunk writes a partial row,
+// a second small kernel adds the partials of every long row in chunk order (deterministic, no
+// atomics on Y).  Without a plan, rows longer than LONG_ROW are finished by their CTA alone.
+// HBM-bound: 8*nnz + 8*(N+1) + 2*N*D*4 bytes per product when X is not L2 resident.
 #include "common.cuh"
 
 namespace {
@@ -16,6 +19,11 @@ namespace {
 constexpr int SPMM_THREADS = 256;
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 constexpr int LONG_ROW = 1024;
+constexpr int PLAN_LONG_ROW = 256;   // rows with more neighbours go through the plan
+constexpr int PLAN_CHUNK = 128;      // neighbours per chunk of a planned row (one warp each)
+
+// plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr
+__host__ __device__ inline int64_t plan_cap(int64_t nnz) { return nnz / PLAN_LONG_ROW + 1; }
 
 struct Epi {
   float alpha, beta;
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
                                                               const int32_t* __restrict__ idx,
                                                               const float* __restrict__ val, int64_t row0, int64_t row1,
                                                               const float* __restrict__ x, int64_t ld_x, Epi ep,
-                                                              float* __restrict__ y, int64_t ld_y) {
+                                                              float* __restrict__ y, int64_t ld_y, int planned) {
   __shared__ int64_t long_rows[SPMM_WARPS];
   __shared__ int n_long;
   __shared__ float4 part[SPMM_WARPS * 2][16];
@@ -74,7 +82,9 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
   const int64_t r = row0 + (int64_t)blockIdx.x * SPMM_WARPS + warp;
   if (r < row1) {
     const int64_t b = ptr[r], e = ptr[r + 1];
-    if (e - b > LONG_ROW) {
+    if (planned && e - b > PLAN_LONG_ROW) {
+      // handled by the chunk kernels
+    } else if (e - b > LONG_ROW) {
       if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = r;
     } else {
       float4 acc = gather64(idx, val, x, ld_x, b + half, e, 2, l16);
@@ -115,6 +125,115 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
       reinterpret_cast<float4*>(y + rr * ld_y)[threadIdx.x] = o;
     }
     __syncthreads();
+  }
+}
+
+// ---- planned long rows ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_collect_kernel(const int64_t* __restrict__ ptr, int64_t n_rows,
+                                                           int64_t cap, int64_t* __restrict__ plan) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  if (ptr[r + 1] - ptr[r] > PLAN_LONG_ROW) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(plan), 1ULL);
+    if ((int64_t)i < cap) plan[2 + i] = r;
+  }
+}
+
+// single block: chunk_ptr = exclusive scan of ceil(nnz_r / PLAN_CHUNK) over the listed rows
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restrict__ ptr, int64_t cap,
+                                                         int64_t* __restrict__ plan) {
+  __shared__ int64_t warp_sums[32];
+  __shared__ int64_t carry;
+  const int64_t n = plan[0] < cap ? plan[0] : cap;
+  int64_t* chunk_ptr = plan + 2 + cap;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    int64_t v = 0;
+    if (i < n) {
+      const int64_t r = plan[2 + i];
+      v = (ptr[r + 1] - ptr[r] + PLAN_CHUNK - 1) / PLAN_CHUNK;
+    }
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    int64_t wbase = 0;
+    for (int k = 0; k < w; ++k) wbase += warp_sums[k];
+    const int64_t c = carry;
+    if (i < n) chunk_ptr[i] = c + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    chunk_ptr[n] = carry;
+    plan[1] = carry;
+  }
+}
+
+// one warp per chunk (grid-stride): partial[c, :] = A[row, chunk] . X
+__global__ void __launch_bounds__(SPMM_THREADS) spmm64_chunks_kernel(const int64_t* __restrict__ ptr,
+                                                                     const int32_t* __restrict__ idx,
+                                                                     const float* __restrict__ val, int64_t row0,
+                                                                     int64_t row1, const float* __restrict__ x,
+                                                                     int64_t ld_x, const int64_t* __restrict__ plan,
+                                                                     int64_t cap, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int64_t n_long = plan[0] < cap ? plan[0] : cap;
+  const int64_t n_chunks = plan[1];
+  const int64_t* long_rows = plan + 2;
+  const int64_t* chunk_ptr = plan + 2 + cap;
+  const int64_t n_warps = (int64_t)gridDim.x * SPMM_WARPS;
+  for (int64_t c = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5); c < n_chunks; c += n_warps) {
+    // the planned row that owns chunk c: last i with chunk_ptr[i] <= c
+    int64_t lo = 0, hi = n_long - 1;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (chunk_ptr[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    const int64_t r = long_rows[lo];
+    if (r < row0 || r >= row1) continue;
+    const int64_t b = ptr[r] + (c - chunk_ptr[lo]) * PLAN_CHUNK;
+    const int64_t rend = ptr[r + 1];
+    const int64_t e = b + PLAN_CHUNK < rend ? b + PLAN_CHUNK : rend;
+    float4 acc = gather64(idx, val, x, ld_x, b + half, e, 2, l16);
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (half == 0) reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
+  }
+}
+
+// one half warp per planned row (grid-stride): Y[row] = epilogue(sum of its partials in chunk order)
+__global__ void __launch_bounds__(SPMM_THREADS) spmm64_reduce_kernel(int64_t row0, int64_t row1,
+                                                                     const int64_t* __restrict__ plan, int64_t cap,
+                                                                     const float* __restrict__ partial, Epi ep,
+                                                                     float* __restrict__ y, int64_t ld_y) {
+  const int l16 = threadIdx.x & 15;
+  const int64_t n_long = plan[0] < cap ? plan[0] : cap;
+  const int64_t* long_rows = plan + 2;
+  const int64_t* chunk_ptr = plan + 2 + cap;
+  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
+  for (int64_t i = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4); i < n_long; i += n_hw) {
+    const int64_t r = long_rows[i];
+    if (r < row0 || r >= row1) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c = chunk_ptr[i]; c < chunk_ptr[i + 1]; ++c)
+      acc = add4(acc, __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16));
+    float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
+    if (ep.z) {
+      const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
+      o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
+    }
+    reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
   }
 }
 
@@ -173,24 +292,64 @@ __global__ void __launch_bounds__(256) sign_noise_kernel(float* __restrict__ e, 
 
 }  // namespace
 
+extern "C" int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz) {
+  (void)n_rows;
+  return (int64_t)sizeof(int64_t) * (3 + 2 * plan_cap(nnz));
+}
+
+extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
+                             int64_t plan_bytes, void* stream) {
+  DMM_CHECK_ARG(ctx && adj_ptr && plan, "dmm_spmm_plan: null argument");
+  DMM_CHECK_ARG(n_rows > 0 && nnz >= 0, "dmm_spmm_plan: bad sizes");
+  DMM_CHECK_ARG(plan_bytes >= dmm_spmm_plan_bytes(n_rows, nnz), "dmm_spmm_plan: plan buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cap = plan_cap(nnz);
+  DMM_CUDA(cudaMemsetAsync(plan, 0, 2 * sizeof(int64_t), st));
+  plan_collect_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(adj_ptr, n_rows, cap, (int64_t*)plan);
+  DMM_LAUNCH_CHECK();
+  plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int64_t dmm_spmm_workspace_bytes(int64_t nnz, int64_t D) {
+  if (D != 64) return 0;
+  // chunks <= nnz / PLAN_CHUNK + (#planned rows <= nnz / PLAN_LONG_ROW + 1)
+  return (nnz / PLAN_CHUNK + plan_cap(nnz) + 1) * 64 * (int64_t)sizeof(float);
+}
+
 extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
                             int64_t row0, int64_t row1, const float* x, int64_t ld_x, int64_t D, float alpha,
-                            float beta, const float* z, int64_t ld_z, float* y, int64_t ld_y, void* stream) {
+                            float beta, const float* z, int64_t ld_z, float* y, int64_t ld_y, const void* plan,
+                            int64_t nnz, void* workspace, int64_t workspace_bytes, void* stream) {
   DMM_CHECK_ARG(ctx && adj_ptr && adj_idx && adj_val && x && y, "dmm_spmm_csr: null argument");
   DMM_CHECK_ARG(D > 0 && D % 4 == 0 && D <= 256, "dmm_spmm_csr: D must be a multiple of 4 and <= 256 (got %lld)", (long long)D);
   DMM_CHECK_ARG(ld_x % 4 == 0 && ld_y % 4 == 0 && ld_x >= D && ld_y >= D && (!z || (ld_z % 4 == 0 && ld_z >= D)),
                 "dmm_spmm_csr: leading dimensions must be >= D and multiples of 4");
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  DMM_CHECK_ARG(al16(x) && al16(y) && al16(z), "dmm_spmm_csr: X/Y/Z must be 16-byte aligned");
+  DMM_CHECK_ARG(al16(x) && al16(y) && al16(z) && al16(workspace), "dmm_spmm_csr: X/Y/Z/workspace must be 16-byte aligned");
   DMM_CHECK_ARG(row0 >= 0 && row1 >= row0, "dmm_spmm_csr: bad row range");
+  const bool planned = plan != nullptr && D == 64;
+  DMM_CHECK_ARG(!planned || (workspace && workspace_bytes >= dmm_spmm_workspace_bytes(nnz, D)),
+                "dmm_spmm_csr: a plan needs a workspace of dmm_spmm_workspace_bytes(nnz, D) bytes");
   if (row1 == row0) return DMM_OK;
   const Epi ep{alpha, z ? beta : 0.f, z, ld_z};
   const unsigned grid = (unsigned)dmm_ceil_div(row1 - row0, SPMM_WARPS);
+  cudaStream_t st = (cudaStream_t)stream;
   if (D == 64) {
-    spmm64_kernel<<<grid, SPMM_THREADS, 0, (cudaStream_t)stream>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y);
+    spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, planned ? 1 : 0);
+    if (planned) {
+      DMM_LAUNCH_CHECK();
+      const int64_t cap = plan_cap(nnz);
+      // persistent grids: the chunk and row counts live on the device (no host sync)
+      spmm64_chunks_kernel<<<(unsigned)(ctx->num_sms * 8), SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x,
+                                                                                (const int64_t*)plan, cap, (float*)workspace);
+      DMM_LAUNCH_CHECK();
+      spmm64_reduce_kernel<<<(unsigned)ctx->num_sms, SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+                                                                           (const float*)workspace, ep, y, ld_y);
+    }
   } else {
-    spmm_generic_kernel<<<grid, SPMM_THREADS, 0, (cudaStream_t)stream>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x,
-                                                                         (int)(D / 4), ep, y, ld_y);
+    spmm_generic_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, (int)(D / 4), ep, y, ld_y);
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;

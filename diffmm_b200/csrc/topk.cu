@@ -344,41 +344,64 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
     return;
   }
 
-  uint32_t key[4 * TOPK_V4];
-  uint32_t tmax = has_tail ? order_key(tail_v) : 0u;
-  const uint32_t tail_key = tmax;
+  // pieces j < jfull are whole for every thread, piece jfull only for tid < jrem, later ones are empty.
+  // The scan of the row stays in the float domain (one FMNMX per score); order-preserving keys, which carry
+  // the exact tie semantics (-0.0 == +0.0, NaN order), are formed only for the thread maximum and the few
+  // candidates.  NaN scores are ignored by fmaxf and re-enter as candidates below (!(x < L) is true for NaN).
+  const int jfull = n4 / NT, jrem = n4 - jfull * NT;
+  const float NEG_INF = __uint_as_float(0xFF800000u);
+  float pmax[TOPK_V4];                         // per-piece maximum: most pieces hold no candidate at all
+  float tmaxf = has_tail ? fmaxf(tail_v, NEG_INF) : NEG_INF;
 #pragma unroll
   for (int j = 0; j < TOPK_V4; ++j) {
-    const bool ok = tid + NT * j < n4;       // pieces past the row hold key 0 and are never candidates
-    key[4 * j + 0] = ok ? order_key(v[j].x) : 0u;
-    key[4 * j + 1] = ok ? order_key(v[j].y) : 0u;
-    key[4 * j + 2] = ok ? order_key(v[j].z) : 0u;
-    key[4 * j + 3] = ok ? order_key(v[j].w) : 0u;
-    tmax = max(max(tmax, key[4 * j]), max(key[4 * j + 1], max(key[4 * j + 2], key[4 * j + 3])));
-  }
-
-  // 2. lower bound L of the k-th largest key from the per-thread maxima
-  uint32_t sv = tmax;
-#pragma unroll
-  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
-      const uint32_t other = __shfl_xor_sync(0xffffffffu, sv, j);
-      const bool desc = (lane & k2) == 0;      // k2 == 32: the whole warp, descending
-      const bool lower = (lane & j) == 0;
-      sv = (lower == desc) ? max(sv, other) : min(sv, other);
+    pmax[j] = NEG_INF;
+    if (j < jfull || (j == jfull && tid < jrem)) {
+      pmax[j] = fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w));
+      tmaxf = fmaxf(tmaxf, pmax[j]);
     }
   }
+  // threads without a (non-NaN) score publish key 0, below every real key
+  const uint32_t tmax = (tmaxf == NEG_INF) ? 0u : order_key(tmaxf);
+
+  // 2. lower bound L of the k-th largest key from the per-thread maxima: this warp's q-th largest
   const int q = (k + NW - 1) / NW;             // 1 .. 32
-  if (lane == q - 1) sm.red[wid] = sv;         // this warp's q-th largest per-thread maximum
+  uint32_t wq;
+  if (q <= 8) {
+    // q rounds of warp max, retiring one holder of the maximum per round
+    uint32_t sv = tmax;
+    bool alive = true;
+    wq = 0u;
+    for (int i = 0; i < q; ++i) {
+      wq = __reduce_max_sync(0xffffffffu, alive ? sv : 0u);
+      const uint32_t holders = __ballot_sync(0xffffffffu, alive && sv == wq);
+      if (holders == 0u) break;                // only retired lanes left: wq == 0
+      if (lane == __ffs(holders) - 1) alive = false;
+    }
+  } else {
+    uint32_t sv = tmax;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, sv, j);
+        const bool desc = (lane & k2) == 0;    // k2 == 32: the whole warp, descending
+        const bool lower = (lane & j) == 0;
+        sv = (lower == desc) ? max(sv, other) : min(sv, other);
+      }
+    }
+    wq = __shfl_sync(0xffffffffu, sv, q - 1);
+  }
+  if (lane == 0) sm.red[wid] = wq;
   if (tid == 0) sm.ncand = 0;
   __syncthreads();
   uint32_t L = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < NW; ++i) L = min(L, sm.red[i]);
 
-  // 3. compact the keys >= L (value, column) into shared memory: one atomic per warp per hit group
-  auto push = [&](bool c, uint32_t kv, int col) {
+  // 3. compact the candidates (key, column) into shared memory: one atomic per warp per hit group.
+  //    L back in the float domain (L == 0: some warp lacks q real maxima, every score is a candidate)
+  const float Lf = (L == 0u) ? NEG_INF : __uint_as_float((L & 0x80000000u) ? (L ^ 0x80000000u) : ~L);
+  auto push = [&](bool c, float x, int col) {
     const uint32_t bal = __ballot_sync(0xffffffffu, c);
     if (bal) {
       int base = 0;
@@ -386,21 +409,27 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
       base = __shfl_sync(0xffffffffu, base, 0);
       const int pos = base + __popc(bal & ((1u << lane) - 1u));
       if (c && pos < TOPK_CAND) {
-        sm.cand[pos] = kv;
+        sm.cand[pos] = order_key(x);
         sm.cand_col[pos] = col;
       }
     }
   };
 #pragma unroll
   for (int j = 0; j < TOPK_V4; ++j) {
-    const bool ok = tid + NT * j < n4;
+    if (j > jfull) break;                      // block-uniform
+    const bool have = j < jfull || tid < jrem;
+    // NaN inside a piece hides from pmax: a piece is also opened when any of its scores is NaN
+    const bool open = have && (!(pmax[j] < Lf) || v[j].x != v[j].x || v[j].y != v[j].y || v[j].z != v[j].z || v[j].w != v[j].w);
+    if (__any_sync(0xffffffffu, open)) {
+      const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) push(ok && key[4 * j + e] >= L, key[4 * j + e], 4 * (tid + NT * j) + e);
+      for (int e = 0; e < 4; ++e) push(open && !(xs[e] < Lf), xs[e], 4 * (tid + NT * j) + e);
+    }
   }
-  if (n_cols & 3) push(has_tail && tail_key >= L, tail_key, tail_col);   // block-uniform condition
+  if (n_cols & 3) push(has_tail && !(tail_v < Lf), tail_v, tail_col);   // block-uniform condition
   __syncthreads();
-  const int m = sm.ncand;                      // >= k by construction of L
-  if (m > NT) {                                // crowded threshold (ties) or loose bound: exact generic path
+  const int m = sm.ncand;                      // >= k by construction of L (except for rows with NaN-only threads)
+  if (m > NT || m < k) {                       // crowded threshold (ties) or loose bound: exact generic path
     __syncthreads();
     topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
     return;

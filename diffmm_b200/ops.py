@@ -168,6 +168,8 @@ class CsrAdj:
     val: torch.Tensor      # fp32  [2E+N]
     n_users: int
     n_items: int
+    plan: Optional[torch.Tensor] = None        # long-row plan of the SpMM (dmm_spmm_plan), built on first use
+    workspace: Optional[torch.Tensor] = None   # partial rows of the planned chunks
 
     @property
     def n_nodes(self):
@@ -208,9 +210,16 @@ def spmm(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None,
     if out is None:
         out = torch.empty((adj.n_nodes, D), dtype=torch.float32, device=x.device)
     row1 = adj.n_nodes if row1 is None else row1
+    nnz = int(adj.nnz)
+    if D == 64 and adj.plan is None:
+        lib = _lib.load()
+        adj.plan = torch.empty(int(lib.dmm_spmm_plan_bytes(adj.n_nodes, nnz)), dtype=torch.uint8, device=x.device)
+        adj.workspace = torch.empty(int(lib.dmm_spmm_workspace_bytes(nnz, D)), dtype=torch.uint8, device=x.device)
+        _lib.call("dmm_spmm_plan", _ctx(x), _p(adj.ptr), adj.n_nodes, nnz, _p(adj.plan), adj.plan.numel(), _stream())
+    plan, ws = (adj.plan, adj.workspace) if D == 64 else (None, None)
     _lib.call("dmm_spmm_csr", _ctx(x), _p(adj.ptr), _p(adj.idx), _p(adj.val), int(row0), int(row1), _p(x),
               _row_major(x, "x"), D, float(alpha), float(beta), _p(z), _row_major(z, "z") if z is not None else 0,
-              _p(out), _row_major(out, "out"), _stream())
+              _p(out), _row_major(out, "out"), _p(plan), nnz, _p(ws), ws.numel() if ws is not None else 0, _stream())
     return out
 
 

@@ -153,11 +153,22 @@ int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* 
  * Y[r0:r1, :] = alpha * A[r0:r1, :] . X (+ beta * Z[r0:r1, :]),  X fp32 [N_cols, D] (ld_x).
  * `row0,row1` select a row block (row-partitioned propagation); Y/Z are indexed by absolute row.
  * D must be a multiple of 4 and <= 256.  A symmetric => the backward is the same call.
- * Replaces torch.sparse.mm (Model.py:90,93,105,111,114,123,130; Main.py:319).                */
+ * Replaces torch.sparse.mm (Model.py:90,93,105,111,114,123,130; Main.py:319).
+ *
+ * Item popularity is heavy tailed, so for D == 64 a `plan` (built once per adjacency by
+ * dmm_spmm_plan; device-resident, no host sync) lists the rows with more than 256 neighbours; they
+ * are cut into 128-neighbour chunks whose partial rows go through `workspace`
+ * (dmm_spmm_workspace_bytes) and are added in chunk order (deterministic).  plan == NULL keeps the
+ * one-CTA-per-long-row path.  `nnz` is the number of stored entries of A (sizes the plan).      */
+int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz);
+int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
+                  int64_t plan_bytes, void* stream);
+int64_t dmm_spmm_workspace_bytes(int64_t nnz, int64_t D);
 int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
                  int64_t row0, int64_t row1, const float* x, int64_t ld_x, int64_t D,
                  float alpha, float beta, const float* z, int64_t ld_z,
-                 float* y, int64_t ld_y, void* stream);
+                 float* y, int64_t ld_y, const void* plan, int64_t nnz, void* workspace,
+                 int64_t workspace_bytes, void* stream);
 
 /* Cross-layer CL perturbation (Main.py:320-321) fused with nothing else:
  * e[r,:] += sign(e[r,:]) * rnd[r,:] / max(||rnd[r,:]||, 1e-12) * noise_degree, in place. */
