@@ -9,8 +9,8 @@
 // per half warp in flight.  Item popularity is heavy tailed (a popular item's row has 10^4..10^5
 // neighbours), so rows longer than PLAN_LONG_ROW are listed once per adjacency in a "plan"
 // (dmm_spmm_plan) and cut into PLAN_CHUNK-neighbour chunks: one warp per chunk writes a partial row,
-// a second small kernel adds the partials of every long row in chunk order (deterministic, no
-// atomics on Y).  Without a plan, rows longer than LONG_ROW are finished by their CTA alone.
+// a second small kernel adds the partials of every long row in a fixed order (deterministic, no
+// atomics on Y); the short rows run one half warp per row.  Without a plan, rows longer than LONG_ROW are finished by their CTA alone.
 // HBM-bound: 8*nnz + 8*(N+1) + 2*N*D*4 bytes per product when X is not L2 resident.
 #include "common.cuh"
 
@@ -19,8 +19,8 @@ namespace {
 constexpr int SPMM_THREADS = 256;
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 constexpr int LONG_ROW = 1024;
-constexpr int PLAN_LONG_ROW = 256;   // rows with more neighbours go through the plan
-constexpr int PLAN_CHUNK = 128;      // neighbours per chunk of a planned row (one warp each)
+constexpr int PLAN_LONG_ROW = 64;    // rows with more neighbours go through the plan
+constexpr int PLAN_CHUNK = 64;       // neighbours per chunk of a planned row (one warp each)
 
 // plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr
 __host__ __device__ inline int64_t plan_cap(int64_t nnz) { return nnz / PLAN_LONG_ROW + 1; }
@@ -128,6 +128,67 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
   }
 }
 
+// Half-warp gather of up to 64 neighbours: the 16 lanes first fetch all column ids / values of the segment
+// with coalesced loads (one round trip), then broadcast them by shuffle and keep BATCH row gathers (256 B each)
+// in flight per half warp.  `hmask` is the shuffle mask of this half warp; the two halves of a warp run
+// independent segments.
+template <int BATCH>
+__device__ __forceinline__ float4 gather64_hw(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                              const float* __restrict__ x, int64_t ld_x, int64_t b, int n, int l16,
+                                              uint32_t hmask) {
+  int32_t mc[4];
+  float mv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = l16 + 16 * k;
+    mc[k] = j < n ? __ldg(idx + b + j) : 0;
+    mv[k] = j < n ? __ldg(val + b + j) : 0.f;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (16 * k >= n) break;                    // uniform within the half warp
+#pragma unroll
+    for (int h = 0; h < 16 / BATCH; ++h) {
+      if (16 * k + BATCH * h >= n) break;
+      float4 xs[BATCH];
+      float vs[BATCH];
+#pragma unroll
+      for (int t = 0; t < BATCH; ++t) {
+        const int32_t c = __shfl_sync(hmask, mc[k], BATCH * h + t, 16);
+        vs[t] = __shfl_sync(hmask, mv[k], BATCH * h + t, 16);
+        xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (16 * k + BATCH * h + t < n) xs[t] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ld_x) + l16);
+      }
+#pragma unroll
+      for (int t = 0; t < BATCH; ++t) acc = fma4(vs[t], xs[t], acc);
+    }
+  }
+  return acc;
+}
+
+// ---- short rows of a planned adjacency: one HALF warp per row (two rows per warp in flight), no barrier ----
+__global__ void __launch_bounds__(SPMM_THREADS) spmm64_short_kernel(const int64_t* __restrict__ ptr,
+                                                                    const int32_t* __restrict__ idx,
+                                                                    const float* __restrict__ val, int64_t row0,
+                                                                    int64_t row1, const float* __restrict__ x,
+                                                                    int64_t ld_x, Epi ep, float* __restrict__ y,
+                                                                    int64_t ld_y) {
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+  const int64_t r = row0 + (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4);
+  if (r >= row1) return;
+  const int64_t b = ptr[r], e = ptr[r + 1];
+  if (e - b > PLAN_LONG_ROW) return;          // chunk kernels
+  const float4 acc = gather64_hw<4>(idx, val, x, ld_x, b, (int)(e - b), l16, hmask);
+  float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
+  if (ep.z) {
+    const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
+    o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
+  }
+  reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
+}
+
 // ---- planned long rows ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) plan_collect_kernel(const int64_t* __restrict__ ptr, int64_t n_rows,
                                                            int64_t cap, int64_t* __restrict__ plan) {
@@ -178,62 +239,100 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
   }
 }
 
-// one warp per chunk (grid-stride): partial[c, :] = A[row, chunk] . X
+// one half warp per chunk (grid-stride): partial[c, :] = A[row, chunk] . X
 __global__ void __launch_bounds__(SPMM_THREADS) spmm64_chunks_kernel(const int64_t* __restrict__ ptr,
                                                                      const int32_t* __restrict__ idx,
                                                                      const float* __restrict__ val, int64_t row0,
                                                                      int64_t row1, const float* __restrict__ x,
                                                                      int64_t ld_x, const int64_t* __restrict__ plan,
                                                                      int64_t cap, float* __restrict__ partial) {
-  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
   const int64_t n_long = plan[0] < cap ? plan[0] : cap;
   const int64_t n_chunks = plan[1];
   const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
-  const int64_t n_warps = (int64_t)gridDim.x * SPMM_WARPS;
-  for (int64_t c = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5); c < n_chunks; c += n_warps) {
+  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
+  for (int64_t c = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4); c < n_chunks; c += n_hw) {
     // the planned row that owns chunk c: last i with chunk_ptr[i] <= c
     int64_t lo = 0, hi = n_long - 1;
     while (lo < hi) {
       const int64_t mid = (lo + hi + 1) >> 1;
-      if (chunk_ptr[mid] <= c) lo = mid; else hi = mid - 1;
+      if (__ldg(chunk_ptr + mid) <= c) lo = mid; else hi = mid - 1;
     }
     const int64_t r = long_rows[lo];
     if (r < row0 || r >= row1) continue;
     const int64_t b = ptr[r] + (c - chunk_ptr[lo]) * PLAN_CHUNK;
     const int64_t rend = ptr[r + 1];
-    const int64_t e = b + PLAN_CHUNK < rend ? b + PLAN_CHUNK : rend;
-    float4 acc = gather64(idx, val, x, ld_x, b + half, e, 2, l16);
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-    if (half == 0) reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
+    const int n = (int)(rend - b < PLAN_CHUNK ? rend - b : PLAN_CHUNK);
+    const float4 acc = gather64_hw<8>(idx, val, x, ld_x, b, n, l16, hmask);
+    reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
   }
 }
 
-// one half warp per planned row (grid-stride): Y[row] = epilogue(sum of its partials in chunk order)
+// Y[row] = epilogue(sum of the row's partials), deterministic.  Pass A: rows with at most REDUCE_SMALL chunks,
+// one half warp per row, all loads in flight.  Pass B: the few big rows, one CTA per row: the 16 half warps
+// stride the partials (4 loads in flight each) and one half warp adds the 16 sums in a fixed order.
+constexpr int REDUCE_SMALL = 16;
 __global__ void __launch_bounds__(SPMM_THREADS) spmm64_reduce_kernel(int64_t row0, int64_t row1,
                                                                      const int64_t* __restrict__ plan, int64_t cap,
                                                                      const float* __restrict__ partial, Epi ep,
                                                                      float* __restrict__ y, int64_t ld_y) {
-  const int l16 = threadIdx.x & 15;
+  __shared__ float4 part[SPMM_THREADS / 16][16];
+  const int l16 = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  constexpr int NHW = SPMM_THREADS / 16;
   const int64_t n_long = plan[0] < cap ? plan[0] : cap;
   const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
-  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
-  for (int64_t i = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4); i < n_long; i += n_hw) {
-    const int64_t r = long_rows[i];
-    if (r < row0 || r >= row1) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = chunk_ptr[i]; c < chunk_ptr[i + 1]; ++c)
-      acc = add4(acc, __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16));
-    float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
+  auto finish = [&](int64_t r, const float4& sum) {
+    float4 o = make_float4(ep.alpha * sum.x, ep.alpha * sum.y, ep.alpha * sum.z, ep.alpha * sum.w);
     if (ep.z) {
       const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
       o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
     }
     reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
+  };
+  // pass A
+  for (int64_t i = (int64_t)blockIdx.x * NHW + hw; i < n_long; i += (int64_t)gridDim.x * NHW) {
+    const int64_t r = long_rows[i];
+    const int64_t cb = chunk_ptr[i];
+    const int nc = (int)(chunk_ptr[i + 1] - cb);
+    if (nc > REDUCE_SMALL || r < row0 || r >= row1) continue;
+    float4 p[REDUCE_SMALL];
+#pragma unroll
+    for (int t = 0; t < REDUCE_SMALL; ++t) {
+      p[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < nc) p[t] = __ldg(reinterpret_cast<const float4*>(partial + (cb + t) * 64) + l16);
+    }
+    float4 sum = p[0];
+#pragma unroll
+    for (int t = 1; t < REDUCE_SMALL; ++t) sum = add4(sum, p[t]);
+    finish(r, sum);
+  }
+  // pass B
+  for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+    const int64_t r = long_rows[i];
+    const int64_t cb = chunk_ptr[i], ce = chunk_ptr[i + 1];
+    if (ce - cb <= REDUCE_SMALL || r < row0 || r >= row1) continue;     // block-uniform
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t c = cb + hw;
+    for (; c + 3 * NHW < ce; c += 4 * NHW) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16);
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(partial + (c + NHW) * 64) + l16);
+      const float4 p2 = __ldg(reinterpret_cast<const float4*>(partial + (c + 2 * NHW) * 64) + l16);
+      const float4 p3 = __ldg(reinterpret_cast<const float4*>(partial + (c + 3 * NHW) * 64) + l16);
+      acc = add4(add4(add4(add4(acc, p0), p1), p2), p3);
+    }
+    for (; c < ce; c += NHW) acc = add4(acc, __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16));
+    part[hw][l16] = acc;
+    __syncthreads();
+    if (hw == 0) {
+      float4 sum = part[0][l16];
+#pragma unroll
+      for (int k = 1; k < NHW; ++k) sum = add4(sum, part[k][l16]);
+      finish(r, sum);
+    }
+    __syncthreads();
   }
 }
 
@@ -337,15 +436,18 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
   const unsigned grid = (unsigned)dmm_ceil_div(row1 - row0, SPMM_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 64) {
-    spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, planned ? 1 : 0);
-    if (planned) {
+    if (!planned) {
+      spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, 0);
+    } else {
+      spmm64_short_kernel<<<(unsigned)dmm_ceil_div(row1 - row0, SPMM_THREADS / 16), SPMM_THREADS, 0, st>>>(
+          adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y);
       DMM_LAUNCH_CHECK();
       const int64_t cap = plan_cap(nnz);
       // persistent grids: the chunk and row counts live on the device (no host sync)
       spmm64_chunks_kernel<<<(unsigned)(ctx->num_sms * 8), SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x,
                                                                                 (const int64_t*)plan, cap, (float*)workspace);
       DMM_LAUNCH_CHECK();
-      spmm64_reduce_kernel<<<(unsigned)ctx->num_sms, SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+      spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 4), SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
                                                                            (const float*)workspace, ep, y, ld_y);
     }
   } else {

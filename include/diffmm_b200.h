@@ -156,9 +156,9 @@ int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* 
  * Replaces torch.sparse.mm (Model.py:90,93,105,111,114,123,130; Main.py:319).
  *
  * Item popularity is heavy tailed, so for D == 64 a `plan` (built once per adjacency by
- * dmm_spmm_plan; device-resident, no host sync) lists the rows with more than 256 neighbours; they
- * are cut into 128-neighbour chunks whose partial rows go through `workspace`
- * (dmm_spmm_workspace_bytes) and are added in chunk order (deterministic).  plan == NULL keeps the
+ * dmm_spmm_plan; device-resident, no host sync) lists the rows with more than 64 neighbours; they
+ * are cut into 64-neighbour chunks whose partial rows go through `workspace`
+ * (dmm_spmm_workspace_bytes) and are added in a fixed order (deterministic).  plan == NULL keeps the
  * one-CTA-per-long-row path.  `nnz` is the number of stored entries of A (sizes the plan).      */
 int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz);
 int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
