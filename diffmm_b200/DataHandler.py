@@ -109,7 +109,7 @@ class DataHandler:
         self.torchBiAdj = self.makeTorchAdj(trainMat, U, I, self.device)
 
         self.trainData = TrainData(trainMat, self.config)
-        self.trainLoader = dataloader.DataLoader(self.trainData, batch_size=self.config.train.batch, shuffle=True, num_workers=0)
+        self.trainLoader = TrainLoader(self.trainData, self.config.train.batch)
         self.testData = TestData(testMat, trainMat)
         self.testLoader = dataloader.DataLoader(self.testData, batch_size=self.config.train.test_batch, shuffle=False, num_workers=0)
 
@@ -142,9 +142,10 @@ class TrainData(torch_dataset):
         for u, i in zip(self.rows, self.cols):
             self.user_pos_items[u].append(i)
         self._keys = None
+        self._csr = None
 
-    def negSampling(self):
-        """One rejection-sampled negative per interaction, in COO order (DataHandler.py:159-169)."""
+    def negSamplingLoop(self):
+        """The reference's loop verbatim in behaviour (DataHandler.py:159-169); kept as the checker of negSampling."""
         item_num = self.config.data.item_num
         dok = self.dokmat
         rows = self.rows
@@ -155,6 +156,42 @@ class TrainData(torch_dataset):
                 if (u, neg_index) not in dok:
                     break
             self.negs[i] = neg_index
+
+    def negSampling(self):
+        """One rejection-sampled negative per interaction, in COO order (DataHandler.py:159-169), WITHOUT changing
+        the numpy RNG stream: legacy ``np.random.randint(n, size=T)`` yields exactly the values of T scalar calls,
+        so a block of draws is taken up front and the reference's loop is replayed over it in native code
+        (dmm_host_neg_sampling: interaction i consumes draws until one is not an item of its user).  The global
+        generator ends in the state the loop would leave: it is rewound and advanced by the draws consumed."""
+        import ctypes as C
+        from . import _lib
+        item_num = int(self.config.data.item_num)
+        n = len(self.rows)
+        if n == 0:
+            return
+        if self._csr is None:
+            self._csr = csr_arrays_from_scipy(coo_matrix((np.ones(n), (self.rows, self.cols)),
+                                                         shape=(int(self.rows.max()) + 1, item_num)))
+        indptr, indices = self._csr
+        rows = np.ascontiguousarray(self.rows, dtype=np.int32)
+        negs = np.empty(n, dtype=np.int32)
+        consumed = C.c_int64(0)
+        state = np.random.get_state()
+        T = n + max(4096, n // 16)
+        lib = _lib.load()
+        while True:
+            np.random.set_state(state)
+            draws = np.ascontiguousarray(np.random.randint(item_num, size=T), dtype=np.int64)
+            rc = lib.dmm_host_neg_sampling(indptr.ctypes.data, indices.ctypes.data, rows.ctypes.data, n,
+                                           draws.ctypes.data, T, negs.ctypes.data, C.byref(consumed))
+            if rc == 0:
+                break
+            if rc != -4:                      # DMM_ERR_WORKSPACE: the stream ran out, draw a longer one
+                _lib.check(rc, "dmm_host_neg_sampling")
+            T *= 2
+        np.random.set_state(state)
+        np.random.randint(item_num, size=int(consumed.value))
+        self.negs = negs
 
     def negSamplingFast(self, rng: np.random.Generator):
         """Vectorised variant (different RNG stream: statistical parity only; opt-in)."""
@@ -174,6 +211,27 @@ class TrainData(torch_dataset):
 
     def __getitem__(self, idx):
         return self.rows[idx], self.cols[idx], self.negs[idx]
+
+
+class TrainLoader:
+    """Iterates (users, pos, neg) batches like DataLoader(TrainData, batch, shuffle=True) (DataHandler.py:117-118).
+    The index stream comes from a real torch DataLoader over range(E), so the CPU-generator consumption (base
+    seed, sampler seed, randperm) is the reference's; the per-sample __getitem__ + default_collate of 1024
+    numpy scalars per batch is replaced by three vectorised gathers (same values, same int32 dtype)."""
+
+    def __init__(self, data: "TrainData", batch_size: int):
+        self.dataset = data
+        self.batch_size = batch_size
+        self._index_loader = dataloader.DataLoader(_IndexOnly(len(data)), batch_size=batch_size, shuffle=True, num_workers=0)
+
+    def __len__(self):
+        return len(self._index_loader)
+
+    def __iter__(self):
+        d = self.dataset
+        for idx in self._index_loader:
+            i = idx.numpy()
+            yield torch.from_numpy(d.rows[i]), torch.from_numpy(d.cols[i]), torch.from_numpy(np.asarray(d.negs)[i])
 
 
 class TestData(torch_dataset):

@@ -203,7 +203,10 @@ class Coach:
         """Phase 3 (Main.py:292-377)."""
         cfg = self.config
         U = cfg.data.user_num
-        ep_loss = ep_rec_loss = ep_reg_loss = ep_cl_loss = 0
+        # running sums stay on the device in float64 (the exact value of the reference's python-float sums of
+        # fp32 .item()s, Main.py:311-312,370,373) and are read once per epoch: no host sync inside the loop
+        zero = torch.zeros((), dtype=torch.float64, device=self.device)
+        ep_loss, ep_rec_loss, ep_reg_loss, ep_cl_loss = zero.clone(), zero.clone(), zero.clone(), zero.clone()
         biadj = _as_csr(self.handler.torchBiAdj)
         for i, batch_data in enumerate(self.handler.trainLoader):
             users, pos_items, neg_items = batch_data
@@ -219,8 +222,8 @@ class Coach:
 
             rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
             reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
-            ep_rec_loss += rec_loss.item()
-            ep_reg_loss += reg_loss.item()
+            ep_rec_loss += rec_loss.detach().double()
+            ep_reg_loss += reg_loss.detach().double()
 
             # cross-layer CL (Main.py:315-330)
             joint_embs = torch.cat([self.model.u_embs, self.model.i_embs], dim=0)
@@ -251,13 +254,13 @@ class Coach:
                 for vu, vi in views:
                     cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
 
-            ep_cl_loss += cl_loss.item()
+            ep_cl_loss += cl_loss.detach().double()
             batch_joint_loss = rec_loss + reg_loss + cl_loss
-            ep_loss += batch_joint_loss.item()
+            ep_loss += batch_joint_loss.detach().double()
             self.opt.zero_grad()
             batch_joint_loss.backward()
             self.opt.step()
-        return ep_loss, ep_rec_loss, ep_reg_loss, ep_cl_loss
+        return ep_loss.item(), ep_rec_loss.item(), ep_reg_loss.item(), ep_cl_loss.item()
 
     def trainEpoch(self):
         t0 = time.perf_counter()
@@ -320,25 +323,32 @@ class Coach:
         self._tick("eval", t0)
         return {"Recall": epRecall / n, "NDCG": epNdcg / n, "Precision": epPrecision / n}
 
+    _MAX_DCG = None
+
     def calcRes(self, top_idxs: np.ndarray, test_u_its: list, users: Tensor):
-        """Main.py:422-448 (same arithmetic)."""
+        """Main.py:422-448 vectorised over the batch with the same float64 arithmetic in the same order
+        (per-user hit sums follow the order of the user's test items, the batch totals are added user by user)."""
         assert top_idxs.shape[0] == len(users)
         topk = self.config.base.topk
-        allRecall = allNdcg = allPrecision = 0
+        if Coach._MAX_DCG is None or len(Coach._MAX_DCG) != topk + 1:
+            Coach._MAX_DCG = [np.sum([np.reciprocal(np.log2(loc + 2)) for loc in range(t)]) for t in range(topk + 1)]
         users = users.tolist() if hasattr(users, "tolist") else list(users)
-        for i in range(len(users)):
-            u_rec_list = list(top_idxs[i])
-            u_its = test_u_its[users[i]]
-            tstNum = len(u_its)
-            maxDcg = np.sum([np.reciprocal(np.log2(loc + 2)) for loc in range(min(tstNum, topk))])
-            recall_hits = dcg = 0
-            for item in u_its:
-                if item in u_rec_list:
-                    recall_hits += 1
-                    dcg += np.reciprocal(np.log2(u_rec_list.index(item) + 2))
-            allRecall += recall_hits / tstNum
-            allNdcg += dcg / maxDcg
-            allPrecision += recall_hits / topk
+        B = len(users)
+        tst_num = np.fromiter((len(test_u_its[u]) for u in users), dtype=np.int64, count=B)
+        seg = np.repeat(np.arange(B), tst_num)
+        items = np.fromiter((it for u in users for it in test_u_its[u]), dtype=np.int64, count=int(tst_num.sum()))
+        eq = top_idxs[seg].astype(np.int64) == items[:, None]                  # [pairs, topk]
+        hit = eq.any(axis=1)
+        pos = eq.argmax(axis=1)                                                # list.index: first occurrence
+        gain = np.where(hit, np.reciprocal(np.log2(pos + 2.0)), 0.0)
+        recall_hits = np.bincount(seg, weights=hit.astype(np.float64), minlength=B)
+        dcg = np.bincount(seg, weights=gain, minlength=B)                      # accumulates in item order
+        max_dcg = np.array([Coach._MAX_DCG[min(int(t), topk)] for t in tst_num])
+        allRecall = allNdcg = allPrecision = 0
+        for r, n_, p in zip((recall_hits / tst_num).tolist(), (dcg / max_dcg).tolist(), (recall_hits / topk).tolist()):
+            allRecall += r
+            allNdcg += n_
+            allPrecision += p
         return allRecall, allNdcg, allPrecision
 
 

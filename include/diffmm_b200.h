@@ -201,6 +201,14 @@ int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2,
 int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,
                          int64_t D, float* dst, int64_t ld_d, void* stream);
 
+/* ---- host helper (no device work) --------------------------------------------------------------
+ * Replays the reference's rejection-sampling loop (TrainData.negSampling, DataHandler.py:159-169)
+ * over `n_draws` values pre-drawn by the caller from the same numpy generator: interaction i
+ * (user rows[i]) consumes draws until one is not in the user's sorted CSR row.  All pointers are
+ * HOST pointers.  *consumed = draws used; DMM_ERR_WORKSPACE if the stream ran out.              */
+int dmm_host_neg_sampling(const int64_t* h_indptr, const int32_t* h_indices, const int32_t* h_rows, int64_t n,
+                          const int64_t* h_draws, int64_t n_draws, int32_t* h_negs, int64_t* consumed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""CPU-only tests of the host logic around the kernels: the stream-exact negative sampler, the vectorised
+train loader and the vectorised Recall/NDCG arithmetic must reproduce the reference's Python loops exactly
+(reference DataHandler.py:145-179, Main.py:422-448)."""
+import numpy as np
+import torch
+from scipy.sparse import coo_matrix
+from torch.utils.data import DataLoader
+
+from diffmm_b200 import Main, synth
+from diffmm_b200.Conf import Config
+from diffmm_b200.DataHandler import TrainData, TrainLoader
+
+
+def _train_data(U, I, mean_deg, seed):
+    inter = synth.interactions(U, I, seed=seed, mean_deg=mean_deg)
+    rows = np.repeat(np.arange(U), np.diff(inter.indptr))
+    m = coo_matrix((np.ones(len(rows)), (rows, inter.indices)), shape=(U, I))
+    cfg = Config()
+    cfg.data.item_num, cfg.data.user_num = I, U
+    return TrainData(m, cfg)
+
+
+def test_neg_sampling_replays_the_reference_loop_and_rng_state():
+    for U, I, md, seed in [(600, 150, 25, 3), (3000, 2000, 6.4, 0), (200, 4000, 35, 9)]:
+        td = _train_data(U, I, md, seed)
+        np.random.seed(7)
+        td.negSamplingLoop()
+        want, want_next = td.negs.copy(), np.random.randint(1 << 30)
+        np.random.seed(7)
+        td.negSampling()
+        got, got_next = td.negs.copy(), np.random.randint(1 << 30)
+        assert got.dtype == np.int32
+        np.testing.assert_array_equal(got, want)
+        assert got_next == want_next                     # the global generator is left where the loop leaves it
+        keys = set(zip(td.rows.tolist(), td.cols.tolist()))
+        assert not any((u, n) in keys for u, n in zip(td.rows.tolist(), got.tolist()))
+
+
+def test_train_loader_matches_torch_dataloader():
+    td = _train_data(500, 300, 8, 1)
+    np.random.seed(0)
+    td.negSampling()
+    torch.manual_seed(123)
+    ref = [tuple(t.clone() for t in b) for b in DataLoader(td, batch_size=128, shuffle=True, num_workers=0)]
+    nxt_ref = torch.rand(1)
+    torch.manual_seed(123)
+    loader = TrainLoader(td, 128)
+    got = list(loader)
+    nxt = torch.rand(1)
+    assert len(loader) == len(ref) == len(got)
+    for a, b in zip(ref, got):
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and torch.equal(x, y)
+    assert torch.equal(nxt, nxt_ref)                      # same CPU-generator consumption
+
+
+def _calc_res_reference(top_idxs, test_u_its, users, topk):
+    allRecall = allNdcg = allPrecision = 0
+    for i in range(len(users)):
+        u_rec_list = list(top_idxs[i])
+        u_its = test_u_its[users[i]]
+        tstNum = len(u_its)
+        maxDcg = np.sum([np.reciprocal(np.log2(loc + 2)) for loc in range(min(tstNum, topk))])
+        recall_hits = dcg = 0
+        for item in u_its:
+            if item in u_rec_list:
+                recall_hits += 1
+                dcg += np.reciprocal(np.log2(u_rec_list.index(item) + 2))
+        allRecall += recall_hits / tstNum
+        allNdcg += dcg / maxDcg
+        allPrecision += recall_hits / topk
+    return allRecall, allNdcg, allPrecision
+
+
+def test_calc_res_is_bit_identical_to_the_reference_loop():
+    class NS:
+        pass
+    coach = Main.Coach.__new__(Main.Coach)
+    coach.config = NS()
+    coach.config.base = NS()
+    coach.config.base.topk = 20
+    rng = np.random.default_rng(0)
+    B, I = 257, 400
+    top = np.stack([rng.permutation(I)[:20] for _ in range(B)])
+    test = [list(rng.choice(I, size=rng.integers(1, 35), replace=False)) for _ in range(B)]
+    users = torch.arange(B)
+    want = _calc_res_reference(top, test, users.tolist(), 20)
+    got = coach.calcRes(top, test, users)
+    assert tuple(float(x) for x in got) == tuple(float(x) for x in want)
