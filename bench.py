@@ -444,6 +444,22 @@ def run_ours(args):
         return
 
     pk = peaks()
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json),
+    # averaged over this run's launch mix; null when a shape has no capture
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["gemm_bf16_tn_kernel"]
+        tot, cnt = 0.0, 0
+        for _, _, _, shape in gemm_events:
+            ent = tr.get("x".join(map(str, shape[:3])))
+            if ent is None or shape[3] != 1:
+                tot, cnt = 0.0, 0
+                break
+            tot += ent["dram_read_bytes"] + ent["dram_write_bytes"]
+            cnt += 1
+        traffic = tot / cnt if cnt else None
+    except Exception:
+        traffic = None
     n_gemm = max(len(gemm_events), 1)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     value = world * U * args.steps / (ms * 1e-3)
@@ -458,7 +474,8 @@ def run_ours(args):
                    "parallelism": (f"user-sharded x{world}: {U_tot} users in total, edge lists all-gathered over NCCL, "
                                    f"adjacency of the whole graph built on every rank") if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "gemm_bf16_tn_kernel (tcgen05)",
+                     "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
+                     "kernel": "gemm_bf16_tn_kernel (tcgen05)",
                      "launches": len(gemm_events), "avg_launch_ms": gemm_ms / n_gemm, "share_of_step": gemm_ms / ms,
                      "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside the step); burst {pk['tf_burst']}",
                      "frac_of_burst": achieved / pk["tf_burst"], "by_shape_MxNxK": by_shape},
