@@ -15,6 +15,8 @@
 // ("bf16x3"), which restores fp32-level accuracy without leaving the bf16 tensor pipe.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -25,12 +27,17 @@ constexpr int EPI_WARPS = 8;   // any 8 consecutive warps cover each TMEM lane q
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int EPI_STAGE_BYTES = 4096 + 128;  // per epilogue warp: one 32 x 32 fp32 chunk (or bf16 hi + lo chunks) + 32 bias values
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 tile of 256 rows x BN columns; each CTA
+// stages its own 128 rows of A and HALF of the B rows, so a pipeline stage is 32 KB instead of 48 KB (6 stages
+// instead of 4 at BN = 256) and the shared-memory / L2 operand traffic per flop drops by a third.
+template <int BN, bool PAIR = false>
 struct Cfg {
+  static constexpr int CTAS = PAIR ? 2 : 1;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_ROWS = BN / CTAS;            // B rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = STAGE_BYTES >= 49152 ? 4 : (STAGE_BYTES >= 32768 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // + alignment slack
@@ -93,6 +100,46 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 flavours.  `bar` is the shared::cluster address of the LEADER CTA's barrier (mapa_shared).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -133,8 +180,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = BLOCK_M) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------ epilogue math
@@ -378,13 +425,17 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
   }
 }
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                     const __grid_constant__ CUtensorMap tm_bs_hi, const __grid_constant__ CUtensorMap tm_bs_lo,
                     const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  // PAIR: CTA rank inside the 2-CTA cluster (0 = leader: issues the MMAs, owns the barriers the peer signals)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int first_item = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -407,19 +458,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(tempty_bar(a), EPI_WARPS * C::CTAS);   // PAIR: the peer's epilogue warps arrive on the leader's barrier
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      // collective over the CTA pair: one warp of each CTA, same columns in both SMs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: no remote arrive may hit an uninitialised barrier
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
@@ -430,20 +489,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      for (int w = first_item; w < p.total_items; w += item_stride) {
         const WorkItem wi = decode_work<BN>(w, p);
         if (wi.col0 >= p.N) continue;
         const bool sub = wi.bn != BN;
-        const uint32_t tx_bytes = (uint32_t)(C::A_BYTES + wi.bn * BLOCK_K * 2);
+        // bytes landing on the (leader's) full barrier per stage: both CTAs' A tiles and B halves
+        const uint32_t tx_bytes = (uint32_t)(C::CTAS * C::A_BYTES + wi.bn * BLOCK_K * 2);
+        const int a_row = (wi.m_blk * C::CTAS + (int)cta_rank) * BLOCK_M;
+        const int b_row = wi.col0 + (int)cta_rank * (wi.bn / C::CTAS);
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap* ma = p.pass_a[ps] ? &tm_a_lo : &tm_a_hi;
           const CUtensorMap* mb = p.pass_b[ps] ? (sub ? &tm_bs_lo : &tm_b_lo) : (sub ? &tm_bs_hi : &tm_b_hi);
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-            mbar_expect_tx(full_bar(stage), tx_bytes);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-            tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, wi.m_blk * BLOCK_M);
-            tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, wi.col0);
+            if (PAIR) {
+              // the leader arms its barrier for the whole pair; the peer's copies complete on the leader's barrier too
+              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+              const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
+              tma_load_2d_pair(sa, ma, lead_bar, kb * BLOCK_K, a_row);
+              tma_load_2d_pair(sa + C::A_BYTES, mb, lead_bar, kb * BLOCK_K, b_row);
+            } else {
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, a_row);
+              tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, b_row);
+            }
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -454,14 +524,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {   // PAIR: only the leader CTA issues the (pair-wide) MMAs
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      for (int w = first_item; w < p.total_items; w += item_stride) {
         const WorkItem wi = decode_work<BN>(w, p);
         if (wi.col0 >= p.N) continue;
-        const uint32_t idesc = make_idesc(wi.bn);
+        const uint32_t idesc = make_idesc(wi.bn, BLOCK_M * C::CTAS);
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
@@ -476,15 +546,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // +32 B per UMMA_K step inside the 128 B swizzle row => +2 in the (addr >> 4) field
-            tcgen05_mma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) {
+              tcgen05_mma_bf16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+            } else {
+              tcgen05_mma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          tcgen05_commit(empty_bar(stage));  // smem slot is free once these MMAs retire
+          // smem slot is free once these MMAs retire (PAIR: in both CTAs, the commit multicasts to the same
+          // barrier offset of the peer)
+          if (PAIR) tcgen05_commit_pair(empty_bar(stage)); else tcgen05_commit(empty_bar(stage));
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tcgen05_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs)
+        if (PAIR) tcgen05_commit_pair(tfull_bar(acc)); else tcgen05_commit(tfull_bar(acc));
         ++it;
       }
     }
@@ -497,9 +574,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     uint8_t* const stg = smem_raw + (smem_base - smem_u32(smem_raw)) + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES +
                          (warp - EPI_WARP0) * EPI_STAGE_BYTES;
     int it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-      const WorkItem wi = decode_work<BN>(w, p);
+    for (int w = first_item; w < p.total_items; w += item_stride) {
+      WorkItem wi = decode_work<BN>(w, p);
       if (wi.col0 >= p.N) continue;
+      wi.m_blk = wi.m_blk * C::CTAS + (int)cta_rank;     // this CTA's 128-row block of the (pair) tile
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       ++it;
@@ -512,16 +590,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        // the MMA issuer (leader CTA) reuses the accumulator stage once every epilogue warp of the pair has left it
+        if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer may still be signalling this CTA's barriers
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+    }
   }
 }
 
@@ -545,15 +631,19 @@ int make_map(dmm_ctx* ctx, CUtensorMap* map, const uint16_t* base, int64_t rows,
   return DMM_OK;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
            const uint16_t* b_lo, int64_t ldb, GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo;
   int rc;
   p.num_n_blocks = (int)dmm_ceil_div(p.N, BN);
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  // work items are tiles of (BLOCK_M * CTAS) rows; one persistent CTA (or CTA pair) per SM (or TPC)
+  const int m_items = (int)dmm_ceil_div(p.M, (int64_t)BLOCK_M * C::CTAS);
+  p.num_m_blocks = m_items;
+  const int tiles = m_items * p.num_n_blocks;
+  const int slots = ctx->num_sms / C::CTAS;
+  const int grid = tiles < slots ? tiles : slots;
   // tail wave: when the last wave would fill at most half of the grid, cut its tiles into column slices
   const int rem = tiles % grid;
   p.split = 1;
@@ -565,20 +655,33 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   p.total_items = p.full_items + (p.split > 1 ? rem * p.split : 0);
   if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
   if ((rc = make_map(ctx, &ma_lo, a_lo ? a_lo : a_hi, p.M, p.K, lda, BLOCK_M))) return rc;
-  if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, BN))) return rc;
-  if ((rc = make_map(ctx, &mb_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, BN))) return rc;
-  if ((rc = make_map(ctx, &mbs_hi, b_hi, p.N, p.K, ldb, p.sub_bn))) return rc;
-  if ((rc = make_map(ctx, &mbs_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, p.sub_bn))) return rc;
+  if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, BN / C::CTAS))) return rc;
+  if ((rc = make_map(ctx, &mb_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, BN / C::CTAS))) return rc;
+  if ((rc = make_map(ctx, &mbs_hi, b_hi, p.N, p.K, ldb, p.sub_bn / C::CTAS))) return rc;
+  if ((rc = make_map(ctx, &mbs_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, p.sub_bn / C::CTAS))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  if (p.ep.res_lo != nullptr || p.ep.out_lo != nullptr) {
-    gemm_bf16_tn_kernel<BN, true><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
+  const bool x3 = p.ep.res_lo != nullptr || p.ep.out_lo != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(grid * C::CTAS));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C::CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = PAIR ? 1 : 0;
+  if (x3) {
+    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, true, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p));
   } else {
-    gemm_bf16_tn_kernel<BN, false><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p);
+    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, false, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p));
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
@@ -630,9 +733,15 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   else if (N <= 128) bn = 128;
   else bn = (p.num_m_blocks * dmm_ceil_div(N, 256) >= ctx->num_sms) ? 256 : 128;
   cudaStream_t st = (cudaStream_t)stream;
+  // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) once there is at least one pair tile per TPC;
+  // DMM_GEMM_PAIR=0 keeps the single-CTA kernel (A/B switch for measurements)
+  static const bool pair_ok = []() { const char* e = getenv("DMM_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = pair_ok && bn == 256 && dmm_ceil_div(M, 2 * BLOCK_M) * dmm_ceil_div(N, 256) >= ctx->num_sms / 2;
   switch (bn) {
-    case 64: return launch<64>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
-    case 128: return launch<128>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
-    default: return launch<256>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case 64: return launch<64, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case 128: return launch<128, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    default:
+      return pair ? launch<256, true>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st)
+                  : launch<256, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
   }
 }

@@ -37,7 +37,9 @@ def _ref(a, b, bias, act, alpha, beta, res):
 
 
 SHAPES = [(128, 256, 64), (128, 64, 64), (128, 128, 128), (200, 300, 210), (1024, 1024, 1000), (300, 7050, 1024),
-          (2048, 1024, 7060), (1024, 64, 6710), (77, 40, 50)]
+          (2048, 1024, 7060), (1024, 64, 6710), (77, 40, 50),
+          # CTA-pair (cta_group::2) kernel: >= 74 tiles of 256 x 256; tail wave cut into 64-column slices; ragged M and N
+          (2048, 2560, 136), (2000, 2500, 136), (5000, 2310, 200)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
