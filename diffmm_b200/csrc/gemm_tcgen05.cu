@@ -107,8 +107,11 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Remote arrive on the leader's barrier.  Relaxed: the only thing the waiter (MMA issuer) depends on is that this
+// warp's tcgen05.ld have completed, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already guarantee;
+// a .release.cluster arrive would also drain this warp's outstanding global stores (MEMBAR + ERRBAR per tile).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -592,7 +595,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       __syncwarp();
       if (lane == 0) {
         // the MMA issuer (leader CTA) reuses the accumulator stage once every epilogue warp of the pair has left it
-        if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+        if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
       }
     }
   }
