@@ -135,7 +135,7 @@ def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, seed=0):
     return dt, len(users), edges
 
 
-def epoch_seconds(name, seed, precision, epochs=2):
+def epoch_seconds(name, seed, precision, epochs=2, cuda_graph=False):
     """One full training epoch + eval (phases 1-3 of Coach.trainEpoch + testEpoch) on the synthetic
     `name`-shape dataset written in the reference's on-disk format; returns the last epoch's phase seconds."""
     import tempfile
@@ -152,6 +152,7 @@ def epoch_seconds(name, seed, precision, epochs=2):
         cfg.data.name = name
         cfg.base.precision = precision
         cfg.train.epoch = epochs
+        cfg.base.cuda_graph = cuda_graph
         cfg.train.test_batch = 1024
         Main.seed_it(seed)
         h = Main.DataHandler(cfg)
@@ -504,6 +505,7 @@ def run_ours(args):
         rebuild.ops.gemm_bf16_tn = orig_gemm
         try:
             line["epoch_sec"] = epoch_seconds(args.workload, args.seed, args.precision)
+            line["epoch_sec_cuda_graph"] = epoch_seconds(args.workload, args.seed, args.precision, cuda_graph=True)
         except Exception as e:  # the headline number must survive a failure of the auxiliary measurement
             line["epoch_sec"] = {"error": repr(e)[:300]}
     print(json.dumps(line), flush=True)

@@ -110,7 +110,8 @@ class Coach:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach(), h.audio_feats.detach()).cuda(self.device)
         else:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach()).cuda(self.device)
-        self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        # graph replay needs the optimiser state (step counter) on the device: capturable Adam, same update rule
+        self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0, capturable=self._use_graph())
         self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
         self.diffusion_model = GaussianDiffusion(self.config).cuda(self.device)
 
@@ -139,6 +140,12 @@ class Coach:
         if self.has_audio:
             d["audio"] = self.audio_denoise_model
         return d
+
+    def _use_graph(self) -> bool:
+        """Phase 3 from a CUDA graph: opt-in (``base.cuda_graph`` or DIFFMM_CUDA_GRAPH=1); never with the CPU-RNG
+        parity mode, whose noise draws happen on the host."""
+        want = bool(getattr(self.config.base, "cuda_graph", False)) or os.environ.get("DIFFMM_CUDA_GRAPH", "0") == "1"
+        return want and torch.cuda.is_available() and not rng.cpu_rng()
 
     def _tick(self, name, t0):
         torch.cuda.synchronize()
@@ -199,68 +206,103 @@ class Coach:
         if self.has_audio:
             self.audio_adj = adjs["audio"]
 
-    def trainJoint(self):
-        """Phase 3 (Main.py:292-377)."""
+    def _joint_step(self, users, pos_items, neg_items, biadj):
+        """One batch of phase 3 (Main.py:297-377): losses, backward, Adam step.  Returns the four detached loss
+        scalars (rec, reg, cl, total) as device tensors."""
         cfg = self.config
         U = cfg.data.user_num
-        # running sums stay on the device in float64 (the exact value of the reference's python-float sums of
-        # fp32 .item()s, Main.py:311-312,370,373) and are read once per epoch: no host sync inside the loop
-        zero = torch.zeros((), dtype=torch.float64, device=self.device)
-        ep_loss, ep_rec_loss, ep_reg_loss, ep_cl_loss = zero.clone(), zero.clone(), zero.clone(), zero.clone()
+        if self.has_audio:
+            gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj, self.audio_adj)
+        else:
+            gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
+        final_user_embs, final_item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
+
+        rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
+        reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
+
+        # cross-layer CL (Main.py:315-330)
+        joint_embs = torch.cat([self.model.u_embs, self.model.i_embs], dim=0)
+        all_embs = []
+        all_embs_cl = joint_embs
+        for k in range(3):
+            joint_embs = spmm(biadj, joint_embs)
+            random_noise = rng.rand_like(joint_embs)
+            joint_embs = _SignNoise.apply(joint_embs, random_noise, cfg.hyper.noise_degree)
+            all_embs.append(joint_embs)
+            if k == 0:
+                all_embs_cl = joint_embs
+        final_embs = torch.mean(torch.stack(all_embs), dim=0)
+        cl1_user_embs, cl1_item_embs = final_embs[:U], final_embs[U:]
+        cl2_user_embs, cl2_item_embs = all_embs_cl[:U], all_embs_cl[U:]
+        cl_loss = (InfoNCE(cl1_user_embs, cl2_user_embs, users, cfg.hyper.cross_cl_temp)
+                   + InfoNCE(cl1_item_embs, cl2_item_embs, pos_items, cfg.hyper.cross_cl_temp)) * cfg.hyper.cross_cl_rate
+
+        T, R = cfg.hyper.modal_cl_temp, cfg.hyper.modal_cl_rate
+        views = [(gcn_output.u_image_embs, gcn_output.i_image_embs), (gcn_output.u_text_embs, gcn_output.i_text_embs)]
+        if self.has_audio:
+            views.append((gcn_output.u_audio_embs, gcn_output.i_audio_embs))
+        if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
+            pairs = [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else [])
+            for a, b in pairs:
+                cl_loss = cl_loss + (InfoNCE(views[a][0], views[b][0], users, T) + InfoNCE(views[a][1], views[b][1], pos_items, T)) * R
+        else:                            # main view as the anchor (Main.py:351-356,363-367)
+            for vu, vi in views:
+                cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
+
+        batch_joint_loss = rec_loss + reg_loss + cl_loss
+        self.opt.zero_grad()
+        batch_joint_loss.backward()
+        self.opt.step()
+        return rec_loss.detach(), reg_loss.detach(), cl_loss.detach(), batch_joint_loss.detach()
+
+    def trainJoint(self):
+        """Phase 3 (Main.py:292-377).  The running sums stay on the device in float64 (the exact value of the
+        reference's python-float sums of fp32 .item()s, Main.py:311-312,370,373) and are read once per epoch: no
+        host sync inside the loop.  With ``_use_graph()`` the full-size batches replay one CUDA graph captured at
+        the start of the epoch (the adjacencies and the learning rate are fixed within an epoch); the batch indices
+        are copied into static buffers, the last, smaller batch runs eagerly."""
+        from . import autograd as _ag
+        cfg = self.config
+        acc = torch.zeros(4, dtype=torch.float64, device=self.device)      # rec, reg, cl, total
         biadj = _as_csr(self.handler.torchBiAdj)
+        B = cfg.train.batch
+        use_graph = self._use_graph()
+        graph = None
+        static = None
+        n_warm = 0
         for i, batch_data in enumerate(self.handler.trainLoader):
             users, pos_items, neg_items = batch_data
             users = users.long().cuda(self.device)
             pos_items = pos_items.long().cuda(self.device)
             neg_items = neg_items.long().cuda(self.device)
-
-            if self.has_audio:
-                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj, self.audio_adj)
-            else:
-                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
-            final_user_embs, final_item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
-
-            rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
-            reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
-            ep_rec_loss += rec_loss.detach().double()
-            ep_reg_loss += reg_loss.detach().double()
-
-            # cross-layer CL (Main.py:315-330)
-            joint_embs = torch.cat([self.model.u_embs, self.model.i_embs], dim=0)
-            all_embs = []
-            all_embs_cl = joint_embs
-            for k in range(3):
-                joint_embs = spmm(biadj, joint_embs)
-                random_noise = rng.rand_like(joint_embs)
-                joint_embs = _SignNoise.apply(joint_embs, random_noise, cfg.hyper.noise_degree)
-                all_embs.append(joint_embs)
-                if k == 0:
-                    all_embs_cl = joint_embs
-            final_embs = torch.mean(torch.stack(all_embs), dim=0)
-            cl1_user_embs, cl1_item_embs = final_embs[:U], final_embs[U:]
-            cl2_user_embs, cl2_item_embs = all_embs_cl[:U], all_embs_cl[U:]
-            cl_loss = (InfoNCE(cl1_user_embs, cl2_user_embs, users, cfg.hyper.cross_cl_temp)
-                       + InfoNCE(cl1_item_embs, cl2_item_embs, pos_items, cfg.hyper.cross_cl_temp)) * cfg.hyper.cross_cl_rate
-
-            T, R = cfg.hyper.modal_cl_temp, cfg.hyper.modal_cl_rate
-            views = [(gcn_output.u_image_embs, gcn_output.i_image_embs), (gcn_output.u_text_embs, gcn_output.i_text_embs)]
-            if self.has_audio:
-                views.append((gcn_output.u_audio_embs, gcn_output.i_audio_embs))
-            if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
-                pairs = [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else [])
-                for a, b in pairs:
-                    cl_loss = cl_loss + (InfoNCE(views[a][0], views[b][0], users, T) + InfoNCE(views[a][1], views[b][1], pos_items, T)) * R
-            else:                            # main view as the anchor (Main.py:351-356,363-367)
-                for vu, vi in views:
-                    cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
-
-            ep_cl_loss += cl_loss.detach().double()
-            batch_joint_loss = rec_loss + reg_loss + cl_loss
-            ep_loss += batch_joint_loss.detach().double()
-            self.opt.zero_grad()
-            batch_joint_loss.backward()
-            self.opt.step()
-        return ep_loss.item(), ep_rec_loss.item(), ep_reg_loss.item(), ep_cl_loss.item()
+            if not use_graph or users.numel() != B:
+                acc += torch.stack(self._joint_step(users, pos_items, neg_items, biadj)).double()
+                continue
+            if static is None:
+                static = [torch.empty(B, dtype=torch.int64, device=self.device) for _ in range(3)]
+            for dst, src in zip(static, (users, pos_items, neg_items)):
+                dst.copy_(src)
+            if graph is None and n_warm < 2:
+                # eager warm-up on a side stream (allocator, SpMM plans, lazy initialisation) before the capture
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    acc += torch.stack(self._joint_step(*static, biadj)).double()
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                n_warm += 1
+                continue
+            if graph is None:
+                _ag._PACK_CACHE.clear()          # packed weights must be (re)built inside the captured step
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    acc += torch.stack(self._joint_step(*static, biadj)).double()
+            graph.replay()
+        out = acc.tolist()
+        if graph is not None:
+            del graph
+            _ag._PACK_CACHE.clear()              # packs written by the replays are one optimiser step stale
+        return out[3], out[0], out[1], out[2]
 
     def trainEpoch(self):
         t0 = time.perf_counter()

@@ -92,7 +92,9 @@ class Model(nn.Module):
         return self.u_embs
 
     def _project(self, layer: nn.Linear, feats: Tensor) -> Tensor:
-        return linear_tn(feats, layer.weight, layer.bias, 0, getattr(self.config.base, "precision", "bf16"))
+        # the feature matrices are constants of the model: their packed operand copies are cached
+        return linear_tn(feats, layer.weight, layer.bias, 0, getattr(self.config.base, "precision", "bf16"),
+                         const_input=not feats.requires_grad)
 
     def getImageFeats(self) -> Tensor:
         return self._project(self.image_layer, self.image_embedding)

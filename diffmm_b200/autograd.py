@@ -57,6 +57,28 @@ def packed_weight(w: torch.Tensor, transpose: bool, split: bool):
     return hi, (lo if split else None)
 
 
+_CONST_CACHE: dict = {}    # (data_ptr, shape, stride) -> (weakref(tensor), version, {transpose: (hi, lo)})
+
+
+def packed_const(x: torch.Tensor, transpose: bool, split: bool):
+    """Packed copies of a constant input the CALLER vouches for (long-lived tensor, e.g. a registered feature
+    matrix).  Keyed by storage address and validated by a weak reference to the very tensor object plus its
+    version counter, so a recycled address or an in-place update can never return stale data."""
+    key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()))
+    ent = _CONST_CACHE.get(key)
+    if ent is None or ent[0]() is not x or ent[1] != x._version:
+        if len(_CONST_CACHE) > 64:
+            for k in [k for k, v in _CONST_CACHE.items() if v[0]() is None]:
+                del _CONST_CACHE[k]
+        ent = (weakref.ref(x), x._version, {})
+        _CONST_CACHE[key] = ent
+    packs = ent[2]
+    if transpose not in packs:
+        packs[transpose] = pack_any(_rows(x.detach()), transpose, True)
+    hi, lo = packs[transpose]
+    return hi, (lo if split else None)
+
+
 def _rows(t: torch.Tensor) -> torch.Tensor:
     """Row-major view/copy with unit inner stride (padded leading dimensions are fine)."""
     if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
@@ -80,12 +102,16 @@ class LinearTN(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act: int, precision: str):
+    def forward(ctx, x, weight, bias, act: int, precision: str, const_input: bool = False):
         split = precision == "bf16x3"
+        x_obj = x                                  # the caller's tensor object: identity key of the constant cache
         x = _rows(x.detach())
         M, K = x.shape
         N = weight.shape[0]
-        x_hi, x_lo = ops.pack_bf16(x, split=split)
+        # const_input: x is a long-lived constant (the modality feature matrices, Model.py:47-58): its packed
+        # copies are cached like the weights' instead of being rebuilt on every batch
+        ctx.const_obj = x_obj if const_input else None
+        x_hi, x_lo = packed_const(x_obj, False, split) if const_input else ops.pack_bf16(x, split=split)
         w_hi, w_lo = packed_weight(weight, False, split)
         y = _new_out(M, N, x.device)
         ops.gemm_bf16_tn(x_hi, x_lo, w_hi, w_lo, M, N, K, bias=bias.detach() if bias is not None else None, act=act,
@@ -111,16 +137,16 @@ class LinearTN(torch.autograd.Function):
             ops.gemm_bf16_tn(g_hi, g_lo, wt_hi, wt_lo, M, K, N, out_f32=dx)
         if ctx.needs_input_grad[1]:
             gt_hi, gt_lo = ops.pack_bf16(g, transpose=True, split=split)
-            xt_hi, xt_lo = pack_any(x, True, split)
+            xt_hi, xt_lo = packed_const(ctx.const_obj, True, split) if ctx.const_obj is not None else pack_any(x, True, split)
             dw = _new_out(N, K, g.device)
             ops.gemm_bf16_tn(gt_hi, gt_lo, xt_hi, xt_lo, N, K, M, out_f32=dw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def linear_tn(x, weight, bias=None, act: int = 0, precision: str = "bf16"):
-    return LinearTN.apply(x, weight, bias, act, check_precision(precision))
+def linear_tn(x, weight, bias=None, act: int = 0, precision: str = "bf16", const_input: bool = False):
+    return LinearTN.apply(x, weight, bias, act, check_precision(precision), const_input)
 
 
 class SpMM(torch.autograd.Function):

@@ -172,6 +172,130 @@ __global__ void __launch_bounds__(256) nce_rows_kernel(const float* __restrict__
   }
 }
 
+// ---- D == 64: register-tiled version ----------------------------------------------------------------
+// The warp-per-anchor kernel above spends its time in shuffle reductions (one 5-step butterfly per logit).
+// Here a CTA owns NCE_BM = 16 anchor rows and walks the other view in tiles of NCE_BN = 64 rows staged in
+// shared memory; thread (r, c) accumulates the 4 logits (r, c + 16 q) with float4 reads along D (no
+// reductions), the softmax statistics of a row are combined over its 16 threads once per TILE, and for the
+// backward the 16 x 64 probability tile goes through shared memory into a second register-tiled product
+// P . B (thread (r, d) owns 4 gradient components).  Same MODE semantics as nce_rows_kernel.
+constexpr int NCE_BM = 16, NCE_BN = 64, NCE_LD = 68;   // 68-float rows: 16-byte aligned, conflict-free column access
+
+template <int MODE>
+__global__ void __launch_bounds__(256) nce_tile64_kernel(const float* __restrict__ na, const float* __restrict__ nb,
+                                                         int64_t B, float inv_temp, const float* __restrict__ lse_in,
+                                                         const float* __restrict__ inv_norm, float coef,
+                                                         float* __restrict__ out_lse, float* __restrict__ out_row_loss,
+                                                         float* __restrict__ out_grad) {
+  __shared__ __align__(16) float As[NCE_BM][NCE_LD];
+  __shared__ __align__(16) float Bs[NCE_BN][NCE_LD];
+  __shared__ float Ps[NCE_BM][NCE_BN + 1];
+  __shared__ float lse_s[NCE_BN];
+  const int tid = threadIdx.x;
+  const int r = tid >> 4, c4 = tid & 15;
+  const int64_t i0 = (int64_t)blockIdx.x * NCE_BM;
+  const int64_t i = i0 + r;
+  const uint32_t hmask = 0xFFFFu << (tid & 16);   // the 16 threads of a row are one half warp
+  {
+    // anchor tile: 16 rows x 16 float4
+    const int64_t row = i0 + (tid >> 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < B) v = __ldg(reinterpret_cast<const float4*>(na + row * 64) + (tid & 15));
+    *reinterpret_cast<float4*>(&As[tid >> 4][4 * (tid & 15)]) = v;
+  }
+  float m = -INFINITY, l = 0.f, diag = -INFINITY;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  const float lse_i = (MODE == 1 && i < B) ? lse_in[i] : 0.f;
+
+  for (int64_t j0 = 0; j0 < B; j0 += NCE_BN) {
+    __syncthreads();   // previous tile fully consumed (also publishes As on the first pass)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int jr = (tid >> 4) + 16 * it;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + jr < B) v = __ldg(reinterpret_cast<const float4*>(nb + (j0 + jr) * 64) + (tid & 15));
+      *reinterpret_cast<float4*>(&Bs[jr][4 * (tid & 15)]) = v;
+    }
+    if (MODE == 2 && tid < NCE_BN) lse_s[tid] = (j0 + tid < B) ? lse_in[j0 + tid] : 0.f;
+    __syncthreads();
+    // logits (r, c4 + 16 q)
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * k4]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[c4 + 16 * q][4 * k4]);
+        s[q] = fmaf(a.x, b.x, s[q]);
+        s[q] = fmaf(a.y, b.y, s[q]);
+        s[q] = fmaf(a.z, b.z, s[q]);
+        s[q] = fmaf(a.w, b.w, s[q]);
+      }
+    }
+    if (MODE == 0) {
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t j = j0 + c4 + 16 * q;
+        s[q] = (j < B) ? s[q] * inv_temp : -INFINITY;
+        if (j == i) diag = s[q];
+        tmax = fmaxf(tmax, s[q]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(hmask, tmax, o, 16));
+      const float mn = fmaxf(m, tmax);          // finite: every tile holds at least one valid column
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part += expf(s[q] - mn);   // exp(-inf) = 0 for masked columns
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o, 16);
+      l = l * expf(m - mn) + part;
+      m = mn;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c4 + 16 * q;
+        const int64_t j = j0 + c;
+        const float lse = (MODE == 1) ? lse_i : lse_s[c];
+        float w = 0.f;
+        if (j < B && i < B) w = expf(s[q] * inv_temp - lse) - (j == i ? 1.f : 0.f);
+        Ps[r][c] = w;
+      }
+      __syncthreads();
+      // g(r, 4 c4 .. 4 c4 + 3) += sum_j P(r, j) B(j, .)
+#pragma unroll 8
+      for (int j = 0; j < NCE_BN; ++j) {
+        const float w = Ps[r][j];
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[j][4 * c4]);
+        g[0] = fmaf(w, b.x, g[0]);
+        g[1] = fmaf(w, b.y, g[1]);
+        g[2] = fmaf(w, b.z, g[2]);
+        g[3] = fmaf(w, b.w, g[3]);
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) diag = fmaxf(diag, __shfl_xor_sync(hmask, diag, o, 16));
+    if (c4 == 0 && i < B) {
+      const float lse = m + logf(l);
+      out_lse[i] = lse;
+      out_row_loss[i] = lse - diag;
+    }
+  } else {
+    // normalisation backward: g_x = inv * (g - n (n . g)) * coef
+    const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * c4]);
+    float dot = a.x * g[0] + a.y * g[1] + a.z * g[2] + a.w * g[3];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
+    if (i < B) {
+      const float sc = inv_norm[i] * coef;
+      *reinterpret_cast<float4*>(out_grad + i * 64 + 4 * c4) =
+          make_float4(sc * (g[0] - a.x * dot), sc * (g[1] - a.y * dot), sc * (g[2] - a.z * dot), sc * (g[3] - a.w * dot));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, int64_t ld_s,
                                                                const int64_t* __restrict__ idx, int64_t B, int D,
                                                                float* __restrict__ dst, int64_t ld_d) {
@@ -186,6 +310,12 @@ template <int MODE>
 int launch_nce(int64_t B, int64_t D, const float* na, const float* nb, float inv_temp, const float* lse_in,
                const float* inv_norm, float coef, float* out_lse, float* out_row_loss, float* out_grad,
                cudaStream_t st) {
+  if (D == 64) {
+    nce_tile64_kernel<MODE><<<(unsigned)dmm_ceil_div(B, NCE_BM), 256, 0, st>>>(na, nb, B, inv_temp, lse_in, inv_norm, coef, out_lse,
+                                                                          out_row_loss, out_grad);
+    DMM_LAUNCH_CHECK();
+    return DMM_OK;
+  }
   const unsigned grid = (unsigned)dmm_ceil_div(B * 32, 256);
   switch (D / 32) {
     case 1: nce_rows_kernel<MODE, 1><<<grid, 256, 0, st>>>(na, nb, B, inv_temp, lse_in, inv_norm, coef, out_lse, out_row_loss, out_grad); break;

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden", "epoch_run")
 
 
-def _run(tmp_path, precision, monkeypatch, cpu_rng=True):
+def _run(tmp_path, precision, monkeypatch, cpu_rng=True, cuda_graph=False):
     from diffmm_b200 import Main
     from diffmm_b200.Conf import Config
     gold = json.load(open(os.path.join(GOLD, "result.json")))
@@ -30,6 +30,7 @@ def _run(tmp_path, precision, monkeypatch, cpu_rng=True):
         sec, key = k.split(".")
         setattr(getattr(cfg, sec), key, v)
     cfg.base.precision = precision
+    cfg.base.cuda_graph = cuda_graph
     Main.seed_it(cfg.base.seed)
     handler = Main.DataHandler(cfg)
     handler.LoadData()
@@ -62,3 +63,20 @@ def test_device_rng_run_is_sane(tmp_path, monkeypatch):
     for got, want in zip(coach.history, gold["epochs"]):
         assert got["train"]["Loss"] == pytest.approx(want["train"]["Loss"], rel=0.1)
         assert torch.isfinite(torch.tensor(list(got["train"].values()))).all()
+
+
+def test_cuda_graph_joint_training_tracks_eager(tmp_path, monkeypatch):
+    """Phase 3 replayed from a CUDA graph (base.cuda_graph) vs the eager loop, device generator, same seeds: the
+    first epoch sees the same batches, negatives and (graph-safe Philox) noise, so its losses agree closely;
+    capturable Adam and the graph's kernel order only move low-order bits."""
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    _, eager = _run(tmp_path / "a", "bf16", monkeypatch, cpu_rng=False, cuda_graph=False)
+    _, graph = _run(tmp_path / "b", "bf16", monkeypatch, cpu_rng=False, cuda_graph=True)
+    assert graph._use_graph() and not eager._use_graph()
+    e0, g0 = eager.history[0]["train"], graph.history[0]["train"]
+    for k in ("Loss", "BPR Loss", "reg loss", "CL loss"):
+        assert g0[k] == pytest.approx(e0[k], rel=5e-3), (k, g0[k], e0[k])
+    e1, g1 = eager.history[1]["train"], graph.history[1]["train"]
+    assert g1["Loss"] == pytest.approx(e1["Loss"], rel=5e-2)
+    assert abs(graph.history[1]["test"]["Recall"] - eager.history[1]["test"]["Recall"]) <= 0.03
