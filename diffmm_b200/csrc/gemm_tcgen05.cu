@@ -253,12 +253,15 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
   auto chunk_ok = [&](int c) -> bool { return c < nchunks && (INTERIOR || wi.col0 + c * 32 < p.N); };
 
   uint4 nh[4], nl[4];
-  float nb = 0.f;
-  // coalesced fetch of chunk c's raw bf16 residual and bias (a 16-byte piece that starts below N always lies
-  // inside the padded row because the leading dimension is a multiple of 8)
+  float nb = 0.f, nb2 = 0.f;   // bias of the chunk being drained next / of the one after it (two chunks of lead)
+  auto fetch_bias = [&](int c) -> float {
+    const int n0 = wi.col0 + c * 32;
+    return (ep.bias && chunk_ok(c) && (INTERIOR || n0 + lane < p.N)) ? __ldg(ep.bias + n0 + lane) : 0.f;
+  };
+  // coalesced fetch of chunk c's raw bf16 residual (a 16-byte piece that starts below N always lies inside the
+  // padded row because the leading dimension is a multiple of 8)
   auto fetch = [&](int c) {
     const int n0 = wi.col0 + c * 32;
-    if (ep.bias) nb = (INTERIOR || n0 + lane < p.N) ? __ldg(ep.bias + n0 + lane) : 0.f;
     if (res16) {
       const int col = n0 + 8 * cp16;
       const int64_t off = (int64_t)(rbase + cr16) * ep.ld_res16 + col;
@@ -272,6 +275,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
     }
   };
   if (chunk_ok(chalf)) fetch(chalf);
+  nb = fetch_bias(chalf);
+  nb2 = fetch_bias(chalf + EPI_WARPS / 4);
   mbar_wait(tfull, tphase, 4);
   tcgen05_fence_after();
 
@@ -298,6 +303,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
     // next chunk's residual / bias: in flight while this chunk is combined and stored (it may alias only the
     // output of the NEXT chunk, which this warp writes later)
     if (chunk_ok(c + EPI_WARPS / 4)) fetch(c + EPI_WARPS / 4);
+    nb = nb2;                                    // staged above; rotate the two-deep bias prefetch
+    nb2 = fetch_bias(c + 2 * (EPI_WARPS / 4));
     // ---- accumulator chunk
     uint32_t r[32];
     __syncwarp();  // tcgen05.ld is .sync.aligned; also publishes the staging tile to the row view
