@@ -29,6 +29,13 @@ constexpr int TOPK_NB = 1 << TOPK_NB_LOG2;   // range-adapted buckets of the gen
 constexpr int TOPK_CAND = 1024;              // candidate keys held in shared memory
 constexpr int TOPK_V4 = 8;                   // float4 loads per thread on the register path (32 keys)
 
+// NaN-propagating maximum (max.NaN.f32): a NaN score surfaces in the piece / thread maximum instead of vanishing
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t order_key(float f) {
   uint32_t u = __float_as_uint(f);
   if (u == 0x80000000u) u = 0u;  // -0.0 ties with +0.0
@@ -144,6 +151,7 @@ template <int NT, bool IN_SMEM>
 __device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_keys, const float* __restrict__ row,
                                                  int n_cols, int k, int64_t o0, int32_t user,
                                                  int32_t* __restrict__ out_users, int32_t* __restrict__ out_items) {
+  static_assert(NT >= 256, "the bucket scan and the radix histograms are laid out for at least 256 threads");
   const int tid = threadIdx.x;
   const bool take_all = !(k < n_cols);
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
@@ -347,17 +355,18 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   // pieces j < jfull are whole for every thread, piece jfull only for tid < jrem, later ones are empty.
   // The scan of the row stays in the float domain (one FMNMX per score); order-preserving keys, which carry
   // the exact tie semantics (-0.0 == +0.0, NaN order), are formed only for the thread maximum and the few
-  // candidates.  NaN scores are ignored by fmaxf and re-enter as candidates below (!(x < L) is true for NaN).
+  // candidates.  The maxima propagate NaN, so a NaN score reaches the thread maximum and the row is handed to the
+  // exact generic path (NaN keys have a total order the float comparisons cannot reproduce).
   const int jfull = n4 / NT, jrem = n4 - jfull * NT;
   const float NEG_INF = __uint_as_float(0xFF800000u);
   float pmax[TOPK_V4];                         // per-piece maximum: most pieces hold no candidate at all
-  float tmaxf = has_tail ? fmaxf(tail_v, NEG_INF) : NEG_INF;
+  float tmaxf = has_tail ? fmax_nan(tail_v, NEG_INF) : NEG_INF;
 #pragma unroll
   for (int j = 0; j < TOPK_V4; ++j) {
     pmax[j] = NEG_INF;
     if (j < jfull || (j == jfull && tid < jrem)) {
-      pmax[j] = fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w));
-      tmaxf = fmaxf(tmaxf, pmax[j]);
+      pmax[j] = fmax_nan(fmax_nan(v[j].x, v[j].y), fmax_nan(v[j].z, v[j].w));
+      tmaxf = fmax_nan(tmaxf, pmax[j]);
     }
   }
   // threads without a (non-NaN) score publish key 0, below every real key
@@ -393,7 +402,12 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   }
   if (lane == 0) sm.red[wid] = wq;
   if (tid == 0) sm.ncand = 0;
-  __syncthreads();
+  // the barrier doubles as the NaN vote: the bound below counts real scores, so a row with any NaN (whose key
+  // order the float scan cannot see) takes the exact generic path
+  if (__syncthreads_or(tmaxf != tmaxf)) {
+    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
+    return;
+  }
   uint32_t L = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < NW; ++i) L = min(L, sm.red[i]);
@@ -418,8 +432,7 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   for (int j = 0; j < TOPK_V4; ++j) {
     if (j > jfull) break;                      // block-uniform
     const bool have = j < jfull || tid < jrem;
-    // NaN inside a piece hides from pmax: a piece is also opened when any of its scores is NaN
-    const bool open = have && (!(pmax[j] < Lf) || v[j].x != v[j].x || v[j].y != v[j].y || v[j].z != v[j].z || v[j].w != v[j].w);
+    const bool open = have && !(pmax[j] < Lf);   // also true when the piece holds a NaN (pmax is NaN)
     if (__any_sync(0xffffffffu, open)) {
       const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
@@ -429,18 +442,17 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   if (n_cols & 3) push(has_tail && !(tail_v < Lf), tail_v, tail_col);   // block-uniform condition
   __syncthreads();
   const int m = sm.ncand;                      // >= k by construction of L (except for rows with NaN-only threads)
-  if (m > NT || m < k) {                       // crowded threshold (ties) or loose bound: exact generic path
+  constexpr int RANK_MAX = 512;                // candidates ranked against each other (m^2 / NT compares per thread)
+  if (m > RANK_MAX || m < k) {                 // crowded threshold (ties) or loose bound: exact generic path
     __syncthreads();
     topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
     return;
   }
-  // exact rank of candidate `tid` among the m candidates by (value desc, column asc)
-  uint32_t my_key = 0u;
-  int my_col = 0;
-  bool sel = false;
-  if (tid < m) {
-    my_key = sm.cand[tid];
-    my_col = sm.cand_col[tid];
+  // exact rank of every candidate among the m candidates by (value desc, column asc); the k best are marked
+  // (one thread per candidate: a warp-cooperative variant executed more instructions in total and measured slower)
+  for (int c = tid; c < m; c += NT) {
+    const uint32_t my_key = sm.cand[c];
+    const int my_col = sm.cand_col[c];
     int before = 0;
     if (m > k) {
       for (int j = 0; j < m; ++j) {
@@ -449,11 +461,13 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
         before += (kj > my_key || (kj == my_key && cj < my_col)) ? 1 : 0;
       }
     }
-    sel = before < k;
+    sm.bucket[c] = before < k ? my_col : 0x7FFFFFFF;
   }
-  if (tid < m) sm.bucket[tid] = sel ? my_col : 0x7FFFFFFF;
   __syncthreads();
-  if (sel) {
+  // output position = number of selected columns below mine (ascending column order)
+  for (int c = tid; c < m; c += NT) {
+    const int my_col = sm.bucket[c];
+    if (my_col == 0x7FFFFFFF) continue;
     int pos = 0;
     for (int j = 0; j < m; ++j) pos += (sm.bucket[j] < my_col) ? 1 : 0;
     out_items[o0 + pos] = my_col;

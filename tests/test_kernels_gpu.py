@@ -103,6 +103,29 @@ def test_topk_ties_and_signed_zero(ops):
         np.testing.assert_array_equal(items[ptr[r]:ptr[r + 1]], w, err_msg=f"row {r}")
 
 
+def test_topk_nan_and_inf_scores_follow_key_order(ops):
+    # +NaN above +inf, -NaN below -inf (bit-pattern order), ties by column: register path hands NaN rows to the generic path
+    rng = np.random.default_rng(8)
+    scores = rng.standard_normal((16, 300)).astype(np.float32)
+    scores[0, [5, 17]] = np.nan
+    scores[1, 7] = np.float32(np.inf)
+    scores[1, 9] = -np.float32(np.inf)
+    scores[2, :] = np.nan
+    neg_nan = np.frombuffer(np.uint32(0xFFC00000).tobytes(), dtype=np.float32)[0]
+    scores[3, [1, 2, 3]] = neg_nan
+    scores[3, 4] = np.nan
+    k = rng.integers(1, 30, 16)
+    k[3] = 299
+    ptr, _, items, _ = _run_topk(ops, scores, k)
+    # the kernel's stated total order (the oracle never sees NaN): order-preserving key of the fp32 bit pattern
+    u = scores.view(np.uint32).astype(np.uint64)
+    u = np.where(u == 0x80000000, 0, u)
+    key = np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.int64)
+    for r in range(scores.shape[0]):
+        order = np.lexsort((np.arange(scores.shape[1]), -key[r]))
+        np.testing.assert_array_equal(items[ptr[r]:ptr[r + 1]], np.sort(order[:k[r]]), err_msg=f"row {r}")
+
+
 def test_topk_k_larger_than_row_sets_status(ops):
     scores = np.zeros((2, 8), dtype=np.float32)
     _, _, _, status = _run_topk(ops, scores, np.array([9, 1]))
