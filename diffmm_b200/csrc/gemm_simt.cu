@@ -43,12 +43,18 @@ __global__ void __launch_bounds__(256) gemm_f32_tn_kernel(const float* __restric
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
-      if (ep.act == 1) v = tanhf(v);
+      const bool has_res = ep.residual != nullptr || ep.res_hi != nullptr;
+      float r = 0.f;
       if (ep.residual) {
-        v = ep.alpha * v + ep.beta * ep.residual[(int64_t)m * ep.ld_res + n];
+        r = ep.residual[(int64_t)m * ep.ld_res + n];
       } else if (ep.res_hi) {
-        float r = dmm_bf16_to_f32(ep.res_hi[(int64_t)m * ep.ld_res16 + n]);
+        r = dmm_bf16_to_f32(ep.res_hi[(int64_t)m * ep.ld_res16 + n]);
         if (ep.res_lo) r += dmm_bf16_to_f32(ep.res_lo[(int64_t)m * ep.ld_res16 + n]);
+      }
+      const bool pre = has_res && ep.res_pre_act != 0;
+      if (pre) v += ep.beta * r;
+      if (ep.act == 1) v = tanhf(v);
+      if (has_res && !pre) {
         v = ep.alpha * v + ep.beta * r;
       } else {
         v *= ep.alpha;

@@ -321,12 +321,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
         t[0] += b0.x; t[1] += b0.y; t[2] += b0.z; t[3] += b0.w;
         t[4] += b1.x; t[5] += b1.y; t[6] += b1.z; t[7] += b1.w;
       }
-      if (ep.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = fast_tanh(t[j]);
-      }
+      float rs[8];
       if (has_res) {
-        float rs[8];
         if (res16) {
           const uint4 h = *at16(0, lane, q);
           const uint32_t wv[4] = {h.x, h.y, h.z, h.w};
@@ -350,6 +346,17 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
           rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
           rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
         }
+      }
+      const bool pre = has_res && ep.res_pre_act != 0;   // residual enters before the activation (K-chunked sums)
+      if (pre) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fmaf(ep.beta, rs[j], t[j]);
+      }
+      if (ep.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = fast_tanh(t[j]);
+      }
+      if (has_res && !pre) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) t[j] = fmaf(ep.alpha, t[j], ep.beta * rs[j]);
       } else if (ep.alpha != 1.f) {
@@ -738,15 +745,26 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   for (int i = p.n_pass; i < 3; ++i) p.pass_a[i] = p.pass_b[i] = 0;
   p.ep = *ep;
 
-  int bn;
-  if (N <= 64) bn = 64;
-  else if (N <= 128) bn = 128;
-  else bn = (p.num_m_blocks * dmm_ceil_div(N, 256) >= ctx->num_sms) ? 256 : 128;
-  cudaStream_t st = (cudaStream_t)stream;
-  // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) once there is at least one pair tile per TPC;
-  // DMM_GEMM_PAIR=0 keeps the single-CTA kernel (A/B switch for measurements)
+  // Tile shape by a small cost model: waves over the SMs (or SM pairs) x work per SM and wave / measured relative
+  // efficiency of the shape (256-wide pair tiles 1.0, single-CTA 256 / 128 / 64 columns 0.93 / 0.80 / 0.55).
+  // DMM_GEMM_PAIR=0 keeps the single-CTA kernels (A/B switch for measurements).
   static const bool pair_ok = []() { const char* e = getenv("DMM_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-  const bool pair = pair_ok && bn == 256 && dmm_ceil_div(M, 2 * BLOCK_M) * dmm_ceil_div(N, 256) >= ctx->num_sms / 2;
+  const int64_t m128 = dmm_ceil_div(M, BLOCK_M), m256 = dmm_ceil_div(M, 2 * BLOCK_M);
+  auto waves = [](int64_t tiles, int64_t slots) { return (double)dmm_ceil_div(tiles, slots); };
+  const int sms = ctx->num_sms;
+  double best = 1e300;
+  int bn = 64;
+  bool pair = false;
+  auto consider = [&](int cand_bn, bool cand_pair, double cost) {
+    if (cost < best) { best = cost; bn = cand_bn; pair = cand_pair; }
+  };
+  consider(64, false, waves(m128 * dmm_ceil_div(N, 64), sms) * 64.0 / 0.55);
+  if (N > 64) consider(128, false, waves(m128 * dmm_ceil_div(N, 128), sms) * 128.0 / 0.80);
+  if (N > 128) {
+    consider(256, false, waves(m128 * dmm_ceil_div(N, 256), sms) * 256.0 / 0.93);
+    if (pair_ok && sms >= 2) consider(256, true, waves(m256 * dmm_ceil_div(N, 256), sms / 2) * 256.0 / 1.0);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
     case 64: return launch<64, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
     case 128: return launch<128, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);

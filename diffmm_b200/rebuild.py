@@ -21,6 +21,7 @@ ranks with no data-path collective except the final edge all-gather (dist.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -45,6 +46,7 @@ class ChainWorkspace:
         self.h_lo = torch.empty((rows, self.ld_h), **bf) if split else None
         self.x = torch.empty((rows, self.ld_x), dtype=torch.float32, device=device)
         self.bias_eff = None      # [S, hidden] fp32, sized on first use
+        self.partial = None       # fp32 partial sums of a K-chunked GEMM1 (scale-out widths only)
 
     def fits(self, rows, n_items, hidden, d_emb, split):
         return (rows <= self.rows and n_items == self.n_items and hidden == self.hidden and d_emb == self.d_emb
@@ -134,7 +136,7 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
             ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, bias1, 1, H, h_hi, h_lo,
                                row_ids=row_ids, row0=row0)
         else:
-            ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias=bias1, act=1, out_hi=h_hi, out_lo=h_lo)
+            _gemm1(ws, a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias1, h_hi, h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))
         # x_t lives only as the bf16 operand (hi, and lo in bf16x3 mode: hi + lo carries 16 mantissa bits):
@@ -152,6 +154,40 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
             if first_sparse and c2 != 0.0:
                 ops.csr_axpy_bf16(csr[0], csr[1], M, I, c2, ax_hi, ax_lo, row_ids=row_ids, row0=row0)
     return xv
+
+
+K_CHUNK = 8192          # columns of W1 per launch once W1 outgrows the L2 (128 k-blocks of 64)
+L2_WEIGHT_BYTES = 48 << 20
+
+
+def _gemm1(ws, a_hi, a_lo, w1_hi, w1_lo, M, H, K, bias, h_hi, h_lo):
+    """h = tanh(x_t W1[:, :K]^T + bias).  At scale-out widths (K = 500k items) W1 is ~1 GB and the persistent CTAs
+    walk 7813 k-blocks; with narrow single-CTA tiles they drifted apart until nothing was shared through the L2
+    (measured: 35 GB of DRAM reads for 5 GB of operands, 461 TFLOP/s).  The tile cost model now picks the CTA-pair
+    kernel there (829 TFLOP/s in one launch).  DIFFMM_K_CHUNK=1 instead issues the contraction in K chunks of 8192
+    columns, each launch re-aligning the CTAs, with the partial sums in an fp32 buffer
+    (dmm_gemm_epilogue.res_pre_act) and bias + tanh in the last chunk: measured equal, kept as an option."""
+    if H * K * 2 <= L2_WEIGHT_BYTES or K <= 2 * K_CHUNK or os.environ.get("DIFFMM_K_CHUNK", "0") != "1":
+        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, K, bias=bias, act=1, out_hi=h_hi, out_lo=h_lo)
+        return
+    ld = ops.pad_to(H, 4)
+    if ws.partial is None or ws.partial.shape[0] < M or ws.partial.shape[1] != ld:
+        ws.partial = torch.empty((ws.rows, ld), dtype=torch.float32, device=a_hi.device)
+    part = ws.partial[:M, :H]
+    k0 = 0
+    while k0 < K:
+        kc = min(K_CHUNK, K - k0)
+        last = k0 + kc >= K
+        sl = slice(k0, k0 + kc)
+        al = a_lo[:, sl] if a_lo is not None else None
+        wl = w1_lo[:, sl] if w1_lo is not None else None
+        res = part if k0 > 0 else None
+        if last:
+            ops.gemm_bf16_tn(a_hi[:, sl], al, w1_hi[:, sl], wl, M, H, kc, bias=bias, act=1, beta=1.0, residual=res,
+                             res_pre_act=True, out_hi=h_hi, out_lo=h_lo)
+        else:
+            ops.gemm_bf16_tn(a_hi[:, sl], al, w1_hi[:, sl], wl, M, H, kc, beta=1.0, residual=res, out_f32=part)
+        k0 += kc
 
 
 def default_block_rows(n_users: int, n_items: int, hidden: int, split: bool, budget_bytes: int = 12 << 30) -> int:

@@ -116,6 +116,8 @@ typedef struct dmm_gemm_epilogue {
   const uint16_t* res_hi; /* residual given as bf16 hi (+ lo) instead of fp32 (exclusive with */
   const uint16_t* res_lo; /* `residual`); may alias out_hi/out_lo: each element is read, then  */
   int64_t ld_res16;       /* written, by the same thread                                      */
+  int32_t res_pre_act;    /* != 0: v = alpha * act(acc + bias + beta * R) — the residual is a partial  */
+                          /* sum of the same contraction (K processed in chunks), added before act    */
 } dmm_gemm_epilogue;
 
 int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,

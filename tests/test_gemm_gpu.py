@@ -87,6 +87,35 @@ def test_tcgen05(ops, M, N, K, mode):
         assert torch.isnan(out[:, N:]).all()          # padding columns are never written
 
 
+def test_tcgen05_k_chunked_pre_activation_residual(ops):
+    """res_pre_act: the residual is a partial sum of the same contraction, added before bias-tanh (K in chunks)."""
+    rng = np.random.default_rng(12)
+    M, N, K, KC = 300, 200, 448, 192
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    a_hi, a_lo = ops.pack_bf16(T(a))
+    b_hi, b_lo = ops.pack_bf16(T(b))
+    part = torch.empty((M, N), device=DEV)
+    out_hi = torch.zeros((M, 208), dtype=torch.bfloat16, device=DEV)
+    out_lo = torch.zeros((M, 208), dtype=torch.bfloat16, device=DEV)
+    k0 = 0
+    while k0 < K:
+        kc = min(KC, K - k0)
+        sl = slice(k0, k0 + kc)
+        res = part if k0 > 0 else None
+        if k0 + kc >= K:
+            ops.gemm_bf16_tn(a_hi[:, sl], a_lo[:, sl], b_hi[:, sl], b_lo[:, sl], M, N, kc, bias=T(bias), act=1, beta=1.0,
+                             residual=res, res_pre_act=True, out_hi=out_hi[:, :N], out_lo=out_lo[:, :N])
+        else:
+            ops.gemm_bf16_tn(a_hi[:, sl], a_lo[:, sl], b_hi[:, sl], b_lo[:, sl], M, N, kc, beta=1.0, residual=res,
+                             out_f32=part)
+        k0 += kc
+    got = (out_hi.float() + out_lo.float())[:, :N].cpu().numpy()
+    want = np.tanh(a.astype(np.float64) @ b.astype(np.float64).T + bias)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=5e-5)
+
+
 def test_tcgen05_no_epilogue_extras(ops):
     rng = np.random.default_rng(9)
     M, N, K = 256, 512, 192
