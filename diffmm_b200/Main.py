@@ -111,7 +111,13 @@ class Coach:
         else:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach()).cuda(self.device)
         # graph replay needs the optimiser state (step counter) on the device: capturable Adam, same update rule
-        self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0, capturable=self._use_graph())
+        if self._use_graph():
+            # device-resident step counter and learning rate: one captured graph serves every epoch (the scheduler
+            # updates a tensor lr in place)
+            self.opt = Adam(self.model.parameters(), lr=torch.tensor(float(self.config.train.lr), device=self.device),
+                            weight_decay=0, capturable=True)
+        else:
+            self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
         self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
         self.diffusion_model = GaussianDiffusion(self.config).cuda(self.device)
 
@@ -255,21 +261,48 @@ class Coach:
         self.opt.step()
         return rec_loss.detach(), reg_loss.detach(), cl_loss.detach(), batch_joint_loss.detach()
 
+    def _bind_static_adjacencies(self):
+        """Graph mode: the rebuilt modality adjacencies of this epoch are copied into persistent buffers (their sizes
+        are fixed: nnz = 2E + N) and the SpMM plans rebuilt in place, so the graph captured in the first epoch stays valid."""
+        if not hasattr(self, "_static_adj"):
+            self._static_adj = {}
+        for name in ("image_adj", "text_adj", "audio_adj"):
+            new = getattr(self, name, None)
+            if new is None:
+                continue
+            st = self._static_adj.get(name)
+            if st is None:
+                self._static_adj[name] = new          # the first epoch's arrays become the persistent ones
+            elif st is not new:
+                st.ptr.copy_(new.ptr)
+                st.idx.copy_(new.idx)
+                st.val.copy_(new.val)
+                ops.spmm_replan(st)
+                setattr(self, name, st)
+
     def trainJoint(self):
         """Phase 3 (Main.py:292-377).  The running sums stay on the device in float64 (the exact value of the
         reference's python-float sums of fp32 .item()s, Main.py:311-312,370,373) and are read once per epoch: no
-        host sync inside the loop.  With ``_use_graph()`` the full-size batches replay one CUDA graph captured at
-        the start of the epoch (the adjacencies and the learning rate are fixed within an epoch); the batch indices
+        host sync inside the loop.  With ``_use_graph()`` the full-size batches replay ONE CUDA graph captured in the
+        first epoch (persistent adjacency buffers, device-resident Adam step and learning rate); the batch indices
         are copied into static buffers, the last, smaller batch runs eagerly."""
         from . import autograd as _ag
         cfg = self.config
-        acc = torch.zeros(4, dtype=torch.float64, device=self.device)      # rec, reg, cl, total
-        biadj = _as_csr(self.handler.torchBiAdj)
         B = cfg.train.batch
         use_graph = self._use_graph()
-        graph = None
-        static = None
-        n_warm = 0
+        if use_graph:
+            self._bind_static_adjacencies()
+            if not hasattr(self, "_joint_acc"):
+                self._joint_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+                self._joint_static = [torch.empty(B, dtype=torch.int64, device=self.device) for _ in range(3)]
+                self._joint_graph = None
+                self._joint_warm = 0
+            acc = self._joint_acc
+            acc.zero_()
+            static = self._joint_static
+        else:
+            acc = torch.zeros(4, dtype=torch.float64, device=self.device)      # rec, reg, cl, total
+        biadj = _as_csr(self.handler.torchBiAdj)
         for i, batch_data in enumerate(self.handler.trainLoader):
             users, pos_items, neg_items = batch_data
             users = users.long().cuda(self.device)
@@ -278,29 +311,26 @@ class Coach:
             if not use_graph or users.numel() != B:
                 acc += torch.stack(self._joint_step(users, pos_items, neg_items, biadj)).double()
                 continue
-            if static is None:
-                static = [torch.empty(B, dtype=torch.int64, device=self.device) for _ in range(3)]
             for dst, src in zip(static, (users, pos_items, neg_items)):
                 dst.copy_(src)
-            if graph is None and n_warm < 2:
+            if self._joint_graph is None and self._joint_warm < 2:
                 # eager warm-up on a side stream (allocator, SpMM plans, lazy initialisation) before the capture
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
                     acc += torch.stack(self._joint_step(*static, biadj)).double()
                 torch.cuda.current_stream(self.device).wait_stream(side)
-                n_warm += 1
+                self._joint_warm += 1
                 continue
-            if graph is None:
+            if self._joint_graph is None:
                 _ag._PACK_CACHE.clear()          # packed weights must be (re)built inside the captured step
                 torch.cuda.synchronize(self.device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                self._joint_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._joint_graph):
                     acc += torch.stack(self._joint_step(*static, biadj)).double()
-            graph.replay()
+            self._joint_graph.replay()
         out = acc.tolist()
-        if graph is not None:
-            del graph
+        if use_graph:
             _ag._PACK_CACHE.clear()              # packs written by the replays are one optimiser step stale
         return out[3], out[0], out[1], out[2]
 

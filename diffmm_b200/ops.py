@@ -226,6 +226,14 @@ def spmm(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None,
     return out
 
 
+def spmm_replan(adj: CsrAdj):
+    """Rebuilds the long-row plan of ``adj`` in place after its arrays were overwritten (same buffers: captured
+    CUDA graphs keep pointing at them)."""
+    if adj.plan is not None:
+        _lib.call("dmm_spmm_plan", _ctx(adj.ptr), _p(adj.ptr), adj.n_nodes, int(adj.nnz), _p(adj.plan), adj.plan.numel(),
+                  _stream())
+
+
 def sign_noise_(e: torch.Tensor, rnd: torch.Tensor, noise_degree: float):
     """In place e += sign(e) * normalize_rows(rnd) * noise_degree (Main.py:320-321)."""
     _lib.call("dmm_sign_noise_", _ctx(e), _p(e), _row_major(e, "e"), _p(rnd), _row_major(rnd, "rnd"), e.shape[0],
