@@ -158,8 +158,12 @@ class Coach:
         self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + (time.perf_counter() - t0)
 
     def trainDiffusion(self):
-        """Phase 1 (Main.py:145-192)."""
-        image_diff_loss, text_diff_loss, audio_diff_loss = 0, 0, 0
+        """Phase 1 (Main.py:145-192).  Same arithmetic as the reference's loop, which reads every loss with .item()
+        (a host sync per modality and batch), normalises the summed loss by the python float total and keeps running
+        python-float sums: here those scalars stay on the device in float64 (IEEE-identical adds and divides, the fp32
+        divisor is the fp32 rounding of the float64 total exactly like torch's scalar division), read once per epoch."""
+        zero = torch.zeros((), dtype=torch.float64, device=self.device)
+        image_diff_loss, text_diff_loss, audio_diff_loss = zero.clone(), zero.clone(), zero.clone()
         for i, batch_data in enumerate(self.handler.diffusionLoader):
             batch_u_items = batch_data[0]
             i_embs = self.model.getItemEmbs()
@@ -168,10 +172,10 @@ class Coach:
 
             batch_image_loss = self.diffusion_model.training_losses(self.image_denoise_model, batch_u_items, i_embs, image_feats)
             loss_image = batch_image_loss.mean()
-            image_diff_loss += loss_image.item()
+            image_diff_loss = image_diff_loss + loss_image.detach().double()
             batch_text_loss = self.diffusion_model.training_losses(self.text_denoise_model, batch_u_items, i_embs, text_feats)
             loss_text = batch_text_loss.mean()
-            text_diff_loss += loss_text.item()
+            text_diff_loss = text_diff_loss + loss_text.detach().double()
 
             self.image_denoise_opt.zero_grad()
             self.text_denoise_opt.zero_grad()
@@ -180,23 +184,23 @@ class Coach:
                 self.audio_denoise_opt.zero_grad()
                 batch_audio_loss = self.diffusion_model.training_losses(self.audio_denoise_model, batch_u_items, i_embs, audio_feats)
                 loss_audio = batch_audio_loss.mean()
-                audio_diff_loss += loss_audio.item()
-                total_loss = loss_image.item() + loss_text.item() + loss_audio.item()
-                batch_diff_loss = (loss_image + loss_text + loss_audio) / total_loss
-                image_diff_loss /= total_loss
-                text_diff_loss /= total_loss
-                audio_diff_loss /= total_loss
+                audio_diff_loss = audio_diff_loss + loss_audio.detach().double()
+                total_loss = loss_image.detach().double() + loss_text.detach().double() + loss_audio.detach().double()
+                batch_diff_loss = (loss_image + loss_text + loss_audio) / total_loss.to(loss_image.dtype)
+                image_diff_loss = image_diff_loss / total_loss
+                text_diff_loss = text_diff_loss / total_loss
+                audio_diff_loss = audio_diff_loss / total_loss
             else:
-                total_loss = loss_image.item() + loss_text.item()
-                batch_diff_loss = (loss_image + loss_text) / total_loss
-                image_diff_loss /= total_loss
-                text_diff_loss /= total_loss
+                total_loss = loss_image.detach().double() + loss_text.detach().double()
+                batch_diff_loss = (loss_image + loss_text) / total_loss.to(loss_image.dtype)
+                image_diff_loss = image_diff_loss / total_loss
+                text_diff_loss = text_diff_loss / total_loss
             batch_diff_loss.backward()
             self.image_denoise_opt.step()
             self.text_denoise_opt.step()
             if self.has_audio:
                 self.audio_denoise_opt.step()
-        return image_diff_loss, text_diff_loss, audio_diff_loss
+        return image_diff_loss.item(), text_diff_loss.item(), audio_diff_loss.item()
 
     def rebuildGraphs(self):
         """Phase 2 (Main.py:195-253) on device.  The shuffled loader of the reference only permutes users,
