@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
                                                              const uint16_t* __restrict__ wt_lo, int64_t ld_w,
                                                              const float* __restrict__ bias, int act, int64_t n_out,
                                                              int slices, uint16_t* __restrict__ h_hi,
-                                                             uint16_t* __restrict__ h_lo, int64_t ld_h) {
+                                                             uint16_t* __restrict__ h_lo, int64_t ld_h,
+                                                             float* __restrict__ z_f32, int64_t ld_z) {
   // one warp per (row, 256-column slice); lane l owns the 8 columns c0 .. c0+7 of the slice
   const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
   const int64_t b = indptr[u], e = indptr[u + 1];
   float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = (bias && c0 + j < n_out) ? bias[c0 + j] : 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   auto add = [&](const uint4& q) {
     const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -262,6 +263,19 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
     }
   }
   if (!col_ok) return;
+  if (z_f32) {
+    // the plain gather-sum x0 . W^T (no bias): the hidden-space chain carries it as its fp32 state
+    if (c0 + 8 <= n_out) {
+      *reinterpret_cast<float4*>(z_f32 + r * ld_z + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(z_f32 + r * ld_z + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      for (int j = 0; j < 8 && c0 + j < n_out; ++j) z_f32[r * ld_z + c0 + j] = acc[j];
+    }
+  }
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += (c0 + j < n_out) ? bias[c0 + j] : 0.f;
+  }
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -283,6 +297,45 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
     for (int j = 0; j < 8 && c0 + j < n_out; ++j) {
       h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
       if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ h = act(z + bias) -> bf16 hi (+ lo)
+// Hidden layer of the hidden-space reverse chain (rebuild.py): z is the fp32 pre-activation state [n_rows, n_cols].
+__global__ void __launch_bounds__(256) bias_act_pack_kernel(const float* __restrict__ z, int64_t ld_z,
+                                                            const float* __restrict__ bias, int64_t n_rows,
+                                                            int64_t n_cols, int act, uint16_t* __restrict__ h_hi,
+                                                            uint16_t* __restrict__ h_lo, int64_t ld_h) {
+  const int64_t n4 = (n_cols + 3) >> 2;
+  const int64_t total = n_rows * n4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / n4, c = (t - r * n4) << 2;
+    float v[4];
+    if (c + 4 <= n_cols) {
+      const float4 q = *reinterpret_cast<const float4*>(z + r * ld_z + c);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      for (int j = 0; j < 4; ++j) v[j] = c + j < n_cols ? z[r * ld_z + c + j] : 0.f;
+    }
+    uint16_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = v[j] + ((bias && c + j < n_cols) ? __ldg(bias + c + j) : 0.f);
+      if (act == 1) x = 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+      dmm_split_bf16(x, hi[j], lo[j]);
+    }
+    if (c + 4 <= n_cols) {
+      *reinterpret_cast<uint2*>(h_hi + r * ld_h + c) =
+          make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+      if (h_lo)
+        *reinterpret_cast<uint2*>(h_lo + r * ld_h + c) =
+            make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+    } else {
+      for (int j = 0; j < 4 && c + j < n_cols; ++j) {
+        h_hi[r * ld_h + c + j] = hi[j];
+        if (h_lo) h_lo[r * ld_h + c + j] = lo[j];
+      }
     }
   }
 }
@@ -398,7 +451,8 @@ extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, c
 extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
                                   int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                                   const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
-                                  uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream) {
+                                  uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z,
+                                  void* stream) {
   DMM_CHECK_ARG(ctx && indptr && indices && wt_hi && h_hi, "dmm_csr_gather_act: null argument");
   DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0 && n_out > 0, "dmm_csr_gather_act: bad shape");
   DMM_CHECK_ARG(ld_w % 8 == 0 && ld_h % 8 == 0 && ld_w >= dmm_ceil_div(n_out, 8) * 8 && ld_h >= n_out,
@@ -406,7 +460,9 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
                 (long long)ld_h);
   DMM_CHECK_ARG(act == 0 || act == 1, "dmm_csr_gather_act: unknown activation %d", act);
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  DMM_CHECK_ARG(al16(wt_hi) && al16(wt_lo) && al16(h_hi) && al16(h_lo), "dmm_csr_gather_act: buffers must be 16-byte aligned");
+  DMM_CHECK_ARG(al16(wt_hi) && al16(wt_lo) && al16(h_hi) && al16(h_lo) && al16(z_f32),
+                "dmm_csr_gather_act: buffers must be 16-byte aligned");
+  DMM_CHECK_ARG(!z_f32 || (ld_z >= n_out && ld_z % 4 == 0), "dmm_csr_gather_act: ld_z must be >= n_out and a multiple of 4");
   if (n_rows == 0) return DMM_OK;
   const int slices = (int)dmm_ceil_div(n_out, 256);
   const int64_t blocks = dmm_ceil_div(n_rows * slices * 32, 256);
@@ -414,10 +470,10 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
   const unsigned grid = (unsigned)blocks;
   if (wt_lo) {
     csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
-                                                                       wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h);
+                                                                       wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
   } else {
     csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
-                                                                        wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h);
+                                                                        wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
@@ -431,6 +487,24 @@ extern "C" int dmm_csr_axpy_bf16(dmm_ctx* ctx, const int64_t* indptr, const int3
   if (n_rows == 0) return DMM_OK;
   csr_axpy_bf16_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, indices, row_ids, row0, n_rows, n_cols, beta, x_hi, x_lo, ld_x);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_bias_act_pack(dmm_ctx* ctx, const float* z, int64_t ld_z, const float* bias, int64_t n_rows,
+                                 int64_t n_cols, int act, uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream) {
+  DMM_CHECK_ARG(ctx && z && h_hi, "dmm_bias_act_pack: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0 && ld_z >= n_cols && ld_h >= n_cols, "dmm_bias_act_pack: bad shape");
+  DMM_CHECK_ARG(ld_z % 4 == 0 && ld_h % 4 == 0, "dmm_bias_act_pack: leading dimensions must be multiples of 4");
+  DMM_CHECK_ARG(act == 0 || act == 1, "dmm_bias_act_pack: unknown activation %d", act);
+  auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+  DMM_CHECK_ARG(al(z, 16) && al(h_hi, 8) && al(h_lo, 8), "dmm_bias_act_pack: z must be 16-byte, h 8-byte aligned");
+  if (n_rows == 0) return DMM_OK;
+  const int64_t total = n_rows * ((n_cols + 3) / 4);
+  int64_t blocks = dmm_ceil_div(total, 256);
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  bias_act_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, ld_z, bias, n_rows, n_cols, act, h_hi, h_lo, ld_h);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

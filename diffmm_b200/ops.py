@@ -91,12 +91,21 @@ def time_bias(emb_w, emb_b, weight, col0, bias, t0, n_t=1, out=None):
     return out
 
 
-def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0):
-    """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo)."""
+def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0,
+                   z_f32=None):
+    """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo); z_f32 (optional)
+    receives the sums without bias."""
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows), int(n_cols),
               _p(wt_hi), _p(wt_lo), _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo),
-              _row_major(h_hi, "h_hi"), _stream())
+              _row_major(h_hi, "h_hi"), _p(z_f32), _row_major(z_f32, "z_f32") if z_f32 is not None else 0, _stream())
+
+
+def bias_act_pack(z, bias, act, h_hi, h_lo=None):
+    """h = act(z + bias) -> bf16 hi (+ lo)."""
+    n_rows, n_cols = z.shape
+    _lib.call("dmm_bias_act_pack", _ctx(z), _p(z), _row_major(z, "z"), _p(bias), int(n_rows), int(n_cols), int(act), _p(h_hi),
+              _p(h_lo), _row_major(h_hi, "h_hi"), _stream())
 
 
 def csr_axpy_bf16(indptr, indices, n_rows, n_cols, beta, x_hi, x_lo, *, row_ids=None, row0=0):

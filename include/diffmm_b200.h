@@ -76,11 +76,18 @@ int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, const float*
 /* First Denoise layer on binary CSR rows (x_t = x0 at the start of the reverse chain, Model.py:300-304):
  * h[r, :] = act(bias + sum_{c in row r} wt[c, :]), wt = W^T packed bf16 hi (+ lo) [n_cols, ld_w],
  * written as bf16 hi (+ lo) [n_rows, ld_h].  The dense contraction of Model.py:212 degenerates to a
- * gather-sum for 0/1 rows; rows are selected like in dmm_csr_rows_to_dense.                   */
+ * gather-sum for 0/1 rows; rows are selected like in dmm_csr_rows_to_dense.  z_f32 (optional,
+ * [n_rows, ld_z]) receives the plain sums x0 . W^T without bias: the fp32 state of the hidden-space
+ * reverse chain.                                                                              */
 int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
                        int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                        const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
-                       uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream);
+                       uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z, void* stream);
+
+/* h = act(z + bias) packed to bf16 hi (+ lo): the hidden layer tanh(z_t + b1'(t)) of the hidden-space
+ * reverse chain, where z_t = x_t W1^T is carried in fp32 (Model.py:212-213 applied to the chain's state). */
+int dmm_bias_act_pack(dmm_ctx* ctx, const float* z, int64_t ld_z, const float* bias, int64_t n_rows,
+                      int64_t n_cols, int act, uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, void* stream);
 
 /* x[r, c] += beta for every CSR entry (r, c) of the selected rows, x given as bf16 hi (+ lo):
  * the c2 * x0 term of the posterior mean (Model.py:375) for binary x0.                        */
