@@ -24,7 +24,7 @@ class GemmEpilogue(C.Structure):
         ("out_f32", c_vp), ("ld_out", c_i64),
         ("out_hi", c_vp), ("out_lo", c_vp), ("ld_out16", c_i64),
         ("res_hi", c_vp), ("res_lo", c_vp), ("ld_res16", c_i64),
-        ("res_pre_act", c_i32),
+        ("res_pre_act", c_i32), ("post_act", c_i32), ("post_bias", c_vp),
     ]
 
 

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256) gemm_f32_tn_kernel(const float* __restric
       }
       if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ld_out + n] = v;
       if (ep.out_hi) {
+        if (ep.post_bias) v += ep.post_bias[n];
+        if (ep.post_act == 1) v = tanhf(v);
         uint16_t h, l;
         dmm_split_bf16(v, h, l);
         ep.out_hi[(int64_t)m * ep.ld_out16 + n] = h;

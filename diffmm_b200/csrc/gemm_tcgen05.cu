@@ -395,6 +395,28 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
       __syncwarp();
     }
     if (ep.out_hi) {
+      if (ep.post_bias != nullptr || ep.post_act != 0) {
+        // second stage on the bf16 output only: out_hi/lo = post_act(v + post_bias) while out_f32 keeps v
+        // (hidden-space chain: z_t goes to out_f32, h_{t-1} = tanh(z_t + b1'(t-1)) to the next operand)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.post_bias) {
+            if (INTERIOR || n0 + 4 * q + 4 <= p.N) {
+              t = __ldg(reinterpret_cast<const float4*>(ep.post_bias + n0) + q);
+            } else {
+              if (n0 + 4 * q + 0 < p.N) t.x = __ldg(ep.post_bias + n0 + 4 * q + 0);
+              if (n0 + 4 * q + 1 < p.N) t.y = __ldg(ep.post_bias + n0 + 4 * q + 1);
+              if (n0 + 4 * q + 2 < p.N) t.z = __ldg(ep.post_bias + n0 + 4 * q + 2);
+            }
+          }
+          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
+        if (ep.post_act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t hi[4], lo[4];
@@ -730,6 +752,9 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   DMM_CHECK_ARG(!ep->out_hi || (ep->ld_out16 >= N && ep->ld_out16 % 8 == 0), "dmm_gemm_bf16_tn: ld_out16 must be >= N and %%8");
   DMM_CHECK_ARG(!ep->out_lo || ep->out_hi, "dmm_gemm_bf16_tn: out_lo requires out_hi");
   DMM_CHECK_ARG(ep->act == 0 || ep->act == 1, "dmm_gemm_bf16_tn: unknown activation %d", ep->act);
+  DMM_CHECK_ARG(ep->post_act == 0 || ep->post_act == 1, "dmm_gemm_bf16_tn: unknown post activation %d", ep->post_act);
+  DMM_CHECK_ARG((!ep->post_bias && !ep->post_act) || ep->out_hi, "dmm_gemm_bf16_tn: the post stage applies to out_hi/out_lo");
+  DMM_CHECK_ARG(al16(ep->post_bias), "dmm_gemm_bf16_tn: post_bias must be 16-byte aligned");
 
   GemmParams p;
   p.M = (int)M;

@@ -124,9 +124,12 @@ def q_sample(x0, noise, coef_a, coef_b, mode, *, x_t=None, a_hi=None, a_lo=None)
 
 
 # ----------------------------------------------------------------------------------------- GEMM
-def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi=None, res_lo=None, res_pre_act=False):
+def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi=None, res_lo=None, res_pre_act=False,
+              post_bias=None, post_act=0):
     ep = GemmEpilogue()
     ep.res_pre_act = int(bool(res_pre_act))
+    ep.post_act = int(post_act)
+    ep.post_bias = post_bias.data_ptr() if post_bias is not None else None
     ep.res_hi = res_hi.data_ptr() if res_hi is not None else None
     ep.res_lo = res_lo.data_ptr() if res_lo is not None else None
     ep.ld_res16 = _row_major(res_hi, "res_hi") if res_hi is not None else 0
@@ -145,18 +148,21 @@ def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi=
 
 
 def gemm_bf16_tn(a_hi, a_lo, b_hi, b_lo, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None,
-                 out_f32=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, res_pre_act=False):
+                 out_f32=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, res_pre_act=False,
+                 post_bias=None, post_act=0):
     """C[M,N] = epi(A[M,K] . B[N,K]^T) on tcgen05; lo operands add the split-bf16 correction passes.
     The residual of the epilogue (alpha * v + beta * R) is fp32 (`residual`) or bf16 hi(+lo) (`res_hi/res_lo`);
-    with res_pre_act it is a partial sum of the same contraction and enters before the activation."""
-    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi, res_lo, res_pre_act)
+    with res_pre_act it is a partial sum of the same contraction and enters before the activation.
+    post_bias / post_act: the bf16 output gets post_act(v + post_bias) while out_f32 keeps v."""
+    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi, res_lo, res_pre_act, post_bias,
+                   post_act)
     _lib.call("dmm_gemm_bf16_tn", _ctx(a_hi), _p(a_hi), _p(a_lo), _row_major(a_hi, "a_hi"), _p(b_hi), _p(b_lo),
               _row_major(b_hi, "b_hi"), int(M), int(N), int(K), C.byref(ep), _stream())
 
 
 def gemm_f32_tn(a, b, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None, out_f32=None,
-                out_hi=None, out_lo=None, res_pre_act=False):
-    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, None, None, res_pre_act)
+                out_hi=None, out_lo=None, res_pre_act=False, post_bias=None, post_act=0):
+    ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, None, None, res_pre_act, post_bias, post_act)
     _lib.call("dmm_gemm_f32_tn", _ctx(a), _p(a), _row_major(a, "a"), _p(b), _row_major(b, "b"), int(M), int(N), int(K),
               C.byref(ep), _stream())
 

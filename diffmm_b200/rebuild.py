@@ -44,6 +44,7 @@ class ChainWorkspace:
         self._a = None            # bf16 operand copy of x_t [rows, ld_a] (+ lo): only the dense-input / full-chain paths
         self.h_hi = torch.empty((rows, self.ld_h), **bf)
         self.h_lo = torch.empty((rows, self.ld_h), **bf) if split else None
+        self._h2 = None           # second hidden operand (the hidden-space chain ping-pongs: a step reads h_t, writes h_{t-1})
         self.x = torch.empty((rows, self.ld_x), dtype=torch.float32, device=device)
         self.z = None             # fp32 hidden pre-activation state [rows, pad4(hidden)] of the hidden-space chain
         self.bias_eff = None      # [S, hidden] fp32, sized on first use
@@ -55,6 +56,13 @@ class ChainWorkspace:
             self._a = (torch.empty((self.rows, self.ld_a), **bf),
                        torch.empty((self.rows, self.ld_a), **bf) if self.split else None)
         return self._a
+
+    def hidden2(self):
+        if self._h2 is None:
+            bf = dict(dtype=torch.bfloat16, device=self.device)
+            self._h2 = (torch.empty((self.rows, self.ld_h), **bf),
+                        torch.empty((self.rows, self.ld_h), **bf) if self.split else None)
+        return self._h2
 
     def state(self):
         if self.z is None:
@@ -166,12 +174,16 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
         _fill_operand(diff, ws, M, I, a_hi, a_lo, x_dense, csr, row_ids, row0, sampling_step, split, noise, dev)
         ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, M, H, I, out_f32=z)
         ops.bias_act_pack(z, ws.bias_eff[S - 1], 1, h_hi, h_lo)
+    g_hi, g_lo = ws.hidden2()
+    g_hi, g_lo = g_hi[:M], (g_lo[:M] if split else None)
     for i in range(S - 1, 0, -1):
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
         c2 = float(np.float32(diff._h_coef2[i]))
-        # z_i = c1 (h_i P^T + q) + c2 z_{i+1}   (fp32 state, in place), then h_{i-1} = tanh(z_i + b1'(i-1))
-        ops.gemm_bf16_tn(h_hi, h_lo, p_hi, p_lo, M, H, H, bias=q, alpha=c1, beta=c2, residual=z, out_f32=z)
-        ops.bias_act_pack(z, ws.bias_eff[i - 1], 1, h_hi, h_lo)
+        # z_i = c1 (h_i P^T + q) + c2 z_{i+1} (fp32 state, in place) and, in the same epilogue,
+        # h_{i-1} = tanh(z_i + b1'(i-1)) into the OTHER operand buffer (other CTAs still read h_i)
+        ops.gemm_bf16_tn(h_hi, h_lo, p_hi, p_lo, M, H, H, bias=q, alpha=c1, beta=c2, residual=z, out_f32=z,
+                         out_hi=g_hi, out_lo=g_lo, post_bias=ws.bias_eff[i - 1], post_act=1)
+        h_hi, h_lo, g_hi, g_lo = g_hi, g_lo, h_hi, h_lo
     c1 = float(np.float32(diff._h_coef1[0]))
     ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, out_f32=xv)
     return xv

@@ -125,6 +125,8 @@ typedef struct dmm_gemm_epilogue {
   int64_t ld_res16;       /* written, by the same thread                                      */
   int32_t res_pre_act;    /* != 0: v = alpha * act(acc + bias + beta * R) — the residual is a partial  */
                           /* sum of the same contraction (K processed in chunks), added before act    */
+  int32_t post_act;       /* second stage on the bf16 output only: out_hi/lo = post_act(v + post_bias) */
+  const float* post_bias; /* while out_f32 keeps v (hidden-space chain: z_t and h_{t-1} in one pass)    */
 } dmm_gemm_epilogue;
 
 int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
