@@ -51,9 +51,11 @@ def packed_weight(w: torch.Tensor, transpose: bool, split: bool):
         ent = (weakref.ref(w), w._version, {})
         _PACK_CACHE[id(w)] = ent
     packs = ent[2]
-    if transpose not in packs:
-        packs[transpose] = pack_any(w.detach(), transpose, True)
-    hi, lo = packs[transpose]
+    have = packs.get(transpose)
+    if have is None or (split and have[1] is None):
+        # the lo part is only built when a caller asks for it (bf16 mode never does: a third less traffic)
+        packs[transpose] = have = pack_any(w.detach(), transpose, split)
+    hi, lo = have
     return hi, (lo if split else None)
 
 

@@ -301,6 +301,20 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
   }
 }
 
+// ------------------------------------------------------------------ y = W[:, :K] x  (fp32, one warp per row)
+// q = W1x b2 of the hidden-space chain: a 1024 x 7050 matrix-vector product is a bandwidth problem, not a GEMM.
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ w, int64_t ld_w, int64_t n_rows,
+                                                        int64_t K, const float* __restrict__ x, float* __restrict__ y) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const float* row = w + r * ld_w;
+  float acc = 0.f;
+  for (int64_t k = lane; k < K; k += 32) acc = fmaf(__ldg(row + k), __ldg(x + k), acc);
+  acc = dmm_warp_sum(acc);
+  if (lane == 0) y[r] = acc;
+}
+
 // ------------------------------------------------------------------ h = act(z + bias) -> bf16 hi (+ lo)
 // Hidden layer of the hidden-space reverse chain (rebuild.py): z is the fp32 pre-activation state [n_rows, n_cols].
 __global__ void __launch_bounds__(256) bias_act_pack_kernel(const float* __restrict__ z, int64_t ld_z,
@@ -505,6 +519,15 @@ extern "C" int dmm_bias_act_pack(dmm_ctx* ctx, const float* z, int64_t ld_z, con
   const int64_t cap = (int64_t)ctx->num_sms * 16;
   if (blocks > cap) blocks = cap;
   bias_act_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, ld_z, bias, n_rows, n_cols, act, h_hi, h_lo, ld_h);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_gemv_f32(dmm_ctx* ctx, const float* w, int64_t ld_w, int64_t n_rows, int64_t K, const float* x,
+                            float* y, void* stream) {
+  DMM_CHECK_ARG(ctx && w && x && y, "dmm_gemv_f32: null argument");
+  DMM_CHECK_ARG(n_rows > 0 && K > 0 && ld_w >= K, "dmm_gemv_f32: bad shape");
+  gemv_rows_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(w, ld_w, n_rows, K, x, y);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

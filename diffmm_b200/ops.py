@@ -101,6 +101,15 @@ def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_o
               _row_major(h_hi, "h_hi"), _p(z_f32), _row_major(z_f32, "z_f32") if z_f32 is not None else 0, _stream())
 
 
+def gemv_f32(w, K, x, out=None):
+    """y = w[:, :K] @ x (fp32)."""
+    n_rows = w.shape[0]
+    if out is None:
+        out = torch.empty(n_rows, dtype=torch.float32, device=w.device)
+    _lib.call("dmm_gemv_f32", _ctx(w), _p(w), _row_major(w, "w"), int(n_rows), int(K), _p(x), _p(out), _stream())
+    return out
+
+
 def bias_act_pack(z, bias, act, h_hi, h_lo=None):
     """h = act(z + bias) -> bf16 hi (+ lo)."""
     n_rows, n_cols = z.shape

@@ -89,21 +89,21 @@ def chain_mode() -> str:
 
 
 def _hidden_operators(den, W1, W2, b2, I, split):
-    """P = W1[:, :I] W2 (H x H) and q = W1[:, :I] b2 (H) of the hidden-space chain, cached per weight version.
-    Both are formed with the three-pass split-bf16 contraction (fp32-faithful): they multiply every step."""
-    key = (W1._version, W2._version, b2._version, W1.data_ptr(), W2.data_ptr())
+    """P = W1[:, :I] W2 (H x H) and q = W1[:, :I] b2 (H) of the hidden-space chain, cached per weight version and
+    precision.  P is one tensor-pipe contraction over the items (three-pass split-bf16, i.e. fp32-faithful, in
+    bf16x3 mode; single pass in bf16 mode, where it is then rounded to bf16 like every other operand); q is an
+    fp32 matrix-vector product on the master weights."""
+    key = (W1._version, W2._version, b2._version, W1.data_ptr(), W2.data_ptr(), split)
     ent = getattr(den, "_dmm_hidden_ops", None)
     if ent is None or ent[0] != key:
         H = W1.shape[0]
-        w1_hi, w1_lo = packed_weight(W1, False, True)            # [H, pad(I + d)], K-major over items
-        w2t_hi, w2t_lo = packed_weight(W2, True, True)           # W2^T [H, pad(I)],  K-major over items
+        w1_hi, w1_lo = packed_weight(W1, False, split)           # [H, pad(I + d)], K-major over items
+        w2t_hi, w2t_lo = packed_weight(W2, True, split)          # W2^T [H, pad(I)],  K-major over items
         P = torch.empty((H, ops.pad_to(H, 4)), dtype=torch.float32, device=W1.device)[:, :H]
         ops.gemm_bf16_tn(w1_hi, w1_lo, w2t_hi, w2t_lo, H, H, I, out_f32=P)
-        b2_hi, b2_lo = ops.pack_bf16(b2.detach().reshape(1, -1), split=True)
-        q = torch.empty((1, ops.pad_to(H, 4)), dtype=torch.float32, device=W1.device)[:, :H]
-        ops.gemm_bf16_tn(b2_hi, b2_lo, w1_hi, w1_lo, 1, H, I, out_f32=q)
-        p_hi, p_lo = ops.pack_bf16(P, split=True)
-        ent = (key, p_hi, p_lo, q.reshape(-1).contiguous())
+        q = ops.gemv_f32(W1.detach(), I, b2.detach())
+        p_hi, p_lo = ops.pack_bf16(P, split=split)
+        ent = (key, p_hi, p_lo, q)
         den._dmm_hidden_ops = ent
     return ent[1], (ent[2] if split else None), ent[3]
 

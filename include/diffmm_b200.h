@@ -84,6 +84,11 @@ int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indic
                        const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
                        uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z, void* stream);
 
+/* y[r] = sum_k w[r, k] x[k], k < K (fp32): q = W1[:, :I] b2 of the hidden-space reverse chain (the image of
+ * the second layer's bias, Model.py:215, under the first layer, Model.py:212).                          */
+int dmm_gemv_f32(dmm_ctx* ctx, const float* w, int64_t ld_w, int64_t n_rows, int64_t K, const float* x,
+                 float* y, void* stream);
+
 /* h = act(z + bias) packed to bf16 hi (+ lo): the hidden layer tanh(z_t + b1'(t)) of the hidden-space
  * reverse chain, where z_t = x_t W1^T is carried in fp32 (Model.py:212-213 applied to the chain's state). */
 int dmm_bias_act_pack(dmm_ctx* ctx, const float* z, int64_t ld_z, const float* bias, int64_t n_rows,

@@ -121,6 +121,29 @@ def test_generate_view(precision):
     assert gd.p_sample.__func__ is gd.generate_view.__func__
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_hidden_space_chain_equals_literal_chain(precision):
+    """The hidden-space chain (z_t = x_t W1x^T carried in fp32, P = W1x W2) is the same function as the literal chain
+    of Model.py:300-322; both are checked against the golden view, and against each other on CSR and dense inputs
+    and with a q_sample'd start (sampling_step = 2)."""
+    from diffmm_b200.Model import GaussianDiffusion
+    from diffmm_b200.rebuild import denoise_chain
+    g = load_golden("generate_view")
+    cfg = make_cfg(precision)
+    den = make_denoise(cfg, params_of(load_golden("training_losses")))
+    gd = GaussianDiffusion(cfg).to(DEV)
+    csr = (T(g["indptr"]), T(g["indices"], torch.int32))
+    tol = TOL[precision]
+    for kw in (dict(csr=csr, row0=0, n_rows=U), dict(x_dense=T(g["x0"])),
+               dict(x_dense=T(g["x0"]), sampling_step=2, noise=T(g["randn"]))):
+        hid = denoise_chain(gd, den, mode="hidden", **kw).clone()
+        full = denoise_chain(gd, den, mode="full", **kw).clone()
+        want = g["view2"] if kw.get("sampling_step") else g["view0"]
+        close(hid, want, tol, "hidden vs golden")
+        close(full, want, tol, "full vs golden")
+        close(hid, full.cpu().numpy(), tol, "hidden vs full")
+
+
 @pytest.mark.parametrize("tag,mods", [("3", ["image", "text", "audio"]), ("2", ["image", "text"])])
 def test_gcn_mm_value_and_grads(tag, mods):
     from diffmm_b200.DataHandler import DataHandler
