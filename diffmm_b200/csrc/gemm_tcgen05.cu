@@ -202,6 +202,18 @@ struct WorkItem {
 };
 // n fastest: the CTAs running together cover every column block of a few row blocks, so each A tile is
 // fetched from HBM once and re-read from L2 by its neighbours
+// MUFU.TANH (max abs error ~5e-4): used where the result is rounded to bf16 anyway (rounding error 2e-3),
+// i.e. by the bf16-only instantiation; the split-bf16 (fp32-faithful) one keeps fast_tanh
+__device__ __forceinline__ float approx_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool X3>
+__device__ __forceinline__ float epi_tanh(float x) {
+  return X3 ? fast_tanh(x) : approx_tanh(x);
+}
+
 template <int BN>
 __device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
   WorkItem it;
@@ -258,8 +270,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
     const int n0 = wi.col0 + c * 32;
     return (ep.bias && chunk_ok(c) && (INTERIOR || n0 + lane < p.N)) ? __ldg(ep.bias + n0 + lane) : 0.f;
   };
-  // coalesced fetch of chunk c's raw bf16 residual (a 16-byte piece that starts below N always lies inside the
-  // padded row because the leading dimension is a multiple of 8)
+  // coalesced fetch of chunk c's raw residual, bf16 hi (+ lo) or fp32 (a 16-byte piece that starts below N always
+  // lies inside the padded row because the leading dimension is a multiple of 8 / 4 elements)
   auto fetch = [&](int c) {
     const int n0 = wi.col0 + c * 32;
     if (res16) {
@@ -271,6 +283,18 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
           nh[i] = *reinterpret_cast<const uint4*>(ep.res_hi + off + (int64_t)(8 * i) * ep.ld_res16);
           if (res16lo) nl[i] = *reinterpret_cast<const uint4*>(ep.res_lo + off + (int64_t)(8 * i) * ep.ld_res16);
         }
+      }
+    } else if (ep.residual) {
+      // fp32 residual (the z state of the hidden-space chain): the same 8 x 16 bytes per thread, coalesced view
+      // (rows cr32 + 4 i, piece cp32); a piece that starts below N lies inside the padded row (ld_res % 4 == 0)
+      const int col = n0 + 4 * cp32;
+      const float* base = ep.residual + (int64_t)(rbase + cr32) * ep.ld_res + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (INTERIOR || (rbase + cr32 + 4 * i < p.M && col < p.N))
+          t = *reinterpret_cast<const uint4*>(base + (int64_t)(4 * i) * ep.ld_res);
+        if (i < 4) nh[i] = t; else nl[i - 4] = t;
       }
     }
   };
@@ -293,12 +317,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
       }
     } else if (ep.residual) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rbase + cr32 + 4 * i, col = n0 + 4 * cp32;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (INTERIOR || (r < p.M && col < p.N)) t = *reinterpret_cast<const float4*>(ep.residual + (int64_t)r * ep.ld_res + col);
-        *reinterpret_cast<float4*>(at32(cr32 + 4 * i, cp32)) = t;
-      }
+      for (int i = 0; i < 8; ++i) *at32(cr32 + 4 * i, cp32) = i < 4 ? nh[i] : nl[i - 4];
     }
     // next chunk's residual / bias: in flight while this chunk is combined and stored (it may alias only the
     // output of the NEXT chunk, which this warp writes later)
@@ -414,7 +433,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
         }
         if (ep.post_act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = epi_tanh<X3>(v[j]);
         }
       }
 #pragma unroll

@@ -6,43 +6,62 @@
 namespace {
 
 // ------------------------------------------------------------------ fp32 -> bf16 hi/lo (no transpose)
+// one thread per 8 destination columns: two float4 loads, one 16-byte store per part (zero pad beyond cols);
+// VEC = false is the scalar-load variant for sources whose rows are not 16-byte aligned
+template <bool VEC>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
                                                         int64_t ld_src, uint16_t* __restrict__ hi,
                                                         uint16_t* __restrict__ lo, int64_t ld_dst) {
-  // one block row-slab: blockIdx.y = row, threads stride over ld_dst (zero pad beyond cols)
-  const int64_t r = blockIdx.y;
-  if (r >= rows) return;
-  const float* s = src + r * ld_src;
-  uint16_t* h = hi + r * ld_dst;
-  uint16_t* l = lo ? lo + r * ld_dst : nullptr;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ld_dst; c += (int64_t)gridDim.x * blockDim.x) {
-    uint16_t vh = 0, vl = 0;
-    if (c < cols) dmm_split_bf16(__ldg(s + c), vh, vl);
-    h[c] = vh;
-    if (l) l[c] = vl;
+  const int64_t n8 = ld_dst >> 3;                      // ld_dst % 8 == 0 (checked by the host)
+  const int64_t total = rows * n8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / n8, c = (t - r * n8) << 3;
+    const float* s = src + r * ld_src + c;
+    float v[8];
+    if (VEC && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b4 = __ldg(reinterpret_cast<const float4*>(s) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c + j < cols ? __ldg(s + j) : 0.f;
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint16_t h0, l0, h1, l1;
+      dmm_split_bf16(v[2 * j], h0, l0);
+      dmm_split_bf16(v[2 * j + 1], h1, l1);
+      ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ld_dst + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * ld_dst + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
-// ------------------------------------------------------------------ fp32 -> bf16 hi/lo, transposed (32x32 smem tile)
+// ------------------------------------------------------------------ fp32 -> bf16 hi/lo, transposed
+// 64 source rows x 32 source columns per CTA through shared memory: 128-byte coalesced fp32 reads, and every
+// thread writes two consecutive destination columns (two source rows) as one 4-byte store: 128-byte lines out
 __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
                                                              int64_t ld_src, uint16_t* __restrict__ hi,
                                                              uint16_t* __restrict__ lo, int64_t ld_dst) {
-  __shared__ float tile[32][33];
-  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  __shared__ float tile[64][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int64_t r = r0 + i, c = c0 + tx;
     tile[i][tx] = (r < rows && c < cols) ? __ldg(src + r * ld_src + c) : 0.f;
   }
   __syncthreads();
-  // dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst
+  // dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst (even)
   for (int i = ty; i < 32; i += 8) {
-    const int64_t c = c0 + i, r = r0 + tx;
+    const int64_t c = c0 + i, r = r0 + 2 * tx;
     if (c < cols && r < ld_dst) {
-      uint16_t vh, vl;
-      dmm_split_bf16(tile[tx][i], vh, vl);
-      hi[c * ld_dst + r] = vh;
-      if (lo) lo[c * ld_dst + r] = vl;
+      uint16_t h0, l0, h1, l1;
+      dmm_split_bf16(tile[2 * tx][i], h0, l0);
+      dmm_split_bf16(tile[2 * tx + 1][i], h1, l1);
+      *reinterpret_cast<uint32_t*>(hi + c * ld_dst + r) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      if (lo) *reinterpret_cast<uint32_t*>(lo + c * ld_dst + r) = (uint32_t)l0 | ((uint32_t)l1 << 16);
     }
   }
 }
@@ -303,16 +322,34 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
 
 // ------------------------------------------------------------------ y = W[:, :K] x  (fp32, one warp per row)
 // q = W1x b2 of the hidden-space chain: a 1024 x 7050 matrix-vector product is a bandwidth problem, not a GEMM.
-__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ w, int64_t ld_w, int64_t n_rows,
+__global__ void __launch_bounds__(128) gemv_rows_kernel(const float* __restrict__ w, int64_t ld_w, int64_t n_rows,
                                                         int64_t K, const float* __restrict__ x, float* __restrict__ y) {
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= n_rows) return;
+  // one CTA (4 warps) per row: enough loads in flight to stream the matrix at HBM speed
+  __shared__ float red[4];
+  const int64_t r = blockIdx.x;
+  const int tid = threadIdx.x;
   const float* row = w + r * ld_w;
   float acc = 0.f;
-  for (int64_t k = lane; k < K; k += 32) acc = fmaf(__ldg(row + k), __ldg(x + k), acc);
+  if (((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
+    const int64_t k4 = K >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll 4
+    for (int64_t k = tid; k < k4; k += 128) {
+      const float4 a = __ldg(row4 + k), b = __ldg(x4 + k);
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
+    for (int64_t k = (k4 << 2) + tid; k < K; k += 128) acc = fmaf(__ldg(row + k), __ldg(x + k), acc);
+  } else {
+    for (int64_t k = tid; k < K; k += 128) acc = fmaf(__ldg(row + k), __ldg(x + k), acc);
+  }
   acc = dmm_warp_sum(acc);
-  if (lane == 0) y[r] = acc;
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) y[r] = (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 // ------------------------------------------------------------------ h = act(z + bias) -> bf16 hi (+ lo)
@@ -387,20 +424,24 @@ extern "C" int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64
                              uint16_t* dst_hi, uint16_t* dst_lo, int64_t ld_dst, int transpose, void* stream) {
   DMM_CHECK_ARG(ctx && src && dst_hi, "dmm_pack_bf16: null argument");
   DMM_CHECK_ARG(rows > 0 && cols > 0 && ld_src >= cols, "dmm_pack_bf16: bad shape");
+  DMM_CHECK_ARG(ld_dst % 8 == 0, "dmm_pack_bf16: ld_dst must be a multiple of 8 (got %lld)", (long long)ld_dst);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(dst_hi) && al16(dst_lo), "dmm_pack_bf16: destinations must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (!transpose) {
     DMM_CHECK_ARG(ld_dst >= cols, "dmm_pack_bf16: ld_dst < cols");
-    DMM_CHECK_ARG(rows < 65536LL * 32768LL, "dmm_pack_bf16: too many rows");
-    // grid.y is limited to 65535: fold rows into chunks
-    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-      const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-      dim3 grid((unsigned)(dmm_ceil_div(ld_dst, 256) < 64 ? dmm_ceil_div(ld_dst, 256) : 64), (unsigned)nr);
-      pack_rows_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, nr, cols, ld_src, dst_hi + r0 * ld_dst,
-                                             dst_lo ? dst_lo + r0 * ld_dst : nullptr, ld_dst);
+    const int64_t total = rows * (ld_dst / 8);
+    int64_t blocks = dmm_ceil_div(total, 256);
+    const int64_t cap = (int64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (al16(src) && ld_src % 4 == 0) {
+      pack_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+    } else {
+      pack_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
     }
   } else {
     DMM_CHECK_ARG(ld_dst >= rows, "dmm_pack_bf16: ld_dst < rows (transposed)");
-    const int64_t gy = dmm_ceil_div(ld_dst, 32);
+    const int64_t gy = dmm_ceil_div(ld_dst, 64);
     DMM_CHECK_ARG(gy < 65536, "dmm_pack_bf16: too many rows for the transposed path");
     dim3 grid((unsigned)dmm_ceil_div(cols, 32), (unsigned)gy);
     pack_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
@@ -527,7 +568,8 @@ extern "C" int dmm_gemv_f32(dmm_ctx* ctx, const float* w, int64_t ld_w, int64_t 
                             float* y, void* stream) {
   DMM_CHECK_ARG(ctx && w && x && y, "dmm_gemv_f32: null argument");
   DMM_CHECK_ARG(n_rows > 0 && K > 0 && ld_w >= K, "dmm_gemv_f32: bad shape");
-  gemv_rows_kernel<<<(unsigned)dmm_ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(w, ld_w, n_rows, K, x, y);
+  DMM_CHECK_ARG(n_rows < (1LL << 31), "dmm_gemv_f32: too many rows");
+  gemv_rows_kernel<<<(unsigned)n_rows, 128, 0, (cudaStream_t)stream>>>(w, ld_w, n_rows, K, x, y);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
