@@ -266,9 +266,14 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
 
   uint4 nh[4], nl[4];
   float nb = 0.f, nb2 = 0.f;   // bias of the chunk being drained next / of the one after it (two chunks of lead)
+  float npb = 0.f, npb2 = 0.f; // same for the post-stage bias
   auto fetch_bias = [&](int c) -> float {
     const int n0 = wi.col0 + c * 32;
     return (ep.bias && chunk_ok(c) && (INTERIOR || n0 + lane < p.N)) ? __ldg(ep.bias + n0 + lane) : 0.f;
+  };
+  auto fetch_post_bias = [&](int c) -> float {
+    const int n0 = wi.col0 + c * 32;
+    return (ep.post_bias && chunk_ok(c) && (INTERIOR || n0 + lane < p.N)) ? __ldg(ep.post_bias + n0 + lane) : 0.f;
   };
   // coalesced fetch of chunk c's raw residual, bf16 hi (+ lo) or fp32 (a 16-byte piece that starts below N always
   // lies inside the padded row because the leading dimension is a multiple of 8 / 4 elements)
@@ -301,6 +306,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
   if (chunk_ok(chalf)) fetch(chalf);
   nb = fetch_bias(chalf);
   nb2 = fetch_bias(chalf + EPI_WARPS / 4);
+  npb = fetch_post_bias(chalf);
+  npb2 = fetch_post_bias(chalf + EPI_WARPS / 4);
   mbar_wait(tfull, tphase, 4);
   tcgen05_fence_after();
 
@@ -324,6 +331,9 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
     if (chunk_ok(c + EPI_WARPS / 4)) fetch(c + EPI_WARPS / 4);
     nb = nb2;                                    // staged above; rotate the two-deep bias prefetch
     nb2 = fetch_bias(c + 2 * (EPI_WARPS / 4));
+    const float pb_now = npb;
+    npb = npb2;
+    npb2 = fetch_post_bias(c + 2 * (EPI_WARPS / 4));
     // ---- accumulator chunk
     uint32_t r[32];
     __syncwarp();  // tcgen05.ld is .sync.aligned; also publishes the staging tile to the row view
@@ -416,20 +426,16 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
     if (ep.out_hi) {
       if (ep.post_bias != nullptr || ep.post_act != 0) {
         // second stage on the bf16 output only: out_hi/lo = post_act(v + post_bias) while out_f32 keeps v
-        // (hidden-space chain: z_t goes to out_f32, h_{t-1} = tanh(z_t + b1'(t-1)) to the next operand)
+        // (hidden-space chain: z_t goes to out_f32, h_{t-1} = tanh(z_t + b1'(t-1)) to the next operand).
+        // The prefetched post bias is broadcast through the (already consumed) bias slot of the staging tile.
+        if (ep.post_bias) {
+          stg_bias[lane] = pb_now;
+          __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.post_bias) {
-            if (INTERIOR || n0 + 4 * q + 4 <= p.N) {
-              t = __ldg(reinterpret_cast<const float4*>(ep.post_bias + n0) + q);
-            } else {
-              if (n0 + 4 * q + 0 < p.N) t.x = __ldg(ep.post_bias + n0 + 4 * q + 0);
-              if (n0 + 4 * q + 1 < p.N) t.y = __ldg(ep.post_bias + n0 + 4 * q + 1);
-              if (n0 + 4 * q + 2 < p.N) t.z = __ldg(ep.post_bias + n0 + 4 * q + 2);
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(stg_bias + 4 * q);
+            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
           }
-          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
         }
         if (ep.post_act == 1) {
 #pragma unroll
