@@ -26,6 +26,10 @@ constexpr int EPI_WARP0 = 3;   // warps 0-2: TMA producer, MMA issuer, TMEM allo
 constexpr int EPI_WARPS = 8;   // any 8 consecutive warps cover each TMEM lane quarter (warp % 4) twice
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int EPI_STAGE_BYTES = 4096 + 128;  // per epilogue warp: one 32 x 32 fp32 chunk (or bf16 hi + lo chunks) + 32 bias values
+constexpr int MAX_STAGES = 8;
+constexpr int BAR_BYTES = 512;    // full[8], empty[8], tmem_full[2], tmem_empty[2], tmem_ptr, residual barriers [EPI_WARPS][3]
+constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory of sm_100
+constexpr int TEPI_MAX_BUF = 3;   // fp32 chunk buffers per epilogue warp of the TMA epilogue (residual ring)
 
 // PAIR: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 tile of 256 rows x BN columns; each CTA
 // stages its own 128 rows of A and HALF of the B rows, so a pipeline stage is 32 KB instead of 48 KB (6 stages
@@ -39,9 +43,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = STAGE_BYTES >= 49152 ? 4 : (STAGE_BYTES >= 32768 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // + alignment slack
-  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "exceeds the 227 KB opt-in shared memory of sm_100");
+  static_assert(STAGES <= MAX_STAGES, "barrier block holds MAX_STAGES ring barriers");
 };
 
 struct GemmParams {
@@ -54,6 +58,12 @@ struct GemmParams {
   int n_pass;
   int pass_a[3];  // 0 = hi, 1 = lo
   int pass_b[3];
+  // shared-memory layout (byte offsets from the 1024-aligned base), chosen per launch:
+  //   [0, stages * STAGE_BYTES) operand ring | off_epi: epilogue staging | off_bar: barriers (BAR_BYTES)
+  // TMA epilogue: off_epi holds EPI_WARPS x nbuf fp32 chunk buffers (4 KB, SWIZZLE_128B boxes), then at off_b16
+  // EPI_WARPS bf16 chunk buffers (2 KB, SWIZZLE_64B boxes), then at off_bias EPI_WARPS x 256 B of bias slots
+  int stages, nbuf;
+  int off_epi, off_b16, off_bias, off_bar;
   dmm_gemm_epilogue ep;
 };
 
@@ -100,6 +110,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Epilogue-side TMA: a 32-row x 32-column box between a swizzled shared-memory chunk buffer and global memory.
+// Stores go through bulk async-groups of the issuing thread (one lane per epilogue warp); boxes are clipped at the
+// tensor bounds (loads zero-fill), so ragged M / N tails need no predicates.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA store reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // cta_group::2 flavours.  `bar` is the shared::cluster address of the LEADER CTA's barrier (mapa_shared).
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -489,36 +515,274 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
   }
 }
 
-template <int BN, bool X3, bool PAIR>
+// ------------------------------------------------------------------------------------------ TMA epilogue
+// Whole epilogue loop of one warp (TMEM lane quarter `warp & 3`, chunk parity (warp - EPI_WARP0) / 4) for the
+// single-pass bf16 outputs (no lo parts, no bf16 residual): every global access of the epilogue is a TMA box.
+//   * fp32 residual (the z state of the hidden-space chain, or the partial sums of a K-chunked contraction): a ring of
+//     `nbuf` swizzled 32 x 32 chunk buffers per warp, filled by cp.async.bulk.tensor loads that run up to nbuf - 1
+//     chunks AHEAD of the consumer and across work items, so a chunk's DRAM latency is hidden behind the chunks before
+//     it instead of being paid inside the warp's dependent chain;
+//   * results are written back IN PLACE into the chunk buffer (row view, same thread) and leave through one
+//     cp.async.bulk.tensor store per chunk (fp32) plus one for the bf16 operand copy; the buffer is reloaded once the
+//     store has read it (bulk async-group of the issuing lane);
+//   * boxes are clipped at the tensor bounds by the TMA unit: no interior / boundary instantiations.
+// Row view <-> box layout: fp32 chunk rows are 128 B with the 16-byte piece index XOR (row & 7) (SWIZZLE_128B), bf16
+// chunk rows are 64 B with the piece index XOR ((row >> 1) & 3) (SWIZZLE_64B): conflict-free for one row per thread.
+template <int BN, bool PAIR>
+__device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, const CUtensorMap* tm_res, const CUtensorMap* tm_o32,
+                                                  const CUtensorMap* tm_o16, uint8_t* const smem_gen,
+                                                  const uint32_t smem_base, const uint32_t tmem_base, const uint32_t tfull0,
+                                                  const uint32_t tempty0, const uint32_t resbar0, const uint32_t cta_rank,
+                                                  const int first_item, const int item_stride, const int warp,
+                                                  const int lane) {
+  constexpr int CTAS = PAIR ? 2 : 1;
+  constexpr int CSTEP = EPI_WARPS / 4;
+  const dmm_gemm_epilogue& ep = p.ep;
+  const int wq = warp - EPI_WARP0;
+  const int ew = warp & 3;
+  const int chalf = wq >> 2;
+  const bool has_res = ep.residual != nullptr;
+  const bool o32 = ep.out_f32 != nullptr, o16 = ep.out_hi != nullptr;
+  const bool both = o32 && o16;
+  const bool pre = has_res && ep.res_pre_act != 0;   // residual enters before the activation (K-chunked sums)
+  const bool post = ep.post_bias != nullptr || ep.post_act != 0;
+  const int nbuf = p.nbuf;
+  uint8_t* const fbuf = smem_gen + p.off_epi + wq * nbuf * 4096;
+  const uint32_t fbuf_s = smem_base + (uint32_t)(p.off_epi + wq * nbuf * 4096);
+  uint8_t* const hbuf = smem_gen + p.off_b16 + wq * 2048;
+  const uint32_t hbuf_s = smem_base + (uint32_t)(p.off_b16 + wq * 2048);
+  float* const stg_bias = reinterpret_cast<float*>(smem_gen + p.off_bias + wq * 256);   // [0,32) bias, [32,64) post bias
+  const uint32_t resbar = resbar0 + 8u * TEPI_MAX_BUF * wq;
+  auto at32 = [](uint8_t* b, int r, int pc) -> float4* {
+    return reinterpret_cast<float4*>(b + r * 128 + ((pc ^ (r & 7)) << 4));
+  };
+  auto at16 = [](uint8_t* b, int r, int pc) -> uint4* {
+    return reinterpret_cast<uint4*>(b + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+  };
+
+  // ---- loader cursor: the (item, chunk) sequence of this warp, up to nbuf - 1 chunks ahead of the consumer
+  int lw = first_item, lc = 0, lseq = 0;
+  WorkItem lwi;
+  bool l_valid = false, l_more = has_res;
+  auto l_next = [&]() -> bool {
+    for (;;) {
+      if (l_valid) {
+        lc += CSTEP;
+        if (lc < (lwi.bn >> 5) && lwi.col0 + lc * 32 < p.N) return true;
+        lw += item_stride;
+        l_valid = false;
+      }
+      if (lw >= p.total_items) return false;
+      lwi = decode_work<BN>(lw, p);
+      if (lwi.col0 >= p.N) {
+        lw += item_stride;
+        continue;
+      }
+      l_valid = true;
+      lc = chalf - CSTEP;
+    }
+  };
+  int seq = 0;   // chunks consumed so far by this warp; chunk s lives in buffer s % nbuf
+  auto top_up = [&]() {
+    while (l_more && lseq <= seq + nbuf - 1) {
+      if (!l_next()) {
+        l_more = false;
+        break;
+      }
+      if (lane == 0) {
+        // the buffer held chunk lseq - nbuf <= seq - 1: its fp32 store (followed by at most one bf16 store group) must
+        // have read the buffer before the TMA load overwrites it
+        if (lseq >= nbuf) {
+          if (both) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        const int j = lseq % nbuf;
+        mbar_expect_tx(resbar + 8u * j, 4096u);
+        tma_load_2d(fbuf_s + (uint32_t)(j * 4096), tm_res, resbar + 8u * j, lwi.col0 + lc * 32,
+                    (lwi.m_blk * CTAS + (int)cta_rank) * BLOCK_M + ew * 32);
+      }
+      ++lseq;
+    }
+  };
+
+  int it = 0;
+  for (int w = first_item; w < p.total_items; w += item_stride) {
+    WorkItem wi = decode_work<BN>(w, p);
+    if (wi.col0 >= p.N) continue;
+    wi.m_blk = wi.m_blk * CTAS + (int)cta_rank;     // this CTA's 128-row block of the (pair) tile
+    const int acc = it & 1;
+    const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+    ++it;
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+    const int row0 = wi.m_blk * BLOCK_M + ew * 32;
+    const int nchunks = wi.bn >> 5;
+    auto chunk_ok = [&](int c) -> bool { return c < nchunks && wi.col0 + c * 32 < p.N; };
+    auto fetch_bias = [&](const float* b, int c) -> float {
+      const int n = wi.col0 + c * 32 + lane;
+      return (b && c < nchunks && n < p.N) ? __ldg(b + n) : 0.f;
+    };
+    float nb = fetch_bias(ep.bias, chalf), nb2 = fetch_bias(ep.bias, chalf + CSTEP);
+    float npb = fetch_bias(ep.post_bias, chalf), npb2 = fetch_bias(ep.post_bias, chalf + CSTEP);
+    top_up();
+    mbar_wait(tfull0 + 8u * acc, acc_phase, 4);
+    tcgen05_fence_after();
+
+#pragma unroll 1
+    for (int c = chalf; chunk_ok(c); c += CSTEP, ++seq) {
+      const int n0 = wi.col0 + c * 32;
+      const int j = seq % nbuf;
+      uint8_t* const fb = fbuf + j * 4096;
+      stg_bias[lane] = nb;
+      stg_bias[32 + lane] = npb;
+      nb = nb2;
+      nb2 = fetch_bias(ep.bias, c + 2 * CSTEP);
+      npb = npb2;
+      npb2 = fetch_bias(ep.post_bias, c + 2 * CSTEP);
+      if (has_res) {
+        top_up();
+        mbar_wait(resbar + 8u * j, (uint32_t)(seq / nbuf) & 1u, 5);
+      } else if (o32 && lane == 0) {
+        // staging buffer of chunk seq - nbuf: its store must have read it
+        if (both) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      }
+      __syncwarp();  // tcgen05.ld is .sync.aligned; publishes the bias slots and lane 0's buffer-free wait
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // 8 columns per step
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = __uint_as_float(r[8 * q + e]);
+        if (ep.bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(stg_bias + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(stg_bias + 8 * q + 4);
+          t[0] += b0.x; t[1] += b0.y; t[2] += b0.z; t[3] += b0.w;
+          t[4] += b1.x; t[5] += b1.y; t[6] += b1.z; t[7] += b1.w;
+        }
+        float rs[8];
+        if (has_res) {
+          const float4 r0 = *at32(fb, lane, 2 * q);
+          const float4 r1 = *at32(fb, lane, 2 * q + 1);
+          rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
+          rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
+        }
+        if (pre) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = fmaf(ep.beta, rs[e], t[e]);
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = fast_tanh(t[e]);
+        }
+        if (has_res && !pre) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = fmaf(ep.alpha, t[e], ep.beta * rs[e]);
+        } else if (ep.alpha != 1.f) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] *= ep.alpha;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[8 * q + e] = t[e];
+      }
+      if (o32) {
+        // in place: this thread read its row of the residual above and owns the same row of the result
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *at32(fb, lane, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_o32, fbuf_s + (uint32_t)(j * 4096), n0, row0);
+          bulk_commit();
+        }
+      }
+      if (o16) {
+        if (post) {
+          // second stage on the bf16 output only: out_hi = post_act(v + post_bias) while out_f32 keeps v
+          if (ep.post_bias) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(stg_bias + 32 + 4 * q);
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+          }
+          if (ep.post_act == 1) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = approx_tanh(v[e]);
+          }
+        }
+        // the bf16 buffer still feeds the previous chunk's store (only this chunk's fp32 store group is newer)
+        if (lane == 0) {
+          if (o32) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);  // .x (low half) first
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          *at16(hbuf, lane, q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_o16, hbuf_s, n0, row0);
+          bulk_commit();
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      // the MMA issuer (leader CTA) reuses the accumulator stage once every epilogue warp of the pair has left it
+      if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_shared(tempty0 + 8u * acc, 0)); else mbar_arrive(tempty0 + 8u * acc);
+    }
+  }
+  if (lane == 0) bulk_wait_all();   // every store has left shared memory and is performed before the CTA retires
+}
+
+// barrier block (byte offsets from smem_base + p.off_bar)
+constexpr uint32_t BAR_FULL = 0, BAR_EMPTY = 8 * MAX_STAGES, BAR_TFULL = 16 * MAX_STAGES, BAR_TEMPTY = BAR_TFULL + 16,
+                   BAR_TMEMPTR = BAR_TEMPTY + 16, BAR_RES = BAR_TMEMPTR + 8;
+static_assert(BAR_RES + 8 * TEPI_MAX_BUF * EPI_WARPS <= BAR_BYTES, "barrier block too small");
+
+template <int BN, bool X3, bool PAIR, bool TEPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                     const __grid_constant__ CUtensorMap tm_bs_hi, const __grid_constant__ CUtensorMap tm_bs_lo,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_o32,
+                    const __grid_constant__ CUtensorMap tm_o16, const GemmParams p) {
   using C = Cfg<BN, PAIR>;
+  static_assert(!(TEPI && X3), "the TMA epilogue serves the single-pass bf16 outputs");
   // PAIR: CTA rank inside the 2-CTA cluster (0 = leader: issues the MMAs, owns the barriers the peer signals)
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int first_item = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
-  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr (4 B)
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
-  volatile uint32_t* tmem_ptr_generic =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + (uint32_t)p.off_bar;
+  const int STAGES = p.stages;
+  auto full_bar = [&](int s) { return bar_base + BAR_FULL + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + BAR_EMPTY + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + BAR_TFULL + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + BAR_TEMPTY + 8u * a; };
+  const uint32_t tmem_ptr_addr = bar_base + BAR_TMEMPTR;
+  volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_gen + p.off_bar + BAR_TMEMPTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+    }
+    if (TEPI) {
+      for (int i = 0; i < TEPI_MAX_BUF * EPI_WARPS; ++i) mbar_init(bar_base + BAR_RES + 8u * i, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -578,7 +842,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               tma_load_2d(sa, ma, full_bar(stage), kb * BLOCK_K, a_row);
               tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), kb * BLOCK_K, b_row);
             }
-            if (++stage == C::STAGES) {
+            if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
@@ -619,7 +883,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           // smem slot is free once these MMAs retire (PAIR: in both CTAs, the commit multicasts to the same
           // barrier offset of the peer)
           if (PAIR) tcgen05_commit_pair(empty_bar(stage)); else tcgen05_commit(empty_bar(stage));
-          if (++stage == C::STAGES) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
@@ -633,10 +897,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp >= EPI_WARP0) {
     // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), (warp - EPI_WARP0) / 4
     // the parity of the 32-column chunks this warp drains.
+    if constexpr (TEPI) {
+      epilogue_warp_tma<BN, PAIR>(p, &tm_res, &tm_o32, &tm_o16, smem_gen, smem_base, tmem_base, tfull_bar(0), tempty_bar(0),
+                                  bar_base + BAR_RES, cta_rank, first_item, item_stride, warp, lane);
+    } else {
     const int ew = warp & 3;
     const int chalf = (warp - EPI_WARP0) >> 2;
-    uint8_t* const stg = smem_raw + (smem_base - smem_u32(smem_raw)) + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES +
-                         (warp - EPI_WARP0) * EPI_STAGE_BYTES;
+    uint8_t* const stg = smem_gen + p.off_epi + (warp - EPI_WARP0) * EPI_STAGE_BYTES;
     int it = 0;
     for (int w = first_item; w < p.total_items; w += item_stride) {
       WorkItem wi = decode_work<BN>(w, p);
@@ -658,6 +925,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         // the MMA issuer (leader CTA) reuses the accumulator stage once every epilogue warp of the pair has left it
         if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
       }
+    }
     }
   }
 
@@ -695,11 +963,30 @@ int make_map(dmm_ctx* ctx, CUtensorMap* map, const uint16_t* base, int64_t rows,
   return DMM_OK;
 }
 
+// 32 x 32 element box of an epilogue tensor ([rows, cols] row-major, leading dimension ld): fp32 rows are 128 B
+// (SWIZZLE_128B), bf16 rows 64 B (SWIZZLE_64B) -- the layouts of the epilogue's chunk buffers
+int make_epi_map(dmm_ctx* ctx, CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t cols, int64_t ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(
+      map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dmm_set_error("cuTensorMapEncodeTiled (epilogue) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld);
+    return DMM_ERR_CUDA;
+  }
+  return DMM_OK;
+}
+
 template <int BN, bool PAIR>
 int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
-           const uint16_t* b_lo, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+           const uint16_t* b_lo, int64_t ldb, GemmParams& p, bool tepi, cudaStream_t stream) {
   using C = Cfg<BN, PAIR>;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, m_res, m_o32, m_o16;
   int rc;
   p.num_n_blocks = (int)dmm_ceil_div(p.N, BN);
   // work items are tiles of (BLOCK_M * CTAS) rows; one persistent CTA (or CTA pair) per SM (or TPC)
@@ -723,17 +1010,56 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   if ((rc = make_map(ctx, &mb_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, BN / C::CTAS))) return rc;
   if ((rc = make_map(ctx, &mbs_hi, b_hi, p.N, p.K, ldb, p.sub_bn / C::CTAS))) return rc;
   if ((rc = make_map(ctx, &mbs_lo, b_lo ? b_lo : b_hi, p.N, p.K, ldb, p.sub_bn / C::CTAS))) return rc;
+  m_res = ma_hi;
+  m_o32 = ma_hi;
+  m_o16 = ma_hi;   // placeholders: never dereferenced unless the matching epilogue pointer is set
+  int smem_bytes;
+  if (tepi) {
+    // Shared-memory layout of the TMA epilogue.  With an fp32 residual every epilogue warp owns a ring of chunk buffers
+    // (prefetch depth nbuf - 1) and the operand ring takes what is left; otherwise one staging buffer per warp.
+    static const int env_nbuf = []() { const char* e = getenv("DMM_GEMM_NBUF"); return e ? atoi(e) : 0; }();
+    const bool has_res = p.ep.residual != nullptr;
+    p.nbuf = has_res ? 2 : 1;   // measured: a 4-stage operand ring + 2 chunk buffers beats 3 stages + 3 buffers
+    if (has_res && env_nbuf >= 2 && env_nbuf <= TEPI_MAX_BUF) p.nbuf = env_nbuf;
+    const int f32_bytes = EPI_WARPS * p.nbuf * 4096;
+    const int b16_bytes = p.ep.out_hi ? EPI_WARPS * 2048 : 0;
+    const int bias_bytes = EPI_WARPS * 256;
+    const int epi_bytes = f32_bytes + b16_bytes + bias_bytes + BAR_BYTES;
+    int stages = (SMEM_LIMIT - 1024 - epi_bytes) / C::STAGE_BYTES;
+    if (stages > C::STAGES) stages = C::STAGES;
+    if (stages < 2) {
+      dmm_set_error("dmm_gemm_bf16_tn: no room for the operand ring next to the TMA epilogue (BN=%d)", BN);
+      return DMM_ERR_INVALID;
+    }
+    p.stages = stages;
+    p.off_epi = stages * C::STAGE_BYTES;
+    p.off_b16 = p.off_epi + f32_bytes;
+    p.off_bias = p.off_b16 + b16_bytes;
+    p.off_bar = p.off_bias + bias_bytes;
+    smem_bytes = p.off_bar + BAR_BYTES + 1024;
+    if (p.ep.residual && (rc = make_epi_map(ctx, &m_res, p.ep.residual, true, p.M, p.N, p.ep.ld_res))) return rc;
+    if (p.ep.out_f32 && (rc = make_epi_map(ctx, &m_o32, p.ep.out_f32, true, p.M, p.N, p.ep.ld_out))) return rc;
+    if (p.ep.out_hi && (rc = make_epi_map(ctx, &m_o16, p.ep.out_hi, false, p.M, p.N, p.ep.ld_out16))) return rc;
+  } else {
+    p.nbuf = 1;
+    p.stages = C::STAGES;
+    p.off_bar = C::STAGES * C::STAGE_BYTES;
+    p.off_epi = p.off_bar + BAR_BYTES;
+    p.off_b16 = p.off_bias = 0;
+    smem_bytes = C::SMEM_BYTES;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   const bool x3 = p.ep.res_lo != nullptr || p.ep.out_lo != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(grid * C::CTAS));
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -742,10 +1068,15 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 1 : 0;
-  if (x3) {
-    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, true, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p));
+  if (tepi) {
+    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, false, PAIR, true>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo,
+                                m_res, m_o32, m_o16, p));
+  } else if (x3) {
+    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, true, PAIR, false>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo,
+                                m_res, m_o32, m_o16, p));
   } else {
-    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, false, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo, p));
+    DMM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, false, PAIR, false>, ma_hi, ma_lo, mb_hi, mb_lo, mbs_hi, mbs_lo,
+                                m_res, m_o32, m_o16, p));
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
@@ -815,11 +1146,15 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
     if (pair_ok && sms >= 2) consider(256, true, waves(m256 * dmm_ceil_div(N, 256), sms / 2) * 256.0 / 1.0);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // TMA epilogue (residual prefetch ring + bulk tensor stores) for the single-pass bf16 configurations;
+  // DMM_GEMM_TEPI=0 keeps the register-staged epilogue (A/B switch for measurements)
+  static const bool tepi_ok = []() { const char* e = getenv("DMM_GEMM_TEPI"); return !(e && e[0] == '0'); }();
+  const bool tepi = tepi_ok && !a_lo && !b_lo && !ep->res_hi && !ep->res_lo && !ep->out_lo && (ep->out_f32 || ep->out_hi);
   switch (bn) {
-    case 64: return launch<64, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
-    case 128: return launch<128, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+    case 64: return launch<64, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
+    case 128: return launch<128, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
     default:
-      return pair ? launch<256, true>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st)
-                  : launch<256, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, st);
+      return pair ? launch<256, true>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st)
+                  : launch<256, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
   }
 }

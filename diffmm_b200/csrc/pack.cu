@@ -258,26 +258,28 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
     }
   };
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int G = LO ? 4 : 8;     // gathered weight rows in flight per lane (16 bytes each, hi and lo)
   for (int64_t k = b; k < e; k += 32) {
-    // the row's item ids: one coalesced load per 32 items, broadcast by shuffle; 4 gathers in flight per lane
+    // the row's item ids: one coalesced load per 32 items, broadcast by shuffle; G gathers in flight per lane (the
+    // 1 % of users with hundreds of interactions would otherwise set the length of the kernel's tail)
     int32_t mine = (k + lane < e) ? indices[k + lane] : -1;
     if (mine >= n_cols) mine = -1;
     const int cnt = (int)((e - k) < 32 ? (e - k) : 32);
-    for (int j = 0; j < cnt; j += 4) {
-      int32_t c[4];
-      uint4 qh[4], ql[4];
+    for (int j = 0; j < cnt; j += G) {
+      int32_t c[G];
+      uint4 qh[G], ql[LO ? G : 1];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+      for (int t = 0; t < G; ++t) c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < G; ++t) {
         const bool ok = col_ok && j + t < cnt && c[t] >= 0;
         qh[t] = ok ? *reinterpret_cast<const uint4*>(wt_hi + (int64_t)c[t] * ld_w + c0) : zero;
-        if (LO) ql[t] = ok ? *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c[t] * ld_w + c0) : zero;
+        if constexpr (LO) ql[t] = ok ? *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c[t] * ld_w + c0) : zero;
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < G; ++t) {
         add(qh[t]);
-        if (LO) add(ql[t]);
+        if constexpr (LO) add(ql[t]);
       }
     }
   }

@@ -21,6 +21,7 @@ ranks with no data-path collective except the final edge all-gather (dist.py).
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict, Optional, Tuple
 
@@ -317,12 +318,29 @@ def default_block_rows(n_users: int, n_items: int, hidden: int, split: bool, bud
     return int(min(n_users, rows))
 
 
+_SIDE_STREAMS: Dict[Tuple[int, int], list] = {}
+
+
+def _side_streams(dev: torch.device, n: int):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _SIDE_STREAMS[key]
+
+
 def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torch.Tensor, indices: torch.Tensor,
                   n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
                   row_range: Optional[Tuple[int, int]] = None, block_rows: Optional[int] = None,
-                  out_items: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                  out_items: Optional[Dict[str, torch.Tensor]] = None, per_modality=None,
+                  per_modality_out: Optional[dict] = None) -> Dict[str, torch.Tensor]:
     """Top-k item ids per modality for users in ``row_range`` (default all), written at the train-CSR
-    offsets (k_u = deg(u), Main.py:215-216,226).  Returns {modality: int32 [E]} (only this range filled)."""
+    offsets (k_u = deg(u), Main.py:215-216,226).  Returns {modality: int32 [E]} (only this range filled).
+
+    The modalities are independent (own Denoise weights, own output), so each one runs as its own pipeline
+    (operand packs, chain, top-k and the optional ``per_modality(items)`` follow-up, e.g. the adjacency build) on a
+    side CUDA stream forked from / joined to the caller's stream: the latency-bound small kernels and the HBM-bound
+    top-k of one modality fill the gaps of the tensor-bound contractions of the other.  DIFFMM_STREAMS=1 keeps
+    everything on the caller's stream."""
     r0, r1 = row_range if row_range is not None else (0, n_users)
     any_den = next(iter(denoise_models.values()))
     precision = check_precision(precision or any_den.precision)
@@ -330,20 +348,39 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     H = any_den.in_layers[0].weight.shape[0]
     if block_rows is None:
         block_rows = default_block_rows(r1 - r0, n_items, H, split)
+        env = os.environ.get("DIFFMM_BLOCK_ROWS")
+        if env:
+            block_rows = max(128, min(block_rows, int(env)))
     E = int(indices.numel())
     dev = indptr.device
     if out_items is None:
         out_items = {m: torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E] for m in denoise_models}
-    ws = None
+    mods = list(denoise_models.items())
+    n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(mods))
+    streams = []
+    if n_streams > 1 and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+        streams = _side_streams(dev, n_streams)
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in streams:
+            st.wait_event(fork)
     with torch.no_grad():
-        for b0 in range(r0, r1, block_rows):
-            b1 = min(b0 + block_rows, r1)
-            for m, den in denoise_models.items():
-                if ws is None or not ws.fits(b1 - b0, n_items, H, den.time_emb_dim, split):
-                    ws = ChainWorkspace(b1 - b0, n_items, H, den.time_emb_dim, split, dev)
-                scores = denoise_chain(diff, den, csr=(indptr, indices), row0=b0, n_rows=b1 - b0,
-                                       sampling_step=sampling_step, precision=precision, ws=ws)
-                ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m])
+        for mi, (m, den) in enumerate(mods):
+            st = streams[mi % len(streams)] if streams else None
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                ws = None
+                for b0 in range(r0, r1, block_rows):
+                    b1 = min(b0 + block_rows, r1)
+                    if ws is None or not ws.fits(b1 - b0, n_items, H, den.time_emb_dim, split):
+                        ws = ChainWorkspace(b1 - b0, n_items, H, den.time_emb_dim, split, dev)
+                    scores = denoise_chain(diff, den, csr=(indptr, indices), row0=b0, n_rows=b1 - b0,
+                                           sampling_step=sampling_step, precision=precision, ws=ws)
+                    ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m])
+                if per_modality is not None:
+                    per_modality_out[m] = per_modality(out_items[m])
+    for st in streams:
+        main.wait_stream(st)
     return out_items
 
 
@@ -360,6 +397,9 @@ def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: 
                               row_range=(r0, r1), block_rows=block_rows)
         items = {m: ddist.allgather_edges(v, indptr, n_users, group, plan) for m, v in items.items()}
     else:
-        items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                              block_rows=block_rows)
+        adjs: Dict[str, ops.CsrAdj] = {}
+        rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
+                      block_rows=block_rows, per_modality=lambda v: ops.build_norm_adj(indptr, v, n_users, n_items),
+                      per_modality_out=adjs)
+        return {m: adjs[m] for m in denoise_models}
     return {m: ops.build_norm_adj(indptr, v, n_users, n_items) for m, v in items.items()}

@@ -112,7 +112,9 @@ int dmm_q_sample(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const float* nois
  * C[M,N] = epilogue( A[M,K] . B[N,K]^T ), both operands K-major bf16, fp32 accumulation in TMEM.
  * a_lo / b_lo (nullable) add the split-bf16 correction passes A_lo.B_hi and A_hi.B_lo, which
  * make the product fp32-faithful (rel ~1e-5) on the bf16 tensor pipe.
- * Replaces cuBLAS SGEMM behind nn.Linear / torch.mm (Model.py:205,208,212,215,416-417).      */
+ * Replaces cuBLAS SGEMM behind nn.Linear / torch.mm (Model.py:205,208,212,215,416-417).
+ * Output rows leave through 16-byte TMA units: the padding columns N .. round_up(N, 4 fp32 / 8 bf16)
+ * of an output row (inside ld_out / ld_out16 by the rules above) may be overwritten.            */
 typedef struct dmm_gemm_epilogue {
   const float* bias;      /* [N] added per column, or NULL                                   */
   int32_t act;            /* 0 none, 1 tanh (Model.py:213)                                   */

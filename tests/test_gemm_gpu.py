@@ -87,6 +87,65 @@ def test_tcgen05(ops, M, N, K, mode):
         assert torch.isnan(out[:, N:]).all()          # padding columns are never written
 
 
+@pytest.mark.parametrize("M,N,K", SHAPES + [(19445, 1024, 1024), (640, 1000, 96)])
+@pytest.mark.parametrize("pad", [8, 32])
+def test_tcgen05_tma_epilogue_hidden_step(ops, M, N, K, pad):
+    """Single-pass bf16 with the TMA epilogue: fp32 state updated IN PLACE (z = alpha (acc + bias) + beta z, residual
+    prefetch ring + bulk tensor stores) and the post stage h = tanh(z + post_bias) as the bf16 operand copy."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    pbias = (rng.standard_normal(N) * 0.3).astype(np.float32)
+    z0 = rng.standard_normal((M, N)).astype(np.float32)
+    a_hi, _ = ops.pack_bf16(T(a), split=False)
+    b_hi, _ = ops.pack_bf16(T(b), split=False)
+    ldn = ops.pad_to(N + (pad - 8), pad)
+    z = torch.full((M, ldn), float("nan"), device=DEV)
+    z[:, :N] = T(z0)
+    h = torch.full((M, ldn), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, bias=T(bias), alpha=0.75, beta=0.5, residual=z[:, :N],
+                     out_f32=z[:, :N], out_hi=h[:, :N], post_bias=T(pbias), post_act=1)
+    torch.cuda.synchronize()
+    want = _ref(_bf16_round(a), _bf16_round(b), bias, 0, 0.75, 0.5, z0)
+    got = z[:, :N].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=5e-5)      # fp32 accumulation over up to 7060 products, no tanh
+    want_h = np.tanh(got.astype(np.float64) + pbias)
+    np.testing.assert_allclose(h[:, :N].float().cpu().numpy(), want_h, rtol=2 ** -8, atol=2e-3)   # MUFU tanh + bf16
+    # the TMA stores move whole 16-byte units: the padding of a row may be written up to the next 16-byte boundary
+    # (4 fp32 / 8 bf16 columns), never beyond
+    n4, n8 = ops.pad_to(N, 4), ops.pad_to(N, 8)
+    if ldn > n4:
+        assert torch.isnan(z[:, n4:]).all()
+    if ldn > n8:
+        assert (h[:, n8:].float() == 7.0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 300, 210), (77, 40, 50), (2000, 2500, 136), (4100, 1024, 512)])
+def test_tcgen05_tma_epilogue_single_outputs(ops, M, N, K):
+    """TMA epilogue with one output kind: tanh -> bf16 operand only (dense first layer), and fp32 only with a
+    pre-activation fp32 residual."""
+    rng = np.random.default_rng(M + N * 11 + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    a_hi, _ = ops.pack_bf16(T(a), split=False)
+    b_hi, _ = ops.pack_bf16(T(b), split=False)
+    ldn = ops.pad_to(N, 8)
+    h = torch.zeros((M, ldn), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, bias=T(bias), act=1, out_hi=h[:, :N])
+    want = _ref(_bf16_round(a), _bf16_round(b), bias, 1, 1.0, 0.0, None)
+    np.testing.assert_allclose(h[:, :N].float().cpu().numpy(), want, rtol=2 ** -8, atol=1e-5)
+    res_t = torch.zeros((M, ldn), device=DEV)
+    res_t[:, :N] = T(res)
+    out = torch.full((M, ldn), float("nan"), device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, bias=T(bias), act=1, alpha=1.5, beta=1.0, residual=res_t[:, :N],
+                     res_pre_act=True, out_f32=out[:, :N])
+    want = 1.5 * np.tanh(_bf16_round(a).astype(np.float64) @ _bf16_round(b).astype(np.float64).T + bias + res)
+    np.testing.assert_allclose(out[:, :N].cpu().numpy(), want, rtol=1e-5, atol=2e-5)
+
+
 def test_tcgen05_k_chunked_pre_activation_residual(ops):
     """res_pre_act: the residual is a partial sum of the same contraction, added before bias-tanh (K in chunks)."""
     rng = np.random.default_rng(12)
