@@ -40,7 +40,7 @@ KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sor
     "dmm_pack_bf16": 1, "dmm_csr_rows_to_dense": 1, "dmm_time_embedding": 1, "dmm_q_sample": 1, "dmm_gemm_bf16_tn": 1,
     "dmm_gemm_f32_tn": 1, "dmm_topk_edges": 1, "dmm_build_norm_adj_csr": 4, "dmm_sign_noise_": 1,
     "dmm_bpr_fwd_bwd": 2, "dmm_infonce_fwd": 3, "dmm_infonce_bwd": 3, "dmm_scatter_add_rows": 1,
-    "dmm_spmm_csr": 3, "dmm_spmm_plan": 2,
+    "dmm_spmm_csr": 2, "dmm_spmm_plan": 3,
 }
 
 

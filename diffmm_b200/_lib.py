@@ -60,6 +60,7 @@ PROTOTYPES = {
     "dmm_sign_noise_": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "dmm_bpr_fwd_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_infonce_workspace_floats": (c_i64, [c_i64, c_i64, C.c_int]),
     "dmm_infonce_fwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dmm_infonce_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_f32,

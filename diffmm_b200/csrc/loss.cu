@@ -174,126 +174,286 @@ __global__ void __launch_bounds__(256) nce_rows_kernel(const float* __restrict__
 
 // ---- D == 64: register-tiled version ----------------------------------------------------------------
 // The warp-per-anchor kernel above spends its time in shuffle reductions (one 5-step butterfly per logit).
-// Here a CTA owns NCE_BM = 16 anchor rows and walks the other view in tiles of NCE_BN = 64 rows staged in
-// shared memory; thread (r, c) accumulates the 4 logits (r, c + 16 q) with float4 reads along D (no
-// reductions), the softmax statistics of a row are combined over its 16 threads once per TILE, and for the
-// backward the 16 x 64 probability tile goes through shared memory into a second register-tiled product
-// P . B (thread (r, d) owns 4 gradient components).  Same MODE semantics as nce_rows_kernel.
-constexpr int NCE_BM = 16, NCE_BN = 64, NCE_LD = 68;   // 68-float rows: 16-byte aligned, conflict-free column access
+// Here the B x B logit matrix is cut into CTA tiles of NT_I = 32 anchors x a range of stream rows: the grid is
+// (B / 32 anchor tiles) x (JS column splits) so that ~128 CTAs are busy at B = 1024 instead of 64, and a CTA walks its
+// range in tiles of NT_J = 64 stream rows staged in shared memory by cp.async (double buffered: the next tile lands
+// while this one is consumed).  Thread (ty, tx) of 8 x 16 owns the 4 x 4 logits (4 ty + rr, tx + 16 q): 8 shared
+// float4 reads feed 64 FMAs, i.e. the FP32 pipe, not shared-memory bandwidth, bounds the tile.
+//   forward : per-split online log-sum-exp (m, l) and the diagonal logit of every anchor -> nce_fwd_combine_kernel
+//             merges the splits, writes lse / row losses and reduces the mean in a fixed order;
+//   backward: w_ij = exp(s_ij / T - lse) - [i == j] goes through shared memory (transposed, one float4 of 4 anchors per
+//             stream row) into a second register-tiled product  g(4 anchors, 4 components) += w . B;  blockIdx.z picks
+//             the side (1: d/d v1 with lse of the anchor; 2: d/d v2, anchors and stream swapped, lse of the stream row);
+//             the per-split partial gradients are added in a fixed order by nce_bwd_combine_kernel, which also applies
+//             the normalisation backward  g_x = inv (g - n (n . g)) coef.   Everything is deterministic.
+constexpr int NT_I = 32, NT_J = 64, NT_LD = 68, NT_PLD = 36, NT_THREADS = 128, NCE_MAX_SPLIT = 4;
+struct NceSmem {
+  float As[NT_I][NT_LD];        // anchors, 68-float rows: 16-byte aligned, conflict-free float4 column walks
+  float Bs[2][NT_J][NT_LD];     // stream tile, double buffered
+  float Ps[NT_J][NT_PLD];       // backward: w transposed [stream row][anchor]
+  float lse_s[2][NT_J];         // backward wrt v2: lse of the stream rows
+};
 
-template <int MODE>
-__global__ void __launch_bounds__(256) nce_tile64_kernel(const float* __restrict__ na, const float* __restrict__ nb,
-                                                         int64_t B, float inv_temp, const float* __restrict__ lse_in,
-                                                         const float* __restrict__ inv_norm, float coef,
-                                                         float* __restrict__ out_lse, float* __restrict__ out_row_loss,
-                                                         float* __restrict__ out_grad) {
-  __shared__ __align__(16) float As[NCE_BM][NCE_LD];
-  __shared__ __align__(16) float Bs[NCE_BN][NCE_LD];
-  __shared__ float Ps[NCE_BM][NCE_BN + 1];
-  __shared__ float lse_s[NCE_BN];
-  const int tid = threadIdx.x;
-  const int r = tid >> 4, c4 = tid & 15;
-  const int64_t i0 = (int64_t)blockIdx.x * NCE_BM;
-  const int64_t i = i0 + r;
-  const uint32_t hmask = 0xFFFFu << (tid & 16);   // the 16 threads of a row are one half warp
-  {
-    // anchor tile: 16 rows x 16 float4
-    const int64_t row = i0 + (tid >> 4);
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(NT_THREADS) nce_tiles_kernel(const float* __restrict__ n1, const float* __restrict__ n2,
+                                                               int64_t B, int64_t JR, float inv_temp,
+                                                               const float* __restrict__ lse, float* __restrict__ part,
+                                                               float* __restrict__ gpart) {
+  extern __shared__ __align__(16) uint8_t nce_raw[];
+  NceSmem& sm = *reinterpret_cast<NceSmem*>(nce_raw);
+  const int mode = FWD ? 0 : 1 + (int)blockIdx.z;
+  const float* __restrict__ na = (mode == 2) ? n2 : n1;   // anchors
+  const float* __restrict__ nb = (mode == 2) ? n1 : n2;   // stream
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const uint32_t hmask = 0xFFFFu << (tid & 16);           // the 16 threads of an anchor quad are one half warp
+  const int64_t i0 = (int64_t)blockIdx.x * NT_I;
+  const int split = blockIdx.y, JS = gridDim.y;
+  const int64_t jbeg = (int64_t)split * JR;
+  const int64_t jend = jbeg + JR < B ? jbeg + JR : B;
+  const int ntiles = jbeg < jend ? (int)((jend - jbeg + NT_J - 1) / NT_J) : 0;
+
+  auto issue = [&](int t) {
+    const int st = t & 1;
+    const int64_t j0 = jbeg + (int64_t)t * NT_J;
+#pragma unroll
+    for (int k = 0; k < NT_J * 16 / NT_THREADS; ++k) {
+      const int idx = tid + NT_THREADS * k;
+      const int row = idx >> 4, pc = idx & 15;
+      const bool ok = j0 + row < jend;
+      cp_async16(&sm.Bs[st][row][4 * pc], nb + (ok ? j0 + row : 0) * 64 + 4 * pc, ok ? 16 : 0);   // rows past the range: zeros
+    }
+    if (mode == 2 && tid < NT_J) {
+      const bool ok = j0 + tid < jend;
+      cp_async4(&sm.lse_s[st][tid], lse + (ok ? j0 + tid : 0), ok ? 4 : 0);
+    }
+  };
+  if (ntiles > 0) issue(0);
+  cp_async_commit();
+#pragma unroll
+  for (int k = 0; k < NT_I * 16 / NT_THREADS; ++k) {
+    const int idx = tid + NT_THREADS * k;
+    const int row = idx >> 4, pc = idx & 15;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < B) v = __ldg(reinterpret_cast<const float4*>(na + row * 64) + (tid & 15));
-    *reinterpret_cast<float4*>(&As[tid >> 4][4 * (tid & 15)]) = v;
+    if (i0 + row < B) v = __ldg(reinterpret_cast<const float4*>(na + (i0 + row) * 64) + pc);
+    *reinterpret_cast<float4*>(&sm.As[row][4 * pc]) = v;
   }
-  float m = -INFINITY, l = 0.f, diag = -INFINITY;
-  float g[4] = {0.f, 0.f, 0.f, 0.f};
-  const float lse_i = (MODE == 1 && i < B) ? lse_in[i] : 0.f;
 
-  for (int64_t j0 = 0; j0 < B; j0 += NCE_BN) {
-    __syncthreads();   // previous tile fully consumed (also publishes As on the first pass)
+  float m[4], l[4], diag[4], lse_i[4];
+  float g[4][4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int jr = (tid >> 4) + 16 * it;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + jr < B) v = __ldg(reinterpret_cast<const float4*>(nb + (j0 + jr) * 64) + (tid & 15));
-      *reinterpret_cast<float4*>(&Bs[jr][4 * (tid & 15)]) = v;
-    }
-    if (MODE == 2 && tid < NCE_BN) lse_s[tid] = (j0 + tid < B) ? lse_in[j0 + tid] : 0.f;
-    __syncthreads();
-    // logits (r, c4 + 16 q)
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rr = 0; rr < 4; ++rr) {
+    m[rr] = -INFINITY;
+    l[rr] = 0.f;
+    diag[rr] = -INFINITY;
+    const int64_t i = i0 + 4 * ty + rr;
+    lse_i[rr] = (mode == 1 && i < B) ? __ldg(lse + i) : 0.f;
 #pragma unroll
+    for (int e = 0; e < 4; ++e) g[rr][e] = 0.f;
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) issue(t + 1);     // its buffer was released by the barrier that closed tile t - 1
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();                      // tile t (and, on the first pass, the anchors) visible to every thread
+    const int st = t & 1;
+    const int64_t j0 = jbeg + (int64_t)t * NT_J;
+    float s[4][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[rr][q] = 0.f;
+#pragma unroll 4
     for (int k4 = 0; k4 < 16; ++k4) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * k4]);
+      float4 a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[c4 + 16 * q][4 * k4]);
-        s[q] = fmaf(a.x, b.x, s[q]);
-        s[q] = fmaf(a.y, b.y, s[q]);
-        s[q] = fmaf(a.z, b.z, s[q]);
-        s[q] = fmaf(a.w, b.w, s[q]);
-      }
+      for (int rr = 0; rr < 4; ++rr) a[rr] = *reinterpret_cast<const float4*>(&sm.As[4 * ty + rr][4 * k4]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(&sm.Bs[st][tx + 16 * q][4 * k4]);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s[rr][q] = fmaf(a[rr].x, b[q].x, s[rr][q]);
+          s[rr][q] = fmaf(a[rr].y, b[q].y, s[rr][q]);
+          s[rr][q] = fmaf(a[rr].z, b[q].z, s[rr][q]);
+          s[rr][q] = fmaf(a[rr].w, b[q].w, s[rr][q]);
+        }
     }
-    if (MODE == 0) {
-      float tmax = -INFINITY;
+    if (FWD) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t j = j0 + c4 + 16 * q;
-        s[q] = (j < B) ? s[q] * inv_temp : -INFINITY;
-        if (j == i) diag = s[q];
-        tmax = fmaxf(tmax, s[q]);
+      for (int rr = 0; rr < 4; ++rr) {
+        const int64_t i = i0 + 4 * ty + rr;
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t j = j0 + tx + 16 * q;
+          s[rr][q] = (j < jend) ? s[rr][q] * inv_temp : -INFINITY;
+          if (j == i) diag[rr] = s[rr][q];
+          tmax = fmaxf(tmax, s[rr][q]);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(hmask, tmax, o, 16));
+        const float mn = fmaxf(m[rr], tmax);      // finite: every tile holds at least one valid column
+        float pt = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pt += expf(s[rr][q] - mn);   // exp(-inf) = 0 for masked columns
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) pt += __shfl_xor_sync(hmask, pt, o, 16);
+        l[rr] = l[rr] * expf(m[rr] - mn) + pt;
+        m[rr] = mn;
       }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(hmask, tmax, o, 16));
-      const float mn = fmaxf(m, tmax);          // finite: every tile holds at least one valid column
-      float part = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) part += expf(s[q] - mn);   // exp(-inf) = 0 for masked columns
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o, 16);
-      l = l * expf(m - mn) + part;
-      m = mn;
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int c = c4 + 16 * q;
+        const int c = tx + 16 * q;
         const int64_t j = j0 + c;
-        const float lse = (MODE == 1) ? lse_i : lse_s[c];
-        float w = 0.f;
-        if (j < B && i < B) w = expf(s[q] * inv_temp - lse) - (j == i ? 1.f : 0.f);
-        Ps[r][c] = w;
+        float w[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int64_t i = i0 + 4 * ty + rr;
+          const float ls = (mode == 1) ? lse_i[rr] : sm.lse_s[st][c];
+          w[rr] = (j < jend && i < B) ? expf(s[rr][q] * inv_temp - ls) - (j == i ? 1.f : 0.f) : 0.f;
+        }
+        *reinterpret_cast<float4*>(&sm.Ps[c][4 * ty]) = make_float4(w[0], w[1], w[2], w[3]);
       }
       __syncthreads();
-      // g(r, 4 c4 .. 4 c4 + 3) += sum_j P(r, j) B(j, .)
+      // g(4 ty + rr, 4 tx + e) += sum_j w(rr, j) B(j, 4 tx + e)
 #pragma unroll 8
-      for (int j = 0; j < NCE_BN; ++j) {
-        const float w = Ps[r][j];
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[j][4 * c4]);
-        g[0] = fmaf(w, b.x, g[0]);
-        g[1] = fmaf(w, b.y, g[1]);
-        g[2] = fmaf(w, b.z, g[2]);
-        g[3] = fmaf(w, b.w, g[3]);
+      for (int j = 0; j < NT_J; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(&sm.Ps[j][4 * ty]);
+        const float4 b = *reinterpret_cast<const float4*>(&sm.Bs[st][j][4 * tx]);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          g[rr][0] = fmaf(wv[rr], b.x, g[rr][0]);
+          g[rr][1] = fmaf(wv[rr], b.y, g[rr][1]);
+          g[rr][2] = fmaf(wv[rr], b.z, g[rr][2]);
+          g[rr][3] = fmaf(wv[rr], b.w, g[rr][3]);
+        }
       }
     }
+    __syncthreads();   // tile t and Ps fully consumed
   }
-  if (MODE == 0) {
+  cp_async_wait<0>();
+
+  if (FWD) {
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) diag = fmaxf(diag, __shfl_xor_sync(hmask, diag, o, 16));
-    if (c4 == 0 && i < B) {
-      const float lse = m + logf(l);
-      out_lse[i] = lse;
-      out_row_loss[i] = lse - diag;
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t i = i0 + 4 * ty + rr;
+      float dg = diag[rr];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dg = fmaxf(dg, __shfl_xor_sync(hmask, dg, o, 16));
+      if (tx == 0 && i < B) {
+        float* o3 = part + (i * JS + split) * 3;
+        o3[0] = m[rr];
+        o3[1] = l[rr];
+        o3[2] = dg;
+      }
     }
   } else {
-    // normalisation backward: g_x = inv * (g - n (n . g)) * coef
-    const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * c4]);
-    float dot = a.x * g[0] + a.y * g[1] + a.z * g[2] + a.w * g[3];
+    float* gp = gpart + ((int64_t)(mode - 1) * JS + split) * B * 64;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
-    if (i < B) {
-      const float sc = inv_norm[i] * coef;
-      *reinterpret_cast<float4*>(out_grad + i * 64 + 4 * c4) =
-          make_float4(sc * (g[0] - a.x * dot), sc * (g[1] - a.y * dot), sc * (g[2] - a.z * dot), sc * (g[3] - a.w * dot));
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t i = i0 + 4 * ty + rr;
+      if (i < B) *reinterpret_cast<float4*>(gp + i * 64 + 4 * tx) = make_float4(g[rr][0], g[rr][1], g[rr][2], g[rr][3]);
     }
   }
+}
+
+// merges the per-split (m, l, diag) of every anchor, writes lse and the row loss, reduces the mean (one CTA, fixed order)
+__global__ void __launch_bounds__(1024) nce_fwd_combine_kernel(const float* __restrict__ part, int JS, int64_t B, float scale,
+                                                               float* __restrict__ out_lse, float* __restrict__ row_loss,
+                                                               float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < B; i += 1024) {
+    float M = -INFINITY, dg = -INFINITY;
+    for (int k = 0; k < JS; ++k) {
+      M = fmaxf(M, part[(i * JS + k) * 3]);
+      dg = fmaxf(dg, part[(i * JS + k) * 3 + 2]);
+    }
+    float L = 0.f;
+    for (int k = 0; k < JS; ++k) {
+      const float mk = part[(i * JS + k) * 3], lk = part[(i * JS + k) * 3 + 1];
+      if (lk > 0.f) L += lk * expf(mk - M);
+    }
+    const float lse = M + logf(L);
+    out_lse[i] = lse;
+    row_loss[i] = lse - dg;
+    acc += lse - dg;
+  }
+  acc = dmm_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = red[threadIdx.x];
+    t = dmm_warp_sum(t);
+    if (threadIdx.x == 0) *out = t * scale;
+  }
+}
+
+// adds the per-split partial gradients (fixed order) and applies the normalisation backward; one half warp per row,
+// rows [0, B): d/d v1 (n1, inv1), rows [B, 2B): d/d v2 (n2, inv2)
+__global__ void __launch_bounds__(256) nce_bwd_combine_kernel(const float* __restrict__ gpart, int JS, int64_t B,
+                                                              const float* __restrict__ n1, const float* __restrict__ n2,
+                                                              const float* __restrict__ inv1, const float* __restrict__ inv2,
+                                                              float coef, float* __restrict__ g1, float* __restrict__ g2) {
+  const int64_t x = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+  if (x >= 2 * B) return;
+  const int side = x >= B ? 1 : 0;
+  const int64_t i = x - (int64_t)side * B;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < JS; ++k) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(gpart + (((int64_t)side * JS + k) * B + i) * 64) + l16);
+    g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
+  }
+  const float4 n = __ldg(reinterpret_cast<const float4*>((side ? n2 : n1) + i * 64) + l16);
+  float dot = n.x * g.x + n.y * g.y + n.z * g.z + n.w * g.w;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
+  const float sc = (side ? inv2 : inv1)[i] * coef;
+  *reinterpret_cast<float4*>((side ? g2 : g1) + i * 64 + 4 * l16) =
+      make_float4(sc * (g.x - n.x * dot), sc * (g.y - n.y * dot), sc * (g.z - n.z * dot), sc * (g.w - n.w * dot));
+}
+
+inline int nce_splits(int64_t B) {
+  int64_t js = (B + 255) / 256;
+  return (int)(js < 1 ? 1 : (js > NCE_MAX_SPLIT ? NCE_MAX_SPLIT : js));
+}
+inline int64_t nce_split_rows(int64_t B, int JS) { return ((B + JS - 1) / JS + NT_J - 1) / NT_J * NT_J; }
+
+template <bool FWD>
+int launch_nce_tiles(int64_t B, const float* n1, const float* n2, float inv_temp, const float* lse, float* part,
+                     float* gpart, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMM_CUDA(cudaFuncSetAttribute(nce_tiles_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NceSmem)));
+    attr_set = true;
+  }
+  const int JS = nce_splits(B);
+  dim3 grid((unsigned)dmm_ceil_div(B, NT_I), (unsigned)JS, FWD ? 1u : 2u);
+  nce_tiles_kernel<FWD><<<grid, NT_THREADS, sizeof(NceSmem), st>>>(n1, n2, B, nce_split_rows(B, JS), inv_temp, lse, part, gpart);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
 }
 
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, int64_t ld_s,
@@ -310,12 +470,6 @@ template <int MODE>
 int launch_nce(int64_t B, int64_t D, const float* na, const float* nb, float inv_temp, const float* lse_in,
                const float* inv_norm, float coef, float* out_lse, float* out_row_loss, float* out_grad,
                cudaStream_t st) {
-  if (D == 64) {
-    nce_tile64_kernel<MODE><<<(unsigned)dmm_ceil_div(B, NCE_BM), 256, 0, st>>>(na, nb, B, inv_temp, lse_in, inv_norm, coef, out_lse,
-                                                                          out_row_loss, out_grad);
-    DMM_LAUNCH_CHECK();
-    return DMM_OK;
-  }
   const unsigned grid = (unsigned)dmm_ceil_div(B * 32, 256);
   switch (D / 32) {
     case 1: nce_rows_kernel<MODE, 1><<<grid, 256, 0, st>>>(na, nb, B, inv_temp, lse_in, inv_norm, coef, out_lse, out_row_loss, out_grad); break;
@@ -360,11 +514,25 @@ extern "C" int dmm_infonce_fwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
   float* n2 = workspace + B * D;
   nce_gather_norm_kernel<<<(unsigned)dmm_ceil_div(B * 32, 256), 256, 0, st>>>(v1, ld1, v2, ld2, idx, B, (int)D, n1, n2, inv1, inv2);
   DMM_LAUNCH_CHECK();
+  if (D == 64) {
+    float* part = workspace + 2 * B * D;     // [B][JS][3]
+    int rc = launch_nce_tiles<true>(B, n1, n2, 1.f / temperature, nullptr, part, nullptr, st);
+    if (rc) return rc;
+    nce_fwd_combine_kernel<<<1, 1024, 0, st>>>(part, nce_splits(B), B, 1.f / (float)B, lse, row_loss, loss);
+    DMM_LAUNCH_CHECK();
+    return DMM_OK;
+  }
   int rc = launch_nce<0>(B, D, n1, n2, 1.f / temperature, nullptr, nullptr, 0.f, lse, row_loss, nullptr, st);
   if (rc) return rc;
   mean_reduce_kernel<<<1, 1024, 0, st>>>(row_loss, B, 1.f / (float)B, loss);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
+}
+
+extern "C" int64_t dmm_infonce_workspace_floats(int64_t B, int64_t D, int backward) {
+  int64_t n = 2 * B * D;                       // normalised gathers of both views
+  if (D == 64) n += backward ? 2 * (int64_t)nce_splits(B) * B * D : 3 * (int64_t)nce_splits(B) * B;
+  return n;
 }
 
 extern "C" int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2, int64_t ld2,
@@ -381,6 +549,15 @@ extern "C" int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
                                                                               nullptr, nullptr);
   DMM_LAUNCH_CHECK();
   const float coef = grad_scale / ((float)B * temperature);
+  if (D == 64) {
+    float* gpart = workspace + 2 * B * D;    // [2 sides][JS][B][64]
+    int rc = launch_nce_tiles<false>(B, n1, n2, 1.f / temperature, lse, nullptr, gpart, st);
+    if (rc) return rc;
+    nce_bwd_combine_kernel<<<(unsigned)dmm_ceil_div(2 * B * 16, 256), 256, 0, st>>>(gpart, nce_splits(B), B, n1, n2, inv1, inv2,
+                                                                                  coef, g1, g2);
+    DMM_LAUNCH_CHECK();
+    return DMM_OK;
+  }
   int rc = launch_nce<1>(B, D, n1, n2, 1.f / temperature, lse, inv1, coef, nullptr, nullptr, g1, st);
   if (rc) return rc;
   return launch_nce<2>(B, D, n2, n1, 1.f / temperature, lse, inv2, coef, nullptr, nullptr, g2, st);

@@ -22,8 +22,10 @@ constexpr int LONG_ROW = 1024;
 constexpr int PLAN_LONG_ROW = 64;    // rows with more neighbours go through the plan
 constexpr int PLAN_CHUNK = 64;       // neighbours per chunk of a planned row (one warp each)
 
-// plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr
+// plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr,
+// then int32 chunk_owner[plan_max_chunks]: index (into the long row list) of the row that owns each chunk
 __host__ __device__ inline int64_t plan_cap(int64_t nnz) { return nnz / PLAN_LONG_ROW + 1; }
+__host__ __device__ inline int64_t plan_max_chunks(int64_t nnz) { return nnz / PLAN_CHUNK + plan_cap(nnz) + 1; }
 
 struct Epi {
   float alpha, beta;
@@ -135,30 +137,33 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
 template <int BATCH>
 __device__ __forceinline__ float4 gather64_hw(const int32_t* __restrict__ idx, const float* __restrict__ val,
                                               const float* __restrict__ x, int64_t ld_x, int64_t b, int n, int l16,
-                                              uint32_t hmask) {
-  int32_t mc[4];
-  float mv[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int j = l16 + 16 * k;
-    mc[k] = j < n ? __ldg(idx + b + j) : 0;
-    mv[k] = j < n ? __ldg(val + b + j) : 0.f;
-  }
+                                              uint32_t hmask, int32_t mc, float mv) {
+  // blocks of 16 neighbours: lane l16 holds (column, value) number l16 of the block.  (mc, mv) is the FIRST block's
+  // pair, fetched by the caller (one row ahead, see hw_first_block); the next block's pair is fetched before this
+  // block's gathers are issued.  Most rows (users: ~7 interactions + the self loop) are a single block, so the
+  // per-row instruction count stays close to the per-neighbour work.
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (16 * k >= n) break;                    // uniform within the half warp
-#pragma unroll
-    for (int h = 0; h < 16 / BATCH; ++h) {
-      if (16 * k + BATCH * h >= n) break;
+  const int32_t* ip = idx + b + l16;
+  const float* vp = val + b + l16;
+#pragma unroll 1
+  for (int base = 0; base < n; base += 16) {     // uniform within the half warp
+    const int cnt = n - base < 16 ? n - base : 16;
+    const int32_t cur_c = mc;
+    const float cur_v = mv;
+    if (base + 16 < n) {
+      mc = base + 16 + l16 < n ? __ldg(ip + base + 16) : 0;
+      mv = base + 16 + l16 < n ? __ldg(vp + base + 16) : 0.f;
+    }
+#pragma unroll 1
+    for (int h = 0; h < cnt; h += BATCH) {
       float4 xs[BATCH];
       float vs[BATCH];
 #pragma unroll
       for (int t = 0; t < BATCH; ++t) {
-        const int32_t c = __shfl_sync(hmask, mc[k], BATCH * h + t, 16);
-        vs[t] = __shfl_sync(hmask, mv[k], BATCH * h + t, 16);
+        const int32_t c = __shfl_sync(hmask, cur_c, h + t, 16);
+        vs[t] = __shfl_sync(hmask, cur_v, h + t, 16);
         xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (16 * k + BATCH * h + t < n) xs[t] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ld_x) + l16);
+        if (h + t < cnt) xs[t] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ld_x) + l16);
       }
 #pragma unroll
       for (int t = 0; t < BATCH; ++t) acc = fma4(vs[t], xs[t], acc);
@@ -166,27 +171,58 @@ __device__ __forceinline__ float4 gather64_hw(const int32_t* __restrict__ idx, c
   }
   return acc;
 }
+// first block of a segment [b, b + n): lane l16's (column, value) pair
+__device__ __forceinline__ void hw_first_block(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t b,
+                                               int n, int l16, int32_t& mc, float& mv) {
+  mc = l16 < n ? __ldg(idx + b + l16) : 0;
+  mv = l16 < n ? __ldg(val + b + l16) : 0.f;
+}
 
-// ---- short rows of a planned adjacency: one HALF warp per row (two rows per warp in flight), no barrier ----
-__global__ void __launch_bounds__(SPMM_THREADS) spmm64_short_kernel(const int64_t* __restrict__ ptr,
-                                                                    const int32_t* __restrict__ idx,
-                                                                    const float* __restrict__ val, int64_t row0,
-                                                                    int64_t row1, const float* __restrict__ x,
-                                                                    int64_t ld_x, Epi ep, float* __restrict__ y,
-                                                                    int64_t ld_y) {
+// ---- short rows of a planned adjacency: one HALF warp per row, rows strided over all resident half warps ----
+// A row is three dependent memory round trips (row pointers -> column ids / values -> gathered rows of X), and at ~14
+// neighbours per row that latency chain, not bandwidth, sets the pace.  The half warp therefore keeps a two-deep
+// software pipeline across its rows: while row i is gathered, the (column, value) block of row i + 1 and the row
+// pointers of row i + 2 are already in flight.
+__device__ __forceinline__ void spmm64_short_rows(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                  const float* __restrict__ val, int64_t row0, int64_t row1,
+                                                  const float* __restrict__ x, int64_t ld_x, const Epi& ep,
+                                                  float* __restrict__ y, int64_t ld_y, int64_t hw_id, int64_t n_hw) {
   const int l16 = threadIdx.x & 15;
   const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  const int64_t r = row0 + (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4);
+  int64_t r = row0 + hw_id;
   if (r >= row1) return;
-  const int64_t b = ptr[r], e = ptr[r + 1];
-  if (e - b > PLAN_LONG_ROW) return;          // chunk kernels
-  const float4 acc = gather64_hw<4>(idx, val, x, ld_x, b, (int)(e - b), l16, hmask);
-  float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
-  if (ep.z) {
-    const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
-    o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
+  auto row_ptr = [&](int64_t rr, int64_t& b, int& n) {
+    b = 0;
+    n = 0;
+    if (rr < row1) {
+      b = __ldg(ptr + rr);
+      const int64_t len = __ldg(ptr + rr + 1) - b;
+      n = len > PLAN_LONG_ROW ? 0 : (int)len;        // long rows belong to the chunk path: nothing to gather here
+      if (len > PLAN_LONG_ROW) b = -1;
+    }
+  };
+  int64_t b0, b1, b2;
+  int n0, n1, n2;
+  row_ptr(r, b0, n0);
+  row_ptr(r + n_hw, b1, n1);
+  int32_t c0, c1;
+  float v0, v1;
+  hw_first_block(idx, val, b0 < 0 ? 0 : b0, n0, l16, c0, v0);
+  for (; r < row1; r += n_hw) {
+    row_ptr(r + 2 * n_hw, b2, n2);
+    hw_first_block(idx, val, b1 < 0 ? 0 : b1, n1, l16, c1, v1);
+    if (b0 >= 0) {
+      const float4 acc = gather64_hw<4>(idx, val, x, ld_x, b0, n0, l16, hmask, c0, v0);
+      float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
+      if (ep.z) {
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
+        o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
+      }
+      reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
+    }
+    b0 = b1; n0 = n1; c0 = c1; v0 = v1;
+    b1 = b2; n1 = n2;
   }
-  reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
 }
 
 // ---- planned long rows ---------------------------------------------------------------------------
@@ -239,35 +275,61 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
   }
 }
 
-// one half warp per chunk (grid-stride): partial[c, :] = A[row, chunk] . X
-__global__ void __launch_bounds__(SPMM_THREADS) spmm64_chunks_kernel(const int64_t* __restrict__ ptr,
-                                                                     const int32_t* __restrict__ idx,
-                                                                     const float* __restrict__ val, int64_t row0,
-                                                                     int64_t row1, const float* __restrict__ x,
-                                                                     int64_t ld_x, const int64_t* __restrict__ plan,
-                                                                     int64_t cap, float* __restrict__ partial) {
+// chunk_owner[c] = i for every chunk c of planned row i (one warp per planned row)
+__global__ void __launch_bounds__(256) plan_owner_kernel(int64_t cap, int64_t* __restrict__ plan) {
+  const int64_t n = plan[0] < cap ? plan[0] : cap;
+  const int64_t* chunk_ptr = plan + 2 + cap;
+  int32_t* owner = reinterpret_cast<int32_t*>(plan + 3 + 2 * cap);
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t c0 = chunk_ptr[i], c1 = chunk_ptr[i + 1];
+    for (int64_t c = c0 + lane; c < c1; c += 32) owner[c] = (int32_t)i;
+  }
+}
+
+// one half warp per chunk (strided over all resident half warps): partial[c, :] = A[row, chunk] . X
+__device__ __forceinline__ void spmm64_chunks(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                              const float* __restrict__ val, int64_t row0, int64_t row1,
+                                              const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ plan,
+                                              int64_t cap, float* __restrict__ partial, int64_t hw_id, int64_t n_hw) {
   const int l16 = threadIdx.x & 15;
   const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
   const int64_t n_long = plan[0] < cap ? plan[0] : cap;
   const int64_t n_chunks = plan[1];
   const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
-  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
-  for (int64_t c = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4); c < n_chunks; c += n_hw) {
-    // the planned row that owns chunk c: last i with chunk_ptr[i] <= c
-    int64_t lo = 0, hi = n_long - 1;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi + 1) >> 1;
-      if (__ldg(chunk_ptr + mid) <= c) lo = mid; else hi = mid - 1;
-    }
+  const int32_t* owner = reinterpret_cast<const int32_t*>(plan + 3 + 2 * cap);
+  (void)n_long;
+  for (int64_t c = hw_id; c < n_chunks; c += n_hw) {
+    const int64_t lo = __ldg(owner + c);           // the planned row that owns chunk c
     const int64_t r = long_rows[lo];
     if (r < row0 || r >= row1) continue;
     const int64_t b = ptr[r] + (c - chunk_ptr[lo]) * PLAN_CHUNK;
     const int64_t rend = ptr[r + 1];
     const int n = (int)(rend - b < PLAN_CHUNK ? rend - b : PLAN_CHUNK);
-    const float4 acc = gather64_hw<8>(idx, val, x, ld_x, b, n, l16, hmask);
+    int32_t mc;
+    float mv;
+    hw_first_block(idx, val, b, n, l16, mc, mv);
+    const float4 acc = gather64_hw<8>(idx, val, x, ld_x, b, n, l16, hmask, mc, mv);
     reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
   }
+}
+
+// One persistent launch for both kinds of rows of a planned adjacency (grid = SMs x resident CTAs, so every half warp
+// is live from the start and the strided assignment is balanced): each half warp first takes its share of the
+// 64-neighbour chunks of the long rows, then its share of the short rows.  The two kinds write disjoint outputs
+// (partials vs. Y rows), so nothing orders them; only the reduce of the partials follows.
+__global__ void __launch_bounds__(SPMM_THREADS, 4) spmm64_planned_kernel(const int64_t* __restrict__ ptr,
+                                                                         const int32_t* __restrict__ idx,
+                                                                         const float* __restrict__ val, int64_t row0,
+                                                                         int64_t row1, const float* __restrict__ x,
+                                                                         int64_t ld_x, Epi ep, float* __restrict__ y,
+                                                                         int64_t ld_y, const int64_t* __restrict__ plan,
+                                                                         int64_t cap, float* __restrict__ partial) {
+  const int64_t hw_id = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4);
+  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
+  spmm64_chunks(ptr, idx, val, row0, row1, x, ld_x, plan, cap, partial, hw_id, n_hw);
+  spmm64_short_rows(ptr, idx, val, row0, row1, x, ld_x, ep, y, ld_y, hw_id, n_hw);
 }
 
 // Y[row] = epilogue(sum of the row's partials), deterministic.  Pass A: rows with at most REDUCE_SMALL chunks,
@@ -393,7 +455,7 @@ __global__ void __launch_bounds__(256) sign_noise_kernel(float* __restrict__ e, 
 
 extern "C" int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz) {
   (void)n_rows;
-  return (int64_t)sizeof(int64_t) * (3 + 2 * plan_cap(nnz));
+  return (int64_t)sizeof(int64_t) * (3 + 2 * plan_cap(nnz)) + (int64_t)sizeof(int32_t) * plan_max_chunks(nnz);
 }
 
 extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
@@ -407,6 +469,8 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
   plan_collect_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(adj_ptr, n_rows, cap, (int64_t*)plan);
   DMM_LAUNCH_CHECK();
   plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
+  DMM_LAUNCH_CHECK();
+  plan_owner_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(cap, (int64_t*)plan);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
@@ -439,13 +503,18 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
     if (!planned) {
       spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, 0);
     } else {
-      spmm64_short_kernel<<<(unsigned)dmm_ceil_div(row1 - row0, SPMM_THREADS / 16), SPMM_THREADS, 0, st>>>(
-          adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y);
-      DMM_LAUNCH_CHECK();
       const int64_t cap = plan_cap(nnz);
-      // persistent grids: the chunk and row counts live on the device (no host sync)
-      spmm64_chunks_kernel<<<(unsigned)(ctx->num_sms * 8), SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x,
-                                                                                (const int64_t*)plan, cap, (float*)workspace);
+      static int resident = 0;                 // CTAs of the persistent kernel per SM
+      if (resident == 0) {
+        DMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, spmm64_planned_kernel, SPMM_THREADS, 0));
+        if (resident < 1) resident = 1;
+      }
+      int64_t blocks = (int64_t)ctx->num_sms * resident;
+      const int64_t useful = dmm_ceil_div((row1 - row0) + nnz / PLAN_CHUNK, SPMM_THREADS / 16);   // small graphs: fewer CTAs
+      if (blocks > useful) blocks = useful;
+      if (blocks < 1) blocks = 1;
+      spmm64_planned_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y,
+                                                                        ld_y, (const int64_t*)plan, cap, (float*)workspace);
       DMM_LAUNCH_CHECK();
       spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 4), SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
                                                                            (const float*)workspace, ep, y, ld_y);

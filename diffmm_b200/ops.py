@@ -281,7 +281,7 @@ def bpr_fwd_bwd(u_emb, i_emb, users, pos, neg, grad_scale=1.0, want_grad=True):
 def infonce_fwd(v1, v2, idx, temperature):
     B, D = idx.numel(), v1.shape[1]
     dev = v1.device
-    ws = torch.empty(2 * B * D, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_lib.load().dmm_infonce_workspace_floats(B, D, 0)), dtype=torch.float32, device=dev)
     row_loss = torch.empty(B, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     lse = torch.empty(B, dtype=torch.float32, device=dev)
@@ -296,7 +296,7 @@ def infonce_bwd(v1, v2, idx, temperature, saved, grad_scale=1.0):
     B, D = idx.numel(), v1.shape[1]
     dev = v1.device
     lse, inv1, inv2 = saved
-    ws = torch.empty(2 * B * D, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_lib.load().dmm_infonce_workspace_floats(B, D, 1)), dtype=torch.float32, device=dev)
     g1 = torch.empty((B, D), dtype=torch.float32, device=dev)
     g2 = torch.empty((B, D), dtype=torch.float32, device=dev)
     _lib.call("dmm_infonce_bwd", _ctx(v1), _p(v1), _row_major(v1, "v1"), _p(v2), _row_major(v2, "v2"), _p(idx), B, D,

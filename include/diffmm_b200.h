@@ -205,15 +205,18 @@ int dmm_bpr_fwd_bwd(dmm_ctx* ctx, const float* u_emb, int64_t ld_u, const float*
 /* InfoNCE (Utils/Utils.py:57-75) on gathered rows idx[b] of v1/v2: row-L2 normalise, logits/temp,
  * -mean diag log-softmax, never materialising the B x B matrix in HBM.  Forward writes loss and
  * saves per-row log-sum-exp (lse, [B]) and inverse norms (inv1, inv2, [B]); backward writes
- * d(loss)/d(gathered rows) [B, D] for both views (caller scatter-adds by idx).               */
+ * d(loss)/d(gathered rows) [B, D] for both views (caller scatter-adds by idx).
+ * `workspace` holds dmm_infonce_workspace_floats(B, D, backward) floats (the normalised gathers
+ * plus, for D == 64, the per-column-split partial results of the tiled kernels).             */
+int64_t dmm_infonce_workspace_floats(int64_t B, int64_t D, int backward);
 int dmm_infonce_fwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2, int64_t ld2,
                     const int64_t* idx, int64_t B, int64_t D, float temperature,
-                    float* workspace /* 2*B*D floats */, float* row_loss /* [B] scratch */, float* loss,
+                    float* workspace, float* row_loss /* [B] scratch */, float* loss,
                     float* lse, float* inv1, float* inv2, void* stream);
 int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2, int64_t ld2,
                     const int64_t* idx, int64_t B, int64_t D, float temperature,
                     const float* lse, const float* inv1, const float* inv2, float grad_scale,
-                    float* workspace /* 2*B*D floats */, float* g1, float* g2, void* stream);
+                    float* workspace, float* g1, float* g2, void* stream);
 
 /* Scatter-add of per-batch row gradients into a table gradient: dst[idx[b], :] += src[b, :]. */
 int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,

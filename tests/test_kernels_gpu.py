@@ -250,6 +250,30 @@ def test_infonce_b1024_vs_oracle(ops):
     np.testing.assert_allclose(loss.item(), O.info_nce(v1, v2, idx, 0.5), rtol=2e-5)
 
 
+@pytest.mark.parametrize("B", [1, 31, 64, 257, 1000, 1024, 1500])
+def test_infonce_tiled_fwd_bwd_vs_torch(ops, B):
+    """Tiled D = 64 kernels (anchor tiles x column splits, cp.async double buffering) against torch fp32 autograd of
+    Utils/Utils.py:57-75, ragged batch sizes, repeated indices."""
+    rng = np.random.default_rng(B)
+    n = 700
+    v1 = torch.tensor(rng.standard_normal((n, 64)).astype(np.float32), device=DEV, requires_grad=True)
+    v2 = torch.tensor((v1.detach().cpu().numpy() + 0.7 * rng.standard_normal((n, 64))).astype(np.float32), device=DEV,
+                      requires_grad=True)
+    idx = T(rng.integers(0, n, B))
+    a = torch.nn.functional.normalize(v1[idx], dim=1)
+    b = torch.nn.functional.normalize(v2[idx], dim=1)
+    want = -torch.diag(torch.log_softmax(a @ b.T / 0.2, dim=1)).mean()
+    want.backward()
+    loss, saved = ops.infonce_fwd(v1.detach(), v2.detach(), idx, 0.2)
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=2e-5)
+    g1, g2 = ops.infonce_bwd(v1.detach(), v2.detach(), idx, 0.2, saved, grad_scale=1.0)
+    d1 = ops.scatter_add_rows(g1, idx, torch.zeros_like(v1))
+    d2 = ops.scatter_add_rows(g2, idx, torch.zeros_like(v2))
+    scale = float(v1.grad.abs().max())
+    np.testing.assert_allclose(d1.cpu().numpy(), v1.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(d2.cpu().numpy(), v2.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * scale)
+
+
 # ------------------------------------------------------------------------------------------- staging kernels
 def test_pack_bf16_split_and_transpose(ops):
     rng = np.random.default_rng(1)
