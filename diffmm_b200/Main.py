@@ -123,15 +123,22 @@ class Coach:
 
         out_dims = ast.literal_eval(self.config.base.denoise_dim) + [self.config.data.item_num]
         in_dims = out_dims[::-1]
+        def denoise_adam(params):
+            # graph mode: phase 1 is replayed from a CUDA graph as well (device-resident step counter and lr)
+            if self._use_graph():
+                return Adam(params, lr=torch.tensor(float(self.config.train.lr), device=self.device), weight_decay=0,
+                            capturable=True)
+            return Adam(params, lr=self.config.train.lr, weight_decay=0)
+
         self.image_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
-        self.image_denoise_opt = Adam(self.image_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        self.image_denoise_opt = denoise_adam(self.image_denoise_model.parameters())
         self.image_scheduler = CosineAnnealingLR(self.image_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
         self.text_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
-        self.text_denoise_opt = Adam(self.text_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+        self.text_denoise_opt = denoise_adam(self.text_denoise_model.parameters())
         self.text_scheduler = CosineAnnealingLR(self.text_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
         if self.has_audio:
             self.audio_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
-            self.audio_denoise_opt = Adam(self.audio_denoise_model.parameters(), lr=self.config.train.lr, weight_decay=0)
+            self.audio_denoise_opt = denoise_adam(self.audio_denoise_model.parameters())
             self.audio_scheduler = CosineAnnealingLR(self.audio_denoise_opt, T_max=self.config.train.epoch, eta_min=1e-4)
 
     def makeTorchAdj(self, u_list, i_list, edge_list):
@@ -162,6 +169,8 @@ class Coach:
         (a host sync per modality and batch), normalises the summed loss by the python float total and keeps running
         python-float sums: here those scalars stay on the device in float64 (IEEE-identical adds and divides, the fp32
         divisor is the fp32 rounding of the float64 total exactly like torch's scalar division), read once per epoch."""
+        if self._use_graph():
+            return self._trainDiffusionGraph()
         zero = torch.zeros((), dtype=torch.float64, device=self.device)
         image_diff_loss, text_diff_loss, audio_diff_loss = zero.clone(), zero.clone(), zero.clone()
         for i, batch_data in enumerate(self.handler.diffusionLoader):
@@ -201,6 +210,87 @@ class Coach:
             if self.has_audio:
                 self.audio_denoise_opt.step()
         return image_diff_loss.item(), text_diff_loss.item(), audio_diff_loss.item()
+
+    def _diffusion_step(self, batch_u_items, ts, acc):
+        """One batch of phase 1 with the timesteps given (drawn on the host in the reference's order): the M per-row
+        losses, their normalised sum, backward, M Adam steps; acc[k] <- (acc[k] + loss_k) / total in place (float64),
+        the running sums of Main.py:155-182.  No host sync, no host tensor: capturable."""
+        i_embs = self.model.getItemEmbs()
+        dens = [self.image_denoise_model, self.text_denoise_model]
+        opts = [self.image_denoise_opt, self.text_denoise_opt]
+        feats = [self.model.getImageFeats().detach(), self.model.getTextFeats().detach()]
+        if self.has_audio:
+            dens.append(self.audio_denoise_model)
+            opts.append(self.audio_denoise_opt)
+            feats.append(self.model.getAudioFeats().detach())
+        losses = [self.diffusion_model.training_losses(d, batch_u_items, i_embs, f, timesteps=t).mean()
+                  for d, f, t in zip(dens, feats, ts)]
+        for o in opts:
+            o.zero_grad()
+        # the item embeddings also receive a (never used: Main.py:375 zeroes it first) gradient here; dropping the old
+        # one keeps a captured backward from accumulating into a tensor that lives outside the graph's memory pool
+        self.model.zero_grad(set_to_none=True)
+        total = losses[0].detach().double()
+        for l in losses[1:]:
+            total = total + l.detach().double()
+        summed = losses[0]
+        for l in losses[1:]:
+            summed = summed + l
+        batch_diff_loss = summed / total.to(summed.dtype)
+        for k, l in enumerate(losses):
+            acc[k] = (acc[k] + l.detach().double()) / total
+        batch_diff_loss.backward()
+        for o in opts:
+            o.step()
+
+    def _trainDiffusionGraph(self):
+        """Phase 1 replayed from ONE CUDA graph (captured in the first epoch after two eager warm-up batches): the
+        batch rows and the host-drawn timesteps are copied into static buffers; the last, smaller batch runs eagerly.
+        The device noise comes from torch's graph-safe Philox offsets."""
+        from . import autograd as _ag
+        B = self.config.train.batch
+        M = 3 if self.has_audio else 2
+        S = self.diffusion_model.steps
+        I = self.config.data.item_num
+        if not hasattr(self, "_diff_acc"):
+            self._diff_acc = torch.zeros(3, dtype=torch.float64, device=self.device)
+            self._diff_rows = torch.zeros((B, ops.pad_to(I, 4)), dtype=torch.float32, device=self.device)[:, :I]
+            self._diff_ts = [torch.zeros(B, dtype=torch.int64, device=self.device) for _ in range(M)]
+            self._diff_graph = None
+            self._diff_warm = 0
+        acc = self._diff_acc
+        acc.zero_()
+        for batch_data in self.handler.diffusionLoader:
+            rows = batch_data[0]
+            n = rows.shape[0]
+            ts = [torch.randint(0, S, (n,)).long() for _ in range(M)]          # Model.py:397 draws, image / text / audio
+            if n != B:
+                self._diffusion_step(rows, [t.to(self.device) for t in ts], acc)
+                continue
+            self._diff_rows.copy_(rows)
+            for dst, src in zip(self._diff_ts, ts):
+                dst.copy_(src, non_blocking=True)
+            if self._diff_graph is None and self._diff_warm < 2:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._diffusion_step(self._diff_rows, self._diff_ts, acc)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._diff_warm += 1
+                continue
+            if self._diff_graph is None:
+                _ag._PACK_CACHE.clear()          # packed weights must be (re)built inside the captured step
+                torch.cuda.synchronize(self.device)
+                self._diff_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._diff_graph):
+                    self._diffusion_step(self._diff_rows, self._diff_ts, acc)
+            self._diff_graph.replay()
+        # a replay updates the weights without bumping their version counters: drop everything derived from them
+        _ag._PACK_CACHE.clear()
+        for den in self._denoise_dict().values():
+            den._dmm_hidden_ops = None
+        out = acc.tolist()
+        return out[0], out[1], out[2]
 
     def rebuildGraphs(self):
         """Phase 2 (Main.py:195-253) on device.  The shuffled loader of the reference only permutes users,

@@ -305,7 +305,7 @@ class GaussianDiffusion(nn.Module):
         reconstruction_loss = F.mse_loss(model_output, x_start, reduction="none").mean(dim=-1)
         timesteps_minus1 = torch.clamp(timesteps - 1, min=0)
         weight = self.SNR(timesteps_minus1) - self.SNR(timesteps)
-        weight = torch.where(timesteps == 0, torch.tensor(1.0, device=weight.device), weight)
+        weight = torch.where(timesteps == 0, 1.0, weight)      # scalar branch: no host tensor (CUDA-graph capturable)
         reconstruction_loss = weight * reconstruction_loss
 
         prec = model.precision
