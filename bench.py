@@ -44,6 +44,15 @@ KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sor
 }
 
 
+_RESULT_FD = 1
+
+
+def emit(line):
+    """Writes the result line to the process's original stdout (see main)."""
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -282,7 +291,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_sample} users x {len(w['modalities'])} modalities x {args.steps} steps"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -349,14 +358,17 @@ def run_ours(args):
         _ag._PACK_CACHE.clear()
         for dn in dens.values():
             dn._dmm_hidden_ops = None
-        if world > 1:
-            items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1))
-            items = {m: ddist.allgather_edges(v, ip, U_tot, None, plan) for m, v in items.items()}
-            return {m: ops.build_norm_adj(ip, v, U_tot, I) for m, v in items.items()}, items
-        adjs = {}
-        items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1),
-                                      per_modality=lambda v: ops.build_norm_adj(ip, v, U_tot, I), per_modality_out=adjs)
-        return adjs, items
+        # per modality, on that modality's stream: chain + top-k on the rank's user block, then (N > 1) the NCCL
+        # all-gather of the edge list and the normalised adjacency of the whole graph
+        res = {}
+
+        def follow(v):
+            if world > 1:
+                v = ddist.allgather_edges(v, ip, U_tot, None, plan)
+            return ops.build_norm_adj(ip, v, U_tot, I), v
+        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1), per_modality=follow,
+                              per_modality_out=res)
+        return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
 
     def step_device():
         return rebuild_step(d_indptr, d_indices)
@@ -587,7 +599,7 @@ def run_ours(args):
             line["epoch_sec_cuda_graph"] = epoch_seconds(args.workload, args.seed, args.precision, cuda_graph=True)
         except Exception as e:  # the headline number must survive a failure of the auxiliary measurement
             line["epoch_sec"] = {"error": repr(e)[:300]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         td.destroy_process_group()
 
@@ -607,10 +619,23 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the top-k / SpMM / adjacency roofline measurements")
     ap.add_argument("--no-epoch", action="store_true", help="skip the full-epoch (phases 1-3 + eval) timing")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) write to stderr
+    # while the run is in progress; the saved descriptor is restored for the result line
+    global _RESULT_FD
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _RESULT_FD = real_stdout
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        _RESULT_FD = 1
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":

@@ -391,15 +391,15 @@ def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: 
     With a torch.distributed ``group`` of more than one rank, users are row-sharded and the edge lists
     all-gathered (dist.py); every rank then builds the same adjacency."""
     from . import dist as ddist
-    if group is not None and ddist.world_size(group) > 1:
-        r0, r1 = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr)
-        items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                              row_range=(r0, r1), block_rows=block_rows)
-        items = {m: ddist.allgather_edges(v, indptr, n_users, group, plan) for m, v in items.items()}
-    else:
-        adjs: Dict[str, ops.CsrAdj] = {}
-        rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                      block_rows=block_rows, per_modality=lambda v: ops.build_norm_adj(indptr, v, n_users, n_items),
-                      per_modality_out=adjs)
-        return {m: adjs[m] for m in denoise_models}
-    return {m: ops.build_norm_adj(indptr, v, n_users, n_items) for m, v in items.items()}
+    sharded = group is not None and ddist.world_size(group) > 1
+    row_range = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr) if sharded else None
+
+    def follow(v):
+        # on the modality's stream: (sharded) all-gather of the edge list, then the adjacency of the whole graph
+        if sharded:
+            v = ddist.allgather_edges(v, indptr, n_users, group, plan)
+        return ops.build_norm_adj(indptr, v, n_users, n_items)
+    adjs: Dict[str, ops.CsrAdj] = {}
+    rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision, row_range=row_range,
+                  block_rows=block_rows, per_modality=follow, per_modality_out=adjs)
+    return {m: adjs[m] for m in denoise_models}
