@@ -23,7 +23,7 @@ constexpr int PLAN_LONG_ROW = 64;    // rows with more neighbours go through the
 constexpr int PLAN_CHUNK = 64;       // neighbours per chunk of a planned row (one warp each)
 
 // plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr,
-// then int32 chunk_owner[plan_max_chunks]: index (into the long row list) of the row that owns each chunk
+// then (16-byte aligned) one descriptor per chunk, int4 {row, neighbours, first entry lo, first entry hi}
 __host__ __device__ inline int64_t plan_cap(int64_t nnz) { return nnz / PLAN_LONG_ROW + 1; }
 __host__ __device__ inline int64_t plan_max_chunks(int64_t nnz) { return nnz / PLAN_CHUNK + plan_cap(nnz) + 1; }
 
@@ -275,15 +275,25 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
   }
 }
 
-// chunk_owner[c] = i for every chunk c of planned row i (one warp per planned row)
-__global__ void __launch_bounds__(256) plan_owner_kernel(int64_t cap, int64_t* __restrict__ plan) {
+// first word of the chunk descriptors inside the plan (16-byte aligned: the plan buffer is, and the offset is even)
+__host__ __device__ inline int64_t plan_desc_word(int64_t cap) { return (3 + 2 * cap + 1) & ~(int64_t)1; }
+
+// descriptor of every chunk c of planned row i: {row, neighbours in the chunk, first entry} (one warp per planned row)
+__global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restrict__ ptr, int64_t cap, int64_t* __restrict__ plan) {
   const int64_t n = plan[0] < cap ? plan[0] : cap;
+  const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
-  int32_t* owner = reinterpret_cast<int32_t*>(plan + 3 + 2 * cap);
+  int4* desc = reinterpret_cast<int4*>(plan + plan_desc_word(cap));
   const int lane = threadIdx.x & 31;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t r = long_rows[i];
+    const int64_t rb = ptr[r], re = ptr[r + 1];
     const int64_t c0 = chunk_ptr[i], c1 = chunk_ptr[i + 1];
-    for (int64_t c = c0 + lane; c < c1; c += 32) owner[c] = (int32_t)i;
+    for (int64_t c = c0 + lane; c < c1; c += 32) {
+      const int64_t b = rb + (c - c0) * PLAN_CHUNK;
+      const int nn = (int)(re - b < PLAN_CHUNK ? re - b : PLAN_CHUNK);
+      desc[c] = make_int4((int)r, nn, (int)(uint32_t)(b & 0xFFFFFFFFll), (int)(b >> 32));
+    }
   }
 }
 
@@ -292,21 +302,17 @@ __device__ __forceinline__ void spmm64_chunks(const int64_t* __restrict__ ptr, c
                                               const float* __restrict__ val, int64_t row0, int64_t row1,
                                               const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ plan,
                                               int64_t cap, float* __restrict__ partial, int64_t hw_id, int64_t n_hw) {
+  (void)ptr;
   const int l16 = threadIdx.x & 15;
   const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  const int64_t n_long = plan[0] < cap ? plan[0] : cap;
   const int64_t n_chunks = plan[1];
-  const int64_t* long_rows = plan + 2;
-  const int64_t* chunk_ptr = plan + 2 + cap;
-  const int32_t* owner = reinterpret_cast<const int32_t*>(plan + 3 + 2 * cap);
-  (void)n_long;
+  const int4* desc = reinterpret_cast<const int4*>(plan + plan_desc_word(cap));
   for (int64_t c = hw_id; c < n_chunks; c += n_hw) {
-    const int64_t lo = __ldg(owner + c);           // the planned row that owns chunk c
-    const int64_t r = long_rows[lo];
+    const int4 d = __ldg(desc + c);
+    const int64_t r = d.x;
     if (r < row0 || r >= row1) continue;
-    const int64_t b = ptr[r] + (c - chunk_ptr[lo]) * PLAN_CHUNK;
-    const int64_t rend = ptr[r + 1];
-    const int n = (int)(rend - b < PLAN_CHUNK ? rend - b : PLAN_CHUNK);
+    const int n = d.y;
+    const int64_t b = (int64_t)(uint32_t)d.z | ((int64_t)d.w << 32);
     int32_t mc;
     float mv;
     hw_first_block(idx, val, b, n, l16, mc, mv);
@@ -328,6 +334,18 @@ __global__ void __launch_bounds__(SPMM_THREADS, 4) spmm64_planned_kernel(const i
                                                                          int64_t cap, float* __restrict__ partial) {
   const int64_t hw_id = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4);
   const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
+  // Small graphs (fewer chunks than half of the resident half warps): the first n_chunks half warps take ONE chunk
+  // each and the others share the short rows, so the two dependent chains run side by side instead of back to back
+  // (the launch is latency bound there).  Otherwise every half warp takes its share of both.
+  const int64_t n_chunks = plan[1];
+  if (2 * n_chunks <= n_hw) {
+    if (hw_id < n_chunks) {
+      spmm64_chunks(ptr, idx, val, row0, row1, x, ld_x, plan, cap, partial, hw_id, n_hw);
+    } else {
+      spmm64_short_rows(ptr, idx, val, row0, row1, x, ld_x, ep, y, ld_y, hw_id - n_chunks, n_hw - n_chunks);
+    }
+    return;
+  }
   spmm64_chunks(ptr, idx, val, row0, row1, x, ld_x, plan, cap, partial, hw_id, n_hw);
   spmm64_short_rows(ptr, idx, val, row0, row1, x, ld_x, ep, y, ld_y, hw_id, n_hw);
 }
@@ -455,7 +473,7 @@ __global__ void __launch_bounds__(256) sign_noise_kernel(float* __restrict__ e, 
 
 extern "C" int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz) {
   (void)n_rows;
-  return (int64_t)sizeof(int64_t) * (3 + 2 * plan_cap(nnz)) + (int64_t)sizeof(int32_t) * plan_max_chunks(nnz);
+  return (int64_t)sizeof(int64_t) * (4 + 2 * plan_cap(nnz)) + (int64_t)sizeof(int4) * plan_max_chunks(nnz);
 }
 
 extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
@@ -470,7 +488,7 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
   DMM_LAUNCH_CHECK();
   plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
   DMM_LAUNCH_CHECK();
-  plan_owner_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(cap, (int64_t*)plan);
+  plan_desc_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

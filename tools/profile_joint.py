@@ -32,3 +32,9 @@ tot = sum(e.self_device_time_total for e in ev)
 print(f"GPU time per step: {tot / N / 1e3:.3f} ms over {sum(e.count for e in ev) / N:.0f} kernels/step")
 for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:40]:
     print(f"{e.self_device_time_total / N:9.1f} us/step  x{e.count / N:5.1f}  {e.key[:110]}")
+
+kern = [e for e in ev if not e.key.startswith(("aten::", "Optimizer", "InfoNCEFn", "SpMM", "LinearTN", "_SignNoise", "autograd", "Memcpy", "Memset", "BPR", "bpr", "ScatterRows")) or e.key.startswith(("Memcpy", "Memset"))]
+print("--- by launch count (kernels only) ---")
+print(f"kernels/step: {sum(e.count for e in kern) / N:.0f}")
+for e in sorted(kern, key=lambda e: -e.count)[:45]:
+    print(f"x{e.count / N:6.1f}  {e.self_device_time_total / N:8.1f} us/step  {e.key[:120]}")
