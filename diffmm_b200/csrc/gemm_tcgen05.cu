@@ -1145,6 +1145,13 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
     consider(256, false, waves(m128 * dmm_ceil_div(N, 256), sms) * 256.0 / 0.93);
     if (pair_ok && sms >= 2) consider(256, true, waves(m256 * dmm_ceil_div(N, 256), sms / 2) * 256.0 / 1.0);
   }
+  // DMM_GEMM_BN=64|128|256 (with DMM_GEMM_PAIR) overrides the cost model (tile-shape experiments)
+  static const int force_bn = []() { const char* e = getenv("DMM_GEMM_BN"); return e ? atoi(e) : 0; }();
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
+    static const bool force_pair = []() { const char* e = getenv("DMM_GEMM_PAIR"); return e && e[0] == '1'; }();
+    bn = force_bn;
+    pair = force_bn == 256 && force_pair;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // TMA epilogue (residual prefetch ring + bulk tensor stores) for the single-pass bf16 configurations;
   // DMM_GEMM_TEPI=0 keeps the register-staged epilogue (A/B switch for measurements)
