@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(256) time_bias_kernel(int64_t t0, int d, const
 template <bool LO>
 __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __restrict__ indptr,
                                                              const int32_t* __restrict__ indices,
-                                                             const int64_t* __restrict__ row_ids, int64_t row0,
+                                                             const int64_t* __restrict__ row_ids,
+                                                             const int32_t* __restrict__ order, int64_t row0,
                                                              int64_t n_rows, int64_t n_cols,
                                                              const uint16_t* __restrict__ wt_hi,
                                                              const uint16_t* __restrict__ wt_lo, int64_t ld_w,
@@ -240,8 +241,9 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
   // one warp per (row, 256-column slice); lane l owns the 8 columns c0 .. c0+7 of the slice
   const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t r = wg / slices;
-  if (r >= n_rows) return;
+  const int64_t slot = wg / slices;
+  if (slot >= n_rows) return;
+  const int64_t r = order ? (int64_t)__ldg(order + slot) : slot;     // scheduling order only: outputs go to row r
   const int64_t c0 = (wg % slices) * 256 + 8 * lane;
   const bool col_ok = c0 < n_out;             // a piece that starts below n_out lies inside the padded row
   const int64_t u = row_ids ? row_ids[r] : row0 + r;
@@ -320,6 +322,30 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
       if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
     }
   }
+}
+
+// ------------------------------------------------------------------ scheduling order: long rows first
+// order[] = a permutation of 0..n_rows-1 with every row of more than `threshold` entries in front (slots taken from
+// the front by the long rows, from the back by the others; warp-aggregated atomics on two counters).  The order
+// among equals is arbitrary: it only decides WHEN dmm_csr_gather_act schedules a row, never what it computes.
+__global__ void __launch_bounds__(256) rows_long_first_kernel(const int64_t* __restrict__ indptr, int64_t row0, int64_t n_rows,
+                                                              int threshold, int32_t* __restrict__ order,
+                                                              int32_t* __restrict__ counters) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool in = r < n_rows;
+  const bool heavy = in && (indptr[row0 + r + 1] - indptr[row0 + r] > threshold);
+  const uint32_t mh = __ballot_sync(0xffffffffu, heavy), ml = __ballot_sync(0xffffffffu, in && !heavy);
+  int bh = 0, bl = 0;
+  if (lane == 0) {
+    if (mh) bh = atomicAdd(counters, __popc(mh));
+    if (ml) bl = atomicAdd(counters + 1, __popc(ml));
+  }
+  bh = __shfl_sync(0xffffffffu, bh, 0);
+  bl = __shfl_sync(0xffffffffu, bl, 0);
+  const uint32_t below = (1u << lane) - 1u;
+  if (heavy) order[bh + __popc(mh & below)] = (int32_t)r;
+  else if (in) order[n_rows - 1 - (bl + __popc(ml & below))] = (int32_t)r;
 }
 
 // ------------------------------------------------------------------ y = W[:, :K] x  (fp32, one warp per row)
@@ -506,6 +532,7 @@ extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, c
 }
 
 extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                                  const int32_t* order,
                                   int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                                   const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
                                   uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z,
@@ -526,10 +553,10 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
   DMM_CHECK_ARG(blocks < (1LL << 31), "dmm_csr_gather_act: too many rows");
   const unsigned grid = (unsigned)blocks;
   if (wt_lo) {
-    csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
+    csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, order, row0, n_rows, n_cols, wt_hi,
                                                                        wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
   } else {
-    csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_rows, n_cols, wt_hi,
+    csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, order, row0, n_rows, n_cols, wt_hi,
                                                                         wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
   }
   DMM_LAUNCH_CHECK();
@@ -572,6 +599,18 @@ extern "C" int dmm_gemv_f32(dmm_ctx* ctx, const float* w, int64_t ld_w, int64_t 
   DMM_CHECK_ARG(n_rows > 0 && K > 0 && ld_w >= K, "dmm_gemv_f32: bad shape");
   DMM_CHECK_ARG(n_rows < (1LL << 31), "dmm_gemv_f32: too many rows");
   gemv_rows_kernel<<<(unsigned)n_rows, 128, 0, (cudaStream_t)stream>>>(w, ld_w, n_rows, K, x, y);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_rows_long_first(dmm_ctx* ctx, const int64_t* indptr, int64_t row0, int64_t n_rows, int64_t threshold,
+                                   int32_t* order, int32_t* counters, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && order && counters, "dmm_rows_long_first: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31) && threshold >= 0 && threshold < (1LL << 31), "dmm_rows_long_first: bad sizes");
+  if (n_rows == 0) return DMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DMM_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
+  rows_long_first_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(indptr, row0, n_rows, (int)threshold, order, counters);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

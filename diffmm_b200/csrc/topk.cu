@@ -293,11 +293,12 @@ template <bool IN_SMEM>
 __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_rows,
                                                          int n_cols, const int64_t* __restrict__ out_ptr,
                                                          int64_t row_base, int32_t* __restrict__ out_users,
-                                                         int32_t* __restrict__ out_items, int32_t* __restrict__ status) {
+                                                         int32_t* __restrict__ out_items, int32_t* __restrict__ status,
+                                                         const int32_t* __restrict__ order) {
   extern __shared__ uint32_t s_keys[];  // n_cols keys when IN_SMEM
   __shared__ TopkSmem<256> sm;
-  const int64_t r = blockIdx.x;
-  if (r >= n_rows) return;
+  if ((int64_t)blockIdx.x >= n_rows) return;
+  const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;   // scheduling order only
   const int64_t o0 = out_ptr[r], o1 = out_ptr[r + 1];
   int k = (int)(o1 - o0);
   if (k <= 0) return;
@@ -314,11 +315,13 @@ template <int NT>
 __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_rows,
                                                            int n_cols, const int64_t* __restrict__ out_ptr,
                                                            int64_t row_base, int32_t* __restrict__ out_users,
-                                                           int32_t* __restrict__ out_items, int32_t* __restrict__ status) {
+                                                           int32_t* __restrict__ out_items, int32_t* __restrict__ status,
+                                                           const int32_t* __restrict__ order) {
   __shared__ TopkSmem<NT> sm;
   constexpr int NW = NT / 32;
-  const int64_t r = blockIdx.x;
-  if (r >= n_rows) return;
+  if ((int64_t)blockIdx.x >= n_rows) return;
+  // scheduling order only (rows with a large k take the slower exact paths: started first, they overlap the rest)
+  const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
   const float* row = scores + r * ld;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
@@ -477,16 +480,16 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
 
 template <int NT>
 void launch_reg(const float* scores, int64_t ld, int64_t n_rows, int n_cols, const int64_t* out_ptr, int64_t row_base,
-                int32_t* out_users, int32_t* out_items, int32_t* status, cudaStream_t st) {
+                int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order, cudaStream_t st) {
   topk_rows_reg_kernel<NT><<<(unsigned)n_rows, NT, 0, st>>>(scores, ld, n_rows, n_cols, out_ptr, row_base, out_users,
-                                                           out_items, status);
+                                                           out_items, status, order);
 }
 
 }  // namespace
 
 extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                               const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
-                              int32_t* status, void* stream) {
+                              int32_t* status, const int32_t* order, void* stream) {
   DMM_CHECK_ARG(ctx && scores && out_ptr && out_items, "dmm_topk_edges: null argument");
   DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges: bad shape n_cols=%lld ld=%lld",
                 (long long)n_cols, (long long)ld);
@@ -498,11 +501,11 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
   if (force_generic) {
     // fall through to the generic kernels below
   } else if (n_cols <= 256 * PER_THREAD) {
-    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, st);
+    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
   } else if (n_cols <= 512 * PER_THREAD) {
-    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, st);
+    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
   } else if (n_cols <= 1024 * PER_THREAD) {
-    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, st);
+    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
   }
   if (force_generic || n_cols > 1024 * PER_THREAD) {
     const size_t smem = (size_t)n_cols * sizeof(uint32_t);
@@ -515,10 +518,10 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
         configured = cap;
       }
       topk_edges_kernel<true><<<(unsigned)n_rows, 256, smem, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                  out_users, out_items, status);
+                                                                  out_users, out_items, status, order);
     } else {
       topk_edges_kernel<false><<<(unsigned)n_rows, 256, 0, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                out_users, out_items, status);
+                                                                out_users, out_items, status, order);
     }
   }
   DMM_LAUNCH_CHECK();

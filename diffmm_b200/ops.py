@@ -92,13 +92,25 @@ def time_bias(emb_w, emb_b, weight, col0, bias, t0, n_t=1, out=None):
 
 
 def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0,
-                   z_f32=None):
+                   z_f32=None, order=None):
     """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo); z_f32 (optional)
-    receives the sums without bias."""
+    receives the sums without bias.  order (int32 permutation of the rows): scheduling order, e.g. longest rows first."""
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
-    _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows), int(n_cols),
+    assert order is None or (order.dtype == torch.int32 and order.numel() == n_rows)
+    _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), _p(order), int(row0), int(n_rows),
+              int(n_cols),
               _p(wt_hi), _p(wt_lo), _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo),
               _row_major(h_hi, "h_hi"), _p(z_f32), _row_major(z_f32, "z_f32") if z_f32 is not None else 0, _stream())
+
+
+def rows_long_first(indptr, row0, n_rows, threshold=32):
+    """int32 permutation of the block's rows with the rows of more than `threshold` entries in front (scheduling order
+    of csr_gather_act; arbitrary among equals)."""
+    order = torch.empty(n_rows, dtype=torch.int32, device=indptr.device)
+    counters = torch.empty(2, dtype=torch.int32, device=indptr.device)
+    _lib.call("dmm_rows_long_first", _ctx(indptr), _p(indptr), int(row0), int(n_rows), int(threshold), _p(order), _p(counters),
+              _stream())
+    return order
 
 
 def gemv_f32(w, K, x, out=None):
@@ -177,13 +189,14 @@ def gemm_f32_tn(a, b, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residua
 
 
 # ----------------------------------------------------------------------------------------- top-k
-def topk_edges(scores, n_cols, out_ptr, row_base, out_users, out_items, status=None):
-    """Emits, for each row r, the (out_ptr[r+1]-out_ptr[r]) largest columns (ascending) at out_ptr[r]."""
+def topk_edges(scores, n_cols, out_ptr, row_base, out_users, out_items, status=None, order=None):
+    """Emits, for each row r, the (out_ptr[r+1]-out_ptr[r]) largest columns (ascending) at out_ptr[r].
+    order (int32 permutation of the rows): scheduling order, e.g. largest k first."""
     assert scores.dtype == torch.float32 and out_ptr.dtype == torch.int64 and out_items.dtype == torch.int32
     n_rows = scores.shape[0]
     assert out_ptr.numel() >= n_rows + 1
     _lib.call("dmm_topk_edges", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(out_ptr),
-              int(row_base), _p(out_users), _p(out_items), _p(status), _stream())
+              int(row_base), _p(out_users), _p(out_items), _p(status), _p(order), _stream())
 
 
 # ----------------------------------------------------------------------------------------- adjacency

@@ -113,7 +113,8 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
                   csr: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, row_ids: Optional[torch.Tensor] = None,
                   row0: int = 0, n_rows: Optional[int] = None, sampling_step: int = 0,
                   precision: Optional[str] = None, ws: Optional[ChainWorkspace] = None,
-                  noise: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
+                  noise: Optional[torch.Tensor] = None, mode: Optional[str] = None,
+                  order: Optional[torch.Tensor] = None) -> torch.Tensor:
     """generate_view (Model.py:300-322) for a block of users given as dense rows or CSR rows.
     Returns the fp32 [n_rows, I] scores (a view of the workspace: consume before the next call).
 
@@ -149,7 +150,7 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     c2_last = float(np.float32(diff._h_coef2[0]))
     if mode == "full" or c2_last != 0.0 or S < 2:
         return _denoise_chain_full(diff, den, ws, M, x_dense=x_dense, csr=csr, row_ids=row_ids, row0=row0,
-                                   sampling_step=sampling_step, split=split, noise=noise)
+                                   sampling_step=sampling_step, split=split, noise=noise, order=order)
 
     h_hi, h_lo, x = ws.h_hi[:M], (ws.h_lo[:M] if split else None), ws.x[:M]
     xv = x[:, :I]
@@ -167,7 +168,7 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     if sampling_step == 0 and csr is not None:
         w1t_hi, w1t_lo = packed_weight(W1, True, split)                    # W1^T [I + d, pad(H)]: gathered by item id
         ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, ws.bias_eff[S - 1], 1, H, h_hi, h_lo,
-                           row_ids=row_ids, row0=row0, z_f32=z)
+                           row_ids=row_ids, row0=row0, z_f32=z, order=order)
     else:
         a_hi, a_lo = ws.operand()
         a_hi = a_hi[:M]
@@ -216,7 +217,7 @@ def _fill_operand(diff, ws, M, I, a_hi, a_lo, x_dense, csr, row_ids, row0, sampl
         ops.q_sample(x0, noise, ca, cb, 1, a_hi=a_hi, a_lo=a_lo)
 
 
-def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampling_step, split, noise):
+def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampling_step, split, noise, order=None):
     """The literal chain: S x (first layer + tanh, second layer + posterior mean) in item space."""
     lin1, lin2 = _single_layer(den)
     W1, b1, W2, b2 = lin1.weight, lin1.bias, lin2.weight, lin2.bias
@@ -254,7 +255,7 @@ def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampli
         first_sparse = sparse_first and i == S - 1
         if first_sparse:
             ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, bias1, 1, H, h_hi, h_lo,
-                               row_ids=row_ids, row0=row0)
+                               row_ids=row_ids, row0=row0, order=order)
         else:
             _gemm1(ws, a_hi, a_lo, w1_hi, w1_lo, M, H, I, bias1, h_hi, h_lo)
         c1 = float(np.float32(diff._h_coef1[i]))          # fp64 table -> .float() (Model.py:352)
@@ -318,6 +319,24 @@ def default_block_rows(n_users: int, n_items: int, hidden: int, split: bool, bud
     return int(min(n_users, rows))
 
 
+_ORDER_CACHE: dict = {}
+
+
+def longest_rows_first(indptr: torch.Tensor, row0: int, n_rows: int) -> torch.Tensor:
+    """Scheduling order of dmm_csr_gather_act for the user block [row0, row0 + n_rows): users with more than 32
+    interactions first (int32 permutation).  A user with hundreds of interactions is a chain of dozens of dependent
+    gather rounds; scheduled last it IS the tail of the launch (measured: a third of the kernel), scheduled first it
+    overlaps everything else.  One small kernel (dmm_rows_long_first), no host sync; cached per indptr tensor (same
+    object, same version)."""
+    key = (id(indptr), indptr._version, indptr.data_ptr(), row0, n_rows)
+    ent = _ORDER_CACHE.get("last")
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    order = ops.rows_long_first(indptr, row0, n_rows, 32)
+    _ORDER_CACHE["last"] = (key, order, indptr)        # the tensor is kept alive so that id() stays unique
+    return order
+
+
 _SIDE_STREAMS: Dict[Tuple[int, int], list] = {}
 
 
@@ -356,6 +375,8 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     if out_items is None:
         out_items = {m: torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E] for m in denoise_models}
     mods = list(denoise_models.items())
+    orders = {b0: longest_rows_first(indptr, b0, min(b0 + block_rows, r1) - b0) for b0 in range(r0, r1, block_rows)} \
+        if sampling_step == 0 else {}
     n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(mods))
     streams = []
     if n_streams > 1 and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
@@ -375,8 +396,8 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
                     if ws is None or not ws.fits(b1 - b0, n_items, H, den.time_emb_dim, split):
                         ws = ChainWorkspace(b1 - b0, n_items, H, den.time_emb_dim, split, dev)
                     scores = denoise_chain(diff, den, csr=(indptr, indices), row0=b0, n_rows=b1 - b0,
-                                           sampling_step=sampling_step, precision=precision, ws=ws)
-                    ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m])
+                                           sampling_step=sampling_step, precision=precision, ws=ws, order=orders.get(b0))
+                    ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m], order=orders.get(b0))
                 if per_modality is not None:
                     per_modality_out[m] = per_modality(out_items[m])
     for st in streams:

@@ -78,11 +78,19 @@ int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, const float*
  * written as bf16 hi (+ lo) [n_rows, ld_h].  The dense contraction of Model.py:212 degenerates to a
  * gather-sum for 0/1 rows; rows are selected like in dmm_csr_rows_to_dense.  z_f32 (optional,
  * [n_rows, ld_z]) receives the plain sums x0 . W^T without bias: the fp32 state of the hidden-space
- * reverse chain.                                                                              */
+ * reverse chain.  `order` (optional, int32 [n_rows], a permutation of 0..n_rows-1) is the order in which
+ * the rows are SCHEDULED (results do not depend on it): with the users of hundreds of interactions first,
+ * their long gather chains overlap the rest of the grid instead of forming its tail.            */
 int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
-                       int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
+                       const int32_t* order, int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                        const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
                        uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z, void* stream);
+
+/* Scheduling order for dmm_csr_gather_act: order[] (int32 [n_rows]) becomes a permutation of 0..n_rows-1 with every
+ * row of the block [row0, row0 + n_rows) that has more than `threshold` entries in front (arbitrary order among
+ * equals; `counters` is 2 int32 of device scratch).  No host sync.                                         */
+int dmm_rows_long_first(dmm_ctx* ctx, const int64_t* indptr, int64_t row0, int64_t n_rows, int64_t threshold,
+                        int32_t* order, int32_t* counters, void* stream);
 
 /* y[r] = sum_k w[r, k] x[k], k < K (fp32): q = W1[:, :I] b2 of the hidden-space reverse chain (the image of
  * the second layer's bias, Model.py:215, under the first layer, Model.py:212).                          */
@@ -148,11 +156,13 @@ int dmm_gemm_f32_tn(dmm_ctx* ctx, const float* a, int64_t lda, const float* b, i
  * For row r of scores [n_rows, n_cols] (ld) emits the k_r = out_ptr[r+1]-out_ptr[r] largest
  * entries' column indices into out_items[out_ptr[r] .. out_ptr[r+1]) sorted ascending by column,
  * and row_base + r into out_users.  Tie-break: value descending, then column ascending.
- * k_r > n_cols is an error flagged in *status (device int, optional).
+ * k_r > n_cols is an error flagged in *status (device int, optional).  `order` (optional, int32
+ * permutation of 0..n_rows-1, e.g. from dmm_rows_long_first) is the order in which rows are scheduled;
+ * results do not depend on it.
  * Replaces the per-user torch.topk loop + int(indices[j]) syncs of Main.py:224-230.          */
 int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                    const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
-                   int32_t* status, void* stream);
+                   int32_t* status, const int32_t* order, void* stream);
 
 /* ---- normalised bipartite adjacency ---------------------------------------------------------
  * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and

@@ -274,6 +274,45 @@ def test_infonce_tiled_fwd_bwd_vs_torch(ops, B):
     np.testing.assert_allclose(d2.cpu().numpy(), v2.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * scale)
 
 
+@pytest.mark.parametrize("n_out", [1024, 200])
+def test_csr_gather_act_vs_dense_and_scheduling_order(ops, n_out):
+    """First Denoise layer on binary CSR rows (dmm_csr_gather_act) against the dense product on the same bf16 weights;
+    the scheduling order (longest rows first, or any permutation) must not change a single bit."""
+    rng = np.random.default_rng(n_out)
+    U, I = 300, 900
+    deg = rng.integers(0, 12, U)
+    deg[[5, 77, 200]] = [400, 650, 129]                      # users with hundreds of interactions
+    indptr = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(I, d, replace=False)) for d in deg]).astype(np.int32)
+    w = (rng.standard_normal((n_out, I)) * 0.05).astype(np.float32)          # first layer [H, I]
+    bias = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+    wt_hi, _ = ops.pack_bf16(T(w), transpose=True, split=False)              # W^T [I, pad(H)]
+    ld = ops.pad_to(n_out, 8)
+
+    def run(order):
+        h = torch.full((U, ld), 3.0, dtype=torch.bfloat16, device=DEV)
+        z = torch.full((U, ld), float("nan"), device=DEV)
+        ops.csr_gather_act(T(indptr), T(indices), U, I, wt_hi, None, T(bias), 1, n_out, h[:, :n_out], None, z_f32=z[:, :n_out],
+                           order=order)
+        return h, z
+
+    h0, z0 = run(None)
+    x0 = np.zeros((U, I), dtype=np.float32)
+    for u in range(U):
+        x0[u, indices[indptr[u]:indptr[u + 1]]] = 1.0
+    want_z = x0.astype(np.float64) @ wt_hi[:, :n_out].float().cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(z0[:, :n_out].cpu().numpy(), want_z, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(h0[:, :n_out].float().cpu().numpy(), np.tanh(want_z + bias), rtol=2 ** -8, atol=1e-5)
+    from diffmm_b200.rebuild import longest_rows_first
+    order = longest_rows_first(T(indptr), 0, U)
+    assert order.dtype == torch.int32 and sorted(order.tolist()) == list(range(U))
+    assert sorted(order[:3].tolist()) == [5, 77, 200]          # the users with more than 32 interactions come first
+    for o in (order, T(rng.permutation(U).astype(np.int32))):
+        h1, z1 = run(o)
+        assert torch.equal(h1, h0) and torch.equal(z1[:, :n_out], z0[:, :n_out])
+
+
 # ------------------------------------------------------------------------------------------- staging kernels
 def test_pack_bf16_split_and_transpose(ops):
     rng = np.random.default_rng(1)
