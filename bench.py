@@ -147,7 +147,7 @@ def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, seed=0):
     return dt, len(users), edges
 
 
-def epoch_seconds(name, seed, precision, epochs=2, cuda_graph=False):
+def epoch_seconds(name, seed, precision, epochs=3, cuda_graph=False):
     """One full training epoch + eval (phases 1-3 of Coach.trainEpoch + testEpoch) on the synthetic
     `name`-shape dataset written in the reference's on-disk format; returns the last epoch's phase seconds."""
     import tempfile
