@@ -235,3 +235,34 @@ def test_rebuild_modal_adj_end_to_end(precision, min_overlap):
     if precision == "bf16x3" and hit == tot:
         np.testing.assert_array_equal(adj.idx.cpu().numpy(), wi)
         np.testing.assert_array_equal(adj.ptr.cpu().numpy(), wp)
+
+
+def test_rebuild_stream_pipelines_are_bit_identical(monkeypatch):
+    """The modalities run as concurrent stream pipelines (rebuild.rebuild_edges, DIFFMM_STREAMS): edges and adjacencies
+    must equal the single-stream run bit for bit, on a user set large enough that the pipelines really overlap, with
+    users of hundreds of interactions (long-rows-first scheduling of the gather and the top-k)."""
+    from diffmm_b200 import synth
+    from diffmm_b200.Model import Denoise, GaussianDiffusion
+    from diffmm_b200.rebuild import rebuild_modal_adj
+    n_users, n_items = 3000, 1500
+    inter = synth.interactions(n_users, n_items, seed=3)
+    cfg = make_cfg("bf16")
+    cfg.data.user_num, cfg.data.item_num = n_users, n_items
+    torch.manual_seed(5)
+    dims = [256, n_items]
+    dens = {m: Denoise(dims[::-1], dims, cfg).to(DEV) for m in ("image", "text", "audio")}
+    gd = GaussianDiffusion(cfg).to(DEV)
+    indptr = torch.from_numpy(inter.indptr).to(DEV)
+    indices = torch.from_numpy(inter.indices).to(DEV)
+    out = {}
+    for n in ("1", "2", "3"):
+        monkeypatch.setenv("DIFFMM_STREAMS", n)
+        adjs = rebuild_modal_adj(gd, dens, indptr, indices, n_users, n_items)
+        torch.cuda.synchronize()
+        out[n] = {m: (a.ptr.clone(), a.idx.clone(), a.val.clone()) for m, a in adjs.items()}
+    for n in ("2", "3"):
+        for m in dens:
+            for a, b in zip(out["1"][m], out[n][m]):
+                assert torch.equal(a, b), (n, m)
+    # three different Denoise models: the modalities must not have been mixed up
+    assert not torch.equal(out["1"]["image"][1], out["1"]["text"][1])
