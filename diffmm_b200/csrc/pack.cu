@@ -40,28 +40,52 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ fp32 -> bf16 hi/lo, transposed
-// 64 source rows x 32 source columns per CTA through shared memory: 128-byte coalesced fp32 reads, and every
-// thread writes two consecutive destination columns (two source rows) as one 4-byte store: 128-byte lines out
+// 64 source rows x 64 source columns per CTA through a padded fp32 tile in shared memory: float4 loads (256-byte row
+// segments), and every thread converts one column run of 8 source rows into ONE 16-byte store per part (128-byte lines
+// per destination row).  dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst.
+template <bool VEC>
 __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
                                                              int64_t ld_src, uint16_t* __restrict__ hi,
                                                              uint16_t* __restrict__ lo, int64_t ld_dst) {
-  __shared__ float tile[64][33];
-  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 64; i += 8) {
-    const int64_t r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + r * ld_src + c) : 0.f;
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = tid + 256 * k;            // 64 rows x 16 float4
+    const int rr = idx >> 4, q = idx & 15;
+    const int64_t r = r0 + rr, c = c0 + 4 * q;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      if (VEC && c + 4 <= cols) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + r * ld_src + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = c + i < cols ? __ldg(src + r * ld_src + c + i) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tile[rr][4 * q + i] = v[i];
   }
   __syncthreads();
-  // dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst (even)
-  for (int i = ty; i < 32; i += 8) {
-    const int64_t c = c0 + i, r = r0 + 2 * tx;
-    if (c < cols && r < ld_dst) {
-      uint16_t h0, l0, h1, l1;
-      dmm_split_bf16(tile[2 * tx][i], h0, l0);
-      dmm_split_bf16(tile[2 * tx + 1][i], h1, l1);
-      *reinterpret_cast<uint32_t*>(hi + c * ld_dst + r) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-      if (lo) *reinterpret_cast<uint32_t*>(lo + c * ld_dst + r) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = tid + 256 * k;            // 64 destination rows x 8 pieces of 8 source rows
+    const int cc = idx >> 3, pc = idx & 7;
+    const int64_t c = c0 + cc, r = r0 + 8 * pc;
+    if (c < cols && r < ld_dst) {             // ld_dst % 8 == 0: a piece that starts below ld_dst lies inside the row
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint16_t h0, l0, h1, l1;
+        dmm_split_bf16(tile[8 * pc + 2 * j][cc], h0, l0);
+        dmm_split_bf16(tile[8 * pc + 2 * j + 1][cc], h1, l1);
+        ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      }
+      *reinterpret_cast<uint4*>(hi + c * ld_dst + r) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (lo) *reinterpret_cast<uint4*>(lo + c * ld_dst + r) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
 }
@@ -471,8 +495,12 @@ extern "C" int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64
     DMM_CHECK_ARG(ld_dst >= rows, "dmm_pack_bf16: ld_dst < rows (transposed)");
     const int64_t gy = dmm_ceil_div(ld_dst, 64);
     DMM_CHECK_ARG(gy < 65536, "dmm_pack_bf16: too many rows for the transposed path");
-    dim3 grid((unsigned)dmm_ceil_div(cols, 32), (unsigned)gy);
-    pack_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+    dim3 grid((unsigned)dmm_ceil_div(cols, 64), (unsigned)gy);
+    if (al16(src) && ld_src % 4 == 0) {
+      pack_transpose_kernel<true><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+    } else {
+      pack_transpose_kernel<false><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+    }
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
