@@ -59,6 +59,23 @@ def packed_weight(w: torch.Tensor, transpose: bool, split: bool):
     return hi, (lo if split else None)
 
 
+def packed_weight_pair(w: torch.Tensor, split: bool):
+    """Both orientations of a Parameter packed from ONE read (dmm_pack_bf16_pair) and entered into the cache, for
+    weights that are needed both ways at the same version (Linear forward + input gradient; reverse chain).  Falls
+    back to the separate packs for views that are not row-major."""
+    if not isinstance(w, torch.nn.Parameter) or not (w.dim() == 2 and w.stride(1) == 1 and w.stride(0) >= w.shape[1]):
+        return packed_weight(w, False, split), packed_weight(w, True, split)
+    ent = _PACK_CACHE.get(id(w))
+    if ent is None or ent[0]() is not w or ent[1] != w._version:
+        ent = (weakref.ref(w), w._version, {})
+        _PACK_CACHE[id(w)] = ent
+    packs = ent[2]
+    need = [t for t in (False, True) if packs.get(t) is None or (split and packs[t][1] is None)]
+    if len(need) == 2:
+        packs[False], packs[True] = ops.pack_bf16_pair(w.detach(), split=split)
+    return packed_weight(w, False, split), packed_weight(w, True, split)
+
+
 _CONST_CACHE: dict = {}    # (data_ptr, shape, stride) -> (weakref(tensor), version, {transpose: (hi, lo)})
 
 
@@ -114,7 +131,10 @@ class LinearTN(torch.autograd.Function):
         # copies are cached like the weights' instead of being rebuilt on every batch
         ctx.const_obj = x_obj if const_input else None
         x_hi, x_lo = packed_const(x_obj, False, split) if const_input else ops.pack_bf16(x, split=split)
-        w_hi, w_lo = packed_weight(weight, False, split)
+        if ctx.needs_input_grad[0]:
+            (w_hi, w_lo), _ = packed_weight_pair(weight, split)     # backward needs W^T at the same version: one read
+        else:
+            w_hi, w_lo = packed_weight(weight, False, split)
         y = _new_out(M, N, x.device)
         ops.gemm_bf16_tn(x_hi, x_lo, w_hi, w_lo, M, N, K, bias=bias.detach() if bias is not None else None, act=act,
                          out_f32=y)

@@ -43,10 +43,15 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
 // 64 source rows x 64 source columns per CTA through a padded fp32 tile in shared memory: float4 loads (256-byte row
 // segments), and every thread converts one column run of 8 source rows into ONE 16-byte store per part (128-byte lines
 // per destination row).  dst[c, r]: dst rows = src cols (only c < cols exist), dst cols = src rows, zero padded to ld_dst.
+// nat_hi / nat_lo (optional): the same tile also leaves in the source orientation ([rows, ld_nat], zero padded to
+// ld_nat), so a weight that is needed both ways (forward and input-gradient contraction; gather table and operand) is
+// read from HBM once.
 template <bool VEC>
 __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
                                                              int64_t ld_src, uint16_t* __restrict__ hi,
-                                                             uint16_t* __restrict__ lo, int64_t ld_dst) {
+                                                             uint16_t* __restrict__ lo, int64_t ld_dst,
+                                                             uint16_t* __restrict__ nat_hi, uint16_t* __restrict__ nat_lo,
+                                                             int64_t ld_nat) {
   __shared__ float tile[64][65];
   const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
   const int tid = threadIdx.x;
@@ -86,6 +91,27 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
       }
       *reinterpret_cast<uint4*>(hi + c * ld_dst + r) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       if (lo) *reinterpret_cast<uint4*>(lo + c * ld_dst + r) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+  if (nat_hi) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = tid + 256 * k;          // 64 source rows x 8 pieces of 8 source columns
+      const int rr = idx >> 3, pc = idx & 7;
+      const int64_t r = r0 + rr, c = c0 + 8 * pc;
+      if (r < rows && c < ld_nat) {           // ld_nat % 8 == 0; columns past `cols` are zero in the tile
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint16_t h0, l0, h1, l1;
+          dmm_split_bf16(tile[rr][8 * pc + 2 * j], h0, l0);
+          dmm_split_bf16(tile[rr][8 * pc + 2 * j + 1], h1, l1);
+          ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        *reinterpret_cast<uint4*>(nat_hi + r * ld_nat + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (nat_lo) *reinterpret_cast<uint4*>(nat_lo + r * ld_nat + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
     }
   }
 }
@@ -497,10 +523,33 @@ extern "C" int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64
     DMM_CHECK_ARG(gy < 65536, "dmm_pack_bf16: too many rows for the transposed path");
     dim3 grid((unsigned)dmm_ceil_div(cols, 64), (unsigned)gy);
     if (al16(src) && ld_src % 4 == 0) {
-      pack_transpose_kernel<true><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+      pack_transpose_kernel<true><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst, nullptr, nullptr, 0);
     } else {
-      pack_transpose_kernel<false><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst);
+      pack_transpose_kernel<false><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst_hi, dst_lo, ld_dst, nullptr, nullptr, 0);
     }
+  }
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_pack_bf16_pair(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                                  uint16_t* nat_hi, uint16_t* nat_lo, int64_t ld_nat, uint16_t* tr_hi, uint16_t* tr_lo,
+                                  int64_t ld_tr, void* stream) {
+  DMM_CHECK_ARG(ctx && src && nat_hi && tr_hi, "dmm_pack_bf16_pair: null argument");
+  DMM_CHECK_ARG(rows > 0 && cols > 0 && ld_src >= cols, "dmm_pack_bf16_pair: bad shape");
+  DMM_CHECK_ARG(ld_nat % 8 == 0 && ld_tr % 8 == 0 && ld_tr >= rows, "dmm_pack_bf16_pair: bad leading dimensions");
+  DMM_CHECK_ARG(ld_nat >= cols && ld_nat <= (cols + 63) / 64 * 64, "dmm_pack_bf16_pair: ld_nat must lie in [cols, pad64(cols)]");
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(nat_hi) && al16(nat_lo) && al16(tr_hi) && al16(tr_lo), "dmm_pack_bf16_pair: destinations must be 16-byte aligned");
+  DMM_CHECK_ARG((nat_lo == nullptr) == (tr_lo == nullptr), "dmm_pack_bf16_pair: lo parts are all-or-none");
+  const int64_t gy = dmm_ceil_div(ld_tr, 64);
+  DMM_CHECK_ARG(gy < 65536, "dmm_pack_bf16_pair: too many rows");
+  dim3 grid((unsigned)dmm_ceil_div(cols, 64), (unsigned)gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (al16(src) && ld_src % 4 == 0) {
+    pack_transpose_kernel<true><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, tr_hi, tr_lo, ld_tr, nat_hi, nat_lo, ld_nat);
+  } else {
+    pack_transpose_kernel<false><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, tr_hi, tr_lo, ld_tr, nat_hi, nat_lo, ld_nat);
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;

@@ -55,6 +55,20 @@ def pack_bf16(src: torch.Tensor, ld_dst: Optional[int] = None, transpose: bool =
     return hi, lo
 
 
+def pack_bf16_pair(src: torch.Tensor, split: bool = True):
+    """fp32 [R, C] -> ((hi, lo) [R, pad64(C)], (hi, lo) [C, pad64(R)]): both orientations from one read of src."""
+    assert src.dtype == torch.float32
+    ld_src = _row_major(src, "src")
+    R, Cc = src.shape
+    ld_n, ld_t = pad_to(Cc, 64), pad_to(R, 64)
+    bf = dict(dtype=torch.bfloat16, device=src.device)
+    n_hi, t_hi = torch.empty((R, ld_n), **bf), torch.empty((Cc, ld_t), **bf)
+    n_lo, t_lo = (torch.empty_like(n_hi), torch.empty_like(t_hi)) if split else (None, None)
+    _lib.call("dmm_pack_bf16_pair", _ctx(src), _p(src), R, Cc, ld_src, _p(n_hi), _p(n_lo), ld_n, _p(t_hi), _p(t_lo), ld_t,
+              _stream())
+    return (n_hi, n_lo), (t_hi, t_lo)
+
+
 def pack_bf16_into(src: torch.Tensor, hi: torch.Tensor, lo: Optional[torch.Tensor], transpose: bool = False):
     ld_src = _row_major(src, "src")
     ld = _row_major(hi, "hi")

@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import ops, rng
-from .autograd import check_precision, packed_weight
+from .autograd import check_precision, packed_weight, packed_weight_pair
 
 
 class ChainWorkspace:
@@ -98,6 +98,8 @@ def _hidden_operators(den, W1, W2, b2, I, split):
     ent = getattr(den, "_dmm_hidden_ops", None)
     if ent is None or ent[0] != key:
         H = W1.shape[0]
+        packed_weight_pair(W1, split)                            # both orientations of each weight from one read:
+        packed_weight_pair(W2, split)                            # W1 / W1^T (operand, gather table), W2 / W2^T
         w1_hi, w1_lo = packed_weight(W1, False, split)           # [H, pad(I + d)], K-major over items
         w2t_hi, w2t_lo = packed_weight(W2, True, split)          # W2^T [H, pad(I)],  K-major over items
         P = torch.empty((H, ops.pad_to(H, 4)), dtype=torch.float32, device=W1.device)[:, :H]

@@ -49,6 +49,13 @@ int dmm_num_sms(const dmm_ctx* ctx);
 int dmm_pack_bf16(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
                   uint16_t* dst_hi, uint16_t* dst_lo, int64_t ld_dst, int transpose, void* stream);
 
+/* Both orientations of one fp32 matrix from a single read: nat = bf16 hi (+ lo) [rows, ld_nat] (zero padded,
+ * cols <= ld_nat <= pad64(cols)) and tr = its transpose [cols, ld_tr] (ld_tr >= rows).  For weights that feed a
+ * contraction both ways (nn.Linear forward and input gradient; gather table and operand of the reverse chain). */
+int dmm_pack_bf16_pair(dmm_ctx* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                       uint16_t* nat_hi, uint16_t* nat_lo, int64_t ld_nat, uint16_t* tr_hi, uint16_t* tr_lo,
+                       int64_t ld_tr, void* stream);
+
 /* Binary CSR user rows -> dense GEMM operand.  For r in [0, n_rows): row_ids[r] (or row0 + r
  * when row_ids == NULL) selects the CSR row; writes x_f32[r, :] (ld_x, fp32 0/1, optional) and
  * a_bf16[r, :] (ld_a, bf16 0/1, optional), zero filling both up to n_cols.

@@ -330,6 +330,24 @@ def test_pack_bf16_split_and_transpose(ops):
     assert not hit[:, 70:].float().cpu().numpy().any()
 
 
+@pytest.mark.parametrize("shape", [(70, 45), (1024, 7060), (130, 64), (64, 130), (1, 9)])
+@pytest.mark.parametrize("split", [True, False])
+def test_pack_bf16_pair_equals_separate_packs(ops, shape, split):
+    """Both orientations from one read (dmm_pack_bf16_pair) == the two separate dmm_pack_bf16 calls, bit for bit,
+    including the zero padding."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    x = T(rng.standard_normal(shape).astype(np.float32))
+    (n_hi, n_lo), (t_hi, t_lo) = ops.pack_bf16_pair(x, split=split)
+    w_hi, w_lo = ops.pack_bf16(x, split=split)
+    wt_hi, wt_lo = ops.pack_bf16(x, transpose=True, split=split)
+    assert n_hi.shape == w_hi.shape and t_hi.shape == wt_hi.shape
+    assert torch.equal(n_hi.view(torch.int16), w_hi.view(torch.int16)) and torch.equal(t_hi.view(torch.int16), wt_hi.view(torch.int16))
+    if split:
+        assert torch.equal(n_lo.view(torch.int16), w_lo.view(torch.int16)) and torch.equal(t_lo.view(torch.int16), wt_lo.view(torch.int16))
+    else:
+        assert n_lo is None and t_lo is None
+
+
 def test_csr_rows_to_dense(ops):
     g = load_golden("generate_view")
     U, I = g["x0"].shape
