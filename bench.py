@@ -358,16 +358,17 @@ def run_ours(args):
         _ag._PACK_CACHE.clear()
         for dn in dens.values():
             dn._dmm_hidden_ops = None
-        # per modality, on that modality's stream: chain + top-k on the rank's user block, then (N > 1) the NCCL
-        # all-gather of the edge list and the normalised adjacency of the whole graph
+        # per modality, on that modality's stream: chain + top-k on the rank's user block and (N = 1) the normalised
+        # adjacency; N > 1: the NCCL all-gathers of the edge lists follow on the caller's stream, then the whole-graph
+        # adjacencies are built concurrently (rebuild.gather_and_build)
+        if world > 1:
+            items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1))
+            full = {}
+            adjs = rebuild.gather_and_build(items, ip, U_tot, I, None, plan, full_items=full)
+            return adjs, full
         res = {}
-
-        def follow(v):
-            if world > 1:
-                v = ddist.allgather_edges(v, ip, U_tot, None, plan)
-            return ops.build_norm_adj(ip, v, U_tot, I), v
-        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1), per_modality=follow,
-                              per_modality_out=res)
+        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1),
+                              per_modality=lambda v: (ops.build_norm_adj(ip, v, U_tot, I), v), per_modality_out=res)
         return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
 
     def step_device():
