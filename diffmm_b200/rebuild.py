@@ -102,10 +102,19 @@ def _hidden_operators(den, W1, W2, b2, I, split):
         packed_weight_pair(W2, split)                            # W1 / W1^T (operand, gather table), W2 / W2^T
         w1_hi, w1_lo = packed_weight(W1, False, split)           # [H, pad(I + d)], K-major over items
         w2t_hi, w2t_lo = packed_weight(W2, True, split)          # W2^T [H, pad(I)],  K-major over items
-        P = torch.empty((H, ops.pad_to(H, 4)), dtype=torch.float32, device=W1.device)[:, :H]
-        ops.gemm_bf16_tn(w1_hi, w1_lo, w2t_hi, w2t_lo, H, H, I, out_f32=P)
+        if split:
+            P = torch.empty((H, ops.pad_to(H, 4)), dtype=torch.float32, device=W1.device)[:, :H]
+            ops.gemm_bf16_tn(w1_hi, w1_lo, w2t_hi, w2t_lo, H, H, I, out_f32=P)
+            p_hi, p_lo = ops.pack_bf16(P, split=True)
+        else:
+            # single-pass mode: the contraction's epilogue rounds P to the bf16 operand directly (same round-to-nearest
+            # as dmm_pack_bf16 on the fp32 result, one launch and one 4 MB round trip fewer)
+            ld = ops.pad_to(H, 64)
+            p_hi = torch.zeros((H, ld), dtype=torch.bfloat16, device=W1.device) if ld != H else \
+                torch.empty((H, ld), dtype=torch.bfloat16, device=W1.device)
+            ops.gemm_bf16_tn(w1_hi, None, w2t_hi, None, H, H, I, out_hi=p_hi[:, :H])
+            p_lo = None
         q = ops.gemv_f32(W1.detach(), I, b2.detach())
-        p_hi, p_lo = ops.pack_bf16(P, split=split)
         ent = (key, p_hi, p_lo, q)
         den._dmm_hidden_ops = ent
     return ent[1], (ent[2] if split else None), ent[3]
