@@ -51,7 +51,9 @@ PROTOTYPES = {
     "dmm_gemm_bf16_tn": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
                                    C.POINTER(GemmEpilogue), c_vp]),
     "dmm_gemm_f32_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp]),
-    "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_topk_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
+                                 c_vp]),
     "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dmm_spmm_plan_bytes": (c_i64, [c_i64, c_i64]),

@@ -28,6 +28,25 @@ constexpr int TOPK_NB_LOG2 = 11;
 constexpr int TOPK_NB = 1 << TOPK_NB_LOG2;   // range-adapted buckets of the generic path's first pass
 constexpr int TOPK_CAND = 1024;              // candidate keys held in shared memory
 constexpr int TOPK_V4 = 8;                   // float4 loads per thread on the register path (32 keys)
+constexpr int TOPK_SEG_COLS = 8192;          // widest column segment of the segmented path (the 256-thread register kernel)
+constexpr int TOPK_MERGE_CAP = 2048;         // candidates (segments x k) the merge kernel ranks per row
+
+// Rows wider than TOPK_SEG_COLS.  One CTA of 512 / 1024 threads per row keeps only one or two rows per SM in flight and
+// pays 16 / 32-warp barriers between the select phases (measured 1.1 TB/s at 18357 columns, 17 % of HBM).  Instead the
+// row is cut into S column segments that the 256-thread register kernel treats as independent rows (mode 1: the k best
+// of every segment go to a temporary list - the row's k best are among them), a small merge kernel ranks the S * k
+// candidates of a row exactly (value desc, column asc) and emits the k best in ascending column order, and the rows
+// that do not qualify (k > 256, k longer than the last segment, S * k > TOPK_MERGE_CAP, k = 0) take the whole-row
+// kernels as before (mode 2).
+struct SegCfg {
+  int mode;       // 0: plain, 1: segment pass, 2: whole-row pass over the rows the segment pass skipped
+  int S;          // segments per row
+  int seg_cols;   // columns per segment (multiple of 4)
+  int last_len;   // columns of the last segment
+};
+__device__ __forceinline__ bool seg_eligible(const SegCfg& sg, int k) {
+  return k > 0 && k <= 256 && k <= sg.last_len && (int64_t)sg.S * k <= TOPK_MERGE_CAP;
+}
 
 // NaN-propagating maximum (max.NaN.f32): a NaN score surfaces in the piece / thread maximum instead of vanishing
 __device__ __forceinline__ float fmax_nan(float a, float b) {
@@ -150,7 +169,8 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int count, int wa
 template <int NT, bool IN_SMEM>
 __device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_keys, const float* __restrict__ row,
                                                  int n_cols, int k, int64_t o0, int32_t user,
-                                                 int32_t* __restrict__ out_users, int32_t* __restrict__ out_items) {
+                                                 int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
+                                                 int col_off = 0) {
   static_assert(NT >= 256, "the bucket scan and the radix histograms are laid out for at least 256 threads");
   const int tid = threadIdx.x;
   const bool take_all = !(k < n_cols);
@@ -281,7 +301,7 @@ __device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_k
       --eq_take;
     }
     if (sel) {
-      out_items[w] = i;
+      out_items[w] = i + col_off;
       if (out_users) out_users[w] = user;
       ++w;
     }
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict
                                                          int n_cols, const int64_t* __restrict__ out_ptr,
                                                          int64_t row_base, int32_t* __restrict__ out_users,
                                                          int32_t* __restrict__ out_items, int32_t* __restrict__ status,
-                                                         const int32_t* __restrict__ order) {
+                                                         const int32_t* __restrict__ order, SegCfg sg) {
   extern __shared__ uint32_t s_keys[];  // n_cols keys when IN_SMEM
   __shared__ TopkSmem<256> sm;
   if ((int64_t)blockIdx.x >= n_rows) return;
@@ -302,6 +322,7 @@ __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict
   const int64_t o0 = out_ptr[r], o1 = out_ptr[r + 1];
   int k = (int)(o1 - o0);
   if (k <= 0) return;
+  if (sg.mode == 2 && seg_eligible(sg, k)) return;      // done by the segment pass
   if (k > n_cols) {
     if (status && threadIdx.x == 0) atomicExch(status, 1);
     k = n_cols;
@@ -312,17 +333,30 @@ __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict
 
 // ------------------------------------------------------------------------------------------ register kernel
 template <int NT>
-__global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_rows,
-                                                           int n_cols, const int64_t* __restrict__ out_ptr,
+__global__ void __launch_bounds__(NT, NT == 256 ? 5 : 1) topk_rows_reg_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_rows,
+                                                           int n_cols_arg, const int64_t* __restrict__ out_ptr,
                                                            int64_t row_base, int32_t* __restrict__ out_users,
-                                                           int32_t* __restrict__ out_items, int32_t* __restrict__ status,
-                                                           const int32_t* __restrict__ order) {
+                                                           int32_t* __restrict__ out_items_arg, int32_t* __restrict__ status,
+                                                           const int32_t* __restrict__ order, SegCfg sg,
+                                                           int32_t* __restrict__ seg_tmp) {
   __shared__ TopkSmem<NT> sm;
   constexpr int NW = NT / 32;
-  if ((int64_t)blockIdx.x >= n_rows) return;
+  // segment pass (sg.mode == 1): block b is segment b % S of the row scheduled in slot b / S
+  const int seg = sg.mode == 1 ? (int)(blockIdx.x % (unsigned)sg.S) : 0;
+  const int64_t slot = sg.mode == 1 ? (int64_t)(blockIdx.x / (unsigned)sg.S) : (int64_t)blockIdx.x;
+  if (slot >= n_rows) return;
   // scheduling order only (rows with a large k take the slower exact paths: started first, they overlap the rest)
-  const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
-  const float* row = scores + r * ld;
+  const int64_t r = order ? (int64_t)order[slot] : slot;
+  const int col_off = seg * sg.seg_cols;
+  const int n_cols = sg.mode == 1 ? (n_cols_arg - col_off < sg.seg_cols ? n_cols_arg - col_off : sg.seg_cols) : n_cols_arg;
+  const float* row = scores + r * ld + col_off;
+  int32_t* __restrict__ out_items = sg.mode == 1 ? seg_tmp : out_items_arg;
+  if (sg.mode == 1) out_users = nullptr;
+  if (sg.mode != 0) {
+    // each row belongs to exactly one of the two passes: decided before the row is touched (block-uniform)
+    const int kk = (int)(out_ptr[r + 1] - out_ptr[r]);
+    if ((sg.mode == 1) != seg_eligible(sg, kk)) return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool aligned = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
 
@@ -342,16 +376,18 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   float tail_v = 0.f;
   if (has_tail) tail_v = __ldcs(row + tail_col);
 
-  const int64_t o0 = out_ptr[r], o1 = out_ptr[r + 1];
+  int64_t o0 = out_ptr[r];
+  const int64_t o1 = out_ptr[r + 1];
   int k = (int)(o1 - o0);
   if (k <= 0) return;
+  if (sg.mode == 1) o0 = (int64_t)sg.S * (o0 - out_ptr[0]) + (int64_t)seg * k;   // this segment's slot of the temporary list
   if (k > n_cols) {
     if (status && threadIdx.x == 0) atomicExch(status, 1);
     k = n_cols;
   }
   const int32_t user = (int32_t)(row_base + r);
   if (k > NT || k >= n_cols || !aligned) {  // block-uniform
-    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
+    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items, col_off);
     return;
   }
 
@@ -408,7 +444,7 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   // the barrier doubles as the NaN vote: the bound below counts real scores, so a row with any NaN (whose key
   // order the float scan cannot see) takes the exact generic path
   if (__syncthreads_or(tmaxf != tmaxf)) {
-    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
+    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items, col_off);
     return;
   }
   uint32_t L = 0xFFFFFFFFu;
@@ -448,7 +484,7 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
   constexpr int RANK_MAX = 512;                // candidates ranked against each other (m^2 / NT compares per thread)
   if (m > RANK_MAX || m < k) {                 // crowded threshold (ties) or loose bound: exact generic path
     __syncthreads();
-    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items);
+    topk_row_generic<NT, false>(sm, nullptr, row, n_cols, k, o0, user, out_users, out_items, col_off);
     return;
   }
   // exact rank of every candidate among the m candidates by (value desc, column asc); the k best are marked
@@ -473,6 +509,51 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
     if (my_col == 0x7FFFFFFF) continue;
     int pos = 0;
     for (int j = 0; j < m; ++j) pos += (sm.bucket[j] < my_col) ? 1 : 0;
+    out_items[o0 + pos] = my_col + col_off;
+    if (out_users) out_users[o0 + pos] = user;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ merge of the segment lists
+// One CTA per row that went through the segment pass: its S * k candidate columns (k per segment, read from the temporary
+// list) are ranked exactly by (score desc, column asc) on the order-preserving keys of the scores they point at, and
+// the k best leave in ascending column order.
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_rows,
+                                                         const int64_t* __restrict__ out_ptr, int64_t row_base,
+                                                         int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
+                                                         const int32_t* __restrict__ order, SegCfg sg,
+                                                         const int32_t* __restrict__ seg_tmp) {
+  __shared__ uint32_t key[TOPK_MERGE_CAP];
+  __shared__ int col[TOPK_MERGE_CAP];
+  __shared__ int sel[TOPK_MERGE_CAP];
+  if ((int64_t)blockIdx.x >= n_rows) return;
+  const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
+  const int64_t o0 = out_ptr[r];
+  const int k = (int)(out_ptr[r + 1] - o0);
+  if (!seg_eligible(sg, k)) return;
+  const int m = sg.S * k;
+  const int32_t* list = seg_tmp + (int64_t)sg.S * (o0 - out_ptr[0]);
+  const float* row = scores + r * ld;
+  for (int c = threadIdx.x; c < m; c += 128) {
+    const int cc = list[c];
+    col[c] = cc;
+    key[c] = order_key(__ldg(row + cc));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < m; c += 128) {
+    const uint32_t my_key = key[c];
+    const int my_col = col[c];
+    int before = 0;
+    for (int j = 0; j < m; ++j) before += (key[j] > my_key || (key[j] == my_key && col[j] < my_col)) ? 1 : 0;
+    sel[c] = before < k ? my_col : 0x7FFFFFFF;
+  }
+  __syncthreads();
+  const int32_t user = (int32_t)(row_base + r);
+  for (int c = threadIdx.x; c < m; c += 128) {
+    const int my_col = sel[c];
+    if (my_col == 0x7FFFFFFF) continue;
+    int pos = 0;
+    for (int j = 0; j < m; ++j) pos += (sel[j] < my_col) ? 1 : 0;
     out_items[o0 + pos] = my_col;
     if (out_users) out_users[o0 + pos] = user;
   }
@@ -480,16 +561,35 @@ __global__ void __launch_bounds__(NT) topk_rows_reg_kernel(const float* __restri
 
 template <int NT>
 void launch_reg(const float* scores, int64_t ld, int64_t n_rows, int n_cols, const int64_t* out_ptr, int64_t row_base,
-                int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order, cudaStream_t st) {
-  topk_rows_reg_kernel<NT><<<(unsigned)n_rows, NT, 0, st>>>(scores, ld, n_rows, n_cols, out_ptr, row_base, out_users,
-                                                           out_items, status, order);
+                int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order, SegCfg sg, int32_t* seg_tmp,
+                cudaStream_t st) {
+  const int64_t blocks = sg.mode == 1 ? n_rows * sg.S : n_rows;
+  topk_rows_reg_kernel<NT><<<(unsigned)blocks, NT, 0, st>>>(scores, ld, n_rows, n_cols, out_ptr, row_base, out_users,
+                                                           out_items, status, order, sg, seg_tmp);
+}
+
+SegCfg make_seg(int64_t n_cols) {
+  SegCfg sg{0, 0, 0, 0};
+  if (n_cols > TOPK_SEG_COLS) {
+    sg.S = (int)dmm_ceil_div(n_cols, TOPK_SEG_COLS);
+    sg.seg_cols = (int)((dmm_ceil_div(n_cols, sg.S) + 3) / 4 * 4);
+    sg.last_len = (int)(n_cols - (int64_t)(sg.S - 1) * sg.seg_cols);
+    if (sg.last_len <= 0) sg.S = 0;          // cannot happen for n_cols > 8192; guards the arithmetic
+  }
+  return sg;
 }
 
 }  // namespace
 
+extern "C" int64_t dmm_topk_workspace_bytes(int64_t n_cols, int64_t n_edges) {
+  const SegCfg sg = make_seg(n_cols);
+  return sg.S > 0 ? (int64_t)sg.S * (n_edges > 0 ? n_edges : 0) * (int64_t)sizeof(int32_t) : 0;
+}
+
 extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                               const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
-                              int32_t* status, const int32_t* order, void* stream) {
+                              int32_t* status, const int32_t* order, void* workspace, int64_t workspace_bytes,
+                              int64_t n_edges, void* stream) {
   DMM_CHECK_ARG(ctx && scores && out_ptr && out_items, "dmm_topk_edges: null argument");
   DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges: bad shape n_cols=%lld ld=%lld",
                 (long long)n_cols, (long long)ld);
@@ -498,14 +598,37 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
   cudaStream_t st = (cudaStream_t)stream;
   constexpr int PER_THREAD = 4 * TOPK_V4;
   static const bool force_generic = getenv("DMM_TOPK_GENERIC") != nullptr;   // test hook: exercise the generic kernels
+  static const bool seg_ok = []() { const char* e = getenv("DMM_TOPK_SEG"); return !(e && e[0] == '0'); }();   // A/B switch
+
+  // wide rows: segment pass + merge for the rows that qualify, whole-row kernels for the rest (see SegCfg)
+  SegCfg sg = make_seg(n_cols);
+  const bool rows_aligned = (reinterpret_cast<uintptr_t>(scores) & 15u) == 0 && ld % 4 == 0;
+  const bool segmented = seg_ok && !force_generic && sg.S > 0 && rows_aligned && workspace != nullptr && n_edges >= 0 &&
+                         workspace_bytes >= dmm_topk_workspace_bytes(n_cols, n_edges) && n_rows * (int64_t)sg.S < (1LL << 31);
+  if (segmented) {
+    sg.mode = 1;
+    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, nullptr, nullptr, status, order, sg, (int32_t*)workspace, st);
+    DMM_LAUNCH_CHECK();
+    topk_merge_kernel<<<(unsigned)n_rows, 128, 0, st>>>(scores, ld, n_rows, out_ptr, row_base, out_users, out_items, order, sg,
+                                                       (const int32_t*)workspace);
+    DMM_LAUNCH_CHECK();
+    // the few rows the segment pass skipped: the 256-thread generic kernel (8 CTAs per SM; a 1024-thread CTA per row
+    // that only reads two offsets and leaves would cost more in launch waves than the rows it really processes)
+    sg.mode = 2;
+    topk_edges_kernel<false><<<(unsigned)n_rows, 256, 0, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users,
+                                                              out_items, status, order, sg);
+    DMM_LAUNCH_CHECK();
+    return DMM_OK;
+  }
+  sg = SegCfg{0, 0, 0, 0};
   if (force_generic) {
     // fall through to the generic kernels below
   } else if (n_cols <= 256 * PER_THREAD) {
-    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
+    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
   } else if (n_cols <= 512 * PER_THREAD) {
-    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
+    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
   } else if (n_cols <= 1024 * PER_THREAD) {
-    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, st);
+    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
   }
   if (force_generic || n_cols > 1024 * PER_THREAD) {
     const size_t smem = (size_t)n_cols * sizeof(uint32_t);
@@ -518,10 +641,10 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
         configured = cap;
       }
       topk_edges_kernel<true><<<(unsigned)n_rows, 256, smem, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                  out_users, out_items, status, order);
+                                                                  out_users, out_items, status, order, sg);
     } else {
       topk_edges_kernel<false><<<(unsigned)n_rows, 256, 0, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                out_users, out_items, status, order);
+                                                                out_users, out_items, status, order, sg);
     }
   }
   DMM_LAUNCH_CHECK();

@@ -205,12 +205,16 @@ def gemm_f32_tn(a, b, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residua
 # ----------------------------------------------------------------------------------------- top-k
 def topk_edges(scores, n_cols, out_ptr, row_base, out_users, out_items, status=None, order=None):
     """Emits, for each row r, the (out_ptr[r+1]-out_ptr[r]) largest columns (ascending) at out_ptr[r].
-    order (int32 permutation of the rows): scheduling order, e.g. largest k first."""
+    order (int32 permutation of the rows): scheduling order, e.g. largest k first.  Rows wider than 8192 columns use
+    the column-segment pass + merge (a temporary list of segments x emitted entries, bounded by out_items.numel())."""
     assert scores.dtype == torch.float32 and out_ptr.dtype == torch.int64 and out_items.dtype == torch.int32
     n_rows = scores.shape[0]
     assert out_ptr.numel() >= n_rows + 1
+    n_edges = int(out_items.numel())
+    ws_bytes = int(_lib.load().dmm_topk_workspace_bytes(int(n_cols), n_edges))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device) if ws_bytes > 0 else None
     _lib.call("dmm_topk_edges", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(out_ptr),
-              int(row_base), _p(out_users), _p(out_items), _p(status), _p(order), _stream())
+              int(row_base), _p(out_users), _p(out_items), _p(status), _p(order), _p(ws), ws_bytes, n_edges, _stream())
 
 
 # ----------------------------------------------------------------------------------------- adjacency

@@ -165,11 +165,15 @@ int dmm_gemm_f32_tn(dmm_ctx* ctx, const float* a, int64_t lda, const float* b, i
  * and row_base + r into out_users.  Tie-break: value descending, then column ascending.
  * k_r > n_cols is an error flagged in *status (device int, optional).  `order` (optional, int32
  * permutation of 0..n_rows-1, e.g. from dmm_rows_long_first) is the order in which rows are scheduled;
- * results do not depend on it.
+ * results do not depend on it.  Rows wider than 8192 columns go through a column-segment pass plus a merge
+ * when a `workspace` of dmm_topk_workspace_bytes(n_cols, n_edges) bytes is given (n_edges >= the number of
+ * entries this call emits, out_ptr[n_rows] - out_ptr[0]); workspace == NULL keeps one CTA per whole row.
  * Replaces the per-user torch.topk loop + int(indices[j]) syncs of Main.py:224-230.          */
+int64_t dmm_topk_workspace_bytes(int64_t n_cols, int64_t n_edges);
 int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                    const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
-                   int32_t* status, const int32_t* order, void* stream);
+                   int32_t* status, const int32_t* order, void* workspace, int64_t workspace_bytes,
+                   int64_t n_edges, void* stream);
 
 /* ---- normalised bipartite adjacency ---------------------------------------------------------
  * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and
