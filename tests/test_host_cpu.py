@@ -87,3 +87,23 @@ def test_calc_res_is_bit_identical_to_the_reference_loop():
     want = _calc_res_reference(top, test, users.tolist(), 20)
     got = coach.calcRes(top, test, users)
     assert tuple(float(x) for x in got) == tuple(float(x) for x in want)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: stdout carries exactly one JSON line (native banners go to stderr) with the contract's
+    keys; the arm runs the CPU oracle port on a bounded sample (no GPU, no reference checkout needed)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-sample", "32"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "denoise_topk_rebuild_users_per_sec" and d["unit"] == "users/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
