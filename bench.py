@@ -578,7 +578,7 @@ def run_ours(args):
                   "full_chain_ms_per_step": ms_full, "full_chain_users_per_s": world * U / (ms_full * 1e-3)},
         "breakdown_ms_per_step": breakdown,
     }
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:          # reported on rank 0 at N = 1 only (a bounded host-core sample)
         params = {m: oracle_params(d) for m, d in dens.items()}
         # bounded CPU sample: scaled down with the row width so that it stays at ~10 s of host work
         n_cpu = max(16, int(args.cpu_sample * min(1.0, 7050.0 / w["items"])))
