@@ -27,13 +27,36 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: users, items, modalities, hidden, steps, hyper (noise_scale, noise_min, noise_max)
-    "tiktok": dict(users=9308, items=6710, modalities=["image", "text", "audio"], hidden=1024, steps=5, noise=(0.5, 1e-4, 0.02)),
-    "baby": dict(users=19445, items=7050, modalities=["image", "text"], hidden=1024, steps=5, noise=(0.1, 1e-4, 0.02)),
-    "sports": dict(users=35598, items=18357, modalities=["image", "text"], hidden=1024, steps=5, noise=(0.1, 1e-4, 0.02)),
+    # name: users, items, modalities, hidden; the hyper-parameters (noise schedule, steps, sampling_step) come from the
+    # matching conf/*.toml (workload_hyper)
+    "tiktok": dict(users=9308, items=6710, modalities=["image", "text", "audio"], hidden=1024, conf="tiktok.toml"),
+    "baby": dict(users=19445, items=7050, modalities=["image", "text"], hidden=1024, conf="baby.toml"),
+    "sports": dict(users=35598, items=18357, modalities=["image", "text"], hidden=1024, conf="sports.toml"),
     # BASELINE.json configs[4] (2M users x 500k items, 3 modalities): one GPU's slice of the user rows per step
-    "scaleout": dict(users=16384, items=500000, modalities=["image", "text", "audio"], hidden=1024, steps=5, noise=(0.1, 1e-4, 0.02)),
+    "scaleout": dict(users=16384, items=500000, modalities=["image", "text", "audio"], hidden=1024, conf="sports.toml"),
 }
+
+
+def workload_hyper(name, sampling_step=None):
+    """Hyper-parameters of the workload from its conf/*.toml (through the repo's tolerant loader): conf/baby.toml gives
+    sampling_step 5 (the rebuild starts from a q_sample'd x_5), tiktok / sports 0.  --sampling-step overrides."""
+    from diffmm_b200.Conf import load_config
+    cfg = load_config(os.path.join(ROOT, "conf", WORKLOADS[name]["conf"]))
+    ss = cfg.hyper.sampling_step if sampling_step is None else int(sampling_step)
+    return dict(noise=(cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max), steps=int(cfg.hyper.steps),
+                sampling_step=int(ss), conf="conf/" + WORKLOADS[name]["conf"])
+
+
+def config_dict(name, w, hyper, precision):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of the same workload."""
+    return {"workload": f"{name}-shape rebuild phase (Main.py:195-253) with the hyper-parameters of {hyper['conf']}: "
+                        f"{w['users']} users x {w['items']} items per GPU, {len(w['modalities'])} modalities, hidden "
+                        f"{w['hidden']}, {hyper['steps']} reverse steps from sampling_step {hyper['sampling_step']}, "
+                        f"top-k k=deg(u), adjacency build",
+            "users_per_gpu": w["users"], "items": w["items"], "modalities": len(w["modalities"]), "hidden": w["hidden"],
+            "diffusion_steps": hyper["steps"], "sampling_step": hyper["sampling_step"], "conf": hyper["conf"]}
+
+
 METRIC = "denoise_topk_rebuild_users_per_sec"
 UNIT = "users/s"
 KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sort kernels are not counted)
@@ -101,17 +124,19 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(name, device, seed, precision, world=1):
+def build_workload(name, device, seed, precision, world=1, hyper=None):
     import torch
     from diffmm_b200 import synth
     from diffmm_b200.Conf import Config
     from diffmm_b200.Model import Denoise, GaussianDiffusion
     w = WORKLOADS[name]
+    hyper = hyper or workload_hyper(name)
     cfg = Config()
     cfg.base.precision = precision
     cfg.base.denoise_dim = f"[{w['hidden']}]"
-    cfg.hyper.steps = w["steps"]
-    cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = w["noise"]
+    cfg.hyper.steps = hyper["steps"]
+    cfg.hyper.sampling_step = hyper["sampling_step"]
+    cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = hyper["noise"]
     cfg.data.user_num, cfg.data.item_num = w["users"] * world, w["items"]
     inter = synth.interactions(w["users"] * world, w["items"], seed=seed)      # same global dataset on every rank
     torch.manual_seed(seed)
@@ -127,10 +152,11 @@ def oracle_params(den):
                 gate_w=f(den.gate_layer.weight), gate_b=f(den.gate_layer.bias))
 
 
-def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, seed=0):
-    """The reference's phase 2 restated in numpy (oracle/diffmm_oracle.py) on `n_sample` users; returns seconds."""
+def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, hyper, seed=0):
+    """The reference's phase 2 restated in numpy (oracle/diffmm_oracle.py) on `n_sample` users; returns seconds.
+    Only used when oracle/_ref is absent (the port leg; always sampling_step 0)."""
     from oracle import diffmm_oracle as O
-    sched = O.make_schedule(*w["noise"], w["steps"])
+    sched = O.make_schedule(*hyper["noise"], hyper["steps"])
     users = np.arange(min(n_sample, w["users"]))
     ptr, idx = inter.indptr, inter.indices
     t0 = time.perf_counter()
@@ -247,49 +273,103 @@ def aux_rooflines(dev, breakdown, U, I, E, n_mod, pk, seed):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_rebuild_step(ref, diff, dens, x_rows, deg, sampling_step):
+    """The reference's phase 2 for one set of users (Main.py:211-231 verbatim in structure): per modality and batch of
+    1024 users ``generate_view`` (Model.py:300-322) on torch-CPU, then the per-user ``torch.topk`` loop with one
+    ``int(tensor)`` per emitted edge.  Returns (seconds, edges)."""
+    import torch
+    edges = 0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for m, den in dens.items():
+            i_list = []
+            for b0 in range(0, x_rows.shape[0], 1024):
+                batch = x_rows[b0:b0 + 1024]
+                view = diff.generate_view(den, batch, sampling_step)
+                for i in range(batch.shape[0]):
+                    _, indices = torch.topk(view[i], k=int(deg[b0 + i]))
+                    for j in range(indices.shape[0]):
+                        i_list.append(int(indices[j]))
+            edges += len(i_list)
+    return time.perf_counter() - t0, edges
+
+
+def load_reference_arm(w, seed, hyper):
+    """Unmodified reference modules from oracle/_ref (never /root/reference at run time), forced onto the CPU, with
+    Denoise weights drawn exactly like the GPU arm's (same seed, same construction order)."""
+    import torch
+    os.environ["DIFFMM_REFERENCE_ROOT"] = REF_DIR
+    from oracle import ref_shim
+    ref = ref_shim.load_reference(force_cpu=True)
+    cfg = ref_shim.make_config(ref, "tiktok" if len(w["modalities"]) == 3 else "sports")
+    cfg.base.denoise_dim = f"[{w['hidden']}]"
+    cfg.hyper.steps = hyper["steps"]
+    cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = hyper["noise"]
+    cfg.data.user_num, cfg.data.item_num = w["users"], w["items"]
+    torch.manual_seed(seed)
+    diff = ref.Model.GaussianDiffusion(cfg)
+    dens = {m: ref.Model.Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg) for m in w["modalities"]}
+    return ref, diff, dens
+
+
 def run_reference(args):
+    """CPU arm: the reference's own implementation of the rebuild phase on the box's host cores, on the SAME workload,
+    weights (seed) and users as the GPU arm; each step is a bounded sample of `--ref-sample` users (the first ones)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
+    import torch
     from diffmm_b200 import synth
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can (numpy's BLAS pool)
+    w = WORKLOADS[args.workload]
+    hyper = workload_hyper(args.workload, args.sampling_step)
     cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)              # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=cores)
     except Exception:
         pass
     inter = synth.interactions(w["users"], w["items"], seed=args.seed)
-    rng = np.random.default_rng(args.seed)
-    I, H, d = w["items"], w["hidden"], 10
+    n_sample = min(args.ref_sample, w["users"])
+    ptr, idx = inter.indptr, inter.indices
+    deg = np.diff(ptr)[:n_sample]
+    kind = "reference"
+    if os.path.isfile(os.path.join(REF_DIR, "Model.py")):
+        ref, diff, dens = load_reference_arm(w, args.seed, hyper)
+        x = torch.zeros((n_sample, w["items"]), dtype=torch.float32)
+        for u in range(n_sample):
+            x[u, torch.from_numpy(idx[ptr[u]:ptr[u + 1]].astype(np.int64))] = 1.0
 
-    def rand_params():
-        s1, s2 = np.sqrt(2.0 / (I + d + H)), np.sqrt(2.0 / (I + H))
-        return dict(emb_w=rng.standard_normal((d, d), dtype=np.float32) * 0.3, emb_b=np.zeros(d, np.float32),
-                    w1=(rng.standard_normal((H, I + d), dtype=np.float32) * s1), b1=np.zeros(H, np.float32),
-                    w2=(rng.standard_normal((I, H), dtype=np.float32) * s2), b2=np.zeros(I, np.float32),
-                    gate_w=np.zeros((64, 64), np.float32), gate_b=np.zeros(64, np.float32))
-    params = {m: rand_params() for m in w["modalities"]}
-    n_sample = args.ref_sample
+        def step(n):
+            return reference_rebuild_step(ref, diff, dens, x[:n], deg, hyper["sampling_step"])
+    else:   # oracle/_ref not built on this machine: numpy restatement of the same path (oracle/diffmm_oracle.py)
+        kind = "port"
+        _, _, _, dens_t = build_workload(args.workload, "cpu", args.seed, "bf16", 1, hyper)
+        params = {m: oracle_params(d) for m, d in dens_t.items()}
+
+        def step(n):
+            dt, _, e = cpu_rebuild_sample(inter, w, params, n, hyper)
+            return dt, e
     for _ in range(args.warmup):
-        cpu_rebuild_sample(inter, w, params, min(n_sample, 256))
-    total = 0.0
-    users = 0
+        step(min(n_sample, 128))
+    total, users = 0.0, 0
     for _ in range(args.steps):
-        dt, n, _ = cpu_rebuild_sample(inter, w, params, n_sample)
+        dt, _ = step(n_sample)
         total += dt
-        users += n
+        users += n_sample
     val = users / total
+    sample = (f"first {n_sample} of {w['users']} users x {len(w['modalities'])} modalities per step, {args.steps} steps, "
+              f"{total:.1f} s; " + ("unmodified reference modules (oracle/_ref: GaussianDiffusion.generate_view + the "
+                                    "Main.py:224-230 per-user torch.topk loop) on torch-CPU" if kind == "reference" else
+                                    "numpy port (oracle/diffmm_oracle.py)") + f", same seed-{args.seed} weights as the GPU arm")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape rebuild phase (Main.py:195-253), numpy oracle port of the "
-                                   f"reference CPU path, sample of {n_sample} users x {len(w['modalities'])} modalities per step",
-                       "users": w["users"], "items": w["items"], "modalities": len(w["modalities"]), "hidden": w["hidden"],
-                       "diffusion_steps": w["steps"]},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n_sample} users x {len(w['modalities'])} modalities x {args.steps} steps"},
+            "config": config_dict(args.workload, w, hyper, args.precision),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -615,7 +695,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=8192)
-    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=1024, help="users per step of the reference (CPU) arm")
+    ap.add_argument("--sampling-step", type=int, default=None,
+                    help="override the workload's conf/*.toml hyper.sampling_step (0 = rebuild from the binary rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the top-k / SpMM / adjacency roofline measurements")
     ap.add_argument("--no-epoch", action="store_true", help="skip the full-epoch (phases 1-3 + eval) timing")

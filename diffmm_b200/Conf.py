@@ -4,7 +4,8 @@ Differences, all on purpose:
   * nested dataclasses use default_factory (the reference's instance defaults raise on Python >= 3.11);
   * load_config ignores keys the dataclasses do not know (conf/baby.toml, conf/ifashion.toml and
     conf/test.toml carry stale keys that make the reference's loader raise TypeError) and maps the
-    stale spelling ``sampling_steps`` to ``sampling_step``;
+    stale spelling ``sampling_steps`` to ``sampling_step`` (so conf/baby.toml runs the rebuild from a q_sample'd
+    start at step 5, conf/ifashion.toml and conf/test.toml at step 1: the dense-start path of rebuild.denoise_chain);
   * ``base.precision`` ("bf16" | "bf16x3") selects the tensor-pipe mode of the Denoise contractions.
 """
 from __future__ import annotations
@@ -117,4 +118,16 @@ def load_config(path: str) -> Config:
         train=_build(TrainConfig, raw.get("train", {}), ignored, "train"),
     )
     cfg.ignored_keys = ignored  # type: ignore[attr-defined]
+    validate(cfg)
     return cfg
+
+
+def validate(cfg: Config) -> None:
+    """Range checks the reference leaves to an IndexError deep inside the diffusion tables (Model.py:305-306 indexes
+    the schedule with sampling_step - 1)."""
+    if not (0 <= int(cfg.hyper.sampling_step) <= int(cfg.hyper.steps)):
+        raise ValueError(f"hyper.sampling_step must lie in [0, steps = {cfg.hyper.steps}], got {cfg.hyper.sampling_step}")
+    if int(cfg.hyper.steps) < 1:
+        raise ValueError(f"hyper.steps must be >= 1, got {cfg.hyper.steps}")
+    if cfg.base.precision not in ("bf16", "bf16x3"):
+        raise ValueError(f"base.precision must be 'bf16' or 'bf16x3', got {cfg.base.precision!r}")

@@ -52,6 +52,8 @@ class Coach:
         self.config = config
         self.group = group
         self.device = torch.device(f"cuda:{self.config.base.gpu}" if torch.cuda.is_available() else "cpu")
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)      # the kernels launch on the current device (base.gpu), like torch's own
         self.phase_seconds = {}
         _log().info(f"USER: {self.config.data.user_num}, ITEM: {self.config.data.item_num}")
         _log().info(f"NUM OF INTERACTIONS: {len(self.handler.trainData)}")

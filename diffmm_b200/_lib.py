@@ -55,7 +55,7 @@ PROTOTYPES = {
     "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                  c_vp]),
     "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
-    "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dmm_spmm_plan_bytes": (c_i64, [c_i64, c_i64]),
     "dmm_spmm_plan": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "dmm_spmm_workspace_bytes": (c_i64, [c_i64, c_i64]),

@@ -20,7 +20,7 @@ namespace {
 __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __restrict__ row_ptr, int64_t n_users,
                                                            int32_t* __restrict__ edge_user,
                                                            const int32_t* __restrict__ items, int64_t n_items,
-                                                           int32_t* __restrict__ bad) {
+                                                           int32_t* __restrict__ bad, int32_t* __restrict__ status) {
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= n_users) return;
@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __rest
   for (int64_t j = b + lane; j < e; j += 32) {
     edge_user[j] = (int32_t)u;
     const int32_t it = items[j];
-    if (it < 0 || it >= n_items) atomicExch(bad, 1);
+    if (it < 0 || it >= n_items) {
+      atomicExch(bad, 1);
+      if (status) atomicOr(status, 2);
+    }
   }
 }
 
@@ -144,7 +147,8 @@ extern "C" int64_t dmm_build_adj_workspace_bytes(int64_t n_users, int64_t n_item
 
 extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* items, int64_t n_users,
                                       int64_t n_items, int64_t n_edges, int64_t* adj_ptr, int32_t* adj_idx,
-                                      float* adj_val, void* workspace, int64_t workspace_bytes, void* stream) {
+                                      float* adj_val, void* workspace, int64_t workspace_bytes, int32_t* status,
+                                      void* stream) {
   DMM_CHECK_ARG(ctx && row_ptr && adj_ptr && adj_idx && adj_val && workspace, "dmm_build_norm_adj_csr: null argument");
   DMM_CHECK_ARG(n_users > 0 && n_items > 0 && n_edges >= 0, "dmm_build_norm_adj_csr: bad sizes");
   DMM_CHECK_ARG(n_users + n_items < (1LL << 31) && n_edges < (1LL << 31), "dmm_build_norm_adj_csr: int32 index overflow");
@@ -158,7 +162,7 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
   int32_t* bad = w.item_count + n_items;
   DMM_CUDA(cudaMemsetAsync(bad, 0, 4, st));
   expand_users_kernel<<<(unsigned)dmm_ceil_div(n_users * 32, 256), 256, 0, st>>>(row_ptr, n_users, w.edge_user, items, n_items,
-                                                                                bad);
+                                                                                bad, status);
   DMM_LAUNCH_CHECK();
   if (n_edges > 0) {
     int end_bit = 1;

@@ -24,7 +24,8 @@ extern "C" int dmm_init(int device, dmm_ctx** out) {
   int n = 0;
   DMM_CUDA(cudaGetDeviceCount(&n));
   DMM_CHECK_ARG(device >= 0 && device < n, "dmm_init: device %d out of range (%d visible)", device, n);
-  DMM_CUDA(cudaSetDevice(device));
+  // nothing here changes the calling thread's current device (cudaGetDeviceProperties and
+  // cudaGetDriverEntryPoint do not need it)
   cudaDeviceProp prop;
   DMM_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {

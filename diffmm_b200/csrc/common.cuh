@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/diffmm_b200.h"
 
@@ -44,6 +45,14 @@ void dmm_set_error(const char* fmt, ...);
       return DMM_ERR_CUDA;                                                          \
     }                                                                               \
   } while (0)
+
+// One-time per-device setup (cudaFuncSetAttribute and friends are per device): thread-safe, keyed by ctx->device.
+// The guarded calls are idempotent, so two threads racing through `need` at worst repeat them.
+struct DmmPerDeviceOnce {
+  std::atomic<uint64_t> done{0};
+  bool need(const dmm_ctx* c) const { return !((done.load(std::memory_order_acquire) >> (c->device & 63)) & 1ull); }
+  void mark(const dmm_ctx* c) { done.fetch_or(1ull << (c->device & 63), std::memory_order_release); }
+};
 
 static inline int64_t dmm_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

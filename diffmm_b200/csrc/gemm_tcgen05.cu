@@ -1048,14 +1048,15 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
     p.off_b16 = p.off_bias = 0;
     smem_bytes = C::SMEM_BYTES;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DmmPerDeviceOnce attr_once;   // one per template instantiation; per device, thread-safe
+  if (attr_once.need(ctx)) {
     DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, true, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     DMM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, false, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_once.mark(ctx);
   }
-  const bool x3 = p.ep.res_lo != nullptr || p.ep.out_lo != nullptr;
+  // split-bf16 (fp32-faithful) instantiation whenever ANY lo part takes part: it keeps the accurate tanh in the post stage
+  const bool x3 = a_lo != nullptr || b_lo != nullptr || p.ep.res_lo != nullptr || p.ep.out_lo != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(grid * C::CTAS));
   cfg.blockDim = dim3(NUM_THREADS);

@@ -442,12 +442,12 @@ inline int nce_splits(int64_t B) {
 inline int64_t nce_split_rows(int64_t B, int JS) { return ((B + JS - 1) / JS + NT_J - 1) / NT_J * NT_J; }
 
 template <bool FWD>
-int launch_nce_tiles(int64_t B, const float* n1, const float* n2, float inv_temp, const float* lse, float* part,
+int launch_nce_tiles(const dmm_ctx* ctx, int64_t B, const float* n1, const float* n2, float inv_temp, const float* lse, float* part,
                      float* gpart, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DmmPerDeviceOnce attr_once;
+  if (attr_once.need(ctx)) {
     DMM_CUDA(cudaFuncSetAttribute(nce_tiles_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NceSmem)));
-    attr_set = true;
+    attr_once.mark(ctx);
   }
   const int JS = nce_splits(B);
   dim3 grid((unsigned)dmm_ceil_div(B, NT_I), (unsigned)JS, FWD ? 1u : 2u);
@@ -516,7 +516,7 @@ extern "C" int dmm_infonce_fwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
   DMM_LAUNCH_CHECK();
   if (D == 64) {
     float* part = workspace + 2 * B * D;     // [B][JS][3]
-    int rc = launch_nce_tiles<true>(B, n1, n2, 1.f / temperature, nullptr, part, nullptr, st);
+    int rc = launch_nce_tiles<true>(ctx, B, n1, n2, 1.f / temperature, nullptr, part, nullptr, st);
     if (rc) return rc;
     nce_fwd_combine_kernel<<<1, 1024, 0, st>>>(part, nce_splits(B), B, 1.f / (float)B, lse, row_loss, loss);
     DMM_LAUNCH_CHECK();
@@ -551,7 +551,7 @@ extern "C" int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
   const float coef = grad_scale / ((float)B * temperature);
   if (D == 64) {
     float* gpart = workspace + 2 * B * D;    // [2 sides][JS][B][64]
-    int rc = launch_nce_tiles<false>(B, n1, n2, 1.f / temperature, lse, nullptr, gpart, st);
+    int rc = launch_nce_tiles<false>(ctx, B, n1, n2, 1.f / temperature, lse, nullptr, gpart, st);
     if (rc) return rc;
     nce_bwd_combine_kernel<<<(unsigned)dmm_ceil_div(2 * B * 16, 256), 256, 0, st>>>(gpart, nce_splits(B), B, n1, n2, inv1, inv2,
                                                                                   coef, g1, g2);

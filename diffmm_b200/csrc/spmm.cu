@@ -522,10 +522,12 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
       spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, 0);
     } else {
       const int64_t cap = plan_cap(nnz);
-      static int resident = 0;                 // CTAs of the persistent kernel per SM
+      static std::atomic<int> resident_cache{0};   // CTAs of the persistent kernel per SM (same for every sm_100 device)
+      int resident = resident_cache.load(std::memory_order_relaxed);
       if (resident == 0) {
         DMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, spmm64_planned_kernel, SPMM_THREADS, 0));
         if (resident < 1) resident = 1;
+        resident_cache.store(resident, std::memory_order_relaxed);
       }
       int64_t blocks = (int64_t)ctx->num_sms * resident;
       const int64_t useful = dmm_ceil_div((row1 - row0) + nnz / PLAN_CHUNK, SPMM_THREADS / 16);   // small graphs: fewer CTAs

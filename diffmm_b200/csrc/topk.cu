@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict
   if (k <= 0) return;
   if (sg.mode == 2 && seg_eligible(sg, k)) return;      // done by the segment pass
   if (k > n_cols) {
-    if (status && threadIdx.x == 0) atomicExch(status, 1);
+    if (status && threadIdx.x == 0) atomicOr(status, 1);
     k = n_cols;
   }
   topk_row_generic<256, IN_SMEM>(sm, s_keys, scores + r * ld, n_cols, k, o0, (int32_t)(row_base + r), out_users,
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 5 : 1) topk_rows_reg_kernel(co
   if (k <= 0) return;
   if (sg.mode == 1) o0 = (int64_t)sg.S * (o0 - out_ptr[0]) + (int64_t)seg * k;   // this segment's slot of the temporary list
   if (k > n_cols) {
-    if (status && threadIdx.x == 0) atomicExch(status, 1);
+    if (status && threadIdx.x == 0) atomicOr(status, 1);
     k = n_cols;
   }
   const int32_t user = (int32_t)(row_base + r);
@@ -635,10 +635,10 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
     // static shared memory of the kernel (buckets, candidates, scratch) is ~18 KB
     const size_t cap = (size_t)ctx->max_smem_optin > 40960 ? (size_t)ctx->max_smem_optin - 20480 : 0;
     if (smem <= cap) {
-      static size_t configured = 0;
-      if (smem > 24 * 1024 && smem > configured) {
+      static DmmPerDeviceOnce smem_once;
+      if (smem > 24 * 1024 && smem_once.need(ctx)) {
         DMM_CUDA(cudaFuncSetAttribute(topk_edges_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-        configured = cap;
+        smem_once.mark(ctx);
       }
       topk_edges_kernel<true><<<(unsigned)n_rows, 256, smem, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
                                                                   out_users, out_items, status, order, sg);

@@ -23,15 +23,28 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_call_device = 0       # device of the tensors of the C-ABI call being assembled (set by _ctx, read by _stream)
+
+
 def _stream():
-    # raw handle of torch's current stream (torch.cuda.current_stream() builds a Python Stream object: ~15 us)
-    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    # raw handle of torch's current stream ON THE TENSORS' DEVICE (torch.cuda.current_stream() builds a Python Stream
+    # object: ~15 us).  Every wrapper evaluates _ctx(tensor) before _stream() (argument order of _lib.call).
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(_call_device))
 
 
 def _ctx(t: torch.Tensor):
+    """Context of the tensor's device.  Kernels are launched on the CURRENT device, so the tensor must live there:
+    the library never switches devices behind the caller's back (run under ``torch.cuda.device(t.device)``)."""
+    global _call_device
     if not t.is_cuda:
         raise _lib.DiffMMError("diffmm_b200 operators need CUDA tensors (there is no CPU fallback)")
-    return _lib.ctx(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:
+        raise _lib.DiffMMError(f"tensor on cuda:{idx} but the current device is cuda:{cur}: call under "
+                               f"torch.cuda.device({idx}) (Coach does this for base.gpu)")
+    _call_device = idx
+    return _lib.ctx(idx)
 
 
 def _row_major(t: torch.Tensor, name: str) -> int:
@@ -244,7 +257,9 @@ class CsrAdj:
         return torch.sparse_coo_tensor(torch.stack([rows, self.idx.long()]), self.val, (self.n_nodes, self.n_nodes))
 
 
-def build_norm_adj(row_ptr: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int) -> CsrAdj:
+def build_norm_adj(row_ptr: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int,
+                   status: Optional[torch.Tensor] = None) -> CsrAdj:
+    """status (optional int32 [1] on the device): bit 1 is OR-ed in when an item id is out of range."""
     assert row_ptr.dtype == torch.int64 and items.dtype == torch.int32
     E = int(items.numel())
     N = n_users + n_items
@@ -256,7 +271,7 @@ def build_norm_adj(row_ptr: torch.Tensor, items: torch.Tensor, n_users: int, n_i
     idx = torch.empty(2 * E + N, dtype=torch.int32, device=dev)
     val = torch.empty(2 * E + N, dtype=torch.float32, device=dev)
     _lib.call("dmm_build_norm_adj_csr", _ctx(row_ptr), _p(row_ptr), _p(items), n_users, n_items, E, _p(ptr), _p(idx),
-              _p(val), _p(ws), ws_bytes, _stream())
+              _p(val), _p(ws), ws_bytes, _p(status), _stream())
     return CsrAdj(ptr, idx, val, n_users, n_items)
 
 

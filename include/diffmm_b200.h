@@ -37,7 +37,8 @@ enum dmm_status {
 /* ---- library / context ------------------------------------------------------------------ */
 int dmm_version(void);
 const char* dmm_last_error(void);
-/* Binds to CUDA device `device` (must be sm_100); resolves cuTensorMapEncodeTiled. */
+/* Context for CUDA device `device` (must be sm_100); resolves cuTensorMapEncodeTiled.  Does not change the calling
+ * thread's current device: every later call launches on the current device, which must be `device`. */
 int dmm_init(int device, dmm_ctx** out);
 void dmm_destroy(dmm_ctx* ctx);
 int dmm_num_sms(const dmm_ctx* ctx);
@@ -163,7 +164,7 @@ int dmm_gemm_f32_tn(dmm_ctx* ctx, const float* a, int64_t lda, const float* b, i
  * For row r of scores [n_rows, n_cols] (ld) emits the k_r = out_ptr[r+1]-out_ptr[r] largest
  * entries' column indices into out_items[out_ptr[r] .. out_ptr[r+1]) sorted ascending by column,
  * and row_base + r into out_users.  Tie-break: value descending, then column ascending.
- * k_r > n_cols is an error flagged in *status (device int, optional).  `order` (optional, int32
+ * k_r > n_cols is an error flagged by OR-ing bit 0 into *status (device int, optional; never cleared here).  `order` (optional, int32
  * permutation of 0..n_rows-1, e.g. from dmm_rows_long_first) is the order in which rows are scheduled;
  * results do not depend on it.  Rows wider than 8192 columns go through a column-segment pass plus a merge
  * when a `workspace` of dmm_topk_workspace_bytes(n_cols, n_edges) bytes is given (n_edges >= the number of
@@ -180,13 +181,15 @@ int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows
  * unique within a row) builds A = D^-1/2 ([[0,R],[R^T,0]] + I) D^-1/2 as CSR over N = U + I nodes:
  * adj_ptr int64 [N+1], adj_idx int32 [2E+N] (sorted within rows), adj_val fp32 with the
  * reference's fp64 arithmetic (d_r^-1/2 * 1) * d_c^-1/2 rounded to fp32.
+ * An item id outside [0, n_items) is an error flagged by OR-ing bit 1 into *status (device int, optional; the
+ * arrays written for such a list are unspecified and must not be used).
  * Replaces Coach.makeTorchAdj (Main.py:113-116) -> DataHandler.makeTorchAdj / normalizeAdj
  * (DataHandler.py:53-93), which run on the host in scipy.                                    */
 int64_t dmm_build_adj_workspace_bytes(int64_t n_users, int64_t n_items, int64_t n_edges);
 int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* items,
                            int64_t n_users, int64_t n_items, int64_t n_edges,
                            int64_t* adj_ptr, int32_t* adj_idx, float* adj_val,
-                           void* workspace, int64_t workspace_bytes, void* stream);
+                           void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
 
 /* ---- CSR SpMM ------------------------------------------------------------------------------
  * Y[r0:r1, :] = alpha * A[r0:r1, :] . X (+ beta * Z[r0:r1, :]),  X fp32 [N_cols, D] (ld_x).

@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY — never imported by the product path.
 
-Imports the *unmodified* reference (sun2ot/DiffMM, mounted read-only at
-/root/reference) on CPU so that golden vectors can be generated from it
-(oracle/gen_golden.py) and so the numpy oracle (oracle/diffmm_oracle.py)
-can be pinned against it.  /root/reference does not exist on the GPU box;
-nothing under tests/ -m gpu, smoke() or bench.py may import this module.
+Imports the *unmodified* reference (sun2ot/DiffMM) on CPU so that golden
+vectors can be generated from it (oracle/gen_golden.py), so the numpy oracle
+(oracle/diffmm_oracle.py) can be pinned against it, and so bench.py can time
+it as the CPU arm.  The modules come from /root/reference where that is
+mounted (this container) and otherwise from oracle/_ref/, the git-ignored
+unmodified copy made by oracle/build_ref.py that travels to the GPU box with
+the snapshot.  Only tests/, smoke() and bench.py's reference / cpu_baseline
+legs may import this module.
 
 What the shim does:
   * Conf.py:62-66 uses dataclass-instance defaults, which Python >= 3.11
@@ -20,7 +23,20 @@ import re
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DIFFMM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    env = os.environ.get("DIFFMM_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "Model.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 class _QuietLog:
@@ -35,8 +51,12 @@ def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "Model.py"))
 
 
-def load_reference():
-    """Returns a namespace with the reference modules (Conf, Model, DataHandler, Utils, Main)."""
+def load_reference(force_cpu: bool = False):
+    """Returns a namespace with the reference modules (Conf, Model, DataHandler, Utils, Main).
+
+    force_cpu: make the reference take its CPU path even on a machine with a GPU (its modules pick
+    ``cuda:{gpu}`` whenever torch.cuda.is_available(), Model.py:149,227): torch.cuda.is_available is patched to
+    False for the rest of the process — use only in a process that does no GPU work (bench.py --impl reference)."""
     if not available():
         raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
     import torch
@@ -60,6 +80,8 @@ def load_reference():
     sys.modules["Conf"] = conf  # must be registered before exec: @dataclass looks the module up
     exec(compile(src, "Conf_shim", "exec"), conf.__dict__)
 
+    if force_cpu:
+        torch.cuda.is_available = lambda: False
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
         nn.Module.cuda = lambda self, *a, **k: self

@@ -107,3 +107,83 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+# ---------------------------------------------------------------------------------------------- configuration (f4)
+import os
+import pytest
+from diffmm_b200.Conf import load_config
+
+_CONF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "conf")
+_EXPECT = {   # file -> (data.name, seed, sampling_step, cl_method, residual_weight, stale keys the loader must drop)
+    "tiktok.toml": ("tiktok", 1818, 0, 0, 0.5, []),
+    "sports.toml": ("sports", 2233, 0, 1, 0.5, []),
+    "yelp.toml": ("yelp", 125, 0, 1, 0.5, []),
+    "baby.toml": ("baby", 999, 5, 1, 0.2, ["base.trans", "hyper.keepRate", "hyper.e_loss", "hyper.rebuild_k", "train.norm",
+                                           "train.sampling_noise"]),
+    "ifashion.toml": ("ifashion", 1818, 1, 1, 0.5, ["base.trans", "hyper.keepRate", "hyper.e_loss", "train.norm",
+                                                    "train.sampling_noise"]),
+    "test.toml": ("tiktok", 1818, 1, 0, 0.5, ["base.trans", "hyper.keepRate", "hyper.e_loss", "train.norm",
+                                              "train.sampling_noise"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_EXPECT))
+def test_load_config_accepts_every_shipped_toml(name):
+    """All six conf/*.toml of the reference load (three of them carry stale keys its own loader rejects, Conf.py:69-77)."""
+    cfg = load_config(os.path.join(_CONF, name))
+    data_name, seed, sstep, clm, rw, stale = _EXPECT[name]
+    assert (cfg.data.name, cfg.base.seed, cfg.hyper.sampling_step, cfg.base.cl_method) == (data_name, seed, sstep, clm)
+    assert cfg.hyper.residual_weight == rw and cfg.hyper.steps == 5 and cfg.base.denoise_dim == "[1024]"
+    assert sorted(cfg.ignored_keys) == sorted(stale)
+    assert cfg.base.precision == "bf16"
+
+
+@pytest.mark.parametrize("name", sorted(_EXPECT))
+def test_shipped_tomls_carry_the_reference_values(name):
+    ref = os.path.join("/root/reference/conf", name)
+    if not os.path.isfile(ref):
+        pytest.skip("reference tree not present on this machine")
+    import tomllib
+    with open(ref, "rb") as f, open(os.path.join(_CONF, name), "rb") as g:
+        assert tomllib.load(f) == tomllib.load(g)
+
+
+def test_load_config_rejects_a_sampling_step_beyond_the_schedule(tmp_path):
+    p = tmp_path / "bad.toml"
+    p.write_text("[hyper]\nsteps = 5\nsampling_step = 6\n")
+    with pytest.raises(ValueError):
+        load_config(str(p))
+
+
+def test_reference_arm_and_gpu_arm_draw_identical_denoise_weights(monkeypatch):
+    """bench.py's two arms must time the same model: the reference's Denoise (oracle/_ref) and ours are constructed in
+    the same order from the same seed, so their parameters are bit-identical."""
+    import sys
+    root = os.path.dirname(_CONF)
+    if not os.path.isfile(os.path.join(root, "oracle", "_ref", "Model.py")):
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py)")
+    sys.path.insert(0, root)
+    import bench
+    monkeypatch.setitem(bench.WORKLOADS, "baby", dict(users=50, items=70, modalities=["image", "text"], hidden=32,
+                                                      conf="baby.toml"))
+    hyper = bench.workload_hyper("baby")
+    assert hyper["sampling_step"] == 5
+    saved = {k: sys.modules.get(k) for k in ("Conf", "Model", "DataHandler", "Main", "Utils", "Utils.Utils", "Utils.Log")}
+    is_avail, t_cuda, m_cuda = torch.cuda.is_available, torch.Tensor.cuda, torch.nn.Module.cuda
+    try:
+        _, _, diff_o, dens_o = bench.build_workload("baby", "cpu", 3, "bf16", 1, hyper)
+        _, diff_r, dens_r = bench.load_reference_arm(bench.WORKLOADS["baby"], 3, hyper)
+    finally:
+        torch.cuda.is_available, torch.Tensor.cuda, torch.nn.Module.cuda = is_avail, t_cuda, m_cuda
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for m in dens_o:
+        so, sr = dens_o[m].state_dict(), dens_r[m].state_dict()
+        assert list(so) == list(sr)
+        for k in so:
+            assert torch.equal(so[k], sr[k]), (m, k)
+    assert torch.equal(diff_o.posterior_mean_coef1.cpu(), diff_r.posterior_mean_coef1.cpu())
