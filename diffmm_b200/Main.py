@@ -300,13 +300,26 @@ class Coach:
         h = self.handler
         it = iter(h.diffusionLoader.index_batches())
         next(it, None)                                   # base-seed + sampler-seed + randperm draws
+        if not hasattr(self, "_rebuild_status"):
+            self._rebuild_status = torch.zeros(1, dtype=torch.int32, device=self.device)
         adjs = rebuild_modal_adj(self.diffusion_model, self._denoise_dict(), h.train_indptr, h.train_indices,
                                  self.config.data.user_num, self.config.data.item_num,
                                  self.config.hyper.sampling_step, getattr(self.config.base, "precision", "bf16"),
-                                 group=self.group)
+                                 group=self.group, status=self._rebuild_status)
         self.image_adj, self.text_adj = adjs["image"], adjs["text"]
         if self.has_audio:
             self.audio_adj = adjs["audio"]
+
+    def _check_rebuild_status(self):
+        """Device-side error bits of the rebuild (top-k asked for more entries than items; item id out of range in the
+        adjacency build), read once per epoch: a corrupt modality graph must not train silently."""
+        st = getattr(self, "_rebuild_status", None)
+        if st is not None:
+            bits = int(st.item())
+            if bits:
+                st.zero_()
+                raise RuntimeError(f"graph rebuild flagged device-side errors (status bits {bits:#x}: "
+                                   f"1 = a user has more train interactions than there are items, 2 = item id out of range)")
 
     def _joint_step(self, users, pos_items, neg_items, biadj):
         """One batch of phase 3 (Main.py:297-377): losses, backward, Adam step.  Returns the four detached loss
@@ -426,6 +439,7 @@ class Coach:
                     acc += torch.stack(self._joint_step(*static, biadj)).double()
             self._joint_graph.replay()
         out = acc.tolist()
+        self._check_rebuild_status()             # rides on the sync above: no extra round trip per epoch
         if use_graph:
             _ag._PACK_CACHE.clear()              # packs written by the replays are one optimiser step stale
         return out[3], out[0], out[1], out[2]

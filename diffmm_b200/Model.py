@@ -237,6 +237,8 @@ class GaussianDiffusion(nn.Module):
         self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * torch.sqrt(alphas) / (1.0 - self.alphas_cumprod)
         self._h_coef1 = self.posterior_mean_coef1.cpu().numpy()
         self._h_coef2 = self.posterior_mean_coef2.cpu().numpy()
+        self._h_sqrt_ac = self.sqrt_alphas_cumprod.cpu().numpy()
+        self._h_sqrt_1mac = self.sqrt_one_minus_alphas_cumprod.cpu().numpy()
         self._coef_tables_f32 = None
 
     def _tables_f32(self, device):

@@ -25,6 +25,7 @@ class GemmEpilogue(C.Structure):
         ("out_hi", c_vp), ("out_lo", c_vp), ("ld_out16", c_i64),
         ("res_hi", c_vp), ("res_lo", c_vp), ("ld_res16", c_i64),
         ("res_pre_act", c_i32), ("post_act", c_i32), ("post_bias", c_vp),
+        ("cmax", c_vp), ("ld_cmax", c_i64),
     ]
 
 
@@ -40,8 +41,9 @@ PROTOTYPES = {
     "dmm_csr_rows_to_dense": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "dmm_time_embedding": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "dmm_time_bias": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
-    "dmm_csr_gather_act": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, C.c_int, c_i64,
-                                     c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmm_csr_gather_act": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, C.c_int,
+                                     c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmm_csr_qsample_values": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),
     "dmm_rows_long_first": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dmm_gemv_f32": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dmm_bias_act_pack": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_i64, c_vp]),
@@ -54,6 +56,9 @@ PROTOTYPES = {
     "dmm_topk_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                  c_vp]),
+    "dmm_topk_pruned_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "dmm_topk_edges_pruned": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_i64, c_i64, c_vp]),
     "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dmm_spmm_plan_bytes": (c_i64, [c_i64, c_i64]),

@@ -235,6 +235,21 @@ __device__ __forceinline__ float approx_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// NaN-propagating maximum: a NaN anywhere in a chunk surfaces in its maximum (the top-k then takes its exact path)
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// maximum of the valid columns of one row of a 32-column chunk (the values exactly as they are written to out_f32)
+template <bool FULL>
+__device__ __forceinline__ float chunk_row_max(const float (&v)[32], int n0, int N) {
+  float m = __uint_as_float(0xFF800000u);
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (FULL || n0 + j < N) m = fmax_nan(m, v[j]);
+  return m;
+}
 template <bool X3>
 __device__ __forceinline__ float epi_tanh(float x) {
   return X3 ? fast_tanh(x) : approx_tanh(x);
@@ -420,6 +435,10 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const WorkIte
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[8 * q + j] = t[j];
+    }
+    if (ep.cmax) {   // pruning side array of the top-k: this thread's row maximum of the chunk, from registers
+      const float m = (INTERIOR || n0 + 32 <= p.N) ? chunk_row_max<true>(v, n0, p.N) : chunk_row_max<false>(v, n0, p.N);
+      if (INTERIOR || rbase + lane < p.M) ep.cmax[(int64_t)(rbase + lane) * ep.ld_cmax + (n0 >> 5)] = m;
     }
     __syncwarp();  // every row has consumed the staged residual / bias: the tile is reused for the outputs
 
@@ -683,6 +702,10 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, const CUt
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[8 * q + e] = t[e];
+      }
+      if (ep.cmax) {   // pruning side array of the top-k: this thread's row maximum of the chunk, from registers
+        const float m = (n0 + 32 <= p.N) ? chunk_row_max<true>(v, n0, p.N) : chunk_row_max<false>(v, n0, p.N);
+        if (row0 + lane < p.M) ep.cmax[(int64_t)(row0 + lane) * ep.ld_cmax + (n0 >> 5)] = m;
       }
       if (o32) {
         // in place: this thread read its row of the residual above and owns the same row of the result
@@ -1112,6 +1135,7 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   DMM_CHECK_ARG(ep->post_act == 0 || ep->post_act == 1, "dmm_gemm_bf16_tn: unknown post activation %d", ep->post_act);
   DMM_CHECK_ARG((!ep->post_bias && !ep->post_act) || ep->out_hi, "dmm_gemm_bf16_tn: the post stage applies to out_hi/out_lo");
   DMM_CHECK_ARG(al16(ep->post_bias), "dmm_gemm_bf16_tn: post_bias must be 16-byte aligned");
+  DMM_CHECK_ARG(!ep->cmax || ep->ld_cmax >= dmm_ceil_div(N, 32), "dmm_gemm_bf16_tn: ld_cmax must be >= ceil(N / 32)");
 
   GemmParams p;
   p.M = (int)M;

@@ -276,9 +276,10 @@ __global__ void __launch_bounds__(256) time_bias_kernel(int64_t t0, int d, const
 // sampling_step 0): the dense [B, I] x [I, H] contraction of Model.py:212 degenerates to a gather-sum of the
 // rows of W^T.  One warp per user row; lane l owns the 16-byte pieces l, l+32, ... of the H columns, so every
 // gathered weight row is read with full 512-byte warp transactions (the packed W^T is L2 resident).
-template <bool LO>
+template <bool LO, bool WT>
 __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __restrict__ indptr,
                                                              const int32_t* __restrict__ indices,
+                                                             const float* __restrict__ vals,
                                                              const int64_t* __restrict__ row_ids,
                                                              const int32_t* __restrict__ order, int64_t row0,
                                                              int64_t n_rows, int64_t n_cols,
@@ -301,12 +302,17 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  auto add = [&](const uint4& q) {
+  auto add = [&](const uint4& q, float w) {
     const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      acc[2 * j] += __uint_as_float(wv[j] << 16);
-      acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      if constexpr (WT) {      // sparse rows with values (a q_sample'd start): x[c] * W^T[c, :]
+        acc[2 * j] = fmaf(w, __uint_as_float(wv[j] << 16), acc[2 * j]);
+        acc[2 * j + 1] = fmaf(w, __uint_as_float(wv[j] & 0xFFFF0000u), acc[2 * j + 1]);
+      } else {
+        acc[2 * j] += __uint_as_float(wv[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      }
     }
   };
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -316,12 +322,18 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
     // 1 % of users with hundreds of interactions would otherwise set the length of the kernel's tail)
     int32_t mine = (k + lane < e) ? indices[k + lane] : -1;
     if (mine >= n_cols) mine = -1;
+    float my_w = 1.f;
+    if constexpr (WT) my_w = (k + lane < e) ? vals[k + lane] : 0.f;
     const int cnt = (int)((e - k) < 32 ? (e - k) : 32);
     for (int j = 0; j < cnt; j += G) {
       int32_t c[G];
+      float w[G];
       uint4 qh[G], ql[LO ? G : 1];
 #pragma unroll
-      for (int t = 0; t < G; ++t) c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+      for (int t = 0; t < G; ++t) {
+        c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+        w[t] = WT ? __shfl_sync(0xffffffffu, my_w, (j + t) & 31) : 1.f;
+      }
 #pragma unroll
       for (int t = 0; t < G; ++t) {
         const bool ok = col_ok && j + t < cnt && c[t] >= 0;
@@ -330,8 +342,8 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
       }
 #pragma unroll
       for (int t = 0; t < G; ++t) {
-        add(qh[t]);
-        if constexpr (LO) add(ql[t]);
+        add(qh[t], w[t]);
+        if constexpr (LO) add(ql[t], w[t]);
       }
     }
   }
@@ -371,6 +383,55 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
       h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
       if (h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
     }
+  }
+}
+
+// ------------------------------------------------------------------ q_sample on binary CSR rows
+// Default-noise q_sample (Model.py:324-341) of a BINARY row keeps the row's sparsity: noise = sign(x0) * normalize(n)
+// vanishes wherever x0 does, so x_t = a x0 + b noise has the value a + b n_c / max(||n||_2, 1e-12) at the row's items
+// and 0 elsewhere (n = the full randn row: its norm runs over all n_cols columns).  One CTA per row streams the noise
+// row once for the norm and writes the values of the row's entries; the first Denoise layer then stays a (weighted)
+// gather-sum instead of a dense contraction.  HBM-bound: 4 * n_cols bytes read per row.
+__global__ void __launch_bounds__(256) csr_qsample_values_kernel(const int64_t* __restrict__ indptr,
+                                                                 const int32_t* __restrict__ indices,
+                                                                 const int64_t* __restrict__ row_ids, int64_t row0,
+                                                                 int64_t n_cols, const float* __restrict__ noise,
+                                                                 int64_t ld_noise, float coef_a, float coef_b,
+                                                                 float* __restrict__ vals) {
+  __shared__ float red[8];
+  const int64_t r = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t u = row_ids ? row_ids[r] : row0 + r;
+  const int64_t b = indptr[u], e = indptr[u + 1];
+  if (b >= e) return;                                   // block-uniform: nothing to emit for an empty row
+  const float* row = noise + r * ld_noise;
+  float ss = 0.f;
+  if ((reinterpret_cast<uintptr_t>(row) & 15u) == 0) {
+    const int64_t n4 = n_cols >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll 4
+    for (int64_t i = tid; i < n4; i += 256) {
+      const float4 q = __ldcs(row4 + i);
+      ss = fmaf(q.x, q.x, ss);
+      ss = fmaf(q.y, q.y, ss);
+      ss = fmaf(q.z, q.z, ss);
+      ss = fmaf(q.w, q.w, ss);
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n_cols; i += 256) ss = fmaf(row[i], row[i], ss);
+  } else {
+    for (int64_t i = tid; i < n_cols; i += 256) ss = fmaf(row[i], row[i], ss);
+  }
+  ss = dmm_warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+  for (int64_t k = b + tid; k < e; k += 256) {
+    const int32_t c = indices[k];
+    const float n = (c >= 0 && c < n_cols) ? row[c] : 0.f;
+    vals[k] = __fadd_rn(coef_a, __fmul_rn(coef_b, __fmul_rn(n, inv)));
   }
 }
 
@@ -608,8 +669,20 @@ extern "C" int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, c
   return DMM_OK;
 }
 
-extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
-                                  const int32_t* order,
+extern "C" int dmm_csr_qsample_values(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                                      int64_t row0, int64_t n_rows, int64_t n_cols, const float* noise, int64_t ld_noise,
+                                      float coef_a, float coef_b, float* vals, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && indices && noise && vals, "dmm_csr_qsample_values: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31) && n_cols > 0 && ld_noise >= n_cols, "dmm_csr_qsample_values: bad shape");
+  if (n_rows == 0) return DMM_OK;
+  csr_qsample_values_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, row0, n_cols, noise,
+                                                                               ld_noise, coef_a, coef_b, vals);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const float* vals,
+                                  const int64_t* row_ids, const int32_t* order,
                                   int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                                   const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
                                   uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z,
@@ -629,13 +702,17 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
   const int64_t blocks = dmm_ceil_div(n_rows * slices * 32, 256);
   DMM_CHECK_ARG(blocks < (1LL << 31), "dmm_csr_gather_act: too many rows");
   const unsigned grid = (unsigned)blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+#define DMM_GATHER_ARGS indptr, indices, vals, row_ids, order, row0, n_rows, n_cols, wt_hi, wt_lo, ld_w, bias, act, n_out, slices, \
+                        h_hi, h_lo, ld_h, z_f32, ld_z
   if (wt_lo) {
-    csr_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, order, row0, n_rows, n_cols, wt_hi,
-                                                                       wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
+    if (vals) csr_gather_act_kernel<true, true><<<grid, 256, 0, st>>>(DMM_GATHER_ARGS);
+    else csr_gather_act_kernel<true, false><<<grid, 256, 0, st>>>(DMM_GATHER_ARGS);
   } else {
-    csr_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, indices, row_ids, order, row0, n_rows, n_cols, wt_hi,
-                                                                        wt_lo, ld_w, bias, act, n_out, slices, h_hi, h_lo, ld_h, z_f32, ld_z);
+    if (vals) csr_gather_act_kernel<false, true><<<grid, 256, 0, st>>>(DMM_GATHER_ARGS);
+    else csr_gather_act_kernel<false, false><<<grid, 256, 0, st>>>(DMM_GATHER_ARGS);
   }
+#undef DMM_GATHER_ARGS
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

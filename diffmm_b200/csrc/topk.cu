@@ -314,10 +314,12 @@ __global__ void __launch_bounds__(256) topk_edges_kernel(const float* __restrict
                                                          int n_cols, const int64_t* __restrict__ out_ptr,
                                                          int64_t row_base, int32_t* __restrict__ out_users,
                                                          int32_t* __restrict__ out_items, int32_t* __restrict__ status,
-                                                         const int32_t* __restrict__ order, SegCfg sg) {
+                                                         const int32_t* __restrict__ order, SegCfg sg,
+                                                         const int32_t* __restrict__ live) {
   extern __shared__ uint32_t s_keys[];  // n_cols keys when IN_SMEM
   __shared__ TopkSmem<256> sm;
   if ((int64_t)blockIdx.x >= n_rows) return;
+  if (live && (int64_t)blockIdx.x >= (int64_t)*live) return;   // `order` is a device-built list of *live rows
   const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;   // scheduling order only
   const int64_t o0 = out_ptr[r], o1 = out_ptr[r + 1];
   int k = (int)(o1 - o0);
@@ -338,13 +340,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 5 : 1) topk_rows_reg_kernel(co
                                                            int64_t row_base, int32_t* __restrict__ out_users,
                                                            int32_t* __restrict__ out_items_arg, int32_t* __restrict__ status,
                                                            const int32_t* __restrict__ order, SegCfg sg,
-                                                           int32_t* __restrict__ seg_tmp) {
+                                                           int32_t* __restrict__ seg_tmp, const int32_t* __restrict__ live) {
   __shared__ TopkSmem<NT> sm;
   constexpr int NW = NT / 32;
   // segment pass (sg.mode == 1): block b is segment b % S of the row scheduled in slot b / S
   const int seg = sg.mode == 1 ? (int)(blockIdx.x % (unsigned)sg.S) : 0;
   const int64_t slot = sg.mode == 1 ? (int64_t)(blockIdx.x / (unsigned)sg.S) : (int64_t)blockIdx.x;
   if (slot >= n_rows) return;
+  if (live && slot >= (int64_t)*live) return;
   // scheduling order only (rows with a large k take the slower exact paths: started first, they overlap the rest)
   const int64_t r = order ? (int64_t)order[slot] : slot;
   const int col_off = seg * sg.seg_cols;
@@ -522,11 +525,12 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
                                                          const int64_t* __restrict__ out_ptr, int64_t row_base,
                                                          int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
                                                          const int32_t* __restrict__ order, SegCfg sg,
-                                                         const int32_t* __restrict__ seg_tmp) {
+                                                         const int32_t* __restrict__ seg_tmp, const int32_t* __restrict__ live) {
   __shared__ uint32_t key[TOPK_MERGE_CAP];
   __shared__ int col[TOPK_MERGE_CAP];
   __shared__ int sel[TOPK_MERGE_CAP];
   if ((int64_t)blockIdx.x >= n_rows) return;
+  if (live && (int64_t)blockIdx.x >= (int64_t)*live) return;
   const int64_t r = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
   const int64_t o0 = out_ptr[r];
   const int k = (int)(out_ptr[r + 1] - o0);
@@ -562,10 +566,230 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
 template <int NT>
 void launch_reg(const float* scores, int64_t ld, int64_t n_rows, int n_cols, const int64_t* out_ptr, int64_t row_base,
                 int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order, SegCfg sg, int32_t* seg_tmp,
-                cudaStream_t st) {
+                const int32_t* live, cudaStream_t st) {
   const int64_t blocks = sg.mode == 1 ? n_rows * sg.S : n_rows;
   topk_rows_reg_kernel<NT><<<(unsigned)blocks, NT, 0, st>>>(scores, ld, n_rows, n_cols, out_ptr, row_base, out_users,
-                                                           out_items, status, order, sg, seg_tmp);
+                                                           out_items, status, order, sg, seg_tmp, live);
+}
+
+// ------------------------------------------------------------------------------------------ pruned top-k
+// The contraction that writes the scores also writes cmax[r, c] = max of the 32-column chunk c of row r (1/32 of the
+// bytes, dmm_gemm_epilogue.cmax).  The k largest scores of a row lie in the k chunks with the largest maxima (ties:
+// lower chunk first): each of those chunks holds a score >= the k-th largest maximum Lk, so the k-th largest score T
+// is >= Lk, every chunk holding a score > Lk is among them, and a score == T in any other chunk sorts behind k scores
+// that are >= T with lower columns.  So one CTA per row
+//   1. reads the row of chunk maxima (n_chunks floats) into registers and selects its k largest exactly with the
+//      same bound -> compaction -> all-pairs ranking scheme as the register kernel (columns = chunk ids);
+//   2. reads ONLY those k chunks of the score row (128 B each), keeps the scores >= Lk and ranks them exactly by
+//      (score desc, column asc); the k best leave in ascending column order.
+// Per row that is 4 * I / 32 + 128 * k bytes instead of 4 * I (median k is 2-4).  Rows that do not qualify (k above
+// PRUNE_KMAX or more than n_chunks / PRUNE_RATIO, a NaN maximum, crowded ties) are appended to a device list that
+// the whole-row / segmented kernels process afterwards: every row is emitted by exactly one path, bit-identically.
+constexpr int PRUNE_KMAX = 64;
+constexpr int PRUNE_RATIO = 4;
+constexpr int PRUNE_CAND = 512;
+
+struct PruneArgs {
+  const float* scores;
+  int64_t ld;
+  const float* cmax;
+  int64_t ld_cmax;
+  int n_chunks, n_cols;
+  int64_t n_rows;
+  const int64_t* out_ptr;
+  int64_t row_base;
+  int32_t* out_users;
+  int32_t* out_items;
+  int32_t* status;
+  const int32_t* order;
+  int32_t* left_count;
+  int32_t* left_rows;
+};
+
+struct alignas(16) PruneSmem {
+  uint32_t key[PRUNE_CAND];
+  int col[PRUNE_CAND];
+  int sel[PRUNE_CAND];
+  uint32_t red[32];
+  int ncand, nsel, ncand2;
+  uint32_t lk;
+};
+
+__device__ __forceinline__ float key_to_float(uint32_t L) {   // inverse of order_key (L == 0: below every score)
+  return (L == 0u) ? __uint_as_float(0xFF800000u) : __uint_as_float((L & 0x80000000u) ? (L ^ 0x80000000u) : ~L);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
+  __shared__ PruneSmem sm;
+  constexpr int NW = NT / 32;
+  if ((int64_t)blockIdx.x >= a.n_rows) return;
+  const int64_t r = a.order ? (int64_t)a.order[blockIdx.x] : (int64_t)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_chunks = a.n_chunks;
+
+  // 1a. the row of chunk maxima -> registers (issued before anything depends on out_ptr)
+  const float* crow = a.cmax + r * a.ld_cmax;
+  const int n4 = n_chunks >> 2;
+  const float4* crow4 = reinterpret_cast<const float4*>(crow);
+  float4 v[TOPK_V4];
+#pragma unroll
+  for (int j = 0; j < TOPK_V4; ++j) {
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid + NT * j < n4) v[j] = __ldg(crow4 + tid + NT * j);
+  }
+  const int tail_col = (n4 << 2) + tid;
+  const bool has_tail = tid < (n_chunks & 3);
+  float tail_v = 0.f;
+  if (has_tail) tail_v = __ldg(crow + tail_col);
+
+  const int64_t o0 = a.out_ptr[r];
+  const int k = (int)(a.out_ptr[r + 1] - o0);
+  if (k <= 0) return;
+  auto defer = [&]() {
+    if (tid == 0) a.left_rows[atomicAdd(a.left_count, 1)] = (int32_t)r;
+  };
+  if (k > PRUNE_KMAX || k > 32 * NW || (int64_t)k * PRUNE_RATIO > n_chunks || k > a.n_cols) {   // block-uniform
+    defer();
+    return;
+  }
+  const float NEG_INF = __uint_as_float(0xFF800000u);
+  const int jfull = n4 / NT, jrem = n4 - jfull * NT;
+  float pmax[TOPK_V4];
+  float tmaxf = has_tail ? fmax_nan(tail_v, NEG_INF) : NEG_INF;
+#pragma unroll
+  for (int j = 0; j < TOPK_V4; ++j) {
+    pmax[j] = NEG_INF;
+    if (j < jfull || (j == jfull && tid < jrem)) {
+      pmax[j] = fmax_nan(fmax_nan(v[j].x, v[j].y), fmax_nan(v[j].z, v[j].w));
+      tmaxf = fmax_nan(tmaxf, pmax[j]);
+    }
+  }
+  const uint32_t tmax = (tmaxf == NEG_INF) ? 0u : order_key(tmaxf);
+
+  // 1b. lower bound L of the k-th largest chunk maximum: this warp's q-th largest thread maximum, q = ceil(k / warps)
+  const int q = (k + NW - 1) / NW;
+  uint32_t wq;
+  {
+    uint32_t sv = tmax;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, sv, j);
+        const bool desc = (lane & k2) == 0;
+        const bool lower = (lane & j) == 0;
+        sv = (lower == desc) ? max(sv, other) : min(sv, other);
+      }
+    }
+    wq = __shfl_sync(0xffffffffu, sv, q - 1);
+  }
+  if (lane == 0) sm.red[wid] = wq;
+  if (tid == 0) {
+    sm.ncand = 0;
+    sm.nsel = 0;
+    sm.ncand2 = 0;
+    sm.lk = 0xFFFFFFFFu;
+  }
+  if (__syncthreads_or(tmaxf != tmaxf)) {   // a NaN score somewhere in the row: exact whole-row path
+    defer();
+    return;
+  }
+  uint32_t L = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) L = min(L, sm.red[i]);
+  const float Lf = key_to_float(L);
+
+  // 1c. chunk candidates (maximum >= L) -> shared memory, one atomic per warp per hit group
+  auto push = [&](int* counter, bool c, float x, int col) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, c);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(counter, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (c && pos < PRUNE_CAND) {
+        sm.key[pos] = order_key(x);
+        sm.col[pos] = col;
+      }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < TOPK_V4; ++j) {
+    if (j > jfull) break;                      // block-uniform
+    const bool have = j < jfull || tid < jrem;
+    const bool open = have && !(pmax[j] < Lf);
+    if (__any_sync(0xffffffffu, open)) {
+      const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) push(&sm.ncand, open && !(xs[e] < Lf), xs[e], 4 * (tid + NT * j) + e);
+    }
+  }
+  if (n_chunks & 3) push(&sm.ncand, has_tail && !(tail_v < Lf), tail_v, tail_col);
+  __syncthreads();
+  const int m = sm.ncand;
+  if (m > PRUNE_CAND || m < k) {
+    defer();
+    return;
+  }
+  // 1d. the k best chunks by (maximum desc, chunk asc); Lk = the smallest maximum among them
+  for (int c = tid; c < m; c += NT) {
+    const uint32_t my_key = sm.key[c];
+    const int my_col = sm.col[c];
+    int before = 0;
+    if (m > k) {
+      for (int j = 0; j < m; ++j) {
+        const uint32_t kj = sm.key[j];
+        const int cj = sm.col[j];
+        before += (kj > my_key || (kj == my_key && cj < my_col)) ? 1 : 0;
+      }
+    }
+    if (before < k) {
+      sm.sel[atomicAdd(&sm.nsel, 1)] = my_col;
+      atomicMin(&sm.lk, my_key);
+    }
+  }
+  __syncthreads();   // sm.key / sm.col are free again from here on
+  const float Lkf = key_to_float(sm.lk);
+
+  // 2a. the k selected chunks of the score row: one coalesced 128-byte read each, scores >= Lk are the candidates
+  const float* row = a.scores + r * a.ld;
+  for (int i = wid; i < k; i += NW) {
+    const int col = sm.sel[i] * 32 + lane;
+    const bool in = col < a.n_cols;
+    const float x = in ? __ldg(row + col) : NEG_INF;
+    push(&sm.ncand2, in && !(x < Lkf), x, col);
+  }
+  __syncthreads();
+  const int m2 = sm.ncand2;          // >= k: every selected chunk holds its maximum >= Lk
+  if (m2 > PRUNE_CAND || m2 < k) {   // crowded ties at the bound (or a maximum that matches no score: impossible by contract)
+    defer();
+    return;
+  }
+  // 2b. exact rank among the candidates by (score desc, column asc); the k best leave in ascending column order
+  for (int c = tid; c < m2; c += NT) {
+    const uint32_t my_key = sm.key[c];
+    const int my_col = sm.col[c];
+    int before = 0;
+    if (m2 > k) {
+      for (int j = 0; j < m2; ++j) {
+        const uint32_t kj = sm.key[j];
+        const int cj = sm.col[j];
+        before += (kj > my_key || (kj == my_key && cj < my_col)) ? 1 : 0;
+      }
+    }
+    sm.sel[c] = before < k ? my_col : 0x7FFFFFFF;
+  }
+  __syncthreads();
+  const int32_t user = (int32_t)(a.row_base + r);
+  for (int c = tid; c < m2; c += NT) {
+    const int my_col = sm.sel[c];
+    if (my_col == 0x7FFFFFFF) continue;
+    int pos = 0;
+    for (int j = 0; j < m2; ++j) pos += (sm.sel[j] < my_col) ? 1 : 0;
+    a.out_items[o0 + pos] = my_col;
+    if (a.out_users) a.out_users[o0 + pos] = user;
+  }
 }
 
 SegCfg make_seg(int64_t n_cols) {
@@ -586,16 +810,12 @@ extern "C" int64_t dmm_topk_workspace_bytes(int64_t n_cols, int64_t n_edges) {
   return sg.S > 0 ? (int64_t)sg.S * (n_edges > 0 ? n_edges : 0) * (int64_t)sizeof(int32_t) : 0;
 }
 
-extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
-                              const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
-                              int32_t* status, const int32_t* order, void* workspace, int64_t workspace_bytes,
-                              int64_t n_edges, void* stream) {
-  DMM_CHECK_ARG(ctx && scores && out_ptr && out_items, "dmm_topk_edges: null argument");
-  DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges: bad shape n_cols=%lld ld=%lld",
-                (long long)n_cols, (long long)ld);
-  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31), "dmm_topk_edges: bad n_rows");
-  if (n_rows == 0) return DMM_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+// Whole-row / segmented dispatch shared by dmm_topk_edges and the leftover pass of dmm_topk_edges_pruned.
+// `live` (device int32, optional): number of valid entries of `order` when that list was built on the device.
+static int topk_dispatch(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
+                         const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items, int32_t* status,
+                         const int32_t* order, const int32_t* live, void* workspace, int64_t workspace_bytes,
+                         int64_t n_edges, cudaStream_t st) {
   constexpr int PER_THREAD = 4 * TOPK_V4;
   static const bool force_generic = getenv("DMM_TOPK_GENERIC") != nullptr;   // test hook: exercise the generic kernels
   static const bool seg_ok = []() { const char* e = getenv("DMM_TOPK_SEG"); return !(e && e[0] == '0'); }();   // A/B switch
@@ -607,16 +827,17 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
                          workspace_bytes >= dmm_topk_workspace_bytes(n_cols, n_edges) && n_rows * (int64_t)sg.S < (1LL << 31);
   if (segmented) {
     sg.mode = 1;
-    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, nullptr, nullptr, status, order, sg, (int32_t*)workspace, st);
+    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, nullptr, nullptr, status, order, sg, (int32_t*)workspace,
+                    live, st);
     DMM_LAUNCH_CHECK();
     topk_merge_kernel<<<(unsigned)n_rows, 128, 0, st>>>(scores, ld, n_rows, out_ptr, row_base, out_users, out_items, order, sg,
-                                                       (const int32_t*)workspace);
+                                                       (const int32_t*)workspace, live);
     DMM_LAUNCH_CHECK();
     // the few rows the segment pass skipped: the 256-thread generic kernel (8 CTAs per SM; a 1024-thread CTA per row
     // that only reads two offsets and leaves would cost more in launch waves than the rows it really processes)
     sg.mode = 2;
     topk_edges_kernel<false><<<(unsigned)n_rows, 256, 0, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users,
-                                                              out_items, status, order, sg);
+                                                              out_items, status, order, sg, live);
     DMM_LAUNCH_CHECK();
     return DMM_OK;
   }
@@ -624,11 +845,11 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
   if (force_generic) {
     // fall through to the generic kernels below
   } else if (n_cols <= 256 * PER_THREAD) {
-    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
+    launch_reg<256>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, live, st);
   } else if (n_cols <= 512 * PER_THREAD) {
-    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
+    launch_reg<512>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, live, st);
   } else if (n_cols <= 1024 * PER_THREAD) {
-    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, st);
+    launch_reg<1024>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base, out_users, out_items, status, order, sg, nullptr, live, st);
   }
   if (force_generic || n_cols > 1024 * PER_THREAD) {
     const size_t smem = (size_t)n_cols * sizeof(uint32_t);
@@ -641,12 +862,70 @@ extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int
         smem_once.mark(ctx);
       }
       topk_edges_kernel<true><<<(unsigned)n_rows, 256, smem, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                  out_users, out_items, status, order, sg);
+                                                                  out_users, out_items, status, order, sg, live);
     } else {
       topk_edges_kernel<false><<<(unsigned)n_rows, 256, 0, st>>>(scores, ld, n_rows, (int)n_cols, out_ptr, row_base,
-                                                                out_users, out_items, status, order, sg);
+                                                                out_users, out_items, status, order, sg, live);
     }
   }
   DMM_LAUNCH_CHECK();
   return DMM_OK;
+}
+
+extern "C" int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
+                              const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
+                              int32_t* status, const int32_t* order, void* workspace, int64_t workspace_bytes,
+                              int64_t n_edges, void* stream) {
+  DMM_CHECK_ARG(ctx && scores && out_ptr && out_items, "dmm_topk_edges: null argument");
+  DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges: bad shape n_cols=%lld ld=%lld",
+                (long long)n_cols, (long long)ld);
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31), "dmm_topk_edges: bad n_rows");
+  if (n_rows == 0) return DMM_OK;
+  return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, order, nullptr,
+                       workspace, workspace_bytes, n_edges, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ pruned top-k
+namespace {
+inline size_t prune_align(size_t x) { return (x + 255) & ~(size_t)255; }
+inline size_t prune_head_bytes(int64_t n_rows) { return 256 + prune_align((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(int32_t)); }
+}  // namespace
+
+extern "C" int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t n_edges) {
+  return (int64_t)prune_head_bytes(n_rows) + dmm_topk_workspace_bytes(n_cols, n_edges);
+}
+
+extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
+                                     const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
+                                     int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
+                                     void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream) {
+  DMM_CHECK_ARG(ctx && scores && cmax && out_ptr && out_items && workspace, "dmm_topk_edges_pruned: null argument");
+  DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges_pruned: bad shape n_cols=%lld ld=%lld",
+                (long long)n_cols, (long long)ld);
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31), "dmm_topk_edges_pruned: bad n_rows");
+  const int64_t n_chunks = dmm_ceil_div(n_cols, 32);
+  DMM_CHECK_ARG(ld_cmax >= n_chunks && ld_cmax % 4 == 0 && (reinterpret_cast<uintptr_t>(cmax) & 15u) == 0,
+                "dmm_topk_edges_pruned: cmax rows must be 16-byte aligned with ld_cmax %% 4 == 0 and >= ceil(n_cols / 32)");
+  DMM_CHECK_ARG(workspace_bytes >= dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges),
+                "dmm_topk_edges_pruned: workspace smaller than dmm_topk_pruned_workspace_bytes");
+  if (n_rows == 0) return DMM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool prune_ok = []() { const char* e = getenv("DMM_TOPK_PRUNE"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (!prune_ok || n_chunks > 512 * 4 * TOPK_V4 || n_chunks < 8)
+    return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, order, nullptr,
+                         (uint8_t*)workspace + prune_head_bytes(n_rows), workspace_bytes - (int64_t)prune_head_bytes(n_rows),
+                         n_edges, st);
+  int32_t* left_count = (int32_t*)workspace;
+  int32_t* left_rows = (int32_t*)((uint8_t*)workspace + 256);
+  DMM_CUDA(cudaMemsetAsync(left_count, 0, sizeof(int32_t), st));
+  const PruneArgs a{scores, ld, cmax, ld_cmax, (int)n_chunks, (int)n_cols, n_rows, out_ptr, row_base, out_users, out_items,
+                    status, order, left_count, left_rows};
+  if (n_chunks <= 64 * 4 * TOPK_V4) topk_pruned_kernel<64><<<(unsigned)n_rows, 64, 0, st>>>(a);
+  else if (n_chunks <= 256 * 4 * TOPK_V4) topk_pruned_kernel<256><<<(unsigned)n_rows, 256, 0, st>>>(a);
+  else topk_pruned_kernel<512><<<(unsigned)n_rows, 512, 0, st>>>(a);
+  DMM_LAUNCH_CHECK();
+  // the rows the pruned kernel deferred (large k, NaN scores, crowded ties): whole-row / segmented kernels over the list
+  return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, left_rows, left_count,
+                       (uint8_t*)workspace + prune_head_bytes(n_rows), workspace_bytes - (int64_t)prune_head_bytes(n_rows),
+                       n_edges, st);
 }

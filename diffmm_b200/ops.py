@@ -119,15 +119,26 @@ def time_bias(emb_w, emb_b, weight, col0, bias, t0, n_t=1, out=None):
 
 
 def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0,
-                   z_f32=None, order=None):
+                   z_f32=None, order=None, vals=None):
     """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo); z_f32 (optional)
-    receives the sums without bias.  order (int32 permutation of the rows): scheduling order, e.g. longest rows first."""
+    receives the sums without bias.  order (int32 permutation of the rows): scheduling order, e.g. longest rows first.
+    vals (fp32, indexed like indices): entry values of non-binary sparse rows (csr_qsample_values)."""
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     assert order is None or (order.dtype == torch.int32 and order.numel() == n_rows)
-    _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), _p(order), int(row0), int(n_rows),
+    assert vals is None or (vals.dtype == torch.float32 and vals.numel() == indices.numel())
+    _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(vals), _p(row_ids), _p(order), int(row0), int(n_rows),
               int(n_cols),
               _p(wt_hi), _p(wt_lo), _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo),
               _row_major(h_hi, "h_hi"), _p(z_f32), _row_major(z_f32, "z_f32") if z_f32 is not None else 0, _stream())
+
+
+def csr_qsample_values(indptr, indices, n_rows, n_cols, noise, coef_a, coef_b, vals, *, row_ids=None, row0=0):
+    """vals[e] = coef_a + coef_b * noise[r, indices[e]] / max(||noise[r]||, 1e-12) for the entries of the selected binary
+    rows: the default-noise q_sample (Model.py:324-341) keeps a binary row's sparsity pattern."""
+    assert noise.dtype == torch.float32 and vals.dtype == torch.float32 and vals.numel() == indices.numel()
+    _lib.call("dmm_csr_qsample_values", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows), int(n_cols),
+              _p(noise), _row_major(noise, "noise"), float(coef_a), float(coef_b), _p(vals), _stream())
+    return vals
 
 
 def rows_long_first(indptr, row0, n_rows, threshold=32):
@@ -173,8 +184,10 @@ def q_sample(x0, noise, coef_a, coef_b, mode, *, x_t=None, a_hi=None, a_lo=None)
 
 # ----------------------------------------------------------------------------------------- GEMM
 def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi=None, res_lo=None, res_pre_act=False,
-              post_bias=None, post_act=0):
+              post_bias=None, post_act=0, cmax=None):
     ep = GemmEpilogue()
+    ep.cmax = cmax.data_ptr() if cmax is not None else None
+    ep.ld_cmax = _row_major(cmax, "cmax") if cmax is not None else 0
     ep.res_pre_act = int(bool(res_pre_act))
     ep.post_act = int(post_act)
     ep.post_bias = post_bias.data_ptr() if post_bias is not None else None
@@ -197,13 +210,14 @@ def _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi=
 
 def gemm_bf16_tn(a_hi, a_lo, b_hi, b_lo, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None,
                  out_f32=None, out_hi=None, out_lo=None, res_hi=None, res_lo=None, res_pre_act=False,
-                 post_bias=None, post_act=0):
+                 post_bias=None, post_act=0, cmax=None):
     """C[M,N] = epi(A[M,K] . B[N,K]^T) on tcgen05; lo operands add the split-bf16 correction passes.
+    cmax (fp32 [M, >= ceil(N/32)]): per-row maxima of the 32-column chunks of the result (top-k pruning side array).
     The residual of the epilogue (alpha * v + beta * R) is fp32 (`residual`) or bf16 hi(+lo) (`res_hi/res_lo`);
     with res_pre_act it is a partial sum of the same contraction and enters before the activation.
     post_bias / post_act: the bf16 output gets post_act(v + post_bias) while out_f32 keeps v."""
     ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, res_hi, res_lo, res_pre_act, post_bias,
-                   post_act)
+                   post_act, cmax)
     _lib.call("dmm_gemm_bf16_tn", _ctx(a_hi), _p(a_hi), _p(a_lo), _row_major(a_hi, "a_hi"), _p(b_hi), _p(b_lo),
               _row_major(b_hi, "b_hi"), int(M), int(N), int(K), C.byref(ep), _stream())
 
@@ -228,6 +242,26 @@ def topk_edges(scores, n_cols, out_ptr, row_base, out_users, out_items, status=N
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device) if ws_bytes > 0 else None
     _lib.call("dmm_topk_edges", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(out_ptr),
               int(row_base), _p(out_users), _p(out_items), _p(status), _p(order), _p(ws), ws_bytes, n_edges, _stream())
+
+
+def cmax_buffer(n_rows: int, n_cols: int, device) -> torch.Tensor:
+    """fp32 [n_rows, pad4(ceil(n_cols / 32))] side array for gemm_bf16_tn(cmax=...) / topk_edges_pruned."""
+    return torch.empty((n_rows, pad_to((n_cols + 31) // 32, 4)), dtype=torch.float32, device=device)
+
+
+def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_items, status=None, order=None):
+    """topk_edges for scores whose producer also wrote the per-chunk maxima `cmax` (gemm_bf16_tn(cmax=...)): reads only
+    the chunks that can hold a row's k largest scores.  Same output, bit for bit."""
+    assert scores.dtype == torch.float32 and cmax.dtype == torch.float32 and out_ptr.dtype == torch.int64
+    assert out_items.dtype == torch.int32
+    n_rows = scores.shape[0]
+    assert out_ptr.numel() >= n_rows + 1 and cmax.shape[0] >= n_rows
+    n_edges = int(out_items.numel())
+    ws_bytes = int(_lib.load().dmm_topk_pruned_workspace_bytes(n_rows, int(n_cols), n_edges))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
+    _lib.call("dmm_topk_edges_pruned", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(cmax),
+              _row_major(cmax, "cmax"), _p(out_ptr), int(row_base), _p(out_users), _p(out_items), _p(status), _p(order),
+              _p(ws), ws_bytes, n_edges, _stream())
 
 
 # ----------------------------------------------------------------------------------------- adjacency

@@ -50,6 +50,7 @@ class ChainWorkspace:
         self.z = None             # fp32 hidden pre-activation state [rows, pad4(hidden)] of the hidden-space chain
         self.bias_eff = None      # [S, hidden] fp32, sized on first use
         self.partial = None       # fp32 partial sums of a K-chunked GEMM1 (scale-out widths only)
+        self._cmax = None         # fp32 [rows, pad4(ceil(I / 32))] chunk maxima of the scores (top-k pruning side array)
 
     def operand(self):
         if self._a is None:
@@ -69,6 +70,11 @@ class ChainWorkspace:
         if self.z is None:
             self.z = torch.empty((self.rows, ops.pad_to(self.hidden, 4)), dtype=torch.float32, device=self.device)
         return self.z
+
+    def chunk_max(self):
+        if self._cmax is None:
+            self._cmax = ops.cmax_buffer(self.rows, self.n_items, self.device)
+        return self._cmax
 
     def fits(self, rows, n_items, hidden, d_emb, split):
         return (rows <= self.rows and n_items == self.n_items and hidden == self.hidden and d_emb == self.d_emb
@@ -125,9 +131,11 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
                   row0: int = 0, n_rows: Optional[int] = None, sampling_step: int = 0,
                   precision: Optional[str] = None, ws: Optional[ChainWorkspace] = None,
                   noise: Optional[torch.Tensor] = None, mode: Optional[str] = None,
-                  order: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  order: Optional[torch.Tensor] = None, want_cmax: bool = False) -> torch.Tensor:
     """generate_view (Model.py:300-322) for a block of users given as dense rows or CSR rows.
     Returns the fp32 [n_rows, I] scores (a view of the workspace: consume before the next call).
+    want_cmax: the last contraction also writes the per-row maxima of the 32-column chunks of the scores into
+    ``ws.chunk_max()[:n_rows]`` (the pruning side array of ops.topk_edges_pruned).
 
     mode 'hidden' (default).  Between two tanh's the reverse chain is affine: with z_t = x_t W1x^T (W1x = the item
     columns of W1), h_t = tanh(z_t + b1'(t)), pred_t = h_t W2^T + b2 and x_{t-1} = c1 pred_t + c2 x_t
@@ -161,7 +169,7 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     c2_last = float(np.float32(diff._h_coef2[0]))
     if mode == "full" or c2_last != 0.0 or S < 2:
         return _denoise_chain_full(diff, den, ws, M, x_dense=x_dense, csr=csr, row_ids=row_ids, row0=row0,
-                                   sampling_step=sampling_step, split=split, noise=noise, order=order)
+                                   sampling_step=sampling_step, split=split, noise=noise, order=order, want_cmax=want_cmax)
 
     h_hi, h_lo, x = ws.h_hi[:M], (ws.h_lo[:M] if split else None), ws.x[:M]
     xv = x[:, :I]
@@ -176,10 +184,16 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
     w2_hi, w2_lo = packed_weight(W2, False, split)
 
     # z_S = x_S W1x^T and h_{S-1} = tanh(z_S + b1'(S-1))
-    if sampling_step == 0 and csr is not None:
+    if csr is not None:
+        # binary CSR rows: the first layer is a gather-sum over W1^T (x0 is never densified).  A q_sample'd start
+        # (sampling_step > 0, default noise) keeps the rows' sparsity pattern -- sign(x0) zeroes the noise wherever x0
+        # is zero (Model.py:337) -- so only the entry values change (dmm_csr_qsample_values) and the gather is weighted.
+        vals = None
+        if sampling_step > 0:
+            vals = _qsample_values(diff, csr, row_ids, row0, M, I, sampling_step, noise, dev)
         w1t_hi, w1t_lo = packed_weight(W1, True, split)                    # W1^T [I + d, pad(H)]: gathered by item id
         ops.csr_gather_act(csr[0], csr[1], M, I, w1t_hi, w1t_lo, ws.bias_eff[S - 1], 1, H, h_hi, h_lo,
-                           row_ids=row_ids, row0=row0, z_f32=z, order=order)
+                           row_ids=row_ids, row0=row0, z_f32=z, order=order, vals=vals)
     else:
         a_hi, a_lo = ws.operand()
         a_hi = a_hi[:M]
@@ -198,8 +212,37 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
                          out_hi=g_hi, out_lo=g_lo, post_bias=ws.bias_eff[i - 1], post_act=1)
         h_hi, h_lo, g_hi, g_lo = g_hi, g_lo, h_hi, h_lo
     c1 = float(np.float32(diff._h_coef1[0]))
-    ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, out_f32=xv)
+    ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, out_f32=xv,
+                     cmax=ws.chunk_max()[:M] if want_cmax else None)
     return xv
+
+
+NOISE_BLOCK_BYTES = 64 << 20     # randn sub-block of the sparse q_sample: written and re-read while still L2 resident
+
+
+def _qsample_values(diff, csr, row_ids, row0, M, I, sampling_step, noise, dev):
+    """Entry values of x_t = q_sample(x0, sampling_step - 1) for the binary CSR rows [row0, row0 + M) (fp32, indexed like
+    csr[1]; entries of other rows are left untouched).  The randn draw is the reference's (Model.py:337: one full
+    [rows, I] block per call), made in row sub-blocks of NOISE_BLOCK_BYTES so that the noise never round-trips HBM."""
+    indptr, indices = csr
+    vals = torch.empty(indices.numel(), dtype=torch.float32, device=dev)
+    t = sampling_step - 1
+    ca = float(np.float32(diff._h_sqrt_ac[t]))            # fp64 table -> .float() (Model.py:352), host copies: no sync
+    cb = float(np.float32(diff._h_sqrt_1mac[t]))
+    if noise is not None:
+        ops.csr_qsample_values(indptr, indices, M, I, noise, ca, cb, vals, row_ids=row_ids, row0=row0)
+        return vals
+    sub = max(1, min(M, NOISE_BLOCK_BYTES // (4 * I)))
+    buf = torch.empty((sub, ops.pad_to(I, 4)), dtype=torch.float32, device=dev)
+    for s0 in range(0, M, sub):
+        n = min(sub, M - s0)
+        if rng.cpu_rng():
+            buf[:n, :I].copy_(torch.randn((n, I), dtype=torch.float32))
+        else:
+            buf[:n].normal_()             # device generator like randn_like; rows padded to 16 bytes (pad columns unused)
+        ops.csr_qsample_values(indptr, indices, n, I, buf[:n, :I], ca, cb, vals,
+                               row_ids=row_ids[s0:s0 + n] if row_ids is not None else None, row0=row0 + s0)
+    return vals
 
 
 def _fill_operand(diff, ws, M, I, a_hi, a_lo, x_dense, csr, row_ids, row0, sampling_step, split, noise, dev):
@@ -228,7 +271,8 @@ def _fill_operand(diff, ws, M, I, a_hi, a_lo, x_dense, csr, row_ids, row0, sampl
         ops.q_sample(x0, noise, ca, cb, 1, a_hi=a_hi, a_lo=a_lo)
 
 
-def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampling_step, split, noise, order=None):
+def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampling_step, split, noise, order=None,
+                        want_cmax=False):
     """The literal chain: S x (first layer + tanh, second layer + posterior mean) in item space."""
     lin1, lin2 = _single_layer(den)
     W1, b1, W2, b2 = lin1.weight, lin1.bias, lin2.weight, lin2.bias
@@ -278,7 +322,8 @@ def _denoise_chain_full(diff, den, ws, M, *, x_dense, csr, row_ids, row0, sampli
         use_res = c2 != 0.0 and not first_sparse
         if i == 0:
             ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
-                             res_hi=ax_hi if use_res else None, res_lo=ax_lo if use_res else None, out_f32=xv)
+                             res_hi=ax_hi if use_res else None, res_lo=ax_lo if use_res else None, out_f32=xv,
+                             cmax=ws.chunk_max()[:M] if want_cmax else None)
         else:
             ops.gemm_bf16_tn(h_hi, h_lo, w2_hi, w2_lo, M, I, H, bias=b2d, alpha=c1, beta=c2,
                              res_hi=ax_hi if use_res else None, res_lo=ax_lo if use_res else None,
@@ -362,7 +407,7 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
                   n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
                   row_range: Optional[Tuple[int, int]] = None, block_rows: Optional[int] = None,
                   out_items: Optional[Dict[str, torch.Tensor]] = None, per_modality=None,
-                  per_modality_out: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                  per_modality_out: Optional[dict] = None, status: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Top-k item ids per modality for users in ``row_range`` (default all), written at the train-CSR
     offsets (k_u = deg(u), Main.py:215-216,226).  Returns {modality: int32 [E]} (only this range filled).
 
@@ -370,7 +415,8 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     (operand packs, chain, top-k and the optional ``per_modality(items)`` follow-up, e.g. the adjacency build) on a
     side CUDA stream forked from / joined to the caller's stream: the latency-bound small kernels and the HBM-bound
     top-k of one modality fill the gaps of the tensor-bound contractions of the other.  DIFFMM_STREAMS=1 keeps
-    everything on the caller's stream."""
+    everything on the caller's stream.  status (optional int32 [1] device tensor): error bits of the top-k (bit 0:
+    a user with more interactions than items) are OR-ed in; check it at the caller's next host sync."""
     r0, r1 = row_range if row_range is not None else (0, n_users)
     any_den = next(iter(denoise_models.values()))
     precision = check_precision(precision or any_den.precision)
@@ -383,6 +429,7 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
             block_rows = max(128, min(block_rows, int(env)))
     E = int(indices.numel())
     dev = indptr.device
+    prune = os.environ.get("DIFFMM_TOPK_PRUNE", "1") != "0"
     if out_items is None:
         out_items = {m: torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E] for m in denoise_models}
     mods = list(denoise_models.items())
@@ -407,8 +454,14 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
                     if ws is None or not ws.fits(b1 - b0, n_items, H, den.time_emb_dim, split):
                         ws = ChainWorkspace(b1 - b0, n_items, H, den.time_emb_dim, split, dev)
                     scores = denoise_chain(diff, den, csr=(indptr, indices), row0=b0, n_rows=b1 - b0,
-                                           sampling_step=sampling_step, precision=precision, ws=ws, order=orders.get(b0))
-                    ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m], order=orders.get(b0))
+                                           sampling_step=sampling_step, precision=precision, ws=ws, order=orders.get(b0),
+                                           want_cmax=prune)
+                    if prune:      # the contraction left the chunk maxima: the top-k reads only the chunks that matter
+                        ops.topk_edges_pruned(scores, n_items, ws.chunk_max()[:b1 - b0], indptr[b0:], b0, None, out_items[m],
+                                              status=status, order=orders.get(b0))
+                    else:
+                        ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m], status=status,
+                                       order=orders.get(b0))
                 if per_modality is not None:
                     per_modality_out[m] = per_modality(out_items[m])
     for st in streams:
@@ -418,26 +471,31 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
 
 def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torch.Tensor, indices: torch.Tensor,
                       n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
-                      block_rows: Optional[int] = None, group=None, plan=None) -> Dict[str, ops.CsrAdj]:
+                      block_rows: Optional[int] = None, group=None, plan=None,
+                      status: Optional[torch.Tensor] = None) -> Dict[str, ops.CsrAdj]:
     """The whole rebuild phase (Main.py:195-253): {modality: normalised CSR adjacency}.
     With a torch.distributed ``group`` of more than one rank, users are row-sharded and the edge lists
-    all-gathered (dist.py); every rank then builds the same adjacency."""
+    all-gathered (dist.py); every rank then builds the same adjacency.
+    status (optional int32 [1] device tensor, zeroed by the caller): device-side error bits (bit 0: k_u > items in the
+    top-k, bit 1: item id out of range in the adjacency build); the caller reads it at its next host sync."""
     from . import dist as ddist
     sharded = group is not None and ddist.world_size(group) > 1
     if not sharded:
         adjs: Dict[str, ops.CsrAdj] = {}
         rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                      block_rows=block_rows, per_modality=lambda v: ops.build_norm_adj(indptr, v, n_users, n_items),
-                      per_modality_out=adjs)
+                      block_rows=block_rows,
+                      per_modality=lambda v: ops.build_norm_adj(indptr, v, n_users, n_items, status=status),
+                      per_modality_out=adjs, status=status)
         return {m: adjs[m] for m in denoise_models}
     row_range = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr)
     items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                          row_range=row_range, block_rows=block_rows)
-    return gather_and_build(items, indptr, n_users, n_items, group, plan)
+                          row_range=row_range, block_rows=block_rows, status=status)
+    return gather_and_build(items, indptr, n_users, n_items, group, plan, status=status)
 
 
 def gather_and_build(items: Dict[str, torch.Tensor], indptr: torch.Tensor, n_users: int, n_items: int, group=None,
-                     plan=None, full_items: Optional[dict] = None) -> Dict[str, ops.CsrAdj]:
+                     plan=None, full_items: Optional[dict] = None,
+                     status: Optional[torch.Tensor] = None) -> Dict[str, ops.CsrAdj]:
     """Sharded tail of the rebuild: the edge lists are all-gathered on the caller's stream, one collective per modality
     in program order (a collective issued from inside a modality pipeline makes every rank wait for the slowest rank's
     pipeline in the middle of its own: measured 4 % slower at 8 GPUs), then the whole-graph adjacencies are built
@@ -449,7 +507,7 @@ def gather_and_build(items: Dict[str, torch.Tensor], indptr: torch.Tensor, n_use
     dev = indptr.device
     n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(full))
     if n_streams <= 1 or dev.type != "cuda" or torch.cuda.is_current_stream_capturing():
-        return {m: ops.build_norm_adj(indptr, v, n_users, n_items) for m, v in full.items()}
+        return {m: ops.build_norm_adj(indptr, v, n_users, n_items, status=status) for m, v in full.items()}
     streams = _side_streams(dev, n_streams)
     main = torch.cuda.current_stream(dev)
     fork = torch.cuda.Event()
@@ -460,7 +518,7 @@ def gather_and_build(items: Dict[str, torch.Tensor], indptr: torch.Tensor, n_use
         if i < len(streams):
             st.wait_event(fork)
         with torch.cuda.stream(st):
-            adjs[m] = ops.build_norm_adj(indptr, v, n_users, n_items)
+            adjs[m] = ops.build_norm_adj(indptr, v, n_users, n_items, status=status)
     for st in streams:
         main.wait_stream(st)
     return adjs

@@ -88,11 +88,22 @@ int dmm_time_bias(dmm_ctx* ctx, int64_t t0, int64_t n_t, int d_emb, const float*
  * [n_rows, ld_z]) receives the plain sums x0 . W^T without bias: the fp32 state of the hidden-space
  * reverse chain.  `order` (optional, int32 [n_rows], a permutation of 0..n_rows-1) is the order in which
  * the rows are SCHEDULED (results do not depend on it): with the users of hundreds of interactions first,
- * their long gather chains overlap the rest of the grid instead of forming its tail.            */
-int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
-                       const int32_t* order, int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
+ * their long gather chains overlap the rest of the grid instead of forming its tail.  `vals` (optional, fp32,
+ * indexed like `indices`): entry values of a non-binary sparse row (dmm_csr_qsample_values), h = act(bias +
+ * sum_c vals[c] wt[c, :]); NULL = binary rows.                                                  */
+int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const float* vals,
+                       const int64_t* row_ids, const int32_t* order, int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi,
                        const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act, int64_t n_out,
                        uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z, void* stream);
+
+/* q_sample with the default noise (Model.py:324-341) restricted to BINARY CSR rows: sign(x0) zeroes the noise
+ * wherever x0 is zero, so x_t keeps the row's sparsity pattern and only its entry values are needed:
+ * vals[e] = coef_a + coef_b * noise[r, indices[e]] / max(||noise[r, :n_cols]||_2, 1e-12) for every entry e of the
+ * selected rows (vals is indexed like `indices`; noise is the full fp32 randn block [n_rows, ld_noise], read once).
+ * Keeps the first layer of a sampling_step > 0 rebuild (conf/baby.toml: 5) a gather-sum.            */
+int dmm_csr_qsample_values(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                           int64_t row0, int64_t n_rows, int64_t n_cols, const float* noise, int64_t ld_noise,
+                           float coef_a, float coef_b, float* vals, void* stream);
 
 /* Scheduling order for dmm_csr_gather_act: order[] (int32 [n_rows]) becomes a permutation of 0..n_rows-1 with every
  * row of the block [row0, row0 + n_rows) that has more than `threshold` entries in front (arbitrary order among
@@ -150,6 +161,10 @@ typedef struct dmm_gemm_epilogue {
                           /* sum of the same contraction (K processed in chunks), added before act    */
   int32_t post_act;       /* second stage on the bf16 output only: out_hi/lo = post_act(v + post_bias) */
   const float* post_bias; /* while out_f32 keeps v (hidden-space chain: z_t and h_{t-1} in one pass)    */
+  float* cmax;            /* optional fp32 [M, ld_cmax]: cmax[r, c] = max(v[r, 32c .. 32c+31]) over the columns < N,  */
+  int64_t ld_cmax;        /* NaN if any of them is NaN (max.NaN); ld_cmax >= ceil(N / 32).  The pruning side array   */
+                          /* of dmm_topk_edges_pruned: 1/32 of the output bytes, written from the accumulator          */
+                          /* registers, so the top-k never has to re-read the rows the contraction just wrote          */
 } dmm_gemm_epilogue;
 
 int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
@@ -175,6 +190,18 @@ int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows
                    const int64_t* out_ptr, int64_t row_base, int32_t* out_users, int32_t* out_items,
                    int32_t* status, const int32_t* order, void* workspace, int64_t workspace_bytes,
                    int64_t n_edges, void* stream);
+
+/* Same contract and bit-identical output, for scores whose producer also wrote the chunk maxima
+ * cmax[r, c] = max(scores[r, 32c .. 32c+31]) (dmm_gemm_epilogue.cmax; fp32 [n_rows, ld_cmax], ld_cmax % 4 == 0,
+ * NaN-propagating): a row's k largest scores lie in the k chunks with the largest maxima, so the kernel reads
+ * 4 * n_cols / 32 + 128 * k bytes per row instead of 4 * n_cols.  Rows that do not qualify (k > 64, k chunks more than
+ * a quarter of the row, NaN scores, crowded ties) are collected on the device and go through the kernels of
+ * dmm_topk_edges in the same call.  `workspace` (required): dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges). */
+int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t n_edges);
+int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
+                          const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
+                          int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
+                          void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream);
 
 /* ---- normalised bipartite adjacency ---------------------------------------------------------
  * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and

@@ -36,8 +36,10 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_epilogue_struct_layout_matches_c(lib):
     # struct dmm_gemm_epilogue: ptr, i32, f32, f32, (pad), ptr, i64, ptr, i64, ptr, ptr, i64, ptr, ptr, i64, i32, (pad)
-    assert ctypes.sizeof(lib.GemmEpilogue) == 120
+    # ..., ptr post_bias, ptr cmax, i64 ld_cmax
+    assert ctypes.sizeof(lib.GemmEpilogue) == 136
     assert lib.GemmEpilogue.residual.offset == 24 and lib.GemmEpilogue.ld_out16.offset == 72
+    assert lib.GemmEpilogue.cmax.offset == 120 and lib.GemmEpilogue.ld_cmax.offset == 128
 
 
 def test_no_fallback_without_gpu(lib):

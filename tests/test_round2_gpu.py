@@ -1,0 +1,219 @@
+"""GPU parity tests of the round-2 kernels, all through the C ABI:
+  * chunk maxima written by the contraction epilogue (dmm_gemm_epilogue.cmax) == max over the written scores;
+  * dmm_topk_edges_pruned == dmm_topk_edges == numpy oracle, bit for bit (widths 256 .. 500 000 columns, ties, NaN);
+  * the sparse q_sample'd start of the reverse chain (dmm_csr_qsample_values + weighted dmm_csr_gather_act) == the dense
+    q_sample + dense first layer of the reference formulation (Model.py:300-341);
+  * device-side status bits; accurate tanh in the fp32-faithful (bf16x3) training forward."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import diffmm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffmm_b200 import ops as o
+    return o
+
+
+def _ptr(k):
+    p = np.zeros(len(k) + 1, dtype=np.int64)
+    np.cumsum(k, out=p[1:])
+    return p
+
+
+def _chunk_max(scores_t):
+    """torch restatement of the side array: NaN-propagating max over 32-column chunks (tail chunk over its valid columns)."""
+    n_rows, n_cols = scores_t.shape
+    nch = (n_cols + 31) // 32
+    pad = torch.full((n_rows, nch * 32), float("-inf"), device=scores_t.device)
+    pad[:, :n_cols] = scores_t
+    return pad.view(n_rows, nch, 32).amax(dim=2)
+
+
+def _run_pruned(ops, scores, k, order=None):
+    n_rows, n_cols = scores.shape
+    ld = ops.pad_to(n_cols, 4)
+    buf = torch.zeros((n_rows, ld), device=DEV)
+    buf[:, :n_cols] = T(scores)
+    sc = buf[:, :n_cols]
+    cm = ops.cmax_buffer(n_rows, n_cols, DEV)
+    cm.fill_(float("nan"))
+    cm[:, :(n_cols + 31) // 32] = _chunk_max(sc)
+    ptr = _ptr(k)
+    E = int(ptr[-1])
+    users = torch.full((max(E, 1),), -1, dtype=torch.int32, device=DEV)[:E]
+    items = torch.full((max(E, 1),), -1, dtype=torch.int32, device=DEV)[:E]
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.topk_edges_pruned(sc, n_cols, cm, T(ptr), 7, users, items, status=status, order=order)
+    items2 = torch.full((max(E, 1),), -1, dtype=torch.int32, device=DEV)[:E]
+    ops.topk_edges(sc, n_cols, T(ptr), 7, None, items2)
+    torch.cuda.synchronize()
+    return ptr, users.cpu().numpy(), items.cpu().numpy(), items2.cpu().numpy(), int(status.item())
+
+
+@pytest.mark.parametrize("n_cols", [256, 1000, 7050, 18357, 70001, 262144 + 37, 500000])
+def test_pruned_topk_equals_full_topk_and_oracle(ops, n_cols):
+    rng = np.random.default_rng(n_cols)
+    n_rows = 48 if n_cols <= 70001 else 12
+    scores = (rng.standard_normal((n_rows, n_cols)) * 0.05).astype(np.float32)
+    k = np.minimum(rng.integers(0, 30, n_rows), n_cols)
+    k[0], k[1], k[2], k[3], k[4] = 0, 1, min(n_cols, 64), min(n_cols, 65), min(n_cols, 603)
+    k[5] = max(1, min(64, n_cols // 128))
+    ptr, users, items, items_full, status = _run_pruned(ops, scores, k)
+    assert status == 0
+    np.testing.assert_array_equal(items, items_full)
+    want = O.topk_edges(scores, k)
+    for r, w in enumerate(want):
+        np.testing.assert_array_equal(items[ptr[r]:ptr[r + 1]], w, err_msg=f"row {r} k={k[r]}")
+        assert (users[ptr[r]:ptr[r + 1]] == 7 + r).all()
+
+
+def test_pruned_topk_ties_signed_zero_nan_and_order(ops):
+    """Quantised scores (the k-th value is shared by hundreds of columns and by many chunk maxima), +-0, NaN rows: the
+    pruned kernel must defer what it cannot rank exactly and agree with the whole-row kernels everywhere."""
+    rng = np.random.default_rng(5)
+    n_rows, n_cols = 40, 7050
+    scores = rng.integers(-3, 4, (n_rows, n_cols)).astype(np.float32)
+    scores[0, :] = 0.0
+    scores[1, ::2] = -0.0
+    scores[1, 1::2] = 0.0
+    scores[2] = (rng.standard_normal(n_cols) * 0.1).astype(np.float32)
+    scores[2, [40, 4000]] = np.nan
+    scores[3] = (rng.standard_normal(n_cols) * 0.1).astype(np.float32)
+    scores[3, 7] = np.inf
+    scores[3, 6999] = -np.inf
+    scores[4] = np.round(rng.standard_normal(n_cols), 1).astype(np.float32)      # moderate ties
+    for r in range(5, 12):                                                       # the same maximum in many chunks
+        scores[r] = (rng.standard_normal(n_cols) * 0.01).astype(np.float32)
+        scores[r, rng.choice(n_cols, 300, replace=False)] = 1.0
+    k = rng.integers(1, 50, n_rows)
+    order = T(rng.permutation(n_rows).astype(np.int32))
+    ptr, _, items, items_full, _ = _run_pruned(ops, scores, k, order=order)
+    np.testing.assert_array_equal(items, items_full)
+    u = scores.view(np.uint32).astype(np.uint64)
+    u = np.where(u == 0x80000000, 0, u)
+    key = np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.int64)
+    for r in range(n_rows):
+        o = np.lexsort((np.arange(n_cols), -key[r]))
+        np.testing.assert_array_equal(items[ptr[r]:ptr[r + 1]], np.sort(o[:k[r]]), err_msg=f"row {r}")
+
+
+def test_pruned_topk_full_size_matches_torch_topk(ops):
+    """baby-shape block through the pruned path vs torch.topk sets (continuous scores: no ties)."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n_rows, n_cols = 19445, 7050
+    buf = torch.randn((n_rows, ops.pad_to(n_cols, 4)), device=DEV, generator=g)
+    sc = buf[:, :n_cols]
+    rng = np.random.default_rng(2)
+    k = np.clip(np.round(rng.lognormal(1.4, 0.9, n_rows)), 1, 600).astype(np.int64)
+    ptr = _ptr(k)
+    cm = ops.cmax_buffer(n_rows, n_cols, DEV)
+    cm[:, :(n_cols + 31) // 32] = _chunk_max(sc)
+    items = torch.empty(int(ptr[-1]), dtype=torch.int32, device=DEV)
+    ops.topk_edges_pruned(sc, n_cols, cm, T(ptr), 0, None, items)
+    got = items.cpu().numpy()
+    for kk in np.unique(k):
+        rows = np.nonzero(k == kk)[0]
+        want = torch.topk(sc[T(rows)], int(kk), dim=1).indices.sort(dim=1).values.cpu().numpy()
+        have = np.stack([got[ptr[r]:ptr[r + 1]] for r in rows])
+        np.testing.assert_array_equal(have, want)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("M,N,K", [(300, 7050, 256), (129, 100, 64), (1000, 18357, 128)])
+def test_gemm_chunk_maxima_match_the_written_scores(ops, precision, M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    a = torch.randn((M, K), device=DEV, generator=g)
+    b = torch.randn((N, K), device=DEV, generator=g) * 0.1
+    bias = torch.randn(N, device=DEV, generator=g)
+    split = precision == "bf16x3"
+    a_hi, a_lo = ops.pack_bf16(a, split=split)
+    b_hi, b_lo = ops.pack_bf16(b, split=split)
+    out = torch.zeros((M, ops.pad_to(N, 4)), device=DEV)[:, :N]
+    cm = ops.cmax_buffer(M, N, DEV)
+    cm.fill_(float("nan"))
+    ops.gemm_bf16_tn(a_hi, a_lo, b_hi, b_lo, M, N, K, bias=bias, alpha=0.5, out_f32=out, cmax=cm)
+    torch.cuda.synchronize()
+    nch = (N + 31) // 32
+    want = _chunk_max(out)
+    assert torch.equal(cm[:, :nch], want)        # the maxima of exactly the values that were written
+
+
+def test_sparse_qsample_start_equals_dense_qsample_start(ops):
+    """rebuild from a q_sample'd start (conf/baby.toml: sampling_step 5): CSR rows + weighted gather vs the dense
+    formulation of the reference (Model.py:300-341) on the same noise."""
+    from diffmm_b200 import rebuild
+    from diffmm_b200.Conf import Config
+    from diffmm_b200.Model import Denoise, GaussianDiffusion
+    U, I, H = 257, 1000, 128
+    rng = np.random.default_rng(4)
+    k = rng.integers(0, 12, U)
+    k[3] = 300
+    ptr = _ptr(k)
+    idx = np.concatenate([np.sort(rng.choice(I, kk, replace=False)) for kk in k]).astype(np.int32)
+    cfg = Config()
+    cfg.base.precision = "bf16x3"
+    cfg.base.denoise_dim = f"[{H}]"
+    cfg.data.user_num, cfg.data.item_num = U, I
+    torch.manual_seed(0)
+    gd = GaussianDiffusion(cfg).to(DEV)
+    den = Denoise([I, H], [H, I], cfg).to(DEV)
+    x0 = np.zeros((U, I), dtype=np.float32)
+    x0[np.repeat(np.arange(U), k), idx] = 1.0
+    noise = torch.randn((U, I), device=DEV)
+    for ss in (1, 5):
+        dense = rebuild.denoise_chain(gd, den, x_dense=T(x0), sampling_step=ss, noise=noise).clone()
+        sparse = rebuild.denoise_chain(gd, den, csr=(T(ptr), T(idx)), row0=0, n_rows=U, sampling_step=ss, noise=noise).clone()
+        scale = float(dense.abs().max())
+        assert float((dense - sparse).abs().max()) <= 2e-5 * max(scale, 1.0), ss
+        # and against the numpy oracle's generate_view on the explicit x_t
+        t = ss - 1
+        nn = noise.cpu().numpy().astype(np.float64)
+        nrm = np.maximum(np.sqrt((nn ** 2).sum(1, keepdims=True)), 1e-12)
+        sched = O.make_schedule(cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max, cfg.hyper.steps)
+        f = lambda p: p.detach().cpu().numpy()  # noqa: E731
+        params = dict(emb_w=f(den.emb_layer.weight), emb_b=f(den.emb_layer.bias), w1=f(den.in_layers[0].weight),
+                      b1=f(den.in_layers[0].bias), w2=f(den.out_layers[0].weight), b2=f(den.out_layers[0].bias),
+                      gate_w=f(den.gate_layer.weight), gate_b=f(den.gate_layer.bias))
+        a = np.float32(gd.sqrt_alphas_cumprod[t].item())
+        b = np.float32(gd.sqrt_one_minus_alphas_cumprod[t].item())
+        x_t = (a * x0 + b * (np.sign(x0) * (nn / nrm))).astype(np.float32)
+        want = O.generate_view(sched, params, x_t, 0)
+        assert float(np.abs(sparse.cpu().numpy() - want).max()) <= 5e-5 * max(float(np.abs(want).max()), 1.0), ss
+
+
+def test_rebuild_status_bits(ops):
+    ptr = T(np.array([0, 2, 3], dtype=np.int64))
+    items = T(np.array([0, 9, 1], dtype=np.int32))        # item 9 does not exist (n_items = 4)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.build_norm_adj(ptr, items, 2, 4, status=status)
+    assert int(status.item()) & 2
+    status.zero_()
+    scores = torch.zeros((1, 8), device=DEV)
+    out = torch.zeros(9, dtype=torch.int32, device=DEV)
+    ops.topk_edges(scores, 8, T(np.array([0, 9], dtype=np.int64)), 0, None, out, status)
+    assert int(status.item()) & 1
+
+
+def test_bf16x3_training_forward_uses_the_accurate_tanh():
+    """with lo operands the fp32-faithful instantiation (and its accurate tanh) must be selected."""
+    from diffmm_b200.autograd import linear_tn
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn((300, 200), device=DEV, generator=g)
+    w = torch.nn.Parameter(torch.randn((96, 200), device=DEV, generator=g) * 0.1)
+    b = torch.nn.Parameter(torch.randn(96, device=DEV, generator=g) * 0.1)
+    y = linear_tn(x, w, b, 1, "bf16x3")
+    want = torch.tanh(x.double() @ w.double().t() + b.double()).float()
+    assert float((y - want).abs().max()) < 3e-6

@@ -1,0 +1,87 @@
+"""Real-config parity gate (BASELINE.json configs[0]): conf/tiktok.toml on the REAL TikTok
+interactions + image / audio features (9308 x 6710, hidden 1024, 3 modalities), three epochs + eval.
+
+Golden: the UNMODIFIED reference run on CPU by oracle/gen_tiktok_golden.py (8 torch threads) ->
+tests/golden/tiktok_real/result.json; it reproduces BASELINE.md's epoch-0 log (Loss 4.37246, Recall@20 0.05546).
+The same run with 3 torch threads (noise_floor_3threads.json) shows how far the reference moves under a mere change
+of its fp32 summation order: Recall@20 0.05546 / 0.06917 / 0.07374 (8 threads) vs 0.05498 / 0.06803 / 0.07325
+(3 threads), i.e. 0.9 % / 1.7 % / 0.7 % relative, image loss up to 10 %.  north_star's 0.5 % gate is therefore applied
+as: |ours - golden| <= max(0.5 % of golden, 1.5 x |golden - golden_3threads|) per quantity and epoch, and the smooth
+epoch losses (Loss / BPR / reg / CL) are additionally held to 0.5 % flat.  Our run replays the reference's CPU RNG
+stream (DIFFMM_CPU_RNG=1), fp32-faithful contractions (bf16x3)."""
+import json
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "tiktok_real")
+
+
+def _run(tmp_path, monkeypatch, precision, epochs):
+    sys.path.insert(0, ROOT)
+    from oracle.gen_tiktok_golden import materialise      # dataset writer only (numpy / scipy; no reference import)
+    from diffmm_b200 import Main
+    from diffmm_b200.Conf import load_config
+    materialise(GOLD, str(tmp_path))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("DIFFMM_CPU_RNG", "1")
+    cfg = load_config(os.path.join(ROOT, "conf", "tiktok.toml"))
+    cfg.train.epoch = epochs
+    cfg.base.precision = precision
+    Main.seed_it(cfg.base.seed)
+    handler = Main.DataHandler(cfg)
+    handler.LoadData()
+    coach = Main.Coach(handler, cfg)
+    coach.run()
+    return coach
+
+
+def _report(coach, gold, floor, name):
+    rows = []
+    for e, (got, want, fl) in enumerate(zip(coach.history, gold["epochs"], floor["epochs"])):
+        for sec in ("train", "test"):
+            for k, v in want[sec].items():
+                rows.append(dict(epoch=e, key=k, ours=got[sec][k], golden=v, golden_3threads=fl[sec][k],
+                                 rel_err=abs(got[sec][k] - v) / abs(v), ref_spread=abs(fl[sec][k] - v) / abs(v)))
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump(rows, open(os.path.join(out, f"tiktok_real_parity_{name}.json"), "w"), indent=1)
+    except OSError:
+        pass
+    return rows
+
+
+def test_tiktok_real_three_epochs_bf16x3(tmp_path, monkeypatch):
+    gold = json.load(open(os.path.join(GOLD, "result.json")))
+    floor = json.load(open(os.path.join(GOLD, "noise_floor_3threads.json")))
+    coach = _run(tmp_path, monkeypatch, "bf16x3", len(gold["epochs"]))
+    rows = _report(coach, gold, floor, "bf16x3")
+    bad = []
+    for r in rows:
+        tol = max(0.005, 1.5 * r["ref_spread"])
+        if r["key"] in ("Loss", "BPR Loss", "reg loss", "CL loss"):
+            tol = 0.005
+        if r["rel_err"] > tol:
+            bad.append((r["epoch"], r["key"], r["ours"], r["golden"], r["rel_err"], tol))
+    assert not bad, bad
+    # BASELINE.md section 2's published epoch-0 numbers, for the record
+    assert coach.history[0]["train"]["Loss"] == pytest.approx(4.37246, rel=5e-3)
+    assert coach.history[0]["test"]["Recall"] == pytest.approx(0.05546, rel=0.02)
+
+
+def test_tiktok_real_first_epoch_bf16(tmp_path, monkeypatch):
+    """The benchmarked precision (single-pass bf16 contractions) on the same run: one epoch, losses within 1 %,
+    Recall@20 / NDCG@20 within 3 % of the golden (the reference itself moves 0.9 % with its thread count)."""
+    gold = json.load(open(os.path.join(GOLD, "result.json")))
+    floor = json.load(open(os.path.join(GOLD, "noise_floor_3threads.json")))
+    coach = _run(tmp_path, monkeypatch, "bf16", 1)
+    rows = _report(coach, gold, floor, "bf16")
+    for r in rows:
+        if r["key"] in ("Loss", "BPR Loss", "reg loss", "CL loss"):
+            assert r["rel_err"] <= 0.01, r
+        elif r["key"] in ("Recall", "NDCG", "Precision"):
+            assert r["rel_err"] <= 0.03, r
