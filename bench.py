@@ -374,6 +374,25 @@ def run_reference(args):
     emit(line)
 
 
+def cpu_baseline_subprocess(args, w):
+    """The reference arm on a bounded sample, in its own process (it patches torch onto the CPU path and must not share
+    a process with GPU work): same workload, seed and hyper-parameters; ~10-20 s of host-core time."""
+    import subprocess
+    n_cpu = max(64, int(args.cpu_sample * min(1.0, 7050.0 / w["items"])))
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--seed", str(args.seed),
+           "--steps", "1", "--warmup", "1", "--ref-sample", str(n_cpu)]
+    if args.sampling_step is not None:
+        cmd += ["--sampling-step", str(args.sampling_step)]
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        ref_line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        return ref_line["cpu_baseline"]
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -388,11 +407,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     w = WORKLOADS[args.workload]
-    U, I, H, S, mods = w["users"], w["items"], w["hidden"], w["steps"], w["modalities"]
+    hyper = workload_hyper(args.workload, args.sampling_step)
+    SS = hyper["sampling_step"]
+    U, I, H, S, mods = w["users"], w["items"], w["hidden"], hyper["steps"], w["modalities"]
     # weak scaling: the job is world x U users; every rank holds the (small) global CSR and replicated Denoise
     # weights (same seed), runs the chain + top-k on its own user block, then the edge lists are all-gathered
     # (NCCL, one collective per modality) and every rank builds the normalised adjacency of the whole graph
-    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed, args.precision, world)
+    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed, args.precision, world, hyper)
     U_tot = U * world
     r0, r1 = rank * U, (rank + 1) * U
     from diffmm_b200 import dist as ddist
@@ -442,12 +463,12 @@ def run_ours(args):
         # adjacency; N > 1: the NCCL all-gathers of the edge lists follow on the caller's stream, then the whole-graph
         # adjacencies are built concurrently (rebuild.gather_and_build)
         if world > 1:
-            items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1))
+            items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, SS, args.precision, row_range=(r0, r1))
             full = {}
             adjs = rebuild.gather_and_build(items, ip, U_tot, I, None, plan, full_items=full)
             return adjs, full
         res = {}
-        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, 0, args.precision, row_range=(r0, r1),
+        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, SS, args.precision, row_range=(r0, r1),
                               per_modality=lambda v: (ops.build_norm_adj(ip, v, U_tot, I), v), per_modality_out=res)
         return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
 
@@ -625,19 +646,18 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shape rebuild phase (Main.py:195-253): {U} users x {I} items per GPU, "
-                               f"{len(mods)} modalities, hidden {H}, {S} reverse steps, top-k k=deg(u), adjacency build",
-                   "users_per_gpu": U, "items": I, "modalities": len(mods), "hidden": H, "diffusion_steps": S, "edges": E,
-                   "precision": args.precision, "l2": "256 MiB flush write between timed steps; per-step working set > L2",
-                   "streams": n_streams if len(mods) > 1 else 1,
-                   "parallelism": (f"user-sharded x{world}: {U_tot} users in total, edge lists all-gathered over NCCL, "
-                                   f"adjacency of the whole graph built on every rank") if world > 1 else "single GPU"},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
+        "config": config_dict(args.workload, w, hyper, args.precision),
+        "run": {"edges": E, "precision": args.precision, "l2": "256 MiB flush write between timed steps; per-step working set > L2",
+                "streams": n_streams if len(mods) > 1 else 1,
+                "parallelism": (f"user-sharded x{world}: {U_tot} users in total, edge lists all-gathered over NCCL, "
+                                f"adjacency of the whole graph built on every rank") if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tf_burst"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)",
                      "launches": len(gemm_events), "avg_launch_ms": gemm_ms / n_gemm, "share_of_step": gemm_ms / serial_ms,
-                     "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside the step); burst {pk['tf_burst']}",
-                     "frac_of_burst": achieved / pk["tf_burst"], "by_shape_MxNxK": by_shape,
+                     "peak_source": f"{pk['source']} bf16_tflops (burst: the timed region is tens of ms at full clocks); "
+                                    f"sustained {pk['tf_sustained']}",
+                     "frac_of_sustained": achieved / pk["tf_sustained"], "by_shape_MxNxK": by_shape,
                      "measured_in": (f"second pass of the same {args.steps} steps with the modality pipelines serialised on one "
                                      f"stream ({serial_ms / args.steps:.3f} ms/step); in the timed region they overlap on "
                                      f"{n_streams} streams and an event pair also spans the other stream's kernels")
@@ -659,13 +679,7 @@ def run_ours(args):
         "breakdown_ms_per_step": breakdown,
     }
     if world == 1 and not args.no_cpu_baseline:          # reported on rank 0 at N = 1 only (a bounded host-core sample)
-        params = {m: oracle_params(d) for m, d in dens.items()}
-        # bounded CPU sample: scaled down with the row width so that it stays at ~10 s of host work
-        n_cpu = max(16, int(args.cpu_sample * min(1.0, 7050.0 / w["items"])))
-        dt, n, _ = cpu_rebuild_sample(inter, w, params, n_cpu)
-        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"first {n} users x {len(mods)} modalities, numpy oracle of Main.py:195-253 "
-                                          f"(generate_view + per-user top-k), {dt:.1f} s"}
+        line["cpu_baseline"] = cpu_baseline_subprocess(args, w)
     if world == 1 and not args.no_aux:
         try:
             line["aux_rooflines"] = aux_rooflines(dev, breakdown, U, I, E, len(mods), pk, args.seed)
@@ -694,7 +708,7 @@ def main():
     ap.add_argument("--workload", default="baby", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="users of the cpu_baseline sample (scaled down with the row width)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="users per step of the reference (CPU) arm")
     ap.add_argument("--sampling-step", type=int, default=None,
                     help="override the workload's conf/*.toml hyper.sampling_step (0 = rebuild from the binary rows)")
