@@ -478,7 +478,75 @@ class Coach:
         return result
 
     def testEpoch(self):
-        """Main.py:390-420 with the train mask applied from the device CSR instead of dense host rows."""
+        """Main.py:390-448 on the device: scores on the tensor pipe (fp32-faithful bf16x3), train mask written from the
+        train CSR (dmm_eval_mask_scores), top-K (dmm_topk_edges with k = K), ranking + Recall / NDCG / Precision per user in
+        float64 (dmm_eval_metrics) -- no host round trip per batch; ONE device->host copy of the per-user metrics at the
+        end, summed on the host in the reference's order (per test_batch, then across batches) so the totals carry its
+        float64 rounding.  top-K > 32 keeps the host path (testEpochHost)."""
+        K = int(self.config.base.topk)
+        if K > 32 or self.device.type != "cuda":
+            return self.testEpochHost()
+        t0 = time.perf_counter()
+        testData = self.handler.testData
+        iter(self.handler.testLoader)        # the reference's loop draws one DataLoader base seed here (RNG parity)
+        I = self.config.data.item_num
+        ev = getattr(self, "_eval_cache", None)
+        if ev is None or ev["K"] != K:
+            users = np.asarray(testData.test_users, dtype=np.int64)
+            U = self.config.data.user_num
+            tptr = np.zeros(U + 1, dtype=np.int64)
+            for u in users:
+                tptr[u + 1] = len(testData.test_user_its[u])
+            np.cumsum(tptr, out=tptr)
+            titems = np.fromiter((it for u in np.sort(users) for it in testData.test_user_its[u]), dtype=np.int32,
+                                 count=int(tptr[-1]))
+            if Coach._MAX_DCG is None or len(Coach._MAX_DCG) != K + 1:
+                Coach._MAX_DCG = [np.sum([np.reciprocal(np.log2(loc + 2)) for loc in range(t)]) for t in range(K + 1)]
+            inv = np.array([np.reciprocal(np.log2(p + 2)) for p in range(K)], dtype=np.float64)
+            dev = self.device
+            ev = dict(K=K, users=torch.from_numpy(users).to(dev), n=len(users), test_ptr=torch.from_numpy(tptr).to(dev),
+                      test_items=torch.from_numpy(titems).to(dev), inv_log2=torch.from_numpy(inv).to(dev),
+                      max_dcg=torch.tensor([float(v) for v in Coach._MAX_DCG], dtype=torch.float64, device=dev),
+                      out=torch.empty((len(users), 3), dtype=torch.float64, device=dev))
+            self._eval_cache = ev
+        n = ev["n"]
+        chunk = int(max(256, min(8192, (1 << 30) // (4 * max(I, 1)))))
+        with torch.no_grad():
+            if self.has_audio:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj, self.audio_adj)
+            else:
+                gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
+            user_embs, item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
+            h = self.handler
+            for s in range(0, n, chunk):
+                usr = ev["users"][s:s + chunk]
+                b = usr.numel()
+                scores = linear_tn(user_embs[usr], item_embs, None, 0, "bf16x3")            # Main.py:410 U_b I^T
+                ops.eval_mask_scores(h.train_indptr, h.train_indices, usr, scores, I, -1e8)   # * (1 - mask) - mask * 1e8
+                if ev.get("kptr") is None or ev["kptr"].numel() < b + 1:
+                    ev["kptr"] = torch.arange(chunk + 1, dtype=torch.int64, device=self.device) * K
+                top = torch.empty(b * K, dtype=torch.int32, device=self.device)
+                ops.topk_edges(scores, I, ev["kptr"], 0, None, top)                          # Main.py:411
+                ops.eval_metrics(scores, top, K, usr, ev["test_ptr"], ev["test_items"], ev["inv_log2"], ev["max_dcg"],
+                                 ev["out"][s:s + b])
+        vals = ev["out"].cpu().numpy()       # the one host sync of the evaluation
+        epRecall = epNdcg = epPrecision = 0
+        tb = int(self.config.train.test_batch)
+        for s in range(0, n, tb):            # the reference's association: per-batch sums, then the sum of those
+            r = g = p = 0
+            for a, b_, c in vals[s:s + tb].tolist():
+                r += a
+                g += b_
+                p += c
+            epRecall += r
+            epNdcg += g
+            epPrecision += p
+        self._tick("eval", t0)
+        return {"Recall": epRecall / n, "NDCG": epNdcg / n, "Precision": epPrecision / n}
+
+    def testEpochHost(self):
+        """Main.py:390-420 with the train mask applied from the device CSR, torch.topk and the host metric arithmetic
+        (calcRes); the checker of testEpoch and the path for top-K > 32."""
         t0 = time.perf_counter()
         testData = self.handler.testData
         iter(self.handler.testLoader)        # the reference's loop draws one DataLoader base seed here (RNG parity)

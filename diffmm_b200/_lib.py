@@ -57,8 +57,9 @@ PROTOTYPES = {
     "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                  c_vp]),
     "dmm_topk_pruned_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "dmm_topk_prune_plan": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dmm_topk_edges_pruned": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_i64, c_i64, c_vp]),
+                                        c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dmm_spmm_plan_bytes": (c_i64, [c_i64, c_i64]),
@@ -74,6 +75,8 @@ PROTOTYPES = {
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dmm_infonce_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_f32,
                                   c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_eval_mask_scores": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_f32, c_vp]),
+    "dmm_eval_metrics": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dmm_host_neg_sampling": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "dmm_scatter_add_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
 }

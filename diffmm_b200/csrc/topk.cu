@@ -604,7 +604,17 @@ struct PruneArgs {
   const int32_t* order;
   int32_t* left_count;
   int32_t* left_rows;
+  int skip_heavy;      // != 0: rows that fail the k rule are on the caller's precomputed list (dmm_topk_prune_plan): skip them
 };
+
+// The k rule of the pruned path (block-uniform; the same predicate builds the heavy-row list of dmm_topk_prune_plan)
+__host__ __device__ __forceinline__ int prune_kmax(int n_chunks) {
+  const int nw = n_chunks <= 64 * 4 * TOPK_V4 ? 2 : (n_chunks <= 256 * 4 * TOPK_V4 ? 8 : 16);
+  return PRUNE_KMAX < 32 * nw ? PRUNE_KMAX : 32 * nw;
+}
+__host__ __device__ __forceinline__ bool prune_k_ok(int64_t k, int n_chunks, int64_t n_cols) {
+  return k <= prune_kmax(n_chunks) && k * PRUNE_RATIO <= n_chunks && k <= n_cols;
+}
 
 struct alignas(16) PruneSmem {
   uint32_t key[PRUNE_CAND];
@@ -649,8 +659,8 @@ __global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
   auto defer = [&]() {
     if (tid == 0) a.left_rows[atomicAdd(a.left_count, 1)] = (int32_t)r;
   };
-  if (k > PRUNE_KMAX || k > 32 * NW || (int64_t)k * PRUNE_RATIO > n_chunks || k > a.n_cols) {   // block-uniform
-    defer();
+  if (!prune_k_ok(k, n_chunks, a.n_cols)) {   // block-uniform
+    if (!a.skip_heavy) defer();
     return;
   }
   const float NEG_INF = __uint_as_float(0xFF800000u);
@@ -792,6 +802,49 @@ __global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
   }
 }
 
+// rows that fail the k rule, appended in arbitrary order (their output slots are fixed by out_ptr: the order is irrelevant)
+__global__ void __launch_bounds__(256) prune_plan_kernel(const int64_t* __restrict__ out_ptr, int64_t n_rows, int n_chunks,
+                                                         int64_t n_cols, int32_t* __restrict__ heavy_rows,
+                                                         int32_t* __restrict__ count) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool heavy = false;
+  if (r < n_rows) {
+    const int64_t k = out_ptr[r + 1] - out_ptr[r];
+    heavy = k > 0 && !prune_k_ok(k, n_chunks, n_cols);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, heavy);
+  if (m) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (heavy) heavy_rows[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
+  }
+}
+
+// The rows the pruned kernel deferred at run time (NaN maxima, crowded ties: rare): a small persistent grid walks the
+// device-built list with the exact whole-row generic path (any k, any width, any score pattern).
+__global__ void __launch_bounds__(256) topk_deferred_kernel(const float* __restrict__ scores, int64_t ld, int n_cols,
+                                                            const int64_t* __restrict__ out_ptr, int64_t row_base,
+                                                            int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
+                                                            int32_t* __restrict__ status, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ live) {
+  __shared__ TopkSmem<256> sm;
+  const int n = *live;
+  for (int slot = blockIdx.x; slot < n; slot += gridDim.x) {
+    const int64_t r = rows[slot];
+    const int64_t o0 = out_ptr[r];
+    int k = (int)(out_ptr[r + 1] - o0);
+    if (k > n_cols) {
+      if (status && threadIdx.x == 0) atomicOr(status, 1);
+      k = n_cols;
+    }
+    if (k > 0)
+      topk_row_generic<256, false>(sm, nullptr, scores + r * ld, n_cols, k, o0, (int32_t)(row_base + r), out_users, out_items);
+    __syncthreads();
+  }
+}
+
 SegCfg make_seg(int64_t n_cols) {
   SegCfg sg{0, 0, 0, 0};
   if (n_cols > TOPK_SEG_COLS) {
@@ -895,14 +948,29 @@ extern "C" int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_col
   return (int64_t)prune_head_bytes(n_rows) + dmm_topk_workspace_bytes(n_cols, n_edges);
 }
 
+extern "C" int dmm_topk_prune_plan(dmm_ctx* ctx, const int64_t* out_ptr, int64_t n_rows, int64_t n_cols, int32_t* heavy_rows,
+                                   int32_t* count, void* stream) {
+  DMM_CHECK_ARG(ctx && out_ptr && heavy_rows && count, "dmm_topk_prune_plan: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31) && n_cols > 0 && n_cols < (1LL << 31), "dmm_topk_prune_plan: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  DMM_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+  if (n_rows == 0) return DMM_OK;
+  prune_plan_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(out_ptr, n_rows, (int)dmm_ceil_div(n_cols, 32), n_cols,
+                                                                        heavy_rows, count);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
 extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                                      const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
                                      int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
-                                     void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream) {
+                                     const int32_t* heavy_rows, int64_t n_heavy, void* workspace, int64_t workspace_bytes,
+                                     int64_t n_edges, void* stream) {
   DMM_CHECK_ARG(ctx && scores && cmax && out_ptr && out_items && workspace, "dmm_topk_edges_pruned: null argument");
   DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges_pruned: bad shape n_cols=%lld ld=%lld",
                 (long long)n_cols, (long long)ld);
   DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31), "dmm_topk_edges_pruned: bad n_rows");
+  DMM_CHECK_ARG(n_heavy >= 0 && n_heavy <= n_rows && (n_heavy == 0 || heavy_rows), "dmm_topk_edges_pruned: bad heavy-row list");
   const int64_t n_chunks = dmm_ceil_div(n_cols, 32);
   DMM_CHECK_ARG(ld_cmax >= n_chunks && ld_cmax % 4 == 0 && (reinterpret_cast<uintptr_t>(cmax) & 15u) == 0,
                 "dmm_topk_edges_pruned: cmax rows must be 16-byte aligned with ld_cmax %% 4 == 0 and >= ceil(n_cols / 32)");
@@ -910,22 +978,32 @@ extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t 
                 "dmm_topk_edges_pruned: workspace smaller than dmm_topk_pruned_workspace_bytes");
   if (n_rows == 0) return DMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* const seg_ws = (uint8_t*)workspace + prune_head_bytes(n_rows);
+  const int64_t seg_ws_bytes = workspace_bytes - (int64_t)prune_head_bytes(n_rows);
   static const bool prune_ok = []() { const char* e = getenv("DMM_TOPK_PRUNE"); return !(e && e[0] == '0'); }();   // A/B switch
   if (!prune_ok || n_chunks > 512 * 4 * TOPK_V4 || n_chunks < 8)
     return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, order, nullptr,
-                         (uint8_t*)workspace + prune_head_bytes(n_rows), workspace_bytes - (int64_t)prune_head_bytes(n_rows),
-                         n_edges, st);
+                         seg_ws, seg_ws_bytes, n_edges, st);
   int32_t* left_count = (int32_t*)workspace;
   int32_t* left_rows = (int32_t*)((uint8_t*)workspace + 256);
   DMM_CUDA(cudaMemsetAsync(left_count, 0, sizeof(int32_t), st));
+  // 1. the rows that fail the k rule, when the caller precomputed them (dmm_topk_prune_plan): an exactly sized grid of
+  //    the whole-row / segmented kernels over that list, started first (they are the long-running rows)
+  if (heavy_rows != nullptr && n_heavy > 0) {
+    int rc = topk_dispatch(ctx, scores, ld, n_heavy, n_cols, out_ptr, row_base, out_users, out_items, status, heavy_rows, nullptr,
+                           seg_ws, seg_ws_bytes, n_edges, st);
+    if (rc != DMM_OK) return rc;
+  }
+  // 2. everything else: chunk maxima -> k chunks -> exact rank
   const PruneArgs a{scores, ld, cmax, ld_cmax, (int)n_chunks, (int)n_cols, n_rows, out_ptr, row_base, out_users, out_items,
-                    status, order, left_count, left_rows};
+                    status, order, left_count, left_rows, heavy_rows != nullptr ? 1 : 0};
   if (n_chunks <= 64 * 4 * TOPK_V4) topk_pruned_kernel<64><<<(unsigned)n_rows, 64, 0, st>>>(a);
   else if (n_chunks <= 256 * 4 * TOPK_V4) topk_pruned_kernel<256><<<(unsigned)n_rows, 256, 0, st>>>(a);
   else topk_pruned_kernel<512><<<(unsigned)n_rows, 512, 0, st>>>(a);
   DMM_LAUNCH_CHECK();
-  // the rows the pruned kernel deferred (large k, NaN scores, crowded ties): whole-row / segmented kernels over the list
-  return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, left_rows, left_count,
-                       (uint8_t*)workspace + prune_head_bytes(n_rows), workspace_bytes - (int64_t)prune_head_bytes(n_rows),
-                       n_edges, st);
+  // 3. rows deferred at run time (and, without a precomputed list, the rows that fail the k rule): exact generic path
+  topk_deferred_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(scores, ld, (int)n_cols, out_ptr, row_base, out_users,
+                                                                    out_items, status, left_rows, left_count);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
 }

@@ -249,9 +249,19 @@ def cmax_buffer(n_rows: int, n_cols: int, device) -> torch.Tensor:
     return torch.empty((n_rows, pad_to((n_cols + 31) // 32, 4)), dtype=torch.float32, device=device)
 
 
-def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_items, status=None, order=None):
+def topk_prune_plan(out_ptr, n_rows, n_cols):
+    """(heavy_rows int32 [n_heavy], n_heavy): the rows of out_ptr that the pruned top-k hands to the whole-row kernels
+    (k above the pruning limits).  ONE host sync (the count): call once per CSR block and keep the result."""
+    heavy = torch.empty(max(int(n_rows), 1), dtype=torch.int32, device=out_ptr.device)
+    count = torch.empty(1, dtype=torch.int32, device=out_ptr.device)
+    _lib.call("dmm_topk_prune_plan", _ctx(out_ptr), _p(out_ptr), int(n_rows), int(n_cols), _p(heavy), _p(count), _stream())
+    n = int(count.item())
+    return heavy[:n].clone(), n
+
+
+def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_items, status=None, order=None, heavy=None):
     """topk_edges for scores whose producer also wrote the per-chunk maxima `cmax` (gemm_bf16_tn(cmax=...)): reads only
-    the chunks that can hold a row's k largest scores.  Same output, bit for bit."""
+    the chunks that can hold a row's k largest scores.  Same output, bit for bit.  heavy: topk_prune_plan(out_ptr, ...)."""
     assert scores.dtype == torch.float32 and cmax.dtype == torch.float32 and out_ptr.dtype == torch.int64
     assert out_items.dtype == torch.int32
     n_rows = scores.shape[0]
@@ -259,9 +269,10 @@ def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_it
     n_edges = int(out_items.numel())
     ws_bytes = int(_lib.load().dmm_topk_pruned_workspace_bytes(n_rows, int(n_cols), n_edges))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
+    h_rows, n_heavy = heavy if heavy is not None else (None, 0)
     _lib.call("dmm_topk_edges_pruned", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(cmax),
               _row_major(cmax, "cmax"), _p(out_ptr), int(row_base), _p(out_users), _p(out_items), _p(status), _p(order),
-              _p(ws), ws_bytes, n_edges, _stream())
+              _p(h_rows) if heavy is not None else None, int(n_heavy), _p(ws), ws_bytes, n_edges, _stream())
 
 
 # ----------------------------------------------------------------------------------------- adjacency
@@ -388,3 +399,20 @@ def scatter_add_rows(src, idx, dst):
     _lib.call("dmm_scatter_add_rows", _ctx(src), _p(src), _row_major(src, "src"), _p(idx), idx.numel(), src.shape[1],
               _p(dst), _row_major(dst, "dst"), _stream())
     return dst
+
+
+# ----------------------------------------------------------------------------------------- evaluation
+def eval_mask_scores(indptr, indices, row_ids, scores, n_cols, fill=-1e8):
+    """scores[r, train items of user row_ids[r]] = fill (Main.py:410 without dense mask rows)."""
+    assert row_ids.dtype == torch.int64 and scores.dtype == torch.float32
+    _lib.call("dmm_eval_mask_scores", _ctx(scores), _p(indptr), _p(indices), _p(row_ids), int(row_ids.numel()), int(n_cols),
+              _p(scores), _row_major(scores, "scores"), float(fill), _stream())
+
+
+def eval_metrics(scores, top_items, K, row_ids, test_ptr, test_items, inv_log2, max_dcg, out):
+    """out[r] = (recall, ndcg, precision) of user row_ids[r] in float64 (Main.py:422-448)."""
+    assert out.dtype == torch.float64 and inv_log2.dtype == torch.float64 and max_dcg.dtype == torch.float64
+    assert top_items.dtype == torch.int32 and test_items.dtype == torch.int32 and test_ptr.dtype == torch.int64
+    _lib.call("dmm_eval_metrics", _ctx(scores), _p(scores), _row_major(scores, "scores"), int(row_ids.numel()), _p(top_items),
+              int(K), _p(row_ids), _p(test_ptr), _p(test_items), _p(inv_log2), _p(max_dcg), _p(out), _stream())
+    return out

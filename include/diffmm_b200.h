@@ -195,13 +195,19 @@ int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows
  * cmax[r, c] = max(scores[r, 32c .. 32c+31]) (dmm_gemm_epilogue.cmax; fp32 [n_rows, ld_cmax], ld_cmax % 4 == 0,
  * NaN-propagating): a row's k largest scores lie in the k chunks with the largest maxima, so the kernel reads
  * 4 * n_cols / 32 + 128 * k bytes per row instead of 4 * n_cols.  Rows that do not qualify (k > 64, k chunks more than
- * a quarter of the row, NaN scores, crowded ties) are collected on the device and go through the kernels of
- * dmm_topk_edges in the same call.  `workspace` (required): dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges). */
+ * a quarter of the row, NaN scores, crowded ties) go through the exact whole-row kernels in the same call: the rows
+ * that fail the k rule from `heavy_rows` (int32 [n_heavy], built ONCE per out_ptr by dmm_topk_prune_plan, whose device
+ * count the caller reads back: the offsets are the train CSR and never change) with an exactly sized grid; without a
+ * list (heavy_rows == NULL) they are collected on the device like the run-time deferrals and walked by a small
+ * persistent grid.  `workspace` (required): dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges).               */
 int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t n_edges);
+int dmm_topk_prune_plan(dmm_ctx* ctx, const int64_t* out_ptr, int64_t n_rows, int64_t n_cols, int32_t* heavy_rows,
+                        int32_t* count, void* stream);
 int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                           const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
                           int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
-                          void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream);
+                          const int32_t* heavy_rows, int64_t n_heavy, void* workspace, int64_t workspace_bytes,
+                          int64_t n_edges, void* stream);
 
 /* ---- normalised bipartite adjacency ---------------------------------------------------------
  * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and
@@ -272,6 +278,20 @@ int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2,
 /* Scatter-add of per-batch row gradients into a table gradient: dst[idx[b], :] += src[b, :]. */
 int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,
                          int64_t D, float* dst, int64_t ld_d, void* stream);
+
+/* ---- evaluation tail (Main.py:390-448) ------------------------------------------------------------
+ * dmm_eval_mask_scores: scores[r, c] = fill for every train item c of user row_ids[r] (CSR indptr / indices): the
+ * `predict * (1 - trainMask) - trainMask * 1e8` of Main.py:410 with fill = -1e8, without the dense mask rows.
+ * dmm_eval_metrics: for row r (user row_ids[r]) the K columns top_items[r*K .. r*K+K) (from dmm_topk_edges with k = K on
+ * the masked scores) are ranked by (score desc, column asc) and compared with the user's test items
+ * test_items[test_ptr[u] .. test_ptr[u+1]) in stored order: out[3r + 0/1/2] = recall, ndcg, precision in float64 with
+ * calcRes' arithmetic (Main.py:422-448).  inv_log2[p] = 1 / log2(p + 2) (p < K) and max_dcg[t] (t <= K) are HOST-computed
+ * float64 tables passed on the device so that every term equals numpy's.  K <= 32.                    */
+int dmm_eval_mask_scores(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                         int64_t n_rows, int64_t n_cols, float* scores, int64_t ld, float fill, void* stream);
+int dmm_eval_metrics(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, const int32_t* top_items, int64_t K,
+                     const int64_t* row_ids, const int64_t* test_ptr, const int32_t* test_items,
+                     const double* inv_log2, const double* max_dcg, double* out, void* stream);
 
 /* ---- host helper (no device work) --------------------------------------------------------------
  * Replays the reference's rejection-sampling loop (TrainData.negSampling, DataHandler.py:159-169)

