@@ -55,6 +55,14 @@ class Coach:
         if self.device.type == "cuda":
             torch.cuda.set_device(self.device)      # the kernels launch on the current device (base.gpu), like torch's own
         self.phase_seconds = {}
+        # multi-GPU (one process per GPU, `group` = the torch.distributed group): the rebuild is user-sharded
+        # (rebuild_modal_adj) and every propagation product is row-partitioned with one all-gather per layer
+        from . import autograd as _ag
+        from . import dist as ddist
+        if group is not None and ddist.world_size(group) > 1:
+            _ag.set_partition(ddist.PropPartition(self.config.data.user_num, self.config.data.item_num, group))
+        else:
+            _ag.set_partition(None)
         _log().info(f"USER: {self.config.data.user_num}, ITEM: {self.config.data.item_num}")
         _log().info(f"NUM OF INTERACTIONS: {len(self.handler.trainData)}")
 
@@ -160,7 +168,9 @@ class Coach:
         """Phase 3 from a CUDA graph: opt-in (``base.cuda_graph`` or DIFFMM_CUDA_GRAPH=1); never with the CPU-RNG
         parity mode, whose noise draws happen on the host."""
         want = bool(getattr(self.config.base, "cuda_graph", False)) or os.environ.get("DIFFMM_CUDA_GRAPH", "0") == "1"
-        return want and torch.cuda.is_available() and not rng.cpu_rng()
+        from . import dist as ddist
+        multi = self.group is not None and ddist.world_size(self.group) > 1     # collectives stay outside graph capture
+        return want and torch.cuda.is_available() and not rng.cpu_rng() and not multi
 
     def _tick(self, name, t0):
         torch.cuda.synchronize()

@@ -57,9 +57,8 @@ PROTOTYPES = {
     "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                  c_vp]),
     "dmm_topk_pruned_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
-    "dmm_topk_prune_plan": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dmm_topk_edges_pruned": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+                                        c_vp, c_i64, c_i64, c_vp]),
     "dmm_build_adj_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "dmm_build_norm_adj_csr": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dmm_spmm_plan_bytes": (c_i64, [c_i64, c_i64]),

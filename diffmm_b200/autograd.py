@@ -184,7 +184,43 @@ class SpMM(torch.autograd.Function):
         return ops.spmm(ctx.adj, _rows(g)), None
 
 
+class PartitionedSpMM(torch.autograd.Function):
+    """y = A x with the rows of A (and of y) partitioned over the ranks of a process group (dist.PropPartition): every
+    rank runs the CSR SpMM kernel on its own row blocks of the replicated adjacency and the blocks are all-gathered in
+    place (NCCL over NVLink; one exchange per layer).  A is symmetric, so with a replicated upstream gradient g the
+    backward dL/dx = A g is the same partitioned product: rows of A g on the owning rank + all-gather."""
+
+    @staticmethod
+    def _product(adj, x, part):
+        y = torch.empty((adj.n_nodes, x.shape[1]), dtype=torch.float32, device=x.device)
+        for r0, r1 in part.row_ranges():
+            ops.spmm(adj, x, out=y, row0=r0, row1=r1)
+        return part.gather_(y)
+
+    @staticmethod
+    def forward(ctx, x, adj: ops.CsrAdj, part):
+        ctx.adj, ctx.part = adj, part
+        return PartitionedSpMM._product(adj, _rows(x.detach()), part)
+
+    @staticmethod
+    def backward(ctx, g):
+        return PartitionedSpMM._product(ctx.adj, _rows(g), ctx.part), None, None
+
+
+_PARTITION = None      # dist.PropPartition of the running trainer (None: single GPU)
+
+
+def set_partition(part) -> None:
+    """Row-partitions every propagation product of this process (Model.gcn_MM, the cross-layer CL layers of
+    Coach._joint_step) over ``part.group``; None restores the single-GPU path."""
+    global _PARTITION
+    _PARTITION = part if (part is not None and part.world > 1) else None
+
+
 def spmm(adj: ops.CsrAdj, x: torch.Tensor) -> torch.Tensor:
+    part = _PARTITION
+    if part is not None and adj.n_nodes == part.n_nodes and (adj.n_users == part.n_users or adj.n_users == 0):
+        return PartitionedSpMM.apply(x, adj, part)
     return SpMM.apply(x, adj)
 
 

@@ -160,54 +160,25 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int count, int wa
   return prefix;
 }
 
-// Generic row: exact for any k, any score distribution, any row width.  The leading radix digits of fp32
-// scores (sign + exponent) barely discriminate, so ONE histogram pass over range-adapted buckets
-// ((key - kmin) >> sh, monotone in the key) isolates the bucket holding the k-th largest key; only that
-// bucket's keys go through the exact radix select.  Rows whose threshold bucket is crowded (heavy ties)
-// select over the whole row.  s_keys: the row's keys in shared memory when IN_SMEM, else the row is
-// (re-)read from global memory / L2 on every pass.
-template <int NT, bool IN_SMEM>
-__device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_keys, const float* __restrict__ row,
-                                                 int n_cols, int k, int64_t o0, int32_t user,
-                                                 int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
-                                                 int col_off = 0) {
+// Exact selection + emission over `n` keys read through key_at(i) (value desc, index asc; the emitted entries leave in
+// ascending index order as col_of(i)).  kmin / kmax: this thread's partial key range when `scanned`, else the function
+// scans the keys itself.  Uniform across the block; every barrier is reached by every thread.
+template <int NT, typename KeyAt, typename ColOf>
+__device__ __forceinline__ void topk_select_emit(TopkSmem<NT>& sm, KeyAt key_at, ColOf col_of, int n_cols, int k,
+                                                 bool scanned, uint32_t kmin, uint32_t kmax, int64_t o0, int32_t user,
+                                                 int32_t* __restrict__ out_users, int32_t* __restrict__ out_items) {
   static_assert(NT >= 256, "the bucket scan and the radix histograms are laid out for at least 256 threads");
   const int tid = threadIdx.x;
   const bool take_all = !(k < n_cols);
-  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-  auto track = [&](uint32_t key) {
-    kmin = min(kmin, key);
-    kmax = max(kmax, key);
-  };
-  if (IN_SMEM) {
-    // single HBM read of the row; float4 when the row start is 16 B aligned
-    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
-    if (vec) {
-      const int n4 = n_cols >> 2;
-      const float4* row4 = reinterpret_cast<const float4*>(row);
-      for (int i = tid; i < n4; i += NT) {
-        const float4 v = __ldcs(row4 + i);
-        const uint4 q = make_uint4(order_key(v.x), order_key(v.y), order_key(v.z), order_key(v.w));
-        reinterpret_cast<uint4*>(s_keys)[i] = q;
-        track(q.x); track(q.y); track(q.z); track(q.w);
-      }
-      for (int i = (n4 << 2) + tid; i < n_cols; i += NT) {
-        const uint32_t q = order_key(__ldcs(row + i));
-        s_keys[i] = q;
-        track(q);
-      }
-    } else {
-      for (int i = tid; i < n_cols; i += NT) {
-        const uint32_t q = order_key(__ldcs(row + i));
-        s_keys[i] = q;
-        track(q);
-      }
+  if (!scanned && !take_all) {
+    kmin = 0xFFFFFFFFu;
+    kmax = 0u;
+    for (int i = tid; i < n_cols; i += NT) {
+      const uint32_t key = key_at(i);
+      kmin = min(kmin, key);
+      kmax = max(kmax, key);
     }
-  } else if (!take_all) {
-    for (int i = tid; i < n_cols; i += NT) track(order_key(__ldg(row + i)));
   }
-  auto key_at = [&](int i) -> uint32_t { return IN_SMEM ? s_keys[i] : order_key(__ldg(row + i)); };
-
   uint32_t T = 0u;
   int need_eq = 0;
   if (!take_all) {
@@ -301,11 +272,58 @@ __device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_k
       --eq_take;
     }
     if (sel) {
-      out_items[w] = i + col_off;
+      out_items[w] = col_of(i);
       if (out_users) out_users[w] = user;
       ++w;
     }
   }
+}
+
+// Generic row: exact for any k, any score distribution, any row width.  The leading radix digits of fp32
+// scores (sign + exponent) barely discriminate, so ONE histogram pass over range-adapted buckets
+// ((key - kmin) >> sh, monotone in the key) isolates the bucket holding the k-th largest key; only that
+// bucket's keys go through the exact radix select.  Rows whose threshold bucket is crowded (heavy ties)
+// select over the whole row.  s_keys: the row's keys in shared memory when IN_SMEM, else the row is
+// (re-)read from global memory / L2 on every pass.
+template <int NT, bool IN_SMEM>
+__device__ __forceinline__ void topk_row_generic(TopkSmem<NT>& sm, uint32_t* s_keys, const float* __restrict__ row,
+                                                 int n_cols, int k, int64_t o0, int32_t user,
+                                                 int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
+                                                 int col_off = 0) {
+  const int tid = threadIdx.x;
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+  auto track = [&](uint32_t key) {
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  };
+  if (IN_SMEM) {
+    // single HBM read of the row; float4 when the row start is 16 B aligned
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+    if (vec) {
+      const int n4 = n_cols >> 2;
+      const float4* row4 = reinterpret_cast<const float4*>(row);
+      for (int i = tid; i < n4; i += NT) {
+        const float4 v = __ldcs(row4 + i);
+        const uint4 q = make_uint4(order_key(v.x), order_key(v.y), order_key(v.z), order_key(v.w));
+        reinterpret_cast<uint4*>(s_keys)[i] = q;
+        track(q.x); track(q.y); track(q.z); track(q.w);
+      }
+      for (int i = (n4 << 2) + tid; i < n_cols; i += NT) {
+        const uint32_t q = order_key(__ldcs(row + i));
+        s_keys[i] = q;
+        track(q);
+      }
+    } else {
+      for (int i = tid; i < n_cols; i += NT) {
+        const uint32_t q = order_key(__ldcs(row + i));
+        s_keys[i] = q;
+        track(q);
+      }
+    }
+  }
+  auto key_at = [&](int i) -> uint32_t { return IN_SMEM ? s_keys[i] : order_key(__ldg(row + i)); };
+  auto col_of = [&](int i) -> int { return i + col_off; };
+  topk_select_emit<NT>(sm, key_at, col_of, n_cols, k, IN_SMEM, kmin, kmax, o0, user, out_users, out_items);
 }
 
 // ------------------------------------------------------------------------------------------ generic kernel
@@ -604,10 +622,9 @@ struct PruneArgs {
   const int32_t* order;
   int32_t* left_count;
   int32_t* left_rows;
-  int skip_heavy;      // != 0: rows that fail the k rule are on the caller's precomputed list (dmm_topk_prune_plan): skip them
 };
 
-// The k rule of the pruned path (block-uniform; the same predicate builds the heavy-row list of dmm_topk_prune_plan)
+// The k rule of the pruned path (block-uniform)
 __host__ __device__ __forceinline__ int prune_kmax(int n_chunks) {
   const int nw = n_chunks <= 64 * 4 * TOPK_V4 ? 2 : (n_chunks <= 256 * 4 * TOPK_V4 ? 8 : 16);
   return PRUNE_KMAX < 32 * nw ? PRUNE_KMAX : 32 * nw;
@@ -660,7 +677,7 @@ __global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
     if (tid == 0) a.left_rows[atomicAdd(a.left_count, 1)] = (int32_t)r;
   };
   if (!prune_k_ok(k, n_chunks, a.n_cols)) {   // block-uniform
-    if (!a.skip_heavy) defer();
+    defer();
     return;
   }
   const float NEG_INF = __uint_as_float(0xFF800000u);
@@ -764,11 +781,21 @@ __global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
 
   // 2a. the k selected chunks of the score row: one coalesced 128-byte read each, scores >= Lk are the candidates
   const float* row = a.scores + r * a.ld;
-  for (int i = wid; i < k; i += NW) {
-    const int col = sm.sel[i] * 32 + lane;
-    const bool in = col < a.n_cols;
-    const float x = in ? __ldg(row + col) : NEG_INF;
-    push(&sm.ncand2, in && !(x < Lkf), x, col);
+  constexpr int GB = 8;                       // chunk reads in flight per warp (a row with k = 64 is 4 rounds, not 32)
+  for (int i0 = wid; i0 < k; i0 += NW * GB) {
+    float xs[GB];
+    int cols[GB];
+#pragma unroll
+    for (int t = 0; t < GB; ++t) {
+      const int i = i0 + t * NW;
+      cols[t] = i < k ? sm.sel[i] * 32 + lane : 0x7FFFFFFF;
+      xs[t] = cols[t] < a.n_cols ? __ldg(row + cols[t]) : NEG_INF;
+    }
+#pragma unroll
+    for (int t = 0; t < GB; ++t) {
+      if (i0 + t * NW >= k) break;            // warp-uniform
+      push(&sm.ncand2, cols[t] < a.n_cols && !(xs[t] < Lkf), xs[t], cols[t]);
+    }
   }
   __syncthreads();
   const int m2 = sm.ncand2;          // >= k: every selected chunk holds its maximum >= Lk
@@ -802,45 +829,89 @@ __global__ void __launch_bounds__(NT) topk_pruned_kernel(const PruneArgs a) {
   }
 }
 
-// rows that fail the k rule, appended in arbitrary order (their output slots are fixed by out_ptr: the order is irrelevant)
-__global__ void __launch_bounds__(256) prune_plan_kernel(const int64_t* __restrict__ out_ptr, int64_t n_rows, int n_chunks,
-                                                         int64_t n_cols, int32_t* __restrict__ heavy_rows,
-                                                         int32_t* __restrict__ count) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  bool heavy = false;
-  if (r < n_rows) {
-    const int64_t k = out_ptr[r + 1] - out_ptr[r];
-    heavy = k > 0 && !prune_k_ok(k, n_chunks, n_cols);
-  }
-  const uint32_t m = __ballot_sync(0xffffffffu, heavy);
-  if (m) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (heavy) heavy_rows[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
-  }
-}
-
-// The rows the pruned kernel deferred at run time (NaN maxima, crowded ties: rare): a small persistent grid walks the
-// device-built list with the exact whole-row generic path (any k, any width, any score pattern).
+// The rows the pruned kernel deferred (k above its limits: the 1 % of users with hundreds of interactions; NaN maxima;
+// crowded ties): a small persistent grid walks the device-built list.  A row without NaN whose k chunks are at most half
+// of the row takes the same two-level route with the exact radix select instead of the all-pairs ranking:
+//   A. top-k of the row's chunk maxima (keys staged in shared memory when they fit) -> k chunk ids, ascending, into the
+//      row's slot of `chunk_list`;
+//   B. top-k of the k * 32 scores of those chunks (a virtual row: index i -> column chunk_list[i / 32] * 32 + i % 32, so
+//      index order is column order; columns >= n_cols get key 0, below every real score) -> the row's edges.
+// That is 4 * n_chunks + 128 * k bytes per row instead of several passes over 4 * n_cols (a 500 000-column row with
+// k = 600: 140 KB instead of 8 MB).  Everything else takes the exact whole-row generic path.
 __global__ void __launch_bounds__(256) topk_deferred_kernel(const float* __restrict__ scores, int64_t ld, int n_cols,
+                                                            const float* __restrict__ cmax, int64_t ld_cmax, int n_chunks,
                                                             const int64_t* __restrict__ out_ptr, int64_t row_base,
                                                             int32_t* __restrict__ out_users, int32_t* __restrict__ out_items,
                                                             int32_t* __restrict__ status, const int32_t* __restrict__ rows,
-                                                            const int32_t* __restrict__ live) {
+                                                            const int32_t* __restrict__ live,
+                                                            int32_t* __restrict__ chunk_list, int smem_keys) {
+  extern __shared__ uint32_t s_keys[];       // smem_keys staged keys
   __shared__ TopkSmem<256> sm;
+  const int tid = threadIdx.x;
   const int n = *live;
+  const int64_t e0 = out_ptr[0];
   for (int slot = blockIdx.x; slot < n; slot += gridDim.x) {
     const int64_t r = rows[slot];
     const int64_t o0 = out_ptr[r];
     int k = (int)(out_ptr[r + 1] - o0);
     if (k > n_cols) {
-      if (status && threadIdx.x == 0) atomicOr(status, 1);
+      if (status && tid == 0) atomicOr(status, 1);
       k = n_cols;
     }
-    if (k > 0)
-      topk_row_generic<256, false>(sm, nullptr, scores + r * ld, n_cols, k, o0, (int32_t)(row_base + r), out_users, out_items);
+    if (k <= 0) continue;                     // block-uniform
+    const float* row = scores + r * ld;
+    const float* crow = cmax + r * ld_cmax;
+    bool two_level = (int64_t)k * 2 <= n_chunks;
+    if (two_level) {
+      bool nan = false;
+      for (int i = tid; i < n_chunks; i += 256) {
+        const float c = __ldg(crow + i);
+        nan |= c != c;
+      }
+      two_level = !__syncthreads_or(nan);
+    }
+    if (two_level) {
+      int32_t* list = chunk_list + (o0 - e0);
+      // A. the k chunks with the largest maxima
+      if (n_chunks <= smem_keys) {
+        uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+        for (int i = tid; i < n_chunks; i += 256) {
+          const uint32_t q = order_key(__ldg(crow + i));
+          s_keys[i] = q;
+          kmin = min(kmin, q);
+          kmax = max(kmax, q);
+        }
+        topk_select_emit<256>(sm, [&](int i) -> uint32_t { return s_keys[i]; }, [](int i) -> int { return i; }, n_chunks, k,
+                              true, kmin, kmax, 0, 0, nullptr, list);
+      } else {
+        topk_select_emit<256>(sm, [&](int i) -> uint32_t { return order_key(__ldg(crow + i)); }, [](int i) -> int { return i; },
+                              n_chunks, k, false, 0u, 0u, 0, 0, nullptr, list);
+      }
+      __syncthreads();                        // the chunk list (global) is complete and visible to the block
+      // B. the k best of the k * 32 scores of those chunks
+      const int nv = k * 32;
+      auto vcol = [&](int i) -> int { return list[i >> 5] * 32 + (i & 31); };
+      auto vkey = [&](int i) -> uint32_t {
+        const int c = vcol(i);
+        return c < n_cols ? order_key(__ldg(row + c)) : 0u;
+      };
+      if (nv <= smem_keys) {
+        uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll 4
+        for (int i = tid; i < nv; i += 256) {
+          const uint32_t q = vkey(i);
+          s_keys[i] = q;
+          kmin = min(kmin, q);
+          kmax = max(kmax, q);
+        }
+        topk_select_emit<256>(sm, [&](int i) -> uint32_t { return s_keys[i]; }, vcol, nv, k, true, kmin, kmax, o0,
+                              (int32_t)(row_base + r), out_users, out_items);
+      } else {
+        topk_select_emit<256>(sm, vkey, vcol, nv, k, false, 0u, 0u, o0, (int32_t)(row_base + r), out_users, out_items);
+      }
+    } else {
+      topk_row_generic<256, false>(sm, nullptr, row, n_cols, k, o0, (int32_t)(row_base + r), out_users, out_items);
+    }
     __syncthreads();
   }
 }
@@ -945,32 +1016,20 @@ inline size_t prune_head_bytes(int64_t n_rows) { return 256 + prune_align((size_
 }  // namespace
 
 extern "C" int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t n_edges) {
-  return (int64_t)prune_head_bytes(n_rows) + dmm_topk_workspace_bytes(n_cols, n_edges);
-}
-
-extern "C" int dmm_topk_prune_plan(dmm_ctx* ctx, const int64_t* out_ptr, int64_t n_rows, int64_t n_cols, int32_t* heavy_rows,
-                                   int32_t* count, void* stream) {
-  DMM_CHECK_ARG(ctx && out_ptr && heavy_rows && count, "dmm_topk_prune_plan: null argument");
-  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31) && n_cols > 0 && n_cols < (1LL << 31), "dmm_topk_prune_plan: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  DMM_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
-  if (n_rows == 0) return DMM_OK;
-  prune_plan_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(out_ptr, n_rows, (int)dmm_ceil_div(n_cols, 32), n_cols,
-                                                                        heavy_rows, count);
-  DMM_LAUNCH_CHECK();
-  return DMM_OK;
+  // [deferred-row count | deferred-row list | chunk lists of the deferred rows (one slot per emitted entry) | workspace of
+  //  the segmented kernels (only used when pruning is switched off)]
+  return (int64_t)prune_head_bytes(n_rows) + (int64_t)prune_align((size_t)(n_edges > 0 ? n_edges : 1) * sizeof(int32_t)) +
+         dmm_topk_workspace_bytes(n_cols, n_edges);
 }
 
 extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                                      const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
                                      int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
-                                     const int32_t* heavy_rows, int64_t n_heavy, void* workspace, int64_t workspace_bytes,
-                                     int64_t n_edges, void* stream) {
+                                     void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream) {
   DMM_CHECK_ARG(ctx && scores && cmax && out_ptr && out_items && workspace, "dmm_topk_edges_pruned: null argument");
   DMM_CHECK_ARG(n_cols > 0 && n_cols < (1LL << 31) && ld >= n_cols, "dmm_topk_edges_pruned: bad shape n_cols=%lld ld=%lld",
                 (long long)n_cols, (long long)ld);
-  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31), "dmm_topk_edges_pruned: bad n_rows");
-  DMM_CHECK_ARG(n_heavy >= 0 && n_heavy <= n_rows && (n_heavy == 0 || heavy_rows), "dmm_topk_edges_pruned: bad heavy-row list");
+  DMM_CHECK_ARG(n_rows >= 0 && n_rows < (1LL << 31) && n_edges >= 0, "dmm_topk_edges_pruned: bad n_rows / n_edges");
   const int64_t n_chunks = dmm_ceil_div(n_cols, 32);
   DMM_CHECK_ARG(ld_cmax >= n_chunks && ld_cmax % 4 == 0 && (reinterpret_cast<uintptr_t>(cmax) & 15u) == 0,
                 "dmm_topk_edges_pruned: cmax rows must be 16-byte aligned with ld_cmax %% 4 == 0 and >= ceil(n_cols / 32)");
@@ -978,8 +1037,10 @@ extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t 
                 "dmm_topk_edges_pruned: workspace smaller than dmm_topk_pruned_workspace_bytes");
   if (n_rows == 0) return DMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* const seg_ws = (uint8_t*)workspace + prune_head_bytes(n_rows);
-  const int64_t seg_ws_bytes = workspace_bytes - (int64_t)prune_head_bytes(n_rows);
+  const size_t list_bytes = prune_align((size_t)(n_edges > 0 ? n_edges : 1) * sizeof(int32_t));
+  int32_t* const chunk_list = (int32_t*)((uint8_t*)workspace + prune_head_bytes(n_rows));
+  uint8_t* const seg_ws = (uint8_t*)workspace + prune_head_bytes(n_rows) + list_bytes;
+  const int64_t seg_ws_bytes = workspace_bytes - (int64_t)prune_head_bytes(n_rows) - (int64_t)list_bytes;
   static const bool prune_ok = []() { const char* e = getenv("DMM_TOPK_PRUNE"); return !(e && e[0] == '0'); }();   // A/B switch
   if (!prune_ok || n_chunks > 512 * 4 * TOPK_V4 || n_chunks < 8)
     return topk_dispatch(ctx, scores, ld, n_rows, n_cols, out_ptr, row_base, out_users, out_items, status, order, nullptr,
@@ -987,23 +1048,23 @@ extern "C" int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t 
   int32_t* left_count = (int32_t*)workspace;
   int32_t* left_rows = (int32_t*)((uint8_t*)workspace + 256);
   DMM_CUDA(cudaMemsetAsync(left_count, 0, sizeof(int32_t), st));
-  // 1. the rows that fail the k rule, when the caller precomputed them (dmm_topk_prune_plan): an exactly sized grid of
-  //    the whole-row / segmented kernels over that list, started first (they are the long-running rows)
-  if (heavy_rows != nullptr && n_heavy > 0) {
-    int rc = topk_dispatch(ctx, scores, ld, n_heavy, n_cols, out_ptr, row_base, out_users, out_items, status, heavy_rows, nullptr,
-                           seg_ws, seg_ws_bytes, n_edges, st);
-    if (rc != DMM_OK) return rc;
-  }
-  // 2. everything else: chunk maxima -> k chunks -> exact rank
+  // 1. chunk maxima -> k chunks -> exact rank, one small CTA per row; rows it cannot take go to the device list
   const PruneArgs a{scores, ld, cmax, ld_cmax, (int)n_chunks, (int)n_cols, n_rows, out_ptr, row_base, out_users, out_items,
-                    status, order, left_count, left_rows, heavy_rows != nullptr ? 1 : 0};
+                    status, order, left_count, left_rows};
   if (n_chunks <= 64 * 4 * TOPK_V4) topk_pruned_kernel<64><<<(unsigned)n_rows, 64, 0, st>>>(a);
   else if (n_chunks <= 256 * 4 * TOPK_V4) topk_pruned_kernel<256><<<(unsigned)n_rows, 256, 0, st>>>(a);
   else topk_pruned_kernel<512><<<(unsigned)n_rows, 512, 0, st>>>(a);
   DMM_LAUNCH_CHECK();
-  // 3. rows deferred at run time (and, without a precomputed list, the rows that fail the k rule): exact generic path
-  topk_deferred_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(scores, ld, (int)n_cols, out_ptr, row_base, out_users,
-                                                                    out_items, status, left_rows, left_count);
+  // 2. the deferred rows: persistent grid, two-level radix select (keys staged in up to 80 KB of shared memory)
+  constexpr int SMEM_KEYS = 20480;
+  static DmmPerDeviceOnce attr_once;
+  if (attr_once.need(ctx)) {
+    DMM_CUDA(cudaFuncSetAttribute(topk_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_KEYS * 4));
+    attr_once.mark(ctx);
+  }
+  topk_deferred_kernel<<<(unsigned)(ctx->num_sms * 2), 256, SMEM_KEYS * 4, st>>>(
+      scores, ld, (int)n_cols, cmax, ld_cmax, (int)n_chunks, out_ptr, row_base, out_users, out_items, status, left_rows,
+      left_count, chunk_list, SMEM_KEYS);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

@@ -95,3 +95,56 @@ def allgather_rows(x_local: torch.Tensor, blocks: List[Tuple[int, int]], group=N
     recv = torch.empty((seg * world, D), dtype=x_local.dtype, device=x_local.device)
     td.all_gather_into_tensor(recv, send, group=group)
     return torch.cat([recv[r * seg: r * seg + (b - a)] for r, (a, b) in enumerate(blocks)], 0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Row-partitioned propagation (north_star: "embedding tables are row-partitioned for propagation, with NCCL all-gather
+# over NVLink per GCN layer"; reference call sites Model.py:90,93,105,111,114,123,130 and Main.py:319).
+# ------------------------------------------------------------------------------------------------------------------
+class PropPartition:
+    """Row partition of the N = U + I node rows of the symmetric normalised adjacency for one process group.
+
+    Rank r owns the user rows [r su, (r + 1) su) and the item rows U + [r si, (r + 1) si), su = U // W, si = I // W:
+    user rows carry ~deg(u) entries and item rows ~E / I, so cutting BOTH ranges evenly balances the ranks (a single
+    contiguous cut of [users; items] would give the item-row ranks three times the entries of the user-row ranks at the
+    ifashion shape).  The < W leftover rows of either range are computed by every rank (no communication).  Y keeps the
+    natural [users; items] layout: the two evenly divided regions are all-gathered IN PLACE (equal counts, no padding,
+    no unpack copies)."""
+
+    def __init__(self, n_users: int, n_items: int, group=None):
+        self.group = group
+        self.world = world_size(group)
+        self.rank = rank(group)
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.su = self.n_users // self.world
+        self.si = self.n_items // self.world
+
+    @property
+    def n_nodes(self):
+        return self.n_users + self.n_items
+
+    def row_ranges(self):
+        """[(row0, row1)] this rank computes: its user block, its item block, and the replicated leftovers."""
+        U, W, r, su, si = self.n_users, self.world, self.rank, self.su, self.si
+        out = []
+        if su > 0:
+            out.append((r * su, (r + 1) * su))
+        if W * su < U:
+            out.append((W * su, U))
+        if si > 0:
+            out.append((U + r * si, U + (r + 1) * si))
+        if U + W * si < self.n_nodes:
+            out.append((U + W * si, self.n_nodes))
+        return out
+
+    def gather_(self, y: torch.Tensor) -> torch.Tensor:
+        """In-place all-gather of the evenly divided user and item regions of y [N, D] (every rank has written its own
+        blocks and the leftovers): afterwards every rank holds the whole y."""
+        if self.world == 1:
+            return y
+        U, W, r, su, si = self.n_users, self.world, self.rank, self.su, self.si
+        if su > 0:
+            td.all_gather_into_tensor(y[: W * su], y[r * su:(r + 1) * su], group=self.group)
+        if si > 0:
+            td.all_gather_into_tensor(y[U: U + W * si], y[U + r * si: U + (r + 1) * si], group=self.group)
+        return y

@@ -249,19 +249,9 @@ def cmax_buffer(n_rows: int, n_cols: int, device) -> torch.Tensor:
     return torch.empty((n_rows, pad_to((n_cols + 31) // 32, 4)), dtype=torch.float32, device=device)
 
 
-def topk_prune_plan(out_ptr, n_rows, n_cols):
-    """(heavy_rows int32 [n_heavy], n_heavy): the rows of out_ptr that the pruned top-k hands to the whole-row kernels
-    (k above the pruning limits).  ONE host sync (the count): call once per CSR block and keep the result."""
-    heavy = torch.empty(max(int(n_rows), 1), dtype=torch.int32, device=out_ptr.device)
-    count = torch.empty(1, dtype=torch.int32, device=out_ptr.device)
-    _lib.call("dmm_topk_prune_plan", _ctx(out_ptr), _p(out_ptr), int(n_rows), int(n_cols), _p(heavy), _p(count), _stream())
-    n = int(count.item())
-    return heavy[:n].clone(), n
-
-
-def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_items, status=None, order=None, heavy=None):
+def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_items, status=None, order=None):
     """topk_edges for scores whose producer also wrote the per-chunk maxima `cmax` (gemm_bf16_tn(cmax=...)): reads only
-    the chunks that can hold a row's k largest scores.  Same output, bit for bit.  heavy: topk_prune_plan(out_ptr, ...)."""
+    the chunks that can hold a row's k largest scores.  Same output, bit for bit."""
     assert scores.dtype == torch.float32 and cmax.dtype == torch.float32 and out_ptr.dtype == torch.int64
     assert out_items.dtype == torch.int32
     n_rows = scores.shape[0]
@@ -269,10 +259,9 @@ def topk_edges_pruned(scores, n_cols, cmax, out_ptr, row_base, out_users, out_it
     n_edges = int(out_items.numel())
     ws_bytes = int(_lib.load().dmm_topk_pruned_workspace_bytes(n_rows, int(n_cols), n_edges))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
-    h_rows, n_heavy = heavy if heavy is not None else (None, 0)
     _lib.call("dmm_topk_edges_pruned", _ctx(scores), _p(scores), _row_major(scores, "scores"), n_rows, int(n_cols), _p(cmax),
               _row_major(cmax, "cmax"), _p(out_ptr), int(row_base), _p(out_users), _p(out_items), _p(status), _p(order),
-              _p(h_rows) if heavy is not None else None, int(n_heavy), _p(ws), ws_bytes, n_edges, _stream())
+              _p(ws), ws_bytes, n_edges, _stream())
 
 
 # ----------------------------------------------------------------------------------------- adjacency

@@ -393,23 +393,6 @@ def longest_rows_first(indptr: torch.Tensor, row0: int, n_rows: int) -> torch.Te
     return order
 
 
-_PRUNE_PLANS: dict = {}
-
-
-def prune_plan(indptr: torch.Tensor, row0: int, n_rows: int, n_cols: int):
-    """Heavy-row list of the pruned top-k for the user block [row0, row0 + n_rows) (ops.topk_prune_plan), cached per
-    indptr tensor: the emitted counts are the train degrees, which never change, so the one host sync it costs (the
-    length of the list) happens once per dataset and block, not per rebuild."""
-    key = (id(indptr), indptr._version, indptr.data_ptr(), row0, n_rows, n_cols)
-    ent = _PRUNE_PLANS.get(key)
-    if ent is None:
-        if len(_PRUNE_PLANS) > 64:
-            _PRUNE_PLANS.clear()
-        ent = (ops.topk_prune_plan(indptr[row0:], n_rows, n_cols), indptr)     # the tensor is kept alive: id() stays unique
-        _PRUNE_PLANS[key] = ent
-    return ent[0]
-
-
 _SIDE_STREAMS: Dict[Tuple[int, int], list] = {}
 
 
@@ -452,8 +435,6 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     mods = list(denoise_models.items())
     orders = {b0: longest_rows_first(indptr, b0, min(b0 + block_rows, r1) - b0) for b0 in range(r0, r1, block_rows)} \
         if sampling_step == 0 else {}
-    plans = {b0: prune_plan(indptr, b0, min(b0 + block_rows, r1) - b0, n_items) for b0 in range(r0, r1, block_rows)} \
-        if prune else {}
     n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(mods))
     streams = []
     if n_streams > 1 and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
@@ -477,7 +458,7 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
                                            want_cmax=prune)
                     if prune:      # the contraction left the chunk maxima: the top-k reads only the chunks that matter
                         ops.topk_edges_pruned(scores, n_items, ws.chunk_max()[:b1 - b0], indptr[b0:], b0, None, out_items[m],
-                                              status=status, order=orders.get(b0), heavy=plans[b0])
+                                              status=status, order=orders.get(b0))
                     else:
                         ops.topk_edges(scores, n_items, indptr[b0:], b0, None, out_items[m], status=status,
                                        order=orders.get(b0))

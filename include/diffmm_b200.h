@@ -195,19 +195,15 @@ int dmm_topk_edges(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows
  * cmax[r, c] = max(scores[r, 32c .. 32c+31]) (dmm_gemm_epilogue.cmax; fp32 [n_rows, ld_cmax], ld_cmax % 4 == 0,
  * NaN-propagating): a row's k largest scores lie in the k chunks with the largest maxima, so the kernel reads
  * 4 * n_cols / 32 + 128 * k bytes per row instead of 4 * n_cols.  Rows that do not qualify (k > 64, k chunks more than
- * a quarter of the row, NaN scores, crowded ties) go through the exact whole-row kernels in the same call: the rows
- * that fail the k rule from `heavy_rows` (int32 [n_heavy], built ONCE per out_ptr by dmm_topk_prune_plan, whose device
- * count the caller reads back: the offsets are the train CSR and never change) with an exactly sized grid; without a
- * list (heavy_rows == NULL) they are collected on the device like the run-time deferrals and walked by a small
- * persistent grid.  `workspace` (required): dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges).               */
+ * a quarter of the row, NaN scores, crowded ties) are collected on the device and finished in the same call by a small
+ * persistent grid: two-level exact radix select (top-k of the chunk maxima, then top-k of those chunks' scores) or, for
+ * rows with NaN / k chunks above half of the row, the whole-row generic path.
+ * `workspace` (required): dmm_topk_pruned_workspace_bytes(n_rows, n_cols, n_edges).                              */
 int64_t dmm_topk_pruned_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t n_edges);
-int dmm_topk_prune_plan(dmm_ctx* ctx, const int64_t* out_ptr, int64_t n_rows, int64_t n_cols, int32_t* heavy_rows,
-                        int32_t* count, void* stream);
 int dmm_topk_edges_pruned(dmm_ctx* ctx, const float* scores, int64_t ld, int64_t n_rows, int64_t n_cols,
                           const float* cmax, int64_t ld_cmax, const int64_t* out_ptr, int64_t row_base,
                           int32_t* out_users, int32_t* out_items, int32_t* status, const int32_t* order,
-                          const int32_t* heavy_rows, int64_t n_heavy, void* workspace, int64_t workspace_bytes,
-                          int64_t n_edges, void* stream);
+                          void* workspace, int64_t workspace_bytes, int64_t n_edges, void* stream);
 
 /* ---- normalised bipartite adjacency ---------------------------------------------------------
  * From a user->item edge list in CSR form (row_ptr int64 [U+1], items int32 sorted ascending and

@@ -72,3 +72,68 @@ def test_sharded_rebuild_and_propagation_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), 101, 37, ret), nprocs=world, join=True)
     assert dict(ret) == {r: (True, True) for r in range(world)}
+
+
+# ---------------------------------------------------------------------------------------------- partitioned propagation
+def _fake_spmm(adj, x, *, alpha=1.0, beta=0.0, z=None, out=None, row0=0, row1=None):
+    """CPU stand-in of ops.spmm (the CUDA kernel needs a GPU): same row-block contract, numpy oracle arithmetic."""
+    row1 = adj.n_nodes if row1 is None else row1
+    if out is None:
+        out = torch.empty((adj.n_nodes, x.shape[1]), dtype=torch.float32)
+    y = O.spmm_csr(adj.ptr.numpy(), adj.idx.numpy(), adj.val.numpy(), x.detach().numpy())
+    out[row0:row1] = torch.from_numpy(y[row0:row1])
+    return out
+
+
+def _prop_loss(spmm_fn, adj, e0, w):
+    """Three propagation layers with a nonlinearity in between and a scalar loss (the shape of Main.py:315-330)."""
+    e, acc = e0, 0.0
+    for _ in range(3):
+        e = torch.tanh(spmm_fn(adj, e))
+        acc = acc + e
+    return (acc * w).sum()
+
+
+def _prop_worker(rank, world, port, U, I, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diffmm_b200 import autograd as ag, ops
+        ops.spmm = _fake_spmm
+        rng = np.random.default_rng(5)
+        deg = rng.integers(0, 7, U)
+        users = np.repeat(np.arange(U), deg)
+        items = np.concatenate([np.sort(rng.choice(I, k, replace=False)) for k in deg]).astype(np.int32)
+        ptr, idx, val = O.normalized_adj_csr(users, items, U, I)
+        adj = ops.CsrAdj(torch.from_numpy(ptr), torch.from_numpy(idx), torch.from_numpy(val), U, I)
+        N = U + I
+        x = torch.from_numpy(rng.standard_normal((N, 8)).astype(np.float32))
+        w = torch.from_numpy(rng.standard_normal((N, 8)).astype(np.float32))
+        e_single = x.clone().requires_grad_(True)
+        ag.set_partition(None)
+        l1 = _prop_loss(ag.spmm, adj, e_single, w)
+        l1.backward()
+        part = ddist.PropPartition(U, I, td.group.WORLD)
+        assert sum(b - a for a, b in part.row_ranges()) <= N and part.world == world
+        ag.set_partition(part)
+        e_part = x.clone().requires_grad_(True)
+        l2 = _prop_loss(ag.spmm, adj, e_part, w)
+        l2.backward()
+        ag.set_partition(None)
+        ret[rank] = (bool(torch.allclose(l1, l2, rtol=1e-6)), bool(torch.allclose(e_single.grad, e_part.grad, rtol=1e-5, atol=1e-6)),
+                     [tuple(r) for r in part.row_ranges()])
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("U,I", [(40, 24), (41, 23)])      # evenly divisible and with leftover rows on both sides
+def test_partitioned_propagation_values_and_gradients_gloo(U, I):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_prop_worker, args=(world, _free_port(), U, I, ret), nprocs=world, join=True)
+    got = dict(ret)
+    assert all(got[r][0] and got[r][1] for r in range(world)), got
+    covered = sorted(set(x for r in range(world) for a, b in got[r][2] for x in range(a, b)))
+    assert covered == list(range(U + I))

@@ -60,12 +60,7 @@ def _run_pruned(ops, scores, k, order=None):
     ops.topk_edges_pruned(sc, n_cols, cm, d_ptr, 7, users, items, status=status, order=order)
     items2 = torch.full((max(E, 1),), -1, dtype=torch.int32, device=DEV)[:E]
     ops.topk_edges(sc, n_cols, d_ptr, 7, None, items2)
-    # with the precomputed heavy-row list (the rebuild's configuration): same output
-    items3 = torch.full((max(E, 1),), -1, dtype=torch.int32, device=DEV)[:E]
-    plan = ops.topk_prune_plan(d_ptr, n_rows, n_cols)
-    ops.topk_edges_pruned(sc, n_cols, cm, d_ptr, 7, None, items3, order=order, heavy=plan)
     torch.cuda.synchronize()
-    assert torch.equal(items, items3), "pruned top-k with and without the heavy-row plan differ"
     return ptr, users.cpu().numpy(), items.cpu().numpy(), items2.cpu().numpy(), int(status.item())
 
 
@@ -77,6 +72,7 @@ def test_pruned_topk_equals_full_topk_and_oracle(ops, n_cols):
     k = np.minimum(rng.integers(0, 30, n_rows), n_cols)
     k[0], k[1], k[2], k[3], k[4] = 0, 1, min(n_cols, 64), min(n_cols, 65), min(n_cols, 603)
     k[5] = max(1, min(64, n_cols // 128))
+    k[6] = max(1, min(700, n_cols // 64))        # deferred rows: two-level select, keys beyond the shared-memory staging
     ptr, users, items, items_full, status = _run_pruned(ops, scores, k)
     assert status == 0
     np.testing.assert_array_equal(items, items_full)
