@@ -2,14 +2,17 @@
 """Benchmark of the DiffMM hot path on B200: denoise/top-k graph rebuild users per second.
 
     python bench.py --gpus N --steps K --warmup W          # our arm (1 process per GPU under torchrun for N > 1)
-    python bench.py --impl reference ...                   # the reference's CPU path (numpy oracle port) on host cores
+    python bench.py --impl reference ...                   # the unmodified reference (oracle/_ref) on the host cores
 
 A "step" is one full pass of phase 2 (reference Main.py:195-253) over the workload's users: for every
-modality the S-step reverse-diffusion chain (2 tcgen05 GEMMs per step), the per-user top-k (k = deg(u)),
-and the normalised-adjacency build.  Workload (N = 1): conf/baby.toml shape (19445 users x 7050 items,
-2 modalities, hidden 1024, 5 steps), synthetic interactions + random-init weights of that architecture.
-For N > 1 every rank owns a shard of the same size (weak scaling: N x 19445 users), no data-path
-collective except the final edge all-gather.  One JSON line is printed by rank 0.
+modality the S-step reverse-diffusion chain (tcgen05 GEMMs), the per-user top-k (k = deg(u)) and the
+normalised-adjacency build.  Workload (N = 1): conf/baby.toml (19445 users x 7050 items, 2 modalities,
+hidden 1024, 5 steps, sampling_step 5: the rebuild starts from a q_sample'd x_5), synthetic interactions +
+random-init weights of that architecture (same seed in both arms).  For N > 1 every rank owns a shard of the
+same size (weak scaling: N x 19445 users); the only data-path collective is the edge all-gather.  One JSON
+line is printed by rank 0; besides the contract's keys it carries `variants` (sampling_step 0, bf16x3),
+`long_run` (a >= 1 s timed region), `other_workloads` (N > 1: sports strong scaling, 2M x 500k slice),
+`propagation` (row-partitioned SpMM + all-gather at the ifashion shape), `aux_rooflines`, `epoch_sec`.
 """
 from __future__ import annotations
 
@@ -61,7 +64,8 @@ METRIC = "denoise_topk_rebuild_users_per_sec"
 UNIT = "users/s"
 KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sort kernels are not counted)
     "dmm_pack_bf16": 1, "dmm_csr_rows_to_dense": 1, "dmm_time_embedding": 1, "dmm_q_sample": 1, "dmm_gemm_bf16_tn": 1,
-    "dmm_gemm_f32_tn": 1, "dmm_topk_edges": 1, "dmm_build_norm_adj_csr": 4, "dmm_sign_noise_": 1,
+    "dmm_gemm_f32_tn": 1, "dmm_topk_edges": 1, "dmm_topk_edges_pruned": 2, "dmm_csr_qsample_values": 1,
+    "dmm_build_norm_adj_csr": 4, "dmm_sign_noise_": 1,
     "dmm_bpr_fwd_bwd": 2, "dmm_infonce_fwd": 3, "dmm_infonce_bwd": 3, "dmm_scatter_add_rows": 1,
     "dmm_spmm_csr": 2, "dmm_spmm_plan": 3,
 }
@@ -124,24 +128,33 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(name, device, seed, precision, world=1, hyper=None):
+def build_workload(name, device, seed, precision, world=1, hyper=None, users_total=None, init_on_device=False):
+    """Synthetic interactions + random-init Denoise weights of the workload's architecture.  The default workload draws
+    its weights on the CPU generator in the reference's construction order (the reference arm draws the same ones);
+    init_on_device draws them with the device generator instead (the 500k-item models are 6 GB of normals)."""
     import torch
     from diffmm_b200 import synth
     from diffmm_b200.Conf import Config
     from diffmm_b200.Model import Denoise, GaussianDiffusion
     w = WORKLOADS[name]
     hyper = hyper or workload_hyper(name)
+    users_total = w["users"] * world if users_total is None else users_total
     cfg = Config()
     cfg.base.precision = precision
     cfg.base.denoise_dim = f"[{w['hidden']}]"
     cfg.hyper.steps = hyper["steps"]
     cfg.hyper.sampling_step = hyper["sampling_step"]
     cfg.hyper.noise_scale, cfg.hyper.noise_min, cfg.hyper.noise_max = hyper["noise"]
-    cfg.data.user_num, cfg.data.item_num = w["users"] * world, w["items"]
-    inter = synth.interactions(w["users"] * world, w["items"], seed=seed)      # same global dataset on every rank
+    cfg.data.user_num, cfg.data.item_num = users_total, w["items"]
+    inter = synth.interactions(users_total, w["items"], seed=seed)      # same global dataset on every rank
     torch.manual_seed(seed)
     diff = GaussianDiffusion(cfg).to(device)
-    dens = {m: Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg).to(device) for m in w["modalities"]}
+    if init_on_device and str(device) != "cpu":
+        torch.cuda.manual_seed(seed)
+        with torch.device(device):
+            dens = {m: Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg) for m in w["modalities"]}
+    else:
+        dens = {m: Denoise([w["items"], w["hidden"]], [w["hidden"], w["items"]], cfg).to(device) for m in w["modalities"]}
     return cfg, inter, diff, dens
 
 
@@ -223,12 +236,17 @@ def aux_rooflines(dev, breakdown, U, I, E, n_mod, pk, seed):
     import torch
     from diffmm_b200 import ops, synth
     out = {}
-    if "dmm_topk_edges" in breakdown:
-        ms = breakdown["dmm_topk_edges"]["ms_per_step"] / max(breakdown["dmm_topk_edges"]["calls_per_step"], 1)
+    tk = "dmm_topk_edges_pruned" if "dmm_topk_edges_pruned" in breakdown else "dmm_topk_edges"
+    if tk in breakdown:
+        ms = breakdown[tk]["ms_per_step"] / max(breakdown[tk]["calls_per_step"], 1)
         by = 4.0 * I * U + 4.0 * E + 8.0 * (U + 1)
         out["topk_edges"] = {"bound": "hbm", "bytes_per_launch": by, "avg_launch_ms": ms, "achieved": by / (ms * 1e-3) / 1e9,
                              "peak": pk["hbm"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"],
-                             "shape": f"{U} rows x {I} fp32 scores, k = deg(u)"}
+                             "entry_point": tk,
+                             "shape": f"{U} rows x {I} fp32 scores, k = deg(u)",
+                             "note": "against the algorithmic 4*I bytes per row (SURVEY 8d); the pruned kernel reads the chunk "
+                                     "maxima the scores contraction wrote (4*I/32 bytes per row) plus k 128-byte chunks, so "
+                                     "its DRAM traffic is ~1/20 of that figure and the fraction can exceed 1"}
     Ui, Ii, _ = synth.SHAPES["ifashion"]
     inter = synth.interactions(Ui, Ii, seed=seed)
     ptr = torch.from_numpy(inter.indptr).to(dev)
@@ -394,6 +412,75 @@ def cpu_baseline_subprocess(args, w):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class RebuildJob:
+    """One rebuild workload on this rank: the synthetic train CSR (global, replicated: it is small), replicated Denoise
+    weights, the rank's user block, pinned host buffers for the end-to-end leg, and the step functions.
+
+    scaling 'weak': the job is world x users (each rank owns `users` rows); 'strong': `users` rows split over the ranks.
+    N > 1: chain + top-k on the rank's block, ONE NCCL all-gather of the edge lists per modality straight into the final
+    buffers (dist.allgather_edges), then the whole-graph adjacencies on every rank."""
+
+    def __init__(self, name, precision, sampling_step, dev, seed, world, rank, scaling="weak", init_on_device=False):
+        import torch
+        from diffmm_b200 import dist as ddist
+        self.name, self.precision, self.dev, self.world, self.rank = name, precision, dev, world, rank
+        self.w = w = WORKLOADS[name]
+        self.hyper = workload_hyper(name, sampling_step)
+        self.users_total = w["users"] * world if scaling == "weak" else w["users"]
+        self.cfg, self.inter, self.diff, self.dens = build_workload(name, dev, seed, precision, world, self.hyper,
+                                                                    users_total=self.users_total, init_on_device=init_on_device)
+        self.I, self.mods = w["items"], w["modalities"]
+        self.r0, self.r1 = ddist.row_blocks(self.users_total, world)[rank]
+        self.plan = ddist.EdgeGatherPlan(torch.from_numpy(self.inter.indptr), self.users_total, world) if world > 1 else None
+        ptr = self.inter.indptr
+        self.e0, self.e1 = int(ptr[self.r0]), int(ptr[self.r1])
+        self.E = int(self.inter.indices.size)
+        self.h_indptr = torch.from_numpy(ptr).pin_memory()
+        self.h_indices_local = torch.from_numpy(self.inter.indices[self.e0:self.e1].copy()).pin_memory()
+        self.d_indptr = self.h_indptr.to(dev)
+        self.d_indices = torch.from_numpy(self.inter.indices).to(dev)
+        self.d_indices_e2e = torch.zeros_like(self.d_indices)          # only the rank's slice is ever uploaded into it
+        self.h_edges = {m: torch.empty(self.e1 - self.e0, dtype=torch.int32).pin_memory() for m in self.mods}
+
+    def step(self, ip, ix):
+        import torch  # noqa: F401
+        from diffmm_b200 import autograd as _ag, ops, rebuild
+        # everything that depends on the Denoise weights is rebuilt inside the step, as after an epoch of training:
+        # bf16 operand copies of W1 / W2 (and their transposes) and the hidden-space operators P = W1x W2, q = W1x b2
+        _ag._PACK_CACHE.clear()
+        for dn in self.dens.values():
+            dn._dmm_hidden_ops = None
+        U, I, SS = self.users_total, self.I, self.hyper["sampling_step"]
+        if self.world > 1:
+            items = rebuild.rebuild_edges(self.diff, self.dens, ip, ix, U, I, SS, self.precision, row_range=(self.r0, self.r1))
+            full = {}
+            adjs = rebuild.gather_and_build(items, ip, U, I, None, self.plan, full_items=full)
+            return adjs, full
+        res = {}
+        rebuild.rebuild_edges(self.diff, self.dens, ip, ix, U, I, SS, self.precision, row_range=(self.r0, self.r1),
+                              per_modality=lambda v: (ops.build_norm_adj(ip, v, U, I), v), per_modality_out=res)
+        return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
+
+    def step_device(self):
+        return self.step(self.d_indptr, self.d_indices)
+
+    def step_e2e(self):
+        """Public-API call with HOST inputs and outputs: the train CSR offsets and the rank's slice of the item ids come
+        from pinned host memory, the rank's slice of every rebuilt edge list goes back to pinned host memory."""
+        ip = self.h_indptr.to(self.dev, non_blocking=True)
+        self.d_indices_e2e[self.e0:self.e1].copy_(self.h_indices_local, non_blocking=True)
+        adjs, items = self.step(ip, self.d_indices_e2e)
+        for m, v in items.items():
+            self.h_edges[m].copy_(v[self.e0:self.e1], non_blocking=True)
+        return adjs
+
+    def h2d_bytes(self):
+        return int(self.world * self.h_indptr.numel() * 8 + self.E * 4)          # summed over the ranks
+
+    def d2h_bytes(self):
+        return int(len(self.mods) * self.E * 4)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as td
@@ -406,24 +493,37 @@ def run_ours(args):
         td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    w = WORKLOADS[args.workload]
-    hyper = workload_hyper(args.workload, args.sampling_step)
-    SS = hyper["sampling_step"]
-    U, I, H, S, mods = w["users"], w["items"], w["hidden"], hyper["steps"], w["modalities"]
-    # weak scaling: the job is world x U users; every rank holds the (small) global CSR and replicated Denoise
-    # weights (same seed), runs the chain + top-k on its own user block, then the edge lists are all-gathered
-    # (NCCL, one collective per modality) and every rank builds the normalised adjacency of the whole graph
-    cfg, inter, diff, dens = build_workload(args.workload, dev, args.seed, args.precision, world, hyper)
-    U_tot = U * world
-    r0, r1 = rank * U, (rank + 1) * U
-    from diffmm_b200 import dist as ddist
-    plan = ddist.EdgeGatherPlan(torch.from_numpy(inter.indptr), U_tot, world) if world > 1 else None
-    E = int(inter.indices.size)
-    h_indptr = torch.from_numpy(inter.indptr).pin_memory()
-    h_indices = torch.from_numpy(inter.indices).pin_memory()
-    d_indptr, d_indices = h_indptr.to(dev), h_indices.to(dev)
-    h_edges = {m: torch.empty(E, dtype=torch.int32).pin_memory() for m in mods}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm=2):
+        """Sum of the per-step device times (CUDA events on the launching stream, L2 flushed before every step, untimed),
+        max over the ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        ev = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            ev.append((e0, e1))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+
+    job = RebuildJob(args.workload, args.precision, args.sampling_step, dev, args.seed, world, rank, "weak",
+                     init_on_device=args.workload == "scaleout")
+    w, hyper = job.w, job.hyper
+    U, I, H, S, mods, E = w["users"], w["items"], w["hidden"], hyper["steps"], job.mods, job.E
 
     # per-launch instrumentation of the dominant kernel (events on the launching stream)
     gemm_events = []
@@ -451,66 +551,16 @@ def run_ours(args):
     _lib.call = counting_call
     ops._lib.call = counting_call
 
-    from diffmm_b200 import autograd as _ag
-
-    def rebuild_step(ip, ix):
-        # everything that depends on the Denoise weights is rebuilt inside the step, as after an epoch of training:
-        # bf16 operand copies of W1 / W2 (and their transposes) and the hidden-space operators P = W1x W2, q = W1x b2
-        _ag._PACK_CACHE.clear()
-        for dn in dens.values():
-            dn._dmm_hidden_ops = None
-        # per modality, on that modality's stream: chain + top-k on the rank's user block and (N = 1) the normalised
-        # adjacency; N > 1: the NCCL all-gathers of the edge lists follow on the caller's stream, then the whole-graph
-        # adjacencies are built concurrently (rebuild.gather_and_build)
-        if world > 1:
-            items = rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, SS, args.precision, row_range=(r0, r1))
-            full = {}
-            adjs = rebuild.gather_and_build(items, ip, U_tot, I, None, plan, full_items=full)
-            return adjs, full
-        res = {}
-        rebuild.rebuild_edges(diff, dens, ip, ix, U_tot, I, SS, args.precision, row_range=(r0, r1),
-                              per_modality=lambda v: (ops.build_norm_adj(ip, v, U_tot, I), v), per_modality_out=res)
-        return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
-
-    def step_device():
-        return rebuild_step(d_indptr, d_indices)
-
-    def step_e2e():
-        ip = h_indptr.to(dev, non_blocking=True)
-        ix = h_indices.to(dev, non_blocking=True)
-        adjs, items = rebuild_step(ip, ix)
-        for m, v in items.items():
-            h_edges[m].copy_(v, non_blocking=True)
-        return adjs
-
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
+    # ---- the timed region of the contract: W warm-up steps, then exactly K steps, device-resident inputs
     for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-
+        job.step_device()
     sampler = ClockSampler(local)
     sampler.start()
     counts.clear()
-    timed_gemm.on = True
-    ev = []
-    barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)                                    # L2 flush between timed iterations (untimed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_device()
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
+    ms = timed(job.step_device, args.steps, warm=0)
     t_wall = time.perf_counter() - t_wall0
-    timed_gemm.on = False
     launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in counts.items())
-    ms = sum(a.elapsed_time(b) for a, b in ev)
 
     def gemm_stats(events):
         tot_ms = sum(a.elapsed_time(b) for _, a, b, _ in events)
@@ -526,65 +576,18 @@ def run_ours(args):
 
     # The modalities run as concurrent pipelines on two streams (rebuild.rebuild_edges), so an event pair around a
     # contraction inside the timed region also spans whatever the other stream ran meanwhile.  The kernel's own launch
-    # durations therefore come from a second pass of the same step with the pipelines serialised on one stream
-    # (DIFFMM_STREAMS=1, same inputs, same L2 flush, events on the launching stream); the in-step figures are kept beside them.
-    overlapped = gemm_stats(gemm_events)
+    # durations therefore come from a second pass of the same K steps with the pipelines serialised on one stream
+    # (DIFFMM_STREAMS=1, same inputs, same L2 flush, events on the launching stream).
     n_streams = int(os.environ.get("DIFFMM_STREAMS", "2"))
-    serial_ms = ms
-    if n_streams > 1 and len(mods) > 1:
-        os.environ["DIFFMM_STREAMS"] = "1"
-        gemm_events = []
-        for _ in range(2):
-            step_device()
-        barrier()
-        timed_gemm.on = True
-        ev_s = []
-        for _ in range(args.steps):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_device()
-            e1.record()
-            ev_s.append((e0, e1))
-        barrier()
-        timed_gemm.on = False
-        os.environ["DIFFMM_STREAMS"] = str(n_streams)
-        serial_ms = sum(a.elapsed_time(b) for a, b in ev_s)
+    os.environ["DIFFMM_STREAMS"] = "1"
+    for _ in range(2):
+        job.step_device()
+    timed_gemm.on = True
+    serial_ms = timed(job.step_device, args.steps, warm=0)
+    timed_gemm.on = False
     gemm_ms, gemm_flops, by_shape = gemm_stats(gemm_events)
 
-    # end-to-end: host CSR in pinned memory -> device, rebuild, edge lists back to pinned host memory
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    ev2 = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_e2e()
-        e1.record()
-        ev2.append((e0, e1))
-    barrier()
-    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
-
-    # the literal chain (2 item-space contractions per reverse step) timed the same way, for the record
-    os.environ["DIFFMM_CHAIN"] = "full"
-    for _ in range(2):
-        step_device()
-    barrier()
-    ev3 = []
-    for _ in range(max(2, args.steps // 2)):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_device()
-        e1.record()
-        ev3.append((e0, e1))
-    barrier()
-    os.environ.pop("DIFFMM_CHAIN", None)
-    ms_full = sum(a.elapsed_time(b) for a, b in ev3) / len(ev3)
-
-    # per-entry-point device time inside a step (separate untimed pass; events around every C-ABI call)
+    # per-entry-point device time inside a step (one stream: every call's events see only that call)
     per_call = []
 
     def timing_call(name, *a):
@@ -596,27 +599,82 @@ def run_ours(args):
     _lib.call = timing_call
     ops._lib.call = timing_call
     n_bd = 2
-    os.environ["DIFFMM_STREAMS"] = "1"              # one stream: every call's events see only that call
     for _ in range(n_bd):
         flush.fill_(1)
-        step_device()
+        job.step_device()
     barrier()
-    os.environ["DIFFMM_STREAMS"] = str(n_streams)
     _lib.call = orig_call
     ops._lib.call = orig_call
+    os.environ["DIFFMM_STREAMS"] = str(n_streams)
     breakdown = {}
     for name, a, b in per_call:
         d = breakdown.setdefault(name, [0, 0.0])
         d[0] += 1
         d[1] += a.elapsed_time(b)
     breakdown = {k: {"calls_per_step": v[0] // n_bd, "ms_per_step": round(v[1] / n_bd, 4)} for k, v in breakdown.items()}
+
+    # ---- end to end through the public call with host buffers (the headline against the reference arm)
+    ms_e2e = timed(job.step_e2e, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- a >= 1 s timed region of the same step (K steps of ~2 ms are a short sample)
+    n_long = int(min(2000, max(args.steps, np.ceil(1000.0 / max(ms / args.steps, 1e-3)))))
+    ms_long = timed(job.step_device, n_long, warm=0) if not args.no_long else None
+
+    # the literal chain (2 item-space contractions per reverse step) timed the same way, for the record
+    ms_full = None
+    if not args.no_variants:
+        os.environ["DIFFMM_CHAIN"] = "full"
+        ms_full = timed(job.step_device, max(2, args.steps // 2)) / max(2, args.steps // 2)
+        os.environ.pop("DIFFMM_CHAIN", None)
+
+    # ---- variants of the same workload: sampling_step 0 (rebuild from the binary rows) and the fp32-faithful precision
+    variants = {}
+    if not args.no_variants and args.workload != "scaleout":
+        k_var = min(args.steps, 10)
+        ops.gemm_bf16_tn = orig_gemm
+        rebuild.ops.gemm_bf16_tn = orig_gemm
+        todo = []
+        if hyper["sampling_step"] != 0:
+            todo.append(("sampling_step_0", args.precision, 0))
+        if args.precision != "bf16x3":
+            todo.append(("bf16x3", "bf16x3", args.sampling_step))
+        for label, prec, ss in todo:
+            vj = RebuildJob(args.workload, prec, ss, dev, args.seed, world, rank, "weak")
+            v_ms = timed(vj.step_device, k_var, warm=3)
+            v_e2e = timed(vj.step_e2e, k_var, warm=2)
+            variants[label] = {"dtype": prec, "sampling_step": vj.hyper["sampling_step"], "steps": k_var,
+                               "ms_per_step": v_ms / k_var, "value": world * U * k_var / (v_ms * 1e-3),
+                               "e2e_value": world * U * k_var / (v_e2e * 1e-3), "unit": UNIT}
+            del vj
+            torch.cuda.empty_cache()
+
+    # ---- N > 1: the other configurations BASELINE.json names for the multi-GPU runs
+    others = {}
+    if world > 1 and not args.no_others and args.workload == "baby":
+        for label, name, scaling, k_o in (("sports_strong", "sports", "strong", 6), ("scaleout_slice_weak", "scaleout", "weak", 3)):
+            try:
+                oj = RebuildJob(name, args.precision, None, dev, args.seed, world, rank, scaling, init_on_device=True)
+                o_ms = timed(oj.step_device, k_o, warm=3)
+                o_e2e = timed(oj.step_e2e, k_o, warm=1)
+                users = oj.users_total
+                others[label] = {"workload": config_dict(name, oj.w, oj.hyper, args.precision)["workload"], "scaling": scaling,
+                                 "users_total": users, "steps": k_o, "ms_per_step": o_ms / k_o,
+                                 "value": users * k_o / (o_ms * 1e-3), "e2e_value": users * k_o / (o_e2e * 1e-3), "unit": UNIT}
+                del oj
+                torch.cuda.empty_cache()
+            except Exception as e:      # the headline line must survive a failure of an auxiliary measurement
+                others[label] = {"error": repr(e)[:300]}
+
+    # ---- row-partitioned propagation (BASELINE.json configs[3]): ifashion-shaped graph, per-layer SpMM + all-gather
+    prop = None
+    if not args.no_prop:
+        try:
+            prop = propagation_bench(dev, world, rank, args.seed, timed)
+        except Exception as e:
+            prop = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
@@ -649,8 +707,9 @@ def run_ours(args):
         "config": config_dict(args.workload, w, hyper, args.precision),
         "run": {"edges": E, "precision": args.precision, "l2": "256 MiB flush write between timed steps; per-step working set > L2",
                 "streams": n_streams if len(mods) > 1 else 1,
-                "parallelism": (f"user-sharded x{world}: {U_tot} users in total, edge lists all-gathered over NCCL, "
-                                f"adjacency of the whole graph built on every rank") if world > 1 else "single GPU"},
+                "parallelism": (f"user-sharded x{world}: {job.users_total} users in total, one NCCL all-gather of the edge lists "
+                                f"per modality into the final buffers, adjacency of the whole graph on every rank")
+                if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tf_burst"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)",
@@ -658,26 +717,33 @@ def run_ours(args):
                      "peak_source": f"{pk['source']} bf16_tflops (burst: the timed region is tens of ms at full clocks); "
                                     f"sustained {pk['tf_sustained']}",
                      "frac_of_sustained": achieved / pk["tf_sustained"], "by_shape_MxNxK": by_shape,
-                     "measured_in": (f"second pass of the same {args.steps} steps with the modality pipelines serialised on one "
-                                     f"stream ({serial_ms / args.steps:.3f} ms/step); in the timed region they overlap on "
-                                     f"{n_streams} streams and an event pair also spans the other stream's kernels")
-                                    if serial_ms is not ms else "the timed region",
-                     "in_timed_region_overlapped": {"avg_launch_ms": overlapped[0] / max(n_gemm, 1),
-                                                    "tflops": overlapped[1] / (overlapped[0] * 1e-3) / 1e12 if overlapped[0] > 0 else 0.0,
-                                                    "share_of_step": overlapped[0] / ms}},
+                     "algorithmic_flops_per_launch": gemm_flops / n_gemm,
+                     "measured_in": f"second pass of the same {args.steps} steps with the modality pipelines serialised on one "
+                                    f"stream ({serial_ms / args.steps:.3f} ms/step); in the timed region they overlap on "
+                                    f"{n_streams} streams and an event pair would also span the other stream's kernels"},
         "e2e": {"value": world * U * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(world * (h_indptr.numel() * 8 + h_indices.numel() * 4)),
-                "d2h_bytes_per_step": int(world * len(mods) * E * 4)},
+                "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "wall_s_timed_region": t_wall,
         "chain": {"mode": rebuild.chain_mode(),
                   "note": "hidden-space chain: z_t = x_t W1^T carried in fp32, one [rows,H]x[H,H] contraction per intermediate "
                           "step, item space only for the first gather and the last step; P = W1x W2, q = W1x b2 and all "
-                          "operand packs are rebuilt inside every timed step",
-                  "full_chain_ms_per_step": ms_full, "full_chain_users_per_s": world * U / (ms_full * 1e-3)},
+                          "operand packs are rebuilt inside every timed step; the scores contraction also writes the chunk "
+                          "maxima the pruned top-k reads",
+                  "full_chain_ms_per_step": ms_full,
+                  "full_chain_users_per_s": (world * U / (ms_full * 1e-3)) if ms_full else None},
         "breakdown_ms_per_step": breakdown,
     }
+    if ms_long is not None:
+        line["long_run"] = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": world * U * n_long / (ms_long * 1e-3),
+                            "timed_region_s": ms_long * 1e-3, "unit": UNIT}
+    if variants:
+        line["variants"] = variants
+    if others:
+        line["other_workloads"] = others
+    if prop is not None:
+        line["propagation"] = prop
     if world == 1 and not args.no_cpu_baseline:          # reported on rank 0 at N = 1 only (a bounded host-core sample)
         line["cpu_baseline"] = cpu_baseline_subprocess(args, w)
     if world == 1 and not args.no_aux:
@@ -699,6 +765,50 @@ def run_ours(args):
         td.destroy_process_group()
 
 
+def propagation_bench(dev, world, rank, seed, timed):
+    """Row-partitioned propagation at the ifashion shape (300k users x 80k items, D = 64): one product Y = A X as the
+    product path runs it (autograd.spmm -> dist.PropPartition: local row blocks on the CSR SpMM kernel + in-place NCCL
+    all-gather), its two halves timed separately, and the un-partitioned product for comparison."""
+    import torch
+    import torch.distributed as td
+    from diffmm_b200 import autograd as ag, dist as ddist, ops, synth
+    Ui, Ii, _ = synth.SHAPES["ifashion"]
+    inter = synth.interactions(Ui, Ii, seed=seed)
+    ptr = torch.from_numpy(inter.indptr).to(dev)
+    idx = torch.from_numpy(inter.indices).to(dev)
+    adj = ops.build_norm_adj(ptr, idx, Ui, Ii)
+    N, D = Ui + Ii, 64
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn((N, D), device=dev, generator=g)
+    y = torch.empty_like(x)
+    k = 10
+    full_ms = timed(lambda: ops.spmm(adj, x, out=y), k, warm=3) / k
+    out = {"shape": f"ifashion-shaped graph: N = {N} nodes, nnz = {adj.nnz}, D = 64 fp32", "n_gpus": world,
+           "full_product_ms": full_ms, "bytes_per_product": 8.0 * adj.nnz + 8.0 * (N + 1) + 2.0 * N * D * 4}
+    if world > 1:
+        part = ddist.PropPartition(Ui, Ii, td.group.WORLD)
+
+        def local():
+            for r0, r1 in part.row_ranges():
+                ops.spmm(adj, x, out=y, row0=r0, row1=r1)
+        local_ms = timed(local, k, warm=3) / k
+        gather_ms = timed(lambda: part.gather_(y), k, warm=3) / k
+        ag.set_partition(part)
+        part_ms = timed(lambda: ag.spmm(adj, x), k, warm=3) / k
+        ag.set_partition(None)
+        # the partitioned product equals the full one
+        want = ops.spmm(adj, x)
+        ag.set_partition(part)
+        got = ag.spmm(adj, x)
+        ag.set_partition(None)
+        out.update({"local_row_blocks_ms": local_ms, "allgather_ms": gather_ms, "partitioned_product_ms": part_ms,
+                    "allgather_bytes_per_rank": float(N * D * 4) * (world - 1) / world,
+                    "allgather_GBps_per_rank": float(N * D * 4) * (world - 1) / world / (gather_ms * 1e-3) / 1e9,
+                    "matches_full_product": bool(torch.equal(got, want)),
+                    "speedup_vs_full": full_ms / part_ms})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -715,7 +825,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the top-k / SpMM / adjacency roofline measurements")
     ap.add_argument("--no-epoch", action="store_true", help="skip the full-epoch (phases 1-3 + eval) timing")
+    ap.add_argument("--no-variants", action="store_true", help="skip the sampling_step-0 / bf16x3 / literal-chain variants")
+    ap.add_argument("--no-others", action="store_true", help="N > 1: skip the sports strong-scaling and scale-out slice runs")
+    ap.add_argument("--no-prop", action="store_true", help="skip the row-partitioned propagation measurement")
+    ap.add_argument("--no-long", action="store_true", help="skip the >= 1 s timed region of the same step")
+    ap.add_argument("--quick", action="store_true", help="headline only: implies every --no-* switch")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_aux = args.no_epoch = args.no_variants = args.no_others = args.no_prop = args.no_long = True
     # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) write to stderr
     # while the run is in progress; the saved descriptor is restored for the result line
     global _RESULT_FD

@@ -61,25 +61,48 @@ class EdgeGatherPlan:
         self.world = world
 
 
+_UNEVEN_OK = {"nccl": True}     # backends whose all_gather takes unequal segment sizes (cleared on the first failure)
+
+
+def _backend(group=None) -> str:
+    try:
+        return str(td.get_backend(group))
+    except Exception:
+        return ""
+
+
 def allgather_edges(items_local: torch.Tensor, indptr: torch.Tensor, n_users: int, group=None,
                     plan: Optional[EdgeGatherPlan] = None) -> torch.Tensor:
-    """Every rank filled items[indptr[r0]:indptr[r1]) for its user block; returns the complete edge list on
-    every rank.  all-gather-v over padded equal-size segments (one collective per modality)."""
+    """Every rank filled items[indptr[r0]:indptr[r1]) for its user block; returns the complete edge list on every rank.
+
+    NCCL: ONE all-gather with unequal segment sizes straight into the final buffer, in place (torch issues it as a
+    group of broadcasts inside one NCCL group call) -- no padding, no zero fill, no unpack copies.  Other backends
+    (gloo in the CPU tests): padded equal-size segments and one index_select to unpack."""
     world, rk = world_size(group), rank(group)
     if world == 1:
         return items_local
     if plan is None or plan.world != world:
         plan = EdgeGatherPlan(indptr, n_users, world)
     offs, seg = plan.offs, plan.seg
+    be = _backend(group)
+    if _UNEVEN_OK.get(be, False) and all(e > s for s, e in offs):
+        try:
+            views = [items_local[s:e] for s, e in offs]
+            td.all_gather(views, views[rk], group=group)
+            return items_local
+        except (RuntimeError, ValueError):       # pragma: no cover - backend without unequal all_gather
+            _UNEVEN_OK[be] = False
     send = torch.zeros(seg, dtype=items_local.dtype, device=items_local.device)
     s, e = offs[rk]
     send[: e - s] = items_local[s:e]
     recv = torch.empty(seg * world, dtype=items_local.dtype, device=items_local.device)
     td.all_gather_into_tensor(recv, send, group=group)
-    out = torch.empty_like(items_local)
-    for r, (s, e) in enumerate(offs):
-        out[s:e] = recv[r * seg: r * seg + (e - s)]
-    return out
+    src = getattr(plan, "_unpack_index", None)
+    if src is None or src.device != items_local.device:
+        src = torch.cat([torch.arange(r * seg, r * seg + (e - s), dtype=torch.int64) for r, (s, e) in enumerate(offs)])
+        src = src.to(items_local.device)
+        plan._unpack_index = src
+    return recv.index_select(0, src)
 
 
 def allgather_rows(x_local: torch.Tensor, blocks: List[Tuple[int, int]], group=None) -> torch.Tensor:
