@@ -186,7 +186,7 @@ def cpu_rebuild_sample(inter, w, params_by_mod, n_sample, hyper, seed=0):
     return dt, len(users), edges
 
 
-def epoch_seconds(name, seed, precision, epochs=3, cuda_graph=False):
+def epoch_seconds(name, seed, precision, epochs=3, cuda_graph=True):
     """One full training epoch + eval (phases 1-3 of Coach.trainEpoch + testEpoch) on the synthetic
     `name`-shape dataset written in the reference's on-disk format; returns the last epoch's phase seconds."""
     import tempfile
@@ -758,8 +758,9 @@ def run_ours(args):
         ops.gemm_bf16_tn = orig_gemm
         rebuild.ops.gemm_bf16_tn = orig_gemm
         try:
-            line["epoch_sec"] = epoch_seconds(args.workload, args.seed, args.precision)
-            line["epoch_sec_cuda_graph"] = epoch_seconds(args.workload, args.seed, args.precision, cuda_graph=True)
+            # the default configuration (phases 1 and 3 replayed from CUDA graphs) and the eager loop
+            line["epoch_sec"] = epoch_seconds(args.workload, args.seed, args.precision, cuda_graph=True)
+            line["epoch_sec_eager"] = epoch_seconds(args.workload, args.seed, args.precision, cuda_graph=False)
         except Exception as e:  # the headline number must survive a failure of the auxiliary measurement
             line["epoch_sec"] = {"error": repr(e)[:300]}
     emit(line)

@@ -37,7 +37,7 @@ class BaseConfig:
     d_emb_size: int = 10
     cl_method: int = 0
     precision: str = "bf16"     # not in the reference: tensor-pipe mode of the Denoise GEMMs
-    cuda_graph: bool = False    # not in the reference: replay phase 3 (joint training) from a CUDA graph per epoch
+    cuda_graph: bool = True     # not in the reference: phases 1 and 3 replayed from CUDA graphs (single GPU, device RNG)
 
 
 @dataclass

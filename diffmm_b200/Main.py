@@ -165,9 +165,10 @@ class Coach:
         return d
 
     def _use_graph(self) -> bool:
-        """Phase 3 from a CUDA graph: opt-in (``base.cuda_graph`` or DIFFMM_CUDA_GRAPH=1); never with the CPU-RNG
-        parity mode, whose noise draws happen on the host."""
-        want = bool(getattr(self.config.base, "cuda_graph", False)) or os.environ.get("DIFFMM_CUDA_GRAPH", "0") == "1"
+        """Phases 1 and 3 from CUDA graphs: the default (``base.cuda_graph``; DIFFMM_CUDA_GRAPH=0 / 1 overrides); never
+        with the CPU-RNG parity mode, whose noise draws happen on the host, nor across ranks."""
+        env = os.environ.get("DIFFMM_CUDA_GRAPH", "")
+        want = bool(getattr(self.config.base, "cuda_graph", True)) if env not in ("0", "1") else env == "1"
         from . import dist as ddist
         multi = self.group is not None and ddist.world_size(self.group) > 1     # collectives stay outside graph capture
         return want and torch.cuda.is_available() and not rng.cpu_rng() and not multi
@@ -185,11 +186,16 @@ class Coach:
             return self._trainDiffusionGraph()
         zero = torch.zeros((), dtype=torch.float64, device=self.device)
         image_diff_loss, text_diff_loss, audio_diff_loss = zero.clone(), zero.clone(), zero.clone()
-        for i, batch_data in enumerate(self.handler.diffusionLoader):
-            batch_u_items = batch_data[0]
-            i_embs = self.model.getItemEmbs()
+        # Model parameters do not move during phase 1, so the projected features the reference recomputes every batch
+        # (Main.py:149-151,166) are computed once; the item embeddings enter detached: their gradient from this phase is
+        # zeroed before any optimiser step could use it (Main.py:375), and dropping it selects the fused step
+        i_embs = self.model.getItemEmbs().detach()
+        with torch.no_grad():
             image_feats = self.model.getImageFeats().detach()
             text_feats = self.model.getTextFeats().detach()
+            audio_feats = self.model.getAudioFeats().detach() if self.has_audio else None
+        for i, batch_data in enumerate(self.handler.diffusionLoader):
+            batch_u_items = batch_data[0]
 
             batch_image_loss = self.diffusion_model.training_losses(self.image_denoise_model, batch_u_items, i_embs, image_feats)
             loss_image = batch_image_loss.mean()
@@ -201,7 +207,6 @@ class Coach:
             self.image_denoise_opt.zero_grad()
             self.text_denoise_opt.zero_grad()
             if self.has_audio:
-                audio_feats = self.model.getAudioFeats().detach()
                 self.audio_denoise_opt.zero_grad()
                 batch_audio_loss = self.diffusion_model.training_losses(self.audio_denoise_model, batch_u_items, i_embs, audio_feats)
                 loss_audio = batch_audio_loss.mean()
@@ -227,14 +232,16 @@ class Coach:
         """One batch of phase 1 with the timesteps given (drawn on the host in the reference's order): the M per-row
         losses, their normalised sum, backward, M Adam steps; acc[k] <- (acc[k] + loss_k) / total in place (float64),
         the running sums of Main.py:155-182.  No host sync, no host tensor: capturable."""
-        i_embs = self.model.getItemEmbs()
+        i_embs = self.model.getItemEmbs().detach()       # dead gradient dropped (Main.py:375): selects the fused step
         dens = [self.image_denoise_model, self.text_denoise_model]
         opts = [self.image_denoise_opt, self.text_denoise_opt]
-        feats = [self.model.getImageFeats().detach(), self.model.getTextFeats().detach()]
+        with torch.no_grad():
+            feats = [self.model.getImageFeats().detach(), self.model.getTextFeats().detach()]
+            if self.has_audio:
+                feats.append(self.model.getAudioFeats().detach())
         if self.has_audio:
             dens.append(self.audio_denoise_model)
             opts.append(self.audio_denoise_opt)
-            feats.append(self.model.getAudioFeats().detach())
         losses = [self.diffusion_model.training_losses(d, batch_u_items, i_embs, f, timesteps=t).mean()
                   for d, f, t in zip(dens, feats, ts)]
         for o in opts:
@@ -272,11 +279,17 @@ class Coach:
             self._diff_warm = 0
         acc = self._diff_acc
         acc.zero_()
+        from . import train_step as _ts
+        stale = False           # a replay moved the weights without bumping their version counters
         for batch_data in self.handler.diffusionLoader:
             rows = batch_data[0]
             n = rows.shape[0]
             ts = [torch.randint(0, S, (n,)).long() for _ in range(M)]          # Model.py:397 draws, image / text / audio
             if n != B:
+                if stale:       # the eager tail batch must not see operand copies made before the last replayed update
+                    _ag._PACK_CACHE.clear()
+                    _ts.clear_caches()
+                    stale = False
                 self._diffusion_step(rows, [t.to(self.device) for t in ts], acc)
                 continue
             self._diff_rows.copy_(rows)
@@ -292,13 +305,17 @@ class Coach:
                 continue
             if self._diff_graph is None:
                 _ag._PACK_CACHE.clear()          # packed weights must be (re)built inside the captured step
+                from . import train_step as _ts
+                _ts.clear_caches()               # ... and so must the feature / item-embedding operand copies
                 torch.cuda.synchronize(self.device)
                 self._diff_graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._diff_graph):
                     self._diffusion_step(self._diff_rows, self._diff_ts, acc)
             self._diff_graph.replay()
+            stale = True
         # a replay updates the weights without bumping their version counters: drop everything derived from them
         _ag._PACK_CACHE.clear()
+        _ts.clear_caches()
         for den in self._denoise_dict().values():
             den._dmm_hidden_ops = None
         out = acc.tolist()
@@ -428,6 +445,9 @@ class Coach:
             pos_items = pos_items.long().cuda(self.device)
             neg_items = neg_items.long().cuda(self.device)
             if not use_graph or users.numel() != B:
+                if use_graph and getattr(self, "_joint_stale", False):
+                    _ag._PACK_CACHE.clear()      # eager tail batch after replays: operand copies are one update stale
+                    self._joint_stale = False
                 acc += torch.stack(self._joint_step(users, pos_items, neg_items, biadj)).double()
                 continue
             for dst, src in zip(static, (users, pos_items, neg_items)):
@@ -448,6 +468,7 @@ class Coach:
                 with torch.cuda.graph(self._joint_graph):
                     acc += torch.stack(self._joint_step(*static, biadj)).double()
             self._joint_graph.replay()
+            self._joint_stale = True
         out = acc.tolist()
         self._check_rebuild_status()             # rides on the sync above: no extra round trip per epoch
         if use_graph:

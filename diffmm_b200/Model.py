@@ -241,6 +241,21 @@ class GaussianDiffusion(nn.Module):
         self._h_sqrt_1mac = self.sqrt_one_minus_alphas_cumprod.cpu().numpy()
         self._coef_tables_f32 = None
 
+    def _train_tables(self, device):
+        """Device tables of the fused training step: sqrt(abar), sqrt(1 - abar) as fp32 (Model.py:352 casts) and the
+        float64 loss weight w_t = SNR(max(t - 1, 0)) - SNR(t), w_0 = 1 (Model.py:380-383,410-412)."""
+        ent = getattr(self, "_train_tabs", None)
+        if ent is None or ent[0].device != device:
+            ta, tb = self._tables_f32(device)
+            ac = self.alphas_cumprod.to(device)
+            snr = ac / (1 - ac + 1e-8)
+            idx = torch.arange(self.steps, device=device)
+            w = snr[torch.clamp(idx - 1, min=0)] - snr[idx]
+            w = torch.where(idx == 0, 1.0, w).to(torch.float64).contiguous()
+            ent = (ta.contiguous(), tb.contiguous(), w)
+            self._train_tabs = ent
+        return ent
+
     def _tables_f32(self, device):
         if self._coef_tables_f32 is None or self._coef_tables_f32[0].device != device:
             self._coef_tables_f32 = (self.sqrt_alphas_cumprod.float().to(device),
@@ -301,6 +316,15 @@ class GaussianDiffusion(nn.Module):
         timesteps = timesteps.to(x_start.device)
         if noise is None:
             noise = rng.randn_like(x_start)
+        from . import train_step
+        if (train_step.enabled() and x_start.is_cuda and len(model.in_layers) == 1 and len(model.out_layers) == 1
+                and modal_feat is not None and modal_feat.shape[1] == 64 and not modal_feat.requires_grad
+                and not i_embs.requires_grad and not x_start.requires_grad):
+            # the hot configuration (Main.py:153-170 with the dead item-embedding gradient dropped): forward and backward
+            # of the whole loss scheduled by hand on the kernels (train_step.py)
+            core = train_step.denoise_loss(self, model, x_start, timesteps, noise, modal_feat, i_embs)
+            reg_loss = l2_reg_loss(self.config.train.reg, [i_embs], self.device)
+            return core + reg_loss * self.config.train.reg
         x_t = self.forward_cal_xt(x_start, timesteps, noise)
         model_output = model.forward(x_t, timesteps, modal_feat=modal_feat)
 

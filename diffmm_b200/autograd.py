@@ -193,9 +193,7 @@ class PartitionedSpMM(torch.autograd.Function):
     @staticmethod
     def _product(adj, x, part):
         y = torch.empty((adj.n_nodes, x.shape[1]), dtype=torch.float32, device=x.device)
-        for r0, r1 in part.row_ranges():
-            ops.spmm(adj, x, out=y, row0=r0, row1=r1)
-        return part.gather_(y)
+        return part.product_(lambda r0, r1: ops.spmm(adj, x, out=y, row0=r0, row1=r1), y)
 
     @staticmethod
     def forward(ctx, x, adj: ops.CsrAdj, part):

@@ -160,6 +160,36 @@ class PropPartition:
             out.append((U + W * si, self.n_nodes))
         return out
 
+    def product_(self, spmm_rows, y: torch.Tensor) -> torch.Tensor:
+        """Runs ``spmm_rows(row0, row1)`` (writes y[row0:row1]) over this rank's blocks and all-gathers y in place.  On
+        CUDA the all-gather of the user region is issued on a side stream as soon as the user blocks are written, so
+        it travels over NVLink while the item blocks are still being computed."""
+        if self.world == 1 or not y.is_cuda:
+            for r0, r1 in self.row_ranges():
+                spmm_rows(r0, r1)
+            return self.gather_(y)
+        U, W, r, su, si = self.n_users, self.world, self.rank, self.su, self.si
+        main = torch.cuda.current_stream(y.device)
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(device=y.device)
+        comm = self._comm_stream
+        ranges = self.row_ranges()
+        user_ranges = [(a, b) for a, b in ranges if b <= U]
+        item_ranges = [(a, b) for a, b in ranges if a >= U]
+        for a, b in user_ranges:
+            spmm_rows(a, b)
+        if su > 0:
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                td.all_gather_into_tensor(y[: W * su], y[r * su:(r + 1) * su], group=self.group)
+        for a, b in item_ranges:
+            spmm_rows(a, b)
+        if si > 0:
+            td.all_gather_into_tensor(y[U: U + W * si], y[U + r * si: U + (r + 1) * si], group=self.group)
+        main.wait_stream(comm)
+        y.record_stream(comm)
+        return y
+
     def gather_(self, y: torch.Tensor) -> torch.Tensor:
         """In-place all-gather of the evenly divided user and item regions of y [N, D] (every rank has written its own
         blocks and the leftovers): afterwards every rank holds the whole y."""

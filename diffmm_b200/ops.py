@@ -405,3 +405,68 @@ def eval_metrics(scores, top_items, K, row_ids, test_ptr, test_items, inv_log2, 
     _lib.call("dmm_eval_metrics", _ctx(scores), _p(scores), _row_major(scores, "scores"), int(row_ids.numel()), _p(top_items),
               int(K), _p(row_ids), _p(test_ptr), _p(test_items), _p(inv_log2), _p(max_dcg), _p(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------- fused training step
+def train_prep(x0, noise, t, tab_a, tab_b, emb_w, emb_b, a_hi, a_lo, x0_hi, te_raw):
+    """x_t = tab_a[t] x0 + tab_b[t] noise and the time-embedding columns as the bf16 operand a_hi (+ a_lo); x0 as a bf16
+    operand (optional); te_raw = raw [cos, sin] time features (optional)."""
+    B, I = x0.shape
+    _lib.call("dmm_train_prep", _ctx(x0), _p(x0), _row_major(x0, "x0"), _p(noise), _row_major(noise, "noise"), _p(t), _p(tab_a),
+              _p(tab_b), B, I, int(emb_w.shape[0]), _p(emb_w), _p(emb_b), _p(a_hi), _p(a_lo), _row_major(a_hi, "a_hi"),
+              _p(x0_hi), _row_major(x0_hi, "x0_hi") if x0_hi is not None else 0, _p(te_raw), _stream())
+
+
+def gate_fwd(p, gate_w, gate_b, sig, g_hi, g_lo):
+    assert gate_w.shape == (64, 64) and gate_w.is_contiguous() and sig.is_contiguous()
+    _lib.call("dmm_gate_fwd", _ctx(p), _p(p), _row_major(p, "p"), p.shape[0], _p(gate_w), _p(gate_b), _p(sig), _p(g_hi), _p(g_lo),
+              _row_major(g_hi, "g_hi"), _stream())
+
+
+def gate_bwd_pre(dg, p, sig, dpre):
+    _lib.call("dmm_gate_bwd_pre", _ctx(p), _p(dg), _row_major(dg, "dg"), _p(p), _row_major(p, "p"), _p(sig), p.shape[0], _p(dpre),
+              _stream())
+
+
+def diff_loss_fwd(diff, umd, x0f, ui, t, w_tab, sim_weight, loss, mse, um, stats):
+    B, I = diff.shape
+    _lib.call("dmm_diff_loss_fwd", _ctx(diff), _p(diff), _row_major(diff, "diff"), B, I, _p(umd), _row_major(umd, "umd"), _p(x0f),
+              _row_major(x0f, "x0f"), _p(ui), _row_major(ui, "ui"), _p(t), _p(w_tab), float(sim_weight), _p(loss), _p(mse), _p(um),
+              _p(stats), _stream())
+
+
+def diff_loss_bwd(g_loss, um, ui, stats, t, w_tab, sim_weight, n_cols, cm, dumc_hi, dumc_lo, d_ui):
+    B = um.shape[0]
+    _lib.call("dmm_diff_loss_bwd", _ctx(um), _p(g_loss), _p(um), _p(ui), _row_major(ui, "ui"), _p(stats), _p(t), _p(w_tab),
+              float(sim_weight), B, int(n_cols), _p(cm), _p(dumc_hi), _p(dumc_lo), _row_major(dumc_hi, "dumc_hi"), _p(d_ui),
+              _stream())
+
+
+def hidden_bwd(dh, h_hi, h_lo, cm, H, dz, dz_hi, dz_lo, dzt_hi, dzt_lo, hct_hi, hct_lo):
+    B = dh.shape[0]
+    _lib.call("dmm_hidden_bwd", _ctx(dh), _p(dh), _row_major(dh, "dh"), _p(h_hi), _p(h_lo), _row_major(h_hi, "h_hi"), _p(cm), B,
+              int(H), _p(dz), _row_major(dz, "dz"), _p(dz_hi), _p(dz_lo), _row_major(dz_hi, "dz_hi"), _p(dzt_hi), _p(dzt_lo),
+              _p(hct_hi), _p(hct_lo), _row_major(dzt_hi, "dzt_hi"), _stream())
+
+
+def transpose_bf16(src_hi, src_lo, rows, cols, dst_hi, dst_lo):
+    _lib.call("dmm_transpose_bf16", _ctx(src_hi), _p(src_hi), _p(src_lo), _row_major(src_hi, "src_hi"), int(rows), int(cols),
+              _p(dst_hi), _p(dst_lo), _row_major(dst_hi, "dst_hi"), _stream())
+
+
+def colsum(src, row_scale=None):
+    """out[c] = sum_r row_scale[r] * src[r, c] (fp32; rows added in order)."""
+    R, Cc = src.shape
+    out = torch.empty(Cc, dtype=torch.float32, device=src.device)
+    _lib.call("dmm_colsum", _ctx(src), _p(src), _row_major(src, "src"), R, Cc, _p(row_scale), _p(out), _stream())
+    return out
+
+
+def atb_small(x, y):
+    """x^T y for skinny fp32 matrices x [R, m], y [R, n] (m, n <= 64)."""
+    R, m = x.shape
+    n = y.shape[1]
+    ws = torch.empty(int(_lib.load().dmm_atb_small_workspace_floats(m, n)), dtype=torch.float32, device=x.device)
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    _lib.call("dmm_atb_small", _ctx(x), _p(x), _row_major(x, "x"), m, _p(y), _row_major(y, "y"), n, R, _p(ws), _p(out), _stream())
+    return out

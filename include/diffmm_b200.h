@@ -275,6 +275,53 @@ int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2,
 int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,
                          int64_t D, float* dst, int64_t ld_d, void* stream);
 
+/* ---- fused Denoise training step (Model.py:385-428 + :183-220; driver Main.py:145-192) -----------------------------
+ * The step is scheduled by the host layer as twelve dmm_gemm_bf16_tn contractions per modality and batch plus the
+ * kernels below; together they replace the per-op autograd chain (q_sample -> fp32 x_t -> torch.cat -> pack, sigmoid
+ * gate, mse / cosine tails, tanh', bias-gradient sums, operand transposes).
+ *
+ * dmm_train_prep: x_t = tab_a[t_r] x0 + tab_b[t_r] noise (Model.py:338-341; tables = sqrt(abar), sqrt(1 - abar) as fp32)
+ *   written directly as the bf16 operand a_hi (+ a_lo) [n_rows, ld_a] of the first layer, columns [0, n_cols); the time
+ *   embedding (Model.py:196-202) goes to columns [n_cols, n_cols + d_emb); x0_hi (optional) receives x0 as a bf16
+ *   operand; te_raw (optional, fp32 [n_rows, d_emb]) the raw [cos, sin] features for the emb_layer gradient.       */
+int dmm_train_prep(dmm_ctx* ctx, const float* x0, int64_t ld_x0, const float* noise, int64_t ld_noise, const int64_t* t,
+                   const float* tab_a, const float* tab_b, int64_t n_rows, int64_t n_cols, int d_emb, const float* emb_w,
+                   const float* emb_b, uint16_t* a_hi, uint16_t* a_lo, int64_t ld_a, uint16_t* x0_hi, int64_t ld_x0h,
+                   float* te_raw, void* stream);
+/* Gate (Model.py:205-207, latdim 64): sig = sigmoid(p Wg^T + bg) (fp32 [n_rows, 64]), G = p * sig as bf16 operand.
+ * dmm_gate_bwd_pre: dpre = dG * p * sig (1 - sig), the gradient at the gate's pre-activation.                     */
+int dmm_gate_fwd(dmm_ctx* ctx, const float* p, int64_t ld_p, int64_t n_rows, const float* gate_w, const float* gate_b,
+                 float* sig, uint16_t* g_hi, uint16_t* g_lo, int64_t ld_g, void* stream);
+int dmm_gate_bwd_pre(dmm_ctx* ctx, const float* dg, int64_t ld_dg, const float* p, int64_t ld_p, const float* sig,
+                     int64_t n_rows, float* dpre, void* stream);
+/* Loss tail (Model.py:407-425).  diff = out - x0 (fp32, from the second layer's epilogue), umd = diff F, x0f = x0 F,
+ * ui = x0 i_embs (all [n_rows, 64]): loss[r] = w_tab[t_r] * mean(diff_r^2) + sim_weight * (1 - cos(umd + x0f, ui)) in
+ * float64 (the reference's dtypes); um = umd + x0f and stats = (dot, |um|, |ui|) are kept for the backward.
+ * Backward: cm[r] = g_r w_r 2 / n_cols, dumc = (d loss / d um) / cm as a bf16 operand (the backward contractions work
+ * on d_out' = diff + dumc F^T and apply the row scale cm afterwards), d_ui (optional) = d loss / d ui.            */
+int dmm_diff_loss_fwd(dmm_ctx* ctx, const float* diff, int64_t ld_d, int64_t n_rows, int64_t n_cols, const float* umd,
+                      int64_t ld_umd, const float* x0f, int64_t ld_x0f, const float* ui, int64_t ld_ui, const int64_t* t,
+                      const double* w_tab, float sim_weight, double* loss, float* mse, float* um, float* stats, void* stream);
+int dmm_diff_loss_bwd(dmm_ctx* ctx, const double* g_loss, const float* um, const float* ui, int64_t ld_ui, const float* stats,
+                      const int64_t* t, const double* w_tab, float sim_weight, int64_t n_rows, int64_t n_cols, float* cm,
+                      uint16_t* dumc_hi, uint16_t* dumc_lo, int64_t ld_dumc, float* d_ui, void* stream);
+/* Hidden layer backward: dz = cm[r] dh (1 - h^2) (h = h_hi + h_lo) as fp32, as bf16 operand [n_rows, ld_dz16], and
+ * transposed [H, ld_t] together with (cm h)^T [H, ld_t]: the K = batch operands of the weight-gradient contractions. */
+int dmm_hidden_bwd(dmm_ctx* ctx, const float* dh, int64_t ld_dh, const uint16_t* h_hi, const uint16_t* h_lo, int64_t ld_h,
+                   const float* cm, int64_t n_rows, int64_t H, float* dz_f32, int64_t ld_dz, uint16_t* dz_hi, uint16_t* dz_lo,
+                   int64_t ld_dz16, uint16_t* dzt_hi, uint16_t* dzt_lo, uint16_t* hct_hi, uint16_t* hct_lo, int64_t ld_t,
+                   void* stream);
+/* dst[c, r] = src[r, c] for bf16 operands (hi and optionally lo); dst columns up to ld_dst are written (zero padded). */
+int dmm_transpose_bf16(dmm_ctx* ctx, const uint16_t* src_hi, const uint16_t* src_lo, int64_t ld_src, int64_t rows,
+                       int64_t cols, uint16_t* dst_hi, uint16_t* dst_lo, int64_t ld_dst, void* stream);
+/* out[c] = sum_r row_scale[r] * src[r, c] (row_scale NULL = 1): bias gradients, rows added in order (deterministic). */
+int dmm_colsum(dmm_ctx* ctx, const float* src, int64_t ld, int64_t rows, int64_t cols, const float* row_scale, float* out,
+               void* stream);
+/* out[m, n] = x^T y for skinny fp32 x [rows, m], y [rows, n] (m, n <= 64): gate / time-embedding weight gradients. */
+int64_t dmm_atb_small_workspace_floats(int64_t m, int64_t n);
+int dmm_atb_small(dmm_ctx* ctx, const float* x, int64_t ld_x, int64_t m, const float* y, int64_t ld_y, int64_t n, int64_t rows,
+                  float* workspace, float* out, void* stream);
+
 /* ---- evaluation tail (Main.py:390-448) ------------------------------------------------------------
  * dmm_eval_mask_scores: scores[r, c] = fill for every train item c of user row_ids[r] (CSR indptr / indices): the
  * `predict * (1 - trainMask) - trainMask * 1e8` of Main.py:410 with fill = -1e8, without the dense mask rows.

@@ -9,6 +9,7 @@ import json
 import os
 import shutil
 
+import numpy as np
 import pytest
 import torch
 
@@ -95,3 +96,48 @@ def test_device_eval_equals_host_eval(tmp_path, monkeypatch):
     assert dev["Recall"] == host["Recall"] and dev["Precision"] == host["Precision"]
     assert dev["NDCG"] == pytest.approx(host["NDCG"], rel=1e-13)
     assert dev["Recall"] > 0
+
+
+def test_cuda_graph_mode_over_epochs_keeps_derived_state_fresh(tmp_path, monkeypatch):
+    """graph replay updates the weights without bumping their version counters, so everything derived from
+    them (packed operand copies, hidden-space operators, static adjacency buffers + SpMM plans) relies on explicit
+    invalidation.  Dataset with 5 full diffusion batches + a ragged tail and > 5 full joint batches, 3 epochs: both graphs
+    must be captured, and after the last epoch the adjacencies the trainer holds must equal a from-scratch eager rebuild
+    with the trainer's current weights, and the cached packs must equal fresh packs of the current weights."""
+    from diffmm_b200 import Main, autograd as ag, ops, rebuild, synth
+    from diffmm_b200.Conf import Config
+    U, I = 700, 300
+    synth.write_dataset(str(tmp_path), "tiktok", synth.interactions(U, I, seed=3, mean_deg=6.0, heavy_frac=0.02),
+                        synth.features(I, dict(image=16, text=24, audio=8), seed=3))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("DIFFMM_CPU_RNG", "0")
+    cfg = Config()
+    cfg.data.name = "tiktok"
+    cfg.base.denoise_dim, cfg.base.cuda_graph, cfg.base.precision = "[64]", True, "bf16"
+    cfg.train.batch, cfg.train.test_batch, cfg.train.epoch = 128, 128, 3
+    Main.seed_it(7)
+    handler = Main.DataHandler(cfg)
+    handler.LoadData()
+    coach = Main.Coach(handler, cfg)
+    assert len(handler.diffusionLoader) == 6 and U % 128 != 0 and len(handler.trainLoader) > 6
+    coach.run()
+    assert coach._use_graph() and coach._diff_graph is not None and coach._joint_graph is not None
+    assert all(np.isfinite(list(h["train"].values())).all() for h in coach.history)
+    # the adjacencies held after the last epoch vs an eager rebuild from the same (current) weights.  The last epoch's
+    # rebuild ran before its joint phase changed nothing the rebuild depends on (Denoise weights move only in phase 1).
+    ag._PACK_CACHE.clear()
+    for den in coach._denoise_dict().values():
+        den._dmm_hidden_ops = None
+    fresh = rebuild.rebuild_modal_adj(coach.diffusion_model, coach._denoise_dict(), handler.train_indptr, handler.train_indices,
+                                      U, I, cfg.hyper.sampling_step, "bf16")
+    for name, adj in (("image", coach.image_adj), ("text", coach.text_adj), ("audio", coach.audio_adj)):
+        assert torch.equal(adj.ptr, fresh[name].ptr) and torch.equal(adj.idx, fresh[name].idx), name
+        assert torch.equal(adj.val, fresh[name].val), name
+        x = torch.randn((U + I, 64), device=adj.val.device)
+        assert torch.equal(ops.spmm(adj, x), ops.spmm(fresh[name], x)), name      # the in-place re-planned SpMM plan too
+    # cached packs of the Denoise weights == fresh packs of the current values
+    for den in coach._denoise_dict().values():
+        w = den.in_layers[0].weight
+        hi_cached, _ = ag.packed_weight(w, False, False)
+        hi_fresh, _ = ops.pack_bf16(w.detach(), split=False)
+        assert torch.equal(hi_cached, hi_fresh)

@@ -221,3 +221,87 @@ def test_bf16x3_training_forward_uses_the_accurate_tanh():
     assert float((y - torch.tanh(z.double()).float()).abs().max()) < 5e-7      # tanh.approx would be ~5e-4 off
     want = torch.tanh(x.double() @ w.double().t() + b.double()).float()
     assert float((y - want).abs().max()) < 5e-5                                # split-bf16 contraction error at |z| ~ 5
+
+
+# ---------------------------------------------------------------------------------------------- fused training step
+def _denoise_from_golden(cfg, g):
+    from diffmm_b200.Model import Denoise
+    I, H = g["w2"].shape
+    den = Denoise([I, H], [H, I], cfg).to(DEV)
+    with torch.no_grad():
+        den.emb_layer.weight.copy_(T(g["emb_w"])); den.emb_layer.bias.copy_(T(g["emb_b"]))
+        den.in_layers[0].weight.copy_(T(g["w1"])); den.in_layers[0].bias.copy_(T(g["b1"]))
+        den.out_layers[0].weight.copy_(T(g["w2"])); den.out_layers[0].bias.copy_(T(g["b2"]))
+        den.gate_layer.weight.copy_(T(g["gate_w"])); den.gate_layer.bias.copy_(T(g["gate_b"]))
+    return den
+
+
+def _grads(den):
+    return {"w1": den.in_layers[0].weight.grad, "b1": den.in_layers[0].bias.grad, "w2": den.out_layers[0].weight.grad,
+            "b2": den.out_layers[0].bias.grad, "emb_w": den.emb_layer.weight.grad, "emb_b": den.emb_layer.bias.grad,
+            "gate_w": den.gate_layer.weight.grad, "gate_b": den.gate_layer.bias.grad}
+
+
+def _rel(got, want):
+    want = np.asarray(want, dtype=np.float64)
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_fused_training_step_matches_the_reference_golden(precision, monkeypatch):
+    """training_losses on the hand-scheduled step (train_step.py) against the tensors the UNMODIFIED reference produced
+    (tests/golden/training_losses.npz): per-row float64 losses and all eight Denoise gradients."""
+    from conftest import load_golden
+    from diffmm_b200 import train_step
+    from diffmm_b200.Conf import Config
+    from diffmm_b200.Model import GaussianDiffusion
+    g = load_golden("training_losses")
+    calls = []
+    orig = train_step.denoise_loss
+    monkeypatch.setattr(train_step, "denoise_loss", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    cfg = Config()
+    cfg.base.denoise_dim, cfg.base.precision = f"[{g['w2'].shape[1]}]", precision
+    cfg.hyper.noise_scale, cfg.hyper.sim_weight, cfg.train.reg = 0.5, 0.01, 1e-4
+    den = _denoise_from_golden(cfg, g)
+    gd = GaussianDiffusion(cfg).to(DEV)
+    losses = gd.training_losses(den, T(g["x0"]), T(g["i_embs"]), T(g["feat"]), timesteps=T(g["t"]), noise=T(g["noise"]))
+    assert calls, "the fused step was not selected"
+    assert losses.dtype == torch.float64 and losses.shape == (g["x0"].shape[0],)
+    assert _rel(losses, g["losses"]) <= (2e-4 if precision == "bf16x3" else 1e-1)
+    losses.mean().backward()
+    for k, v in _grads(den).items():
+        assert _rel(v, g[f"g.{k}"]) <= (1e-3 if precision == "bf16x3" else 1e-1), k
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_fused_training_step_equals_the_per_op_path(precision, monkeypatch):
+    """Mid-size problem with ragged dimensions (B = 300, I = 1003, H = 136): fused step vs the per-op autograd path
+    (LinearTN + ATen glue) on the same inputs."""
+    from diffmm_b200.Conf import Config
+    from diffmm_b200.Model import Denoise, GaussianDiffusion
+    B, I, H = 300, 1003, 136
+    rng = np.random.default_rng(1)
+    cfg = Config()
+    cfg.base.denoise_dim, cfg.base.precision = f"[{H}]", precision
+    cfg.hyper.noise_scale = 0.5
+    cfg.data.item_num = I
+    torch.manual_seed(5)
+    gd = GaussianDiffusion(cfg).to(DEV)
+    den = Denoise([I, H], [H, I], cfg).to(DEV)
+    x0 = (rng.random((B, I)) < 0.01).astype(np.float32)
+    feat = T(rng.standard_normal((I, 64)).astype(np.float32) * 0.1)
+    i_embs = T(rng.standard_normal((I, 64)).astype(np.float32) * 0.1)
+    t = T(rng.integers(0, 5, B))
+    noise = T(rng.standard_normal((B, I)).astype(np.float32))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DIFFMM_FUSED_TRAIN", mode)
+        den.zero_grad(set_to_none=True)
+        losses = gd.training_losses(den, T(x0), i_embs, feat, timesteps=t, noise=noise)
+        losses.mean().backward()
+        out[mode] = (losses.detach().clone(), {k: v.detach().clone() for k, v in _grads(den).items()})
+    tol_l, tol_g = (1e-4, 2e-3) if precision == "bf16x3" else (3e-2, 1.5e-1)
+    assert _rel(out["1"][0], out["0"][0].cpu().numpy()) <= tol_l
+    for k in out["1"][1]:
+        assert _rel(out["1"][1][k], out["0"][1][k].cpu().numpy()) <= tol_g, k
