@@ -25,7 +25,7 @@ from torch.optim.adam import Adam
 from torch.optim.lr_scheduler import CosineAnnealingLR
 
 from . import ops, rng
-from .autograd import linear_tn, spmm
+from .autograd import joint_losses, linear_tn, spmm
 from .Conf import Config, load_config
 from .DataHandler import DataHandler
 from .Model import Denoise, GaussianDiffusion, Model, _as_csr
@@ -359,7 +359,9 @@ class Coach:
             gcn_output = self.model.gcn_MM(self.handler.torchBiAdj, self.image_adj, self.text_adj)
         final_user_embs, final_item_embs = gcn_output.u_final_embs, gcn_output.i_final_embs
 
-        rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
+        fused = os.environ.get("DIFFMM_FUSED_LOSS", "1") != "0" and cfg.base.latdim == 64
+        if not fused:
+            rec_loss = bpr_loss(final_user_embs[users], final_item_embs[pos_items], final_item_embs[neg_items])
         reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
 
         # cross-layer CL (Main.py:315-330)
@@ -374,22 +376,37 @@ class Coach:
             if k == 0:
                 all_embs_cl = joint_embs
         final_embs = torch.mean(torch.stack(all_embs), dim=0)
-        cl1_user_embs, cl1_item_embs = final_embs[:U], final_embs[U:]
-        cl2_user_embs, cl2_item_embs = all_embs_cl[:U], all_embs_cl[U:]
-        cl_loss = (InfoNCE(cl1_user_embs, cl2_user_embs, users, cfg.hyper.cross_cl_temp)
-                   + InfoNCE(cl1_item_embs, cl2_item_embs, pos_items, cfg.hyper.cross_cl_temp)) * cfg.hyper.cross_cl_rate
-
         T, R = cfg.hyper.modal_cl_temp, cfg.hyper.modal_cl_rate
-        views = [(gcn_output.u_image_embs, gcn_output.i_image_embs), (gcn_output.u_text_embs, gcn_output.i_text_embs)]
-        if self.has_audio:
-            views.append((gcn_output.u_audio_embs, gcn_output.i_audio_embs))
-        if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
-            pairs = [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else [])
-            for a, b in pairs:
-                cl_loss = cl_loss + (InfoNCE(views[a][0], views[b][0], users, T) + InfoNCE(views[a][1], views[b][1], pos_items, T)) * R
-        else:                            # main view as the anchor (Main.py:351-356,363-367)
-            for vu, vi in views:
-                cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
+        n_mod = 3 if self.has_audio else 2
+        if fused:
+            # every loss term of the step in ONE call (dmm_bpr_infonce_fwd / _bwd): tables = [final, z_image, z_text(,
+            # z_audio), cross-layer mean, cross-layer first]; 'u' terms index user rows, 'i' terms item rows (+U)
+            tables = [gcn_output.final_embs, *gcn_output.modal_embs, final_embs, all_embs_cl]
+            i_mean, i_first = 1 + n_mod, 2 + n_mod
+            Tc, Rc = cfg.hyper.cross_cl_temp, cfg.hyper.cross_cl_rate
+            problems = [(i_mean, i_first, "u", Tc, Rc), (i_mean, i_first, "i", Tc, Rc)]
+            if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
+                for a, b in [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else []):
+                    problems += [(1 + a, 1 + b, "u", T, R), (1 + a, 1 + b, "i", T, R)]
+            else:                            # main view as the anchor (Main.py:351-356,363-367)
+                for m in range(n_mod):
+                    problems += [(0, 1 + m, "u", T, R), (0, 1 + m, "i", T, R)]
+            rec_loss, cl_loss = joint_losses(problems, 0, U, users, pos_items, neg_items, tables)
+        else:
+            cl1_user_embs, cl1_item_embs = final_embs[:U], final_embs[U:]
+            cl2_user_embs, cl2_item_embs = all_embs_cl[:U], all_embs_cl[U:]
+            cl_loss = (InfoNCE(cl1_user_embs, cl2_user_embs, users, cfg.hyper.cross_cl_temp)
+                       + InfoNCE(cl1_item_embs, cl2_item_embs, pos_items, cfg.hyper.cross_cl_temp)) * cfg.hyper.cross_cl_rate
+            views = [(gcn_output.u_image_embs, gcn_output.i_image_embs), (gcn_output.u_text_embs, gcn_output.i_text_embs)]
+            if self.has_audio:
+                views.append((gcn_output.u_audio_embs, gcn_output.i_audio_embs))
+            if cfg.base.cl_method == 1:      # pairwise between modalities (Main.py:345-350,360-362)
+                pairs = [(0, 1)] + ([(0, 2), (1, 2)] if self.has_audio else [])
+                for a, b in pairs:
+                    cl_loss = cl_loss + (InfoNCE(views[a][0], views[b][0], users, T) + InfoNCE(views[a][1], views[b][1], pos_items, T)) * R
+            else:                            # main view as the anchor (Main.py:351-356,363-367)
+                for vu, vi in views:
+                    cl_loss = cl_loss + (InfoNCE(final_user_embs, vu, users, T) + InfoNCE(final_item_embs, vi, pos_items, T)) * R
 
         batch_joint_loss = rec_loss + reg_loss + cl_loss
         self.opt.zero_grad()

@@ -56,6 +56,9 @@ class GCNOutput:
     i_text_embs: Tensor
     u_audio_embs: Optional[Tensor] = None
     i_audio_embs: Optional[Tensor] = None
+    # not in the reference: the un-split [N, 64] node tables (final, then one per modality) for the fused loss call
+    final_embs: Optional[Tensor] = None
+    modal_embs: Optional[list] = None
 
 
 class Model(nn.Module):
@@ -134,6 +137,7 @@ class Model(nn.Module):
         out = GCNOutput(final_embs[:user], final_embs[user:], zs[0][:user], zs[0][user:], zs[1][:user], zs[1][user:])
         if self.audio_embedding is not None:
             out.u_audio_embs, out.i_audio_embs = zs[2][:user], zs[2][user:]
+        out.final_embs, out.modal_embs = final_embs, zs
         return out
 
 

@@ -29,6 +29,17 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class NceProblem(C.Structure):
+    """Mirror of struct dmm_nce_problem."""
+    _fields_ = [("v1", c_vp), ("ld1", c_i64), ("v2", c_vp), ("ld2", c_i64), ("idx", c_vp), ("row_offset", c_i64),
+                ("temperature", c_f32), ("weight", c_f32)]
+
+
+class BprProblem(C.Structure):
+    """Mirror of struct dmm_bpr_problem."""
+    _fields_ = [("emb", c_vp), ("ld_emb", c_i64), ("item_offset", c_i64), ("users", c_vp), ("pos", c_vp), ("neg", c_vp)]
+
+
 # name -> (restype, argtypes); every symbol of include/diffmm_b200.h must appear here
 PROTOTYPES = {
     "dmm_version": (C.c_int, []),
@@ -90,6 +101,11 @@ PROTOTYPES = {
     "dmm_atb_small": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dmm_eval_mask_scores": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_f32, c_vp]),
     "dmm_eval_metrics": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dmm_bpr_infonce_workspace_floats": (c_i64, [c_i64, C.c_int, C.c_int]),
+    "dmm_bpr_infonce_fwd": (C.c_int, [c_vp, C.POINTER(NceProblem), C.c_int, C.POINTER(BprProblem), c_i64, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp]),
+    "dmm_bpr_infonce_bwd": (C.c_int, [c_vp, C.POINTER(NceProblem), C.c_int, C.POINTER(BprProblem), c_i64, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp, C.POINTER(c_vp), C.POINTER(c_i64), c_vp]),
     "dmm_host_neg_sampling": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "dmm_scatter_add_rows": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
 }

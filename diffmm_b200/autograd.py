@@ -269,3 +269,38 @@ class BPRFn(torch.autograd.Function):
     def backward(ctx, g):
         gu, gp, gn = ctx.saved_tensors
         return gu * g, gp * g, gn * g
+
+
+class JointLossFn(torch.autograd.Function):
+    """BPR + every InfoNCE term of a joint-training step (Main.py:309,333,345-367) through dmm_bpr_infonce_fwd / _bwd:
+    three launches forward, three backward, gradients scatter-added into one zeroed table per view.
+
+    forward(spec, users, pos, neg, *tables) -> (bpr_loss, contrastive_total); spec = (problems, bpr_table, item_offset)
+    with problems = [(i1, i2, 'u' | 'i', temperature, weight)] indexing `tables` ([N, 64] fp32 node tables)."""
+
+    @staticmethod
+    def forward(ctx, spec, users, pos, neg, *tables):
+        problems, bpr_table, item_off = spec
+        tabs = [_rows(t.detach()) for t in tables]
+        B = users.numel()
+        probs = [(i1, i2, users if kind == "u" else pos, 0 if kind == "u" else item_off, temp, w)
+                 for (i1, i2, kind, temp, w) in problems]
+        bpr = (bpr_table, item_off, users, pos, neg)
+        losses, saved = ops.bpr_infonce_fwd(tabs, probs, bpr, B)
+        ctx.probs, ctx.bpr, ctx.B, ctx.n_tables = probs, bpr, B, len(tables)
+        ctx.save_for_backward(*tabs, *saved)
+        P = len(probs)
+        return losses[P], losses[P + 1]
+
+    @staticmethod
+    def backward(ctx, g_bpr, g_cl):
+        n = ctx.n_tables
+        tabs, saved = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        grads = [torch.zeros_like(t) if ctx.needs_input_grad[4 + k] else None for k, t in enumerate(tabs)]
+        ops.bpr_infonce_bwd(list(tabs), ctx.probs, ctx.bpr, ctx.B, saved, g_cl.contiguous().float(), g_bpr.contiguous().float(),
+                            grads)
+        return (None, None, None, None, *grads)
+
+
+def joint_losses(problems, bpr_table, item_offset, users, pos, neg, tables):
+    return JointLossFn.apply((problems, bpr_table, item_offset), users, pos, neg, *tables)

@@ -210,14 +210,28 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Batch of InfoNCE problems sharing one launch (blockIdx.z = problem, or 2 * problem + side in the backward): problem p
+// keeps its normalised gathers at n_base + p * 2 B 64 (view 1, then view 2), its lse at lse_base + p B, its forward
+// partials at part_base + p * B JS 3 and its backward partials at gpart_base + p * 2 JS B 64.
+constexpr int NCE_MAX_PROBLEMS = 12;
+struct NceBatch {
+  float inv_temp[NCE_MAX_PROBLEMS];
+};
+
 template <bool FWD>
-__global__ void __launch_bounds__(NT_THREADS) nce_tiles_kernel(const float* __restrict__ n1, const float* __restrict__ n2,
-                                                               int64_t B, int64_t JR, float inv_temp,
-                                                               const float* __restrict__ lse, float* __restrict__ part,
-                                                               float* __restrict__ gpart) {
+__global__ void __launch_bounds__(NT_THREADS) nce_tiles_kernel(const float* __restrict__ n_base, int64_t B, int64_t JR,
+                                                               const NceBatch nb_par, const float* __restrict__ lse_base,
+                                                               float* __restrict__ part_base, float* __restrict__ gpart_base) {
   extern __shared__ __align__(16) uint8_t nce_raw[];
   NceSmem& sm = *reinterpret_cast<NceSmem*>(nce_raw);
-  const int mode = FWD ? 0 : 1 + (int)blockIdx.z;
+  const int prob = FWD ? (int)blockIdx.z : (int)(blockIdx.z >> 1);
+  const int mode = FWD ? 0 : 1 + (int)(blockIdx.z & 1);
+  const float inv_temp = nb_par.inv_temp[prob];
+  const float* __restrict__ n1 = n_base + (int64_t)prob * 2 * B * 64;
+  const float* __restrict__ n2 = n1 + B * 64;
+  const float* __restrict__ lse = lse_base ? lse_base + (int64_t)prob * B : nullptr;
+  float* __restrict__ part = part_base ? part_base + (int64_t)prob * B * gridDim.y * 3 : nullptr;
+  float* __restrict__ gpart = gpart_base ? gpart_base + (int64_t)prob * 2 * gridDim.y * B * 64 : nullptr;
   const float* __restrict__ na = (mode == 2) ? n2 : n1;   // anchors
   const float* __restrict__ nb = (mode == 2) ? n1 : n2;   // stream
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -442,16 +456,16 @@ inline int nce_splits(int64_t B) {
 inline int64_t nce_split_rows(int64_t B, int JS) { return ((B + JS - 1) / JS + NT_J - 1) / NT_J * NT_J; }
 
 template <bool FWD>
-int launch_nce_tiles(const dmm_ctx* ctx, int64_t B, const float* n1, const float* n2, float inv_temp, const float* lse, float* part,
-                     float* gpart, cudaStream_t st) {
+int launch_nce_tiles(const dmm_ctx* ctx, int64_t B, const float* n_base, int n_problems, const NceBatch& batch, const float* lse,
+                     float* part, float* gpart, cudaStream_t st) {
   static DmmPerDeviceOnce attr_once;
   if (attr_once.need(ctx)) {
     DMM_CUDA(cudaFuncSetAttribute(nce_tiles_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NceSmem)));
     attr_once.mark(ctx);
   }
   const int JS = nce_splits(B);
-  dim3 grid((unsigned)dmm_ceil_div(B, NT_I), (unsigned)JS, FWD ? 1u : 2u);
-  nce_tiles_kernel<FWD><<<grid, NT_THREADS, sizeof(NceSmem), st>>>(n1, n2, B, nce_split_rows(B, JS), inv_temp, lse, part, gpart);
+  dim3 grid((unsigned)dmm_ceil_div(B, NT_I), (unsigned)JS, (unsigned)(FWD ? n_problems : 2 * n_problems));
+  nce_tiles_kernel<FWD><<<grid, NT_THREADS, sizeof(NceSmem), st>>>(n_base, B, nce_split_rows(B, JS), batch, lse, part, gpart);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
@@ -516,7 +530,9 @@ extern "C" int dmm_infonce_fwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
   DMM_LAUNCH_CHECK();
   if (D == 64) {
     float* part = workspace + 2 * B * D;     // [B][JS][3]
-    int rc = launch_nce_tiles<true>(ctx, B, n1, n2, 1.f / temperature, nullptr, part, nullptr, st);
+    NceBatch one;
+    one.inv_temp[0] = 1.f / temperature;
+    int rc = launch_nce_tiles<true>(ctx, B, n1, 1, one, nullptr, part, nullptr, st);
     if (rc) return rc;
     nce_fwd_combine_kernel<<<1, 1024, 0, st>>>(part, nce_splits(B), B, 1.f / (float)B, lse, row_loss, loss);
     DMM_LAUNCH_CHECK();
@@ -551,7 +567,9 @@ extern "C" int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const
   const float coef = grad_scale / ((float)B * temperature);
   if (D == 64) {
     float* gpart = workspace + 2 * B * D;    // [2 sides][JS][B][64]
-    int rc = launch_nce_tiles<false>(ctx, B, n1, n2, 1.f / temperature, lse, nullptr, gpart, st);
+    NceBatch one;
+    one.inv_temp[0] = 1.f / temperature;
+    int rc = launch_nce_tiles<false>(ctx, B, n1, 1, one, lse, nullptr, gpart, st);
     if (rc) return rc;
     nce_bwd_combine_kernel<<<(unsigned)dmm_ceil_div(2 * B * 16, 256), 256, 0, st>>>(gpart, nce_splits(B), B, n1, n2, inv1, inv2,
                                                                                   coef, g1, g2);
@@ -569,6 +587,268 @@ extern "C" int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s
   DMM_CHECK_ARG(B >= 0 && D > 0 && ld_s >= D && ld_d >= D, "dmm_scatter_add_rows: bad shape");
   if (B == 0) return DMM_OK;
   scatter_add_rows_kernel<<<(unsigned)dmm_ceil_div(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_s, idx, B, (int)D, dst, ld_d);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+// ================================================================================================ fused BPR + InfoNCE
+// One call for EVERY loss of a joint-training step (Main.py:309,333,345-367: BPR + 2 cross-layer + 2M or 2 C(M,2)
+// modality InfoNCE terms): three launches forward and three backward in total instead of ~3 + 3 per term, plus one
+// scatter of all row gradients.  Views are whole node tables [N, 64]; a problem addresses rows `row_off + idx[b]`.
+namespace {
+
+struct GradTabs {                         // destination tables of the backward scatter, by value in the kernel parameters
+  float* tab[2 * NCE_MAX_PROBLEMS + 1];
+  int64_t ld[2 * NCE_MAX_PROBLEMS + 1];
+};
+
+struct FusedSpec {
+  int n_problems;
+  const float* v1[NCE_MAX_PROBLEMS];
+  const float* v2[NCE_MAX_PROBLEMS];
+  int64_t ld1[NCE_MAX_PROBLEMS], ld2[NCE_MAX_PROBLEMS];
+  int64_t off[NCE_MAX_PROBLEMS];          // row offset of the problem's rows inside both views (0 users, U items)
+  const int64_t* idx[NCE_MAX_PROBLEMS];
+  float weight[NCE_MAX_PROBLEMS];         // rate of the term in the contrastive total
+  float temp[NCE_MAX_PROBLEMS];
+  // BPR on the final embeddings: rows users[b], U + pos[b], U + neg[b] of `emb`
+  const float* emb;
+  int64_t ld_emb, item_off;
+  const int64_t *users, *pos, *neg;
+};
+
+// blockIdx.y < n_problems: gather + L2-normalise both views of problem y (one warp per row); blockIdx.y == n_problems:
+// the BPR rows (loss, and with g_bpr the row gradients scaled by *g_bpr / B)
+__global__ void __launch_bounds__(256) fused_gather_kernel(const FusedSpec sp, int64_t B, float* __restrict__ n_base,
+                                                           float* __restrict__ inv_base, float* __restrict__ bpr_row_loss,
+                                                           const float* __restrict__ g_bpr, float* __restrict__ g_bpr_rows) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int p = blockIdx.y;
+  if (p < sp.n_problems) {
+    const int64_t r = sp.off[p] + sp.idx[p][b];
+    const float* a = sp.v1[p] + r * sp.ld1[p];
+    const float* c = sp.v2[p] + r * sp.ld2[p];
+    const float x0 = __ldg(a + lane), x1 = __ldg(a + 32 + lane), y0 = __ldg(c + lane), y1 = __ldg(c + 32 + lane);
+    const float s1 = dmm_warp_sum(fmaf(x0, x0, x1 * x1)), s2 = dmm_warp_sum(fmaf(y0, y0, y1 * y1));
+    const float i1 = 1.f / fmaxf(sqrtf(s1), 1e-12f), i2 = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+    float* n1 = n_base + (int64_t)p * 2 * B * 64 + b * 64;
+    float* n2 = n1 + B * 64;
+    n1[lane] = x0 * i1;
+    n1[32 + lane] = x1 * i1;
+    n2[lane] = y0 * i2;
+    n2[32 + lane] = y1 * i2;
+    if (lane == 0 && inv_base) {
+      inv_base[(int64_t)p * 2 * B + b] = i1;
+      inv_base[(int64_t)p * 2 * B + B + b] = i2;
+    }
+  } else {
+    const float* u = sp.emb + sp.users[b] * sp.ld_emb;
+    const float* q = sp.emb + (sp.item_off + sp.pos[b]) * sp.ld_emb;
+    const float* n = sp.emb + (sp.item_off + sp.neg[b]) * sp.ld_emb;
+    const float u0 = __ldg(u + lane), u1 = __ldg(u + 32 + lane), p0 = __ldg(q + lane), p1 = __ldg(q + 32 + lane),
+                m0 = __ldg(n + lane), m1 = __ldg(n + 32 + lane);
+    const float x = dmm_warp_sum(fmaf(u0, p0 - m0, u1 * (p1 - m1)));       // u.p - u.n
+    const float s = 1.f / (1.f + expf(-x));
+    if (bpr_row_loss && lane == 0) bpr_row_loss[b] = -logf(10e-6f + s);
+    if (g_bpr_rows) {
+      const float d = -(s * (1.f - s)) / (10e-6f + s) * (*g_bpr) / (float)B;
+      float* gu = g_bpr_rows + b * 64;
+      float* gp = g_bpr_rows + (B + b) * 64;
+      float* gn = g_bpr_rows + (2 * B + b) * 64;
+      gu[lane] = d * (p0 - m0);
+      gu[32 + lane] = d * (p1 - m1);
+      gp[lane] = d * u0;
+      gp[32 + lane] = d * u1;
+      gn[lane] = -d * u0;
+      gn[32 + lane] = -d * u1;
+    }
+  }
+}
+
+// one CTA: per problem the split merge + mean (fixed order), then the BPR mean and the weighted contrastive total
+// losses[0 .. P) = InfoNCE means, losses[P] = BPR, losses[P + 1] = sum_p weight_p * losses[p]
+__global__ void __launch_bounds__(1024) fused_fwd_combine_kernel(const FusedSpec sp, const float* __restrict__ part_base, int JS,
+                                                                 int64_t B, float* __restrict__ lse_base,
+                                                                 const float* __restrict__ bpr_row_loss,
+                                                                 float* __restrict__ losses) {
+  __shared__ float red[32];
+  __shared__ float total;
+  if (threadIdx.x == 0) total = 0.f;
+  for (int p = 0; p <= sp.n_problems; ++p) {
+    float acc = 0.f;
+    if (p < sp.n_problems) {
+      const float* part = part_base + (int64_t)p * B * JS * 3;
+      for (int64_t i = threadIdx.x; i < B; i += 1024) {
+        float M = -INFINITY, dg = -INFINITY;
+        for (int k = 0; k < JS; ++k) {
+          M = fmaxf(M, part[(i * JS + k) * 3]);
+          dg = fmaxf(dg, part[(i * JS + k) * 3 + 2]);
+        }
+        float L = 0.f;
+        for (int k = 0; k < JS; ++k) {
+          const float mk = part[(i * JS + k) * 3], lk = part[(i * JS + k) * 3 + 1];
+          if (lk > 0.f) L += lk * expf(mk - M);
+        }
+        const float lse = M + logf(L);
+        lse_base[(int64_t)p * B + i] = lse;
+        acc += lse - dg;
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < B; i += 1024) acc += bpr_row_loss[i];
+    }
+    acc = dmm_warp_sum(acc);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = dmm_warp_sum(red[threadIdx.x]);
+      if (threadIdx.x == 0) {
+        const float mean = t / (float)B;
+        losses[p] = mean;
+        if (p < sp.n_problems) total += sp.weight[p] * mean;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) losses[sp.n_problems + 1] = total;
+}
+
+// partial gradients -> row gradients (normalisation backward, coef = weight_p g_cl / (B T_p)) scattered straight into the
+// gradient tables of the views (atomicAdd: indices repeat inside a batch); z = 2 p + side.  The last z slot scatters the
+// three BPR row-gradient blocks.  One half warp per row.
+__global__ void __launch_bounds__(256) fused_bwd_scatter_kernel(const FusedSpec sp, const float* __restrict__ gpart_base, int JS,
+                                                                int64_t B, const float* __restrict__ n_base,
+                                                                const float* __restrict__ inv_base,
+                                                                const float* __restrict__ g_cl,
+                                                                const float* __restrict__ g_bpr_rows, const GradTabs gt) {
+  const int64_t x = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+  const int z = blockIdx.y;
+  if (z < 2 * sp.n_problems) {
+    if (x >= B) return;
+    const int p = z >> 1, side = z & 1;
+    float* dst = gt.tab[z];
+    if (!dst) return;
+    const float* gpart = gpart_base + (int64_t)p * 2 * JS * B * 64;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < JS; ++k) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(gpart + (((int64_t)side * JS + k) * B + x) * 64) + l16);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    const float4 n = __ldg(reinterpret_cast<const float4*>(n_base + (int64_t)p * 2 * B * 64 + (int64_t)side * B * 64 + x * 64) + l16);
+    float dot = n.x * g.x + n.y * g.y + n.z * g.z + n.w * g.w;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
+    const float sc = inv_base[(int64_t)p * 2 * B + (int64_t)side * B + x] * sp.weight[p] * (*g_cl) / ((float)B * sp.temp[p]);
+    float* row = dst + (sp.off[p] + sp.idx[p][x]) * gt.ld[z] + 4 * l16;
+    atomicAdd(row + 0, sc * (g.x - n.x * dot));
+    atomicAdd(row + 1, sc * (g.y - n.y * dot));
+    atomicAdd(row + 2, sc * (g.z - n.z * dot));
+    atomicAdd(row + 3, sc * (g.w - n.w * dot));
+  } else {
+    if (x >= 3 * B) return;
+    float* dst = gt.tab[z];
+    if (!dst) return;
+    const int kind = (int)(x / B);
+    const int64_t b = x - (int64_t)kind * B;
+    const int64_t r = kind == 0 ? sp.users[b] : sp.item_off + (kind == 1 ? sp.pos[b] : sp.neg[b]);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(g_bpr_rows + x * 64) + l16);
+    float* row = dst + r * gt.ld[z] + 4 * l16;
+    atomicAdd(row + 0, q.x);
+    atomicAdd(row + 1, q.y);
+    atomicAdd(row + 2, q.z);
+    atomicAdd(row + 3, q.w);
+  }
+}
+
+int fill_spec(FusedSpec& sp, const dmm_nce_problem* problems, int n_problems, const dmm_bpr_problem* bpr) {
+  sp.n_problems = n_problems;
+  for (int p = 0; p < n_problems; ++p) {
+    const dmm_nce_problem& q = problems[p];
+    DMM_CHECK_ARG(q.v1 && q.v2 && q.idx && q.ld1 >= 64 && q.ld2 >= 64 && q.temperature > 0.f && q.row_offset >= 0,
+                  "dmm_bpr_infonce: bad problem %d", p);
+    sp.v1[p] = q.v1; sp.v2[p] = q.v2; sp.ld1[p] = q.ld1; sp.ld2[p] = q.ld2; sp.off[p] = q.row_offset; sp.idx[p] = q.idx;
+    sp.weight[p] = q.weight; sp.temp[p] = q.temperature;
+  }
+  DMM_CHECK_ARG(bpr && bpr->emb && bpr->users && bpr->pos && bpr->neg && bpr->ld_emb >= 64, "dmm_bpr_infonce: bad BPR problem");
+  sp.emb = bpr->emb; sp.ld_emb = bpr->ld_emb; sp.item_off = bpr->item_offset;
+  sp.users = bpr->users; sp.pos = bpr->pos; sp.neg = bpr->neg;
+  return DMM_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t dmm_bpr_infonce_workspace_floats(int64_t B, int n_problems, int backward) {
+  const int64_t P = n_problems;
+  int64_t n = P * 2 * B * 64;                                   // normalised gathers
+  if (backward) n += P * 2 * (int64_t)nce_splits(B) * B * 64 + 3 * B * 64;    // gradient partials + BPR row gradients
+  else n += P * 3 * (int64_t)nce_splits(B) * B + B;            // forward partials + BPR row losses
+  return n;
+}
+
+extern "C" int dmm_bpr_infonce_fwd(dmm_ctx* ctx, const dmm_nce_problem* problems, int n_problems, const dmm_bpr_problem* bpr,
+                                   int64_t B, float* workspace, float* losses, float* lse, float* inv, void* stream) {
+  DMM_CHECK_ARG(ctx && problems && workspace && losses && lse && inv, "dmm_bpr_infonce_fwd: null argument");
+  DMM_CHECK_ARG(n_problems >= 1 && n_problems <= NCE_MAX_PROBLEMS && B > 0, "dmm_bpr_infonce_fwd: 1..%d problems", NCE_MAX_PROBLEMS);
+  FusedSpec sp;
+  int rc = fill_spec(sp, problems, n_problems, bpr);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* n_base = workspace;
+  float* part = workspace + (int64_t)n_problems * 2 * B * 64;
+  float* bpr_rows = part + (int64_t)n_problems * 3 * nce_splits(B) * B;
+  fused_gather_kernel<<<dim3((unsigned)dmm_ceil_div(B * 32, 256), (unsigned)(n_problems + 1)), 256, 0, st>>>(
+      sp, B, n_base, inv, bpr_rows, nullptr, nullptr);
+  DMM_LAUNCH_CHECK();
+  NceBatch batch;
+  for (int p = 0; p < n_problems; ++p) batch.inv_temp[p] = 1.f / problems[p].temperature;
+  rc = launch_nce_tiles<true>(ctx, B, n_base, n_problems, batch, nullptr, part, nullptr, st);
+  if (rc) return rc;
+  fused_fwd_combine_kernel<<<1, 1024, 0, st>>>(sp, part, nce_splits(B), B, lse, bpr_rows, losses);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_bpr_infonce_bwd(dmm_ctx* ctx, const dmm_nce_problem* problems, int n_problems, const dmm_bpr_problem* bpr,
+                                   int64_t B, const float* lse, const float* inv, const float* g_cl, const float* g_bpr,
+                                   float* workspace, float* const* grad_tables, const int64_t* grad_ld, void* stream) {
+  DMM_CHECK_ARG(ctx && problems && lse && inv && g_cl && g_bpr && workspace && grad_tables && grad_ld,
+                "dmm_bpr_infonce_bwd: null argument");
+  DMM_CHECK_ARG(n_problems >= 1 && n_problems <= NCE_MAX_PROBLEMS && B > 0, "dmm_bpr_infonce_bwd: 1..%d problems", NCE_MAX_PROBLEMS);
+  FusedSpec sp;
+  int rc = fill_spec(sp, problems, n_problems, bpr);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* n_base = workspace;
+  float* gpart = workspace + (int64_t)n_problems * 2 * B * 64;
+  float* g_bpr_rows = gpart + (int64_t)n_problems * 2 * nce_splits(B) * B * 64;
+  // the normalised gathers are recomputed (cheaper than keeping them alive across the step); the BPR slot writes its
+  // row gradients
+  fused_gather_kernel<<<dim3((unsigned)dmm_ceil_div(B * 32, 256), (unsigned)(n_problems + 1)), 256, 0, st>>>(
+      sp, B, n_base, nullptr, nullptr, g_bpr, g_bpr_rows);
+  DMM_LAUNCH_CHECK();
+  NceBatch batch;
+  for (int p = 0; p < n_problems; ++p) batch.inv_temp[p] = 1.f / problems[p].temperature;
+  rc = launch_nce_tiles<false>(ctx, B, n_base, n_problems, batch, lse, nullptr, gpart, st);
+  if (rc) return rc;
+  GradTabs gt;
+  for (int i = 0; i < 2 * NCE_MAX_PROBLEMS + 1; ++i) {
+    gt.tab[i] = nullptr;
+    gt.ld[i] = 0;
+  }
+  for (int i = 0; i < 2 * n_problems; ++i) {
+    gt.tab[i] = grad_tables[i];
+    gt.ld[i] = grad_ld[i];
+    DMM_CHECK_ARG(!gt.tab[i] || gt.ld[i] >= 64, "dmm_bpr_infonce_bwd: gradient table %d needs ld >= 64", i);
+  }
+  // the BPR slot of the kernel is z = 2 P; the caller passes it as entry 2 P of its arrays
+  float* bpr_tab = grad_tables[2 * n_problems];
+  const int64_t bpr_ld = grad_ld[2 * n_problems];
+  fused_bwd_scatter_kernel<<<dim3((unsigned)dmm_ceil_div(3 * B * 16, 256), (unsigned)(2 * n_problems + 1)), 256, 0, st>>>(
+      sp, gpart, nce_splits(B), B, n_base, inv, g_cl, g_bpr_rows, [&]() { gt.tab[2 * n_problems] = bpr_tab; gt.ld[2 * n_problems] = bpr_ld; return gt; }());
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

@@ -470,3 +470,57 @@ def atb_small(x, y):
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
     _lib.call("dmm_atb_small", _ctx(x), _p(x), _row_major(x, "x"), m, _p(y), _row_major(y, "y"), n, R, _p(ws), _p(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------- fused BPR + InfoNCE
+def _loss_structs(tables, problems, bpr):
+    """problems: [(i1, i2, idx, row_offset, temperature, weight)] over `tables`; bpr: (i_table, item_offset, users, pos, neg)."""
+    P = len(problems)
+    arr = (_lib.NceProblem * P)()
+    for k, (i1, i2, idx, off, temp, weight) in enumerate(problems):
+        a, b = tables[i1], tables[i2]
+        arr[k].v1, arr[k].ld1 = a.data_ptr(), _row_major(a, "view")
+        arr[k].v2, arr[k].ld2 = b.data_ptr(), _row_major(b, "view")
+        arr[k].idx, arr[k].row_offset = idx.data_ptr(), int(off)
+        arr[k].temperature, arr[k].weight = float(temp), float(weight)
+    it, item_off, users, pos, neg = bpr
+    bp = _lib.BprProblem()
+    bp.emb, bp.ld_emb, bp.item_offset = tables[it].data_ptr(), _row_major(tables[it], "emb"), int(item_off)
+    bp.users, bp.pos, bp.neg = users.data_ptr(), pos.data_ptr(), neg.data_ptr()
+    return arr, bp
+
+
+def bpr_infonce_fwd(tables, problems, bpr, B):
+    """Every loss of a joint step in three launches.  Returns (losses [P + 2]: InfoNCE means, BPR, weighted contrastive
+    total; saved = (lse [P, B], inv [P, 2, B]))."""
+    P = len(problems)
+    dev = tables[0].device
+    arr, bp = _loss_structs(tables, problems, bpr)
+    ws = torch.empty(int(_lib.load().dmm_bpr_infonce_workspace_floats(B, P, 0)), dtype=torch.float32, device=dev)
+    losses = torch.empty(P + 2, dtype=torch.float32, device=dev)
+    lse = torch.empty((P, B), dtype=torch.float32, device=dev)
+    inv = torch.empty((P, 2, B), dtype=torch.float32, device=dev)
+    _lib.call("dmm_bpr_infonce_fwd", _ctx(tables[0]), arr, P, C.byref(bp), int(B), _p(ws), _p(losses), _p(lse), _p(inv), _stream())
+    return losses, (lse, inv)
+
+
+def bpr_infonce_bwd(tables, problems, bpr, B, saved, g_cl, g_bpr, grad_tables):
+    """Scatter-adds d(g_bpr BPR + g_cl total) into grad_tables (one zeroed fp32 [N, 64] tensor or None per table)."""
+    P = len(problems)
+    dev = tables[0].device
+    arr, bp = _loss_structs(tables, problems, bpr)
+    lse, inv = saved
+    ws = torch.empty(int(_lib.load().dmm_bpr_infonce_workspace_floats(B, P, 1)), dtype=torch.float32, device=dev)
+    ptrs = (C.c_void_p * (2 * P + 1))()
+    lds = (C.c_int64 * (2 * P + 1))()
+    slots = [(i1, i2) for (i1, i2, *_rest) in problems]
+    for k, (i1, i2) in enumerate(slots):
+        for s, it in enumerate((i1, i2)):
+            g = grad_tables[it]
+            ptrs[2 * k + s] = g.data_ptr() if g is not None else None
+            lds[2 * k + s] = _row_major(g, "grad") if g is not None else 0
+    gb = grad_tables[bpr[0]]
+    ptrs[2 * P] = gb.data_ptr() if gb is not None else None
+    lds[2 * P] = _row_major(gb, "grad") if gb is not None else 0
+    _lib.call("dmm_bpr_infonce_bwd", _ctx(tables[0]), arr, P, C.byref(bp), int(B), _p(lse), _p(inv), _p(g_cl), _p(g_bpr), _p(ws),
+              ptrs, lds, _stream())

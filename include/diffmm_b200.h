@@ -271,6 +271,37 @@ int dmm_infonce_bwd(dmm_ctx* ctx, const float* v1, int64_t ld1, const float* v2,
                     const float* lse, const float* inv1, const float* inv2, float grad_scale,
                     float* workspace, float* g1, float* g2, void* stream);
 
+/* ---- every loss of a joint-training step in one call (Main.py:309,333,345-367) -----------------------------------
+ * BPR on the final embeddings plus up to 12 InfoNCE terms (2 cross-layer + 2 M or 2 C(M, 2) modality terms), D = 64.
+ * A view is a whole node table [N, ld >= 64] (fp32); a term compares rows row_offset + idx[b] of v1 and v2 (row_offset
+ * 0 for the user rows, n_users for the item rows) at `temperature` and enters the contrastive total with `weight`.
+ * Forward (3 launches): losses[0 .. P) = the InfoNCE means, losses[P] = BPR, losses[P + 1] = sum_p weight_p losses[p];
+ *   lse [P, B] and inv [P, 2, B] are kept for the backward.
+ * Backward (3 launches): d(g_bpr * BPR + g_cl * contrastive total) is scatter-ADDED (atomicAdd) into the caller-zeroed
+ *   gradient tables: grad_tables[2 p] / [2 p + 1] (HOST array of device pointers, leading dimensions grad_ld) receive
+ *   the rows of v1 / v2 of term p, grad_tables[2 P] the three BPR row blocks; NULL entries are skipped.  g_cl / g_bpr
+ *   are DEVICE scalars (the upstream gradients), so no host sync is needed.
+ * `problems` and `bpr` are HOST structs (copied into the kernel parameters).
+ * Replaces one bpr_loss and 4-8 InfoNCE calls of Utils/Utils.py:57-98 per step.                                  */
+typedef struct dmm_nce_problem {
+  const float* v1; int64_t ld1;
+  const float* v2; int64_t ld2;
+  const int64_t* idx;     /* [B] device */
+  int64_t row_offset;
+  float temperature, weight;
+} dmm_nce_problem;
+typedef struct dmm_bpr_problem {
+  const float* emb; int64_t ld_emb;      /* final embeddings [N, ld]: users first, items from item_offset */
+  int64_t item_offset;
+  const int64_t *users, *pos, *neg;      /* [B] device */
+} dmm_bpr_problem;
+int64_t dmm_bpr_infonce_workspace_floats(int64_t B, int n_problems, int backward);
+int dmm_bpr_infonce_fwd(dmm_ctx* ctx, const dmm_nce_problem* problems, int n_problems, const dmm_bpr_problem* bpr, int64_t B,
+                        float* workspace, float* losses, float* lse, float* inv, void* stream);
+int dmm_bpr_infonce_bwd(dmm_ctx* ctx, const dmm_nce_problem* problems, int n_problems, const dmm_bpr_problem* bpr, int64_t B,
+                        const float* lse, const float* inv, const float* g_cl, const float* g_bpr, float* workspace,
+                        float* const* grad_tables, const int64_t* grad_ld, void* stream);
+
 /* Scatter-add of per-batch row gradients into a table gradient: dst[idx[b], :] += src[b, :]. */
 int dmm_scatter_add_rows(dmm_ctx* ctx, const float* src, int64_t ld_s, const int64_t* idx, int64_t B,
                          int64_t D, float* dst, int64_t ld_d, void* stream);

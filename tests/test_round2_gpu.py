@@ -256,14 +256,16 @@ def test_fused_training_step_matches_the_reference_golden(precision, monkeypatch
     from diffmm_b200 import train_step
     from diffmm_b200.Conf import Config
     from diffmm_b200.Model import GaussianDiffusion
+    from conftest import params_of
     g = load_golden("training_losses")
     calls = []
     orig = train_step.denoise_loss
     monkeypatch.setattr(train_step, "denoise_loss", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
     cfg = Config()
-    cfg.base.denoise_dim, cfg.base.precision = f"[{g['w2'].shape[1]}]", precision
+    pp = params_of(g)
+    cfg.base.denoise_dim, cfg.base.precision = f"[{pp['w2'].shape[1]}]", precision
     cfg.hyper.noise_scale, cfg.hyper.sim_weight, cfg.train.reg = 0.5, 0.01, 1e-4
-    den = _denoise_from_golden(cfg, g)
+    den = _denoise_from_golden(cfg, pp)
     gd = GaussianDiffusion(cfg).to(DEV)
     losses = gd.training_losses(den, T(g["x0"]), T(g["i_embs"]), T(g["feat"]), timesteps=T(g["t"]), noise=T(g["noise"]))
     assert calls, "the fused step was not selected"
@@ -305,3 +307,48 @@ def test_fused_training_step_equals_the_per_op_path(precision, monkeypatch):
     assert _rel(out["1"][0], out["0"][0].cpu().numpy()) <= tol_l
     for k in out["1"][1]:
         assert _rel(out["1"][1][k], out["0"][1][k].cpu().numpy()) <= tol_g, k
+
+
+# ---------------------------------------------------------------------------------------------- fused BPR + InfoNCE
+@pytest.mark.parametrize("B,n_mod,cl_method", [(1024, 3, 0), (700, 2, 1), (33, 2, 0)])
+def test_fused_joint_losses_equal_the_per_term_losses(B, n_mod, cl_method):
+    """dmm_bpr_infonce_fwd / _bwd (all terms of a joint step in one call) vs bpr_loss + InfoNCE term by term
+    (Utils/Utils.py:57-98, themselves golden-tested against the reference): values and table gradients."""
+    from diffmm_b200.autograd import joint_losses
+    from diffmm_b200.Utils.Utils import InfoNCE, bpr_loss
+    U, I = 900, 500
+    N = U + I
+    g = torch.Generator(device=DEV).manual_seed(B)
+    tabs = [torch.randn((N, 64), device=DEV, generator=g).requires_grad_(True) for _ in range(n_mod + 3)]
+    users = torch.randint(0, U, (B,), device=DEV, generator=g)
+    pos = torch.randint(0, I, (B,), device=DEV, generator=g)
+    neg = torch.randint(0, I, (B,), device=DEV, generator=g)
+    Tc, Rc, T, R = 0.2, 0.5, 0.5, 0.01
+    i_mean, i_first = 1 + n_mod, 2 + n_mod
+    problems = [(i_mean, i_first, "u", Tc, Rc), (i_mean, i_first, "i", Tc, Rc)]
+    if cl_method == 1:
+        for a, b in [(0, 1)] + ([(0, 2), (1, 2)] if n_mod == 3 else []):
+            problems += [(1 + a, 1 + b, "u", T, R), (1 + a, 1 + b, "i", T, R)]
+    else:
+        for m in range(n_mod):
+            problems += [(0, 1 + m, "u", T, R), (0, 1 + m, "i", T, R)]
+    rec, cl = joint_losses(problems, 0, U, users, pos, neg, tabs)
+    (rec * 1.7 + cl * 0.9).backward()
+    got = [t.grad.clone() for t in tabs]
+    for t in tabs:
+        t.grad = None
+    fin = tabs[0]
+    rec_w = bpr_loss(fin[:U][users], fin[U:][pos], fin[U:][neg])
+    cl_w = 0.0
+    for (i1, i2, kind, temp, w) in problems:
+        a, b = tabs[i1], tabs[i2]
+        if kind == "u":
+            cl_w = cl_w + InfoNCE(a[:U], b[:U], users, temp) * w
+        else:
+            cl_w = cl_w + InfoNCE(a[U:], b[U:], pos, temp) * w
+    (rec_w * 1.7 + cl_w * 0.9).backward()
+    assert float((rec - rec_w).abs()) <= 2e-6 * max(1.0, float(rec_w.abs()))
+    assert float((cl - cl_w).abs()) <= 1e-5 * max(1.0, float(cl_w.abs()))
+    for k, t in enumerate(tabs):
+        scale = float(t.grad.abs().max()) + 1e-30
+        assert float((got[k] - t.grad).abs().max()) <= 2e-5 * scale, k
