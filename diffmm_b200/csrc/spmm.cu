@@ -14,6 +14,8 @@
 // HBM-bound: 8*nnz + 8*(N+1) + 2*N*D*4 bytes per product when X is not L2 resident.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int SPMM_THREADS = 256;
@@ -396,12 +398,12 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_reduce_kernel(int64_t row
     if (ce - cb <= REDUCE_SMALL || r < row0 || r >= row1) continue;     // block-uniform
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t c = cb + hw;
-    for (; c + 3 * NHW < ce; c += 4 * NHW) {
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16);
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(partial + (c + NHW) * 64) + l16);
-      const float4 p2 = __ldg(reinterpret_cast<const float4*>(partial + (c + 2 * NHW) * 64) + l16);
-      const float4 p3 = __ldg(reinterpret_cast<const float4*>(partial + (c + 3 * NHW) * 64) + l16);
-      acc = add4(add4(add4(add4(acc, p0), p1), p2), p3);
+    for (; c + 7 * NHW < ce; c += 8 * NHW) {      // 8 partial rows in flight per half warp (the longest row sets the tail)
+      float4 p[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) p[t] = __ldg(reinterpret_cast<const float4*>(partial + (c + t * NHW) * 64) + l16);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc = add4(acc, p[t]);
     }
     for (; c < ce; c += NHW) acc = add4(acc, __ldg(reinterpret_cast<const float4*>(partial + c * 64) + l16));
     part[hw][l16] = acc;
@@ -414,6 +416,103 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_reduce_kernel(int64_t row
     }
     __syncthreads();
   }
+}
+
+// ---- D == 64, lean kernels (v2) ---------------------------------------------------------------------------
+// The persistent kernel above hides the row -> ids -> gathers latency chain with a software pipeline and pays for it in
+// instructions: ncu (profiles/r02_prof_spmm_before.txt) counts 22 warp instructions per stored entry, 13 % of them FFMA,
+// the SMs 52 % busy issuing while DRAM and L2 idle at 24 % / 25 %.  Here latency is hidden by OCCUPANCY instead
+// (14-17 instructions per entry; 252 -> 230 us at the ifashion shape.  What bounds it now is per-entry issue + latency, not
+// bytes: an L2-resident graph of a third of the size and a bf16 gather table both run at the same ~43 ns per 1000 entries;
+// a variant that walked 4 rows per half warp as one entry stream, with a quarter of the dependent round trips, measured
+// equal and was dropped):
+// one half warp per short row (or per 64-neighbour chunk of a long row), 32 registers, 64 resident warps per SM, no
+// cross-row pipeline, 32-bit offsets, and no predicates in the gather: the tail of a 16-neighbour block is padded with
+// (column 0, value 0) so every group of four gathers is issued unconditionally (the padding reads hit one hot line).
+// Ids / values / row pointers are streamed with evict-first loads and Y leaves through streaming stores, so the 126 MB
+// L2 keeps X (97 MB at the ifashion shape) instead of thrashing it with write-once / read-once data.
+// one lane's 4 columns of row c of the gather table: fp32 [N, 64] (16 B per lane) or bf16 [N, 64] (8 B per lane: half
+// the bytes through the L2 and a table that fits it)
+template <bool B16>
+__device__ __forceinline__ float4 load_row4(const void* __restrict__ xt, uint32_t ldu, uint32_t c, int l16) {
+  if constexpr (B16) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(xt) + (size_t)(c * ldu + (uint32_t)l16));
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xFFFF0000u));
+  } else {
+    return __ldg(reinterpret_cast<const float4*>(xt) + (size_t)(c * ldu + (uint32_t)l16));
+  }
+}
+
+template <bool B16>
+__device__ __forceinline__ float4 gather64_lean(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                                const void* __restrict__ x4, uint32_t ld4, uint32_t b, int n, int l16,
+                                                uint32_t hmask) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int base = 0; base < n; base += 16) {
+    const int cnt = n - base < 16 ? n - base : 16;
+    const bool in = l16 < cnt;
+    const uint32_t my_c = in ? (uint32_t)__ldcs(idx + b + base + l16) : 0u;
+    const float my_v = in ? __ldcs(val + b + base + l16) : 0.f;
+#pragma unroll 1
+    for (int h = 0; h < cnt; h += 4) {
+      float4 xs[4];
+      float vs[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t c = __shfl_sync(hmask, my_c, h + t, 16);
+        vs[t] = __shfl_sync(hmask, my_v, h + t, 16);
+        xs[t] = load_row4<B16>(x4, ld4, c, l16);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc = fma4(vs[t], xs[t], acc);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void store_row_cs(float* __restrict__ y, int64_t ld_y, int64_t r, int l16, const float4& acc,
+                                             const Epi& ep) {
+  float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
+  if (ep.z) {
+    const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
+    o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
+  }
+  __stcs(reinterpret_cast<float4*>(y + r * ld_y) + l16, o);
+}
+
+// one half warp per row of [row0, row1); rows longer than PLAN_LONG_ROW belong to the chunk kernel
+template <bool B16>
+__global__ void __launch_bounds__(256, 6) spmm64_rows_lean_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                                  const float* __restrict__ val, int64_t row0, int64_t row1,
+                                                                  const void* __restrict__ x4, uint32_t ld4, Epi ep,
+                                                                  float* __restrict__ y, int64_t ld_y) {
+  const int64_t r = row0 + (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4);
+  if (r >= row1) return;
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+  const int64_t b = __ldcs(ptr + r);
+  const int64_t len = __ldcs(ptr + r + 1) - b;
+  if (len > PLAN_LONG_ROW) return;
+  const float4 acc = gather64_lean<B16>(idx, val, x4, ld4, (uint32_t)b, (int)len, l16, hmask);
+  store_row_cs(y, ld_y, r, l16, acc, ep);
+}
+
+// one half warp per 64-neighbour chunk of the planned (long) rows: partial[c, :] = A[row, chunk] . X
+template <bool B16>
+__global__ void __launch_bounds__(256, 6) spmm64_chunks_lean_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                                                    int64_t row0, int64_t row1, const void* __restrict__ x4,
+                                                                    uint32_t ld4, const int64_t* __restrict__ plan, int64_t cap,
+                                                                    float* __restrict__ partial) {
+  const int64_t c = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
+  if (c >= plan[1]) return;
+  const int l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
+  const int4 d = __ldg(reinterpret_cast<const int4*>(plan + plan_desc_word(cap)) + c);
+  if (d.x < row0 || d.x >= row1) return;
+  const float4 acc = gather64_lean<B16>(idx, val, x4, ld4, (uint32_t)d.z, d.y, l16, hmask);
+  reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
 }
 
 // ---- generic D (multiple of 4, <= 256): one warp per row, lanes stride the float4 columns ----------
@@ -493,6 +592,45 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
   return DMM_OK;
 }
 
+namespace {
+// lean path: short rows (one per half warp), chunks of the long rows, fixed-order reduce
+template <bool B16>
+int launch_lean(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val, int64_t row0, int64_t row1,
+                const void* xt, uint32_t ldu, const Epi& ep, float* y, int64_t ld_y, const void* plan, int64_t nnz,
+                void* workspace, cudaStream_t st) {
+  const int64_t cap = plan_cap(nnz);
+  spmm64_rows_lean_kernel<B16><<<(unsigned)dmm_ceil_div((row1 - row0) * 16, 256), 256, 0, st>>>(adj_ptr, adj_idx, adj_val, row0,
+                                                                                               row1, xt, ldu, ep, y, ld_y);
+  DMM_LAUNCH_CHECK();
+  const int64_t max_chunks = plan_max_chunks(nnz);
+  spmm64_chunks_lean_kernel<B16><<<(unsigned)dmm_ceil_div(max_chunks * 16, 256), 256, 0, st>>>(
+      adj_idx, adj_val, row0, row1, xt, ldu, (const int64_t*)plan, cap, (float*)workspace);
+  DMM_LAUNCH_CHECK();
+  spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 4), SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+                                                                       (const float*)workspace, ep, y, ld_y);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+}  // namespace
+
+extern "C" int dmm_spmm_csr_bf16x(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
+                                  int64_t row0, int64_t row1, const uint16_t* x_bf16, int64_t ld_x, float alpha, float beta,
+                                  const float* z, int64_t ld_z, float* y, int64_t ld_y, const void* plan, int64_t nnz,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  DMM_CHECK_ARG(ctx && adj_ptr && adj_idx && adj_val && x_bf16 && y && plan && workspace, "dmm_spmm_csr_bf16x: null argument");
+  DMM_CHECK_ARG(ld_x % 4 == 0 && ld_x >= 64 && ld_x / 4 < (1LL << 20) && ld_y % 4 == 0 && ld_y >= 64 &&
+                    (!z || (ld_z % 4 == 0 && ld_z >= 64)),
+                "dmm_spmm_csr_bf16x: D is 64; leading dimensions must be multiples of 4");
+  DMM_CHECK_ARG((reinterpret_cast<uintptr_t>(x_bf16) & 7u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
+                "dmm_spmm_csr_bf16x: X must be 8-byte and Y 16-byte aligned");
+  DMM_CHECK_ARG(row0 >= 0 && row1 >= row0 && nnz < (1LL << 31), "dmm_spmm_csr_bf16x: bad row range / nnz");
+  DMM_CHECK_ARG(workspace_bytes >= dmm_spmm_workspace_bytes(nnz, 64), "dmm_spmm_csr_bf16x: workspace too small");
+  if (row1 == row0) return DMM_OK;
+  const Epi ep{alpha, z ? beta : 0.f, z, ld_z};
+  return launch_lean<true>(ctx, adj_ptr, adj_idx, adj_val, row0, row1, x_bf16, (uint32_t)(ld_x / 4), ep, y, ld_y, plan, nnz,
+                           workspace, (cudaStream_t)stream);
+}
+
 extern "C" int64_t dmm_spmm_workspace_bytes(int64_t nnz, int64_t D) {
   if (D != 64) return 0;
   // chunks <= nnz / PLAN_CHUNK + (#planned rows <= nnz / PLAN_LONG_ROW + 1)
@@ -522,6 +660,12 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
       spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, 0);
     } else {
       const int64_t cap = plan_cap(nnz);
+      static const bool lean = []() { const char* e = getenv("DMM_SPMM_V2"); return !(e && e[0] == '0'); }();   // A/B switch
+      const int64_t n_nodes_x = 0;
+      (void)n_nodes_x;
+      if (lean && nnz < (1LL << 31) && ld_x % 4 == 0 && ld_x / 4 < (1LL << 20))
+        return launch_lean<false>(ctx, adj_ptr, adj_idx, adj_val, row0, row1, x, (uint32_t)(ld_x / 4), ep, y, ld_y, plan, nnz,
+                                  workspace, st);
       static std::atomic<int> resident_cache{0};   // CTAs of the persistent kernel per SM (same for every sm_100 device)
       int resident = resident_cache.load(std::memory_order_relaxed);
       if (resident == 0) {

@@ -352,3 +352,33 @@ def test_fused_joint_losses_equal_the_per_term_losses(B, n_mod, cl_method):
     for k, t in enumerate(tabs):
         scale = float(t.grad.abs().max()) + 1e-30
         assert float((got[k] - t.grad).abs().max()) <= 2e-5 * scale, k
+
+
+# ---------------------------------------------------------------------------------------------- SpMM variants
+def test_spmm_lean_kernels_row_ranges_and_bf16_table(ops):
+    """Round-2 SpMM kernels (one half warp per short row, chunked long rows) on a graph with heavy rows: whole product
+    and row-block calls vs the numpy oracle; the bf16 gather table variant within bf16 rounding of the operand."""
+    from diffmm_b200 import synth
+    U, I = 3000, 800
+    inter = synth.interactions(U, I, seed=5, mean_deg=7.0, heavy_frac=0.03)
+    ptr, idx = T(inter.indptr), T(inter.indices)
+    adj = ops.build_norm_adj(ptr, idx, U, I)
+    N = U + I
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((N, 64)).astype(np.float32)
+    want = O.spmm_csr(adj.ptr.cpu().numpy(), adj.idx.cpu().numpy(), adj.val.cpu().numpy(), x)
+    xd = T(x)
+    y = ops.spmm(adj, xd).cpu().numpy()
+    np.testing.assert_allclose(y, want, rtol=2e-5, atol=2e-6)
+    out = torch.full((N, 64), float("nan"), device=DEV)
+    for a, b in [(0, 1000), (1000, U), (U, U + 300), (U + 300, N)]:
+        ops.spmm(adj, xd, out=out, row0=a, row1=b)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-5, atol=2e-6)
+    z = T(rng.standard_normal((N, 64)).astype(np.float32))
+    y2 = ops.spmm(adj, xd, alpha=0.5, beta=2.0, z=z).cpu().numpy()
+    np.testing.assert_allclose(y2, 0.5 * want + 2.0 * z.cpu().numpy(), rtol=3e-5, atol=3e-6)
+    y16 = ops.spmm_bf16x(adj, xd).cpu().numpy()
+    assert np.abs(y16 - want).max() <= 6e-3 * np.abs(want).max()
+    x_r = torch.from_numpy(x).bfloat16().float().numpy()          # the rounded table, exactly
+    want16 = O.spmm_csr(adj.ptr.cpu().numpy(), adj.idx.cpu().numpy(), adj.val.cpu().numpy(), x_r)
+    np.testing.assert_allclose(y16, want16, rtol=2e-5, atol=2e-6)

@@ -1,0 +1,42 @@
+"""SpMM variants on the ifashion-shaped graph (CUDA events, median of 10): fp32 gather table (groups / rows kernels), bf16
+gather table with and without the conversion pass inside the timed call, and an L2-resident control (same nnz per row,
+fewer nodes)."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, '.')
+from diffmm_b200 import ops, synth
+DEV = 'cuda:0'
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def run(U, I, label):
+    inter = synth.interactions(U, I, seed=0)
+    ptr = torch.from_numpy(inter.indptr).to(DEV); idx = torch.from_numpy(inter.indices).to(DEV)
+    adj = ops.build_norm_adj(ptr, idx, U, I)
+    N = U + I
+    x = torch.randn((N, 64), device=DEV); y = torch.empty_like(x)
+    by = 8.0 * adj.nnz + 8.0 * (N + 1) + 2.0 * N * 64 * 4
+    ms = timeit(lambda: ops.spmm(adj, x, out=y))
+    want = y.clone()
+    print(f"{label}: N {N} nnz {adj.nnz}  fp32 table {ms*1e3:7.1f} us = {by/ms/1e6:6.0f} GB/s algorithmic")
+    x16, _ = ops.pack_bf16(x, ld_dst=64, split=False)
+    ms2 = timeit(lambda: ops.spmm_bf16x(adj, x, out=y, x16=x16))
+    err = float((y - want).abs().max() / want.abs().max())
+    print(f"{label}:   bf16 table (given)      {ms2*1e3:7.1f} us = {by/ms2/1e6:6.0f} GB/s algorithmic   max err / scale {err:.2e}")
+    ms3 = timeit(lambda: ops.spmm_bf16x(adj, x, out=y))
+    print(f"{label}:   bf16 table (+ pack pass) {ms3*1e3:7.1f} us = {by/ms3/1e6:6.0f} GB/s algorithmic")
+
+
+run(300000, 80000, "ifashion")
+run(100000, 27000, "third   ")
