@@ -141,6 +141,14 @@ def csr_qsample_values(indptr, indices, n_rows, n_cols, noise, coef_a, coef_b, v
     return vals
 
 
+def csr_qsample_values_rng(indptr, indices, n_rows, n_cols, seed, coef_a, coef_b, vals, *, row_ids=None, row0=0):
+    """csr_qsample_values with the N(0, 1) rows generated inside the kernel (Philox keyed by the device int64 `seed`)."""
+    assert seed.dtype == torch.int64 and seed.is_cuda and vals.dtype == torch.float32 and vals.numel() == indices.numel()
+    _lib.call("dmm_csr_qsample_values_rng", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows),
+              int(n_cols), _p(seed), float(coef_a), float(coef_b), _p(vals), _stream())
+    return vals
+
+
 def rows_long_first(indptr, row0, n_rows, threshold=32):
     """int32 permutation of the block's rows with the rows of more than `threshold` entries in front (scheduling order
     of csr_gather_act; arbitrary among equals)."""

@@ -208,7 +208,8 @@ def denoise_chain(diff, den, *, x_dense: Optional[torch.Tensor] = None,
         c2 = float(np.float32(diff._h_coef2[i]))
         # z_i = c1 (h_i P^T + q) + c2 z_{i+1} (fp32 state, in place) and, in the same epilogue,
         # h_{i-1} = tanh(z_i + b1'(i-1)) into the OTHER operand buffer (other CTAs still read h_i)
-        ops.gemm_bf16_tn(h_hi, h_lo, p_hi, p_lo, M, H, H, bias=q, alpha=c1, beta=c2, residual=z, out_f32=z,
+        # (the last intermediate step only needs h_0: its z is never read again, so it is not written: 80 MB less at baby)
+        ops.gemm_bf16_tn(h_hi, h_lo, p_hi, p_lo, M, H, H, bias=q, alpha=c1, beta=c2, residual=z, out_f32=z if i > 1 else None,
                          out_hi=g_hi, out_lo=g_lo, post_bias=ws.bias_eff[i - 1], post_act=1)
         h_hi, h_lo, g_hi, g_lo = g_hi, g_lo, h_hi, h_lo
     c1 = float(np.float32(diff._h_coef1[0]))
@@ -222,8 +223,9 @@ NOISE_BLOCK_BYTES = 64 << 20     # randn sub-block of the sparse q_sample: writt
 
 def _qsample_values(diff, csr, row_ids, row0, M, I, sampling_step, noise, dev):
     """Entry values of x_t = q_sample(x0, sampling_step - 1) for the binary CSR rows [row0, row0 + M) (fp32, indexed like
-    csr[1]; entries of other rows are left untouched).  The randn draw is the reference's (Model.py:337: one full
-    [rows, I] block per call), made in row sub-blocks of NOISE_BLOCK_BYTES so that the noise never round-trips HBM."""
+    csr[1]; entries of other rows are left untouched).  Device RNG (default): dmm_csr_qsample_values_rng generates the
+    rows in the kernel.  DIFFMM_CPU_RNG=1 / DIFFMM_QSAMPLE_RNG=torch: the randn draw is torch's (Model.py:337), made in row
+    sub-blocks of NOISE_BLOCK_BYTES that stay L2 resident between the generator's write and the kernel's read."""
     indptr, indices = csr
     vals = torch.empty(indices.numel(), dtype=torch.float32, device=dev)
     t = sampling_step - 1
@@ -231,6 +233,12 @@ def _qsample_values(diff, csr, row_ids, row0, M, I, sampling_step, noise, dev):
     cb = float(np.float32(diff._h_sqrt_1mac[t]))
     if noise is not None:
         ops.csr_qsample_values(indptr, indices, M, I, noise, ca, cb, vals, row_ids=row_ids, row0=row0)
+        return vals
+    if not rng.cpu_rng() and os.environ.get("DIFFMM_QSAMPLE_RNG", "fused") == "fused":
+        # default: the randn rows are generated inside the kernel (Philox keyed by one draw of torch's device generator:
+        # reproducible under torch.manual_seed, no host sync), never written to HBM
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=dev)
+        ops.csr_qsample_values_rng(indptr, indices, M, I, seed, ca, cb, vals, row_ids=row_ids, row0=row0)
         return vals
     sub = max(1, min(M, NOISE_BLOCK_BYTES // (4 * I)))
     buf = torch.empty((sub, ops.pad_to(I, 4)), dtype=torch.float32, device=dev)

@@ -105,6 +105,14 @@ int dmm_csr_qsample_values(dmm_ctx* ctx, const int64_t* indptr, const int32_t* i
                            int64_t row0, int64_t n_rows, int64_t n_cols, const float* noise, int64_t ld_noise,
                            float coef_a, float coef_b, float* vals, void* stream);
 
+/* The same values with the standard-normal rows GENERATED in the kernel (Philox4x32-10 keyed by the 64-bit *seed, a
+ * DEVICE scalar drawn from the framework's generator; counter = (row id, column / 4); Box-Muller): no randn block is
+ * written to or read from HBM.  Element (r, c) is a pure function of (seed, r, c): deterministic per seed, independent of
+ * blocking and launch geometry.  i.i.d. N(0, 1) like Model.py:337; not torch's stream.                          */
+int dmm_csr_qsample_values_rng(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int64_t* row_ids,
+                               int64_t row0, int64_t n_rows, int64_t n_cols, const int64_t* seed, float coef_a,
+                               float coef_b, float* vals, void* stream);
+
 /* Scheduling order for dmm_csr_gather_act: order[] (int32 [n_rows]) becomes a permutation of 0..n_rows-1 with every
  * row of the block [row0, row0 + n_rows) that has more than `threshold` entries in front (arbitrary order among
  * equals; `counters` is 2 int32 of device scratch).  No host sync.                                         */

@@ -382,3 +382,38 @@ def test_spmm_lean_kernels_row_ranges_and_bf16_table(ops):
     x_r = torch.from_numpy(x).bfloat16().float().numpy()          # the rounded table, exactly
     want16 = O.spmm_csr(adj.ptr.cpu().numpy(), adj.idx.cpu().numpy(), adj.val.cpu().numpy(), x_r)
     np.testing.assert_allclose(y16, want16, rtol=2e-5, atol=2e-6)
+
+
+def test_fused_rng_qsample_values_are_standard_normal_and_counter_based(ops):
+    """dmm_csr_qsample_values_rng: (vals - a) / b = n_c / ||n|| for i.i.d. N(0, 1) rows generated in the kernel.  Checked:
+    moments of sqrt(I) (vals - a) / b (mean 0, variance 1, kurtosis 3), row norms through the identity
+    sum_c (n_c / ||n||)^2 over a FULL row = 1, determinism per seed, independence of blocking (element (r, c) is a pure
+    function of (seed, r, c)), and a different stream for a different seed."""
+    U, I = 600, 4093
+    rng = np.random.default_rng(0)
+    k = rng.integers(0, 40, U)
+    k[0], k[1] = I, 0                                   # one full row (identity check), one empty row
+    ptr = _ptr(k)
+    idx = np.concatenate([np.sort(rng.choice(I, kk, replace=False)) for kk in k]).astype(np.int32)
+    d_ptr, d_idx = T(ptr), T(idx)
+    a, b = 0.9, 0.4
+    seed = torch.tensor([1234567], dtype=torch.int64, device=DEV)
+    vals = torch.empty(idx.size, dtype=torch.float32, device=DEV)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals)
+    v = vals.cpu().numpy().astype(np.float64)
+    z = (v - a) / b                                      # n_c / ||n||
+    assert abs((z[:I] ** 2).sum() - 1.0) < 1e-4          # row 0 holds every column
+    s = z[I:] * np.sqrt(I)
+    assert abs(s.mean()) < 0.03 and abs(s.var() - 1.0) < 0.05 and abs((s ** 4).mean() / s.var() ** 2 - 3.0) < 0.25
+    # deterministic, and independent of how the rows are blocked / addressed
+    vals2 = torch.empty_like(vals)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, 300, I, seed, a, b, vals2)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, U - 300, I, seed, a, b, vals2, row0=300)
+    assert torch.equal(vals, vals2)
+    vals3 = torch.full_like(vals, float("nan"))
+    ids = torch.arange(U - 1, -1, -1, device=DEV)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals3, row_ids=ids)
+    assert torch.equal(vals, vals3)
+    vals4 = torch.empty_like(vals)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed + 1, a, b, vals4)
+    assert float((vals4 - vals).abs().max()) > 1e-3
