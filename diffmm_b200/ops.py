@@ -141,11 +141,14 @@ def csr_qsample_values(indptr, indices, n_rows, n_cols, noise, coef_a, coef_b, v
     return vals
 
 
-def csr_qsample_values_rng(indptr, indices, n_rows, n_cols, seed, coef_a, coef_b, vals, *, row_ids=None, row0=0):
-    """csr_qsample_values with the N(0, 1) rows generated inside the kernel (Philox keyed by the device int64 `seed`)."""
+def csr_qsample_values_rng(indptr, indices, n_rows, n_cols, seed, coef_a, coef_b, vals, *, row_ids=None, row0=0,
+                           full_rows=False):
+    """csr_qsample_values with the N(0, 1) rows generated inside the kernel (Philox keyed by the device int64 `seed`).
+    full_rows=False draws only the support normals and one chi-square variate for the rest of the squared norm (the
+    same joint distribution of the outputs, O(k) per row)."""
     assert seed.dtype == torch.int64 and seed.is_cuda and vals.dtype == torch.float32 and vals.numel() == indices.numel()
     _lib.call("dmm_csr_qsample_values_rng", _ctx(indptr), _p(indptr), _p(indices), _p(row_ids), int(row0), int(n_rows),
-              int(n_cols), _p(seed), float(coef_a), float(coef_b), _p(vals), _stream())
+              int(n_cols), _p(seed), float(coef_a), float(coef_b), _p(vals), int(bool(full_rows)), _stream())
     return vals
 
 

@@ -234,11 +234,17 @@ def _qsample_values(diff, csr, row_ids, row0, M, I, sampling_step, noise, dev):
     if noise is not None:
         ops.csr_qsample_values(indptr, indices, M, I, noise, ca, cb, vals, row_ids=row_ids, row0=row0)
         return vals
-    if not rng.cpu_rng() and os.environ.get("DIFFMM_QSAMPLE_RNG", "fused") == "fused":
-        # default: the randn rows are generated inside the kernel (Philox keyed by one draw of torch's device generator:
-        # reproducible under torch.manual_seed, no host sync), never written to HBM
+    mode = os.environ.get("DIFFMM_QSAMPLE_RNG", "chi2")
+    if mode not in ("chi2", "philox", "torch"):
+        raise ValueError(f"DIFFMM_QSAMPLE_RNG must be chi2, philox or torch, got {mode!r}")
+    if not rng.cpu_rng() and mode != "torch":
+        # default: the noise is generated inside the kernel (Philox keyed by one draw of torch's device generator:
+        # reproducible under torch.manual_seed, no host sync) and never written to HBM.  'chi2' draws the support normals
+        # and one chi-square variate for the rest of the row's squared norm (same joint distribution of the outputs, O(k)
+        # per row); 'philox' generates all I normals of every row
         seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=dev)
-        ops.csr_qsample_values_rng(indptr, indices, M, I, seed, ca, cb, vals, row_ids=row_ids, row0=row0)
+        ops.csr_qsample_values_rng(indptr, indices, M, I, seed, ca, cb, vals, row_ids=row_ids, row0=row0,
+                                   full_rows=mode == "philox")
         return vals
     sub = max(1, min(M, NOISE_BLOCK_BYTES // (4 * I)))
     buf = torch.empty((sub, ops.pad_to(I, 4)), dtype=torch.float32, device=dev)

@@ -399,21 +399,49 @@ def test_fused_rng_qsample_values_are_standard_normal_and_counter_based(ops):
     a, b = 0.9, 0.4
     seed = torch.tensor([1234567], dtype=torch.int64, device=DEV)
     vals = torch.empty(idx.size, dtype=torch.float32, device=DEV)
-    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals)
+    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals, full_rows=True)
     v = vals.cpu().numpy().astype(np.float64)
     z = (v - a) / b                                      # n_c / ||n||
     assert abs((z[:I] ** 2).sum() - 1.0) < 1e-4          # row 0 holds every column
     s = z[I:] * np.sqrt(I)
     assert abs(s.mean()) < 0.03 and abs(s.var() - 1.0) < 0.05 and abs((s ** 4).mean() / s.var() ** 2 - 3.0) < 0.25
     # deterministic, and independent of how the rows are blocked / addressed
-    vals2 = torch.empty_like(vals)
-    ops.csr_qsample_values_rng(d_ptr, d_idx, 300, I, seed, a, b, vals2)
-    ops.csr_qsample_values_rng(d_ptr, d_idx, U - 300, I, seed, a, b, vals2, row0=300)
-    assert torch.equal(vals, vals2)
-    vals3 = torch.full_like(vals, float("nan"))
-    ids = torch.arange(U - 1, -1, -1, device=DEV)
-    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals3, row_ids=ids)
-    assert torch.equal(vals, vals3)
-    vals4 = torch.empty_like(vals)
-    ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed + 1, a, b, vals4)
-    assert float((vals4 - vals).abs().max()) > 1e-3
+    for full in (True, False):
+        ref = torch.empty_like(vals)
+        ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, ref, full_rows=full)
+        vals2 = torch.empty_like(vals)
+        ops.csr_qsample_values_rng(d_ptr, d_idx, 300, I, seed, a, b, vals2, full_rows=full)
+        ops.csr_qsample_values_rng(d_ptr, d_idx, U - 300, I, seed, a, b, vals2, row0=300, full_rows=full)
+        assert torch.equal(ref, vals2)
+        vals3 = torch.full_like(vals, float("nan"))
+        ids = torch.arange(U - 1, -1, -1, device=DEV)
+        ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed, a, b, vals3, row_ids=ids, full_rows=full)
+        assert torch.equal(ref, vals3)
+        vals4 = torch.empty_like(vals)
+        ops.csr_qsample_values_rng(d_ptr, d_idx, U, I, seed + 1, a, b, vals4, full_rows=full)
+        assert float((vals4 - ref).abs().max()) > 1e-3
+        zz = (ref.cpu().numpy().astype(np.float64) - a) / b
+        assert abs((zz[:I] ** 2).sum() - 1.0) < 1e-4      # full row: the rest of the norm is empty (chi-square with 0 dof)
+        ss = zz[I:] * np.sqrt(I)
+        assert abs(ss.mean()) < 0.03 and abs(ss.var() - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("n_cols", [40, 70, 7050])
+def test_qsample_values_follow_the_exact_beta_law(ops, n_cols):
+    """One interaction per user: z^2 = n_c^2 / ||n||^2 ~ Beta(1/2, (I - 1)/2) exactly.  Checks mean and variance over
+    40 000 rows for both generators: all I normals per row, and support normals + one chi-square(I - 1) variate
+    (explicit normals for I - 1 <= 64, Marsaglia-Tsang above)."""
+    U = 40000
+    rng = np.random.default_rng(n_cols)
+    ptr = np.arange(U + 1, dtype=np.int64)
+    idx = rng.integers(0, n_cols, U).astype(np.int32)
+    seed = torch.tensor([99], dtype=torch.int64, device=DEV)
+    al, be = 0.5, 0.5 * (n_cols - 1)
+    mean = al / (al + be)
+    var = al * be / ((al + be) ** 2 * (al + be + 1))
+    for full in (True, False):
+        vals = torch.empty(U, dtype=torch.float32, device=DEV)
+        ops.csr_qsample_values_rng(T(ptr), T(idx), U, n_cols, seed, 0.0, 1.0, vals, full_rows=full)
+        z2 = vals.cpu().numpy().astype(np.float64) ** 2
+        assert abs(z2.mean() - mean) < 5.0 * np.sqrt(var / U), (full, z2.mean(), mean)
+        assert abs(z2.var() - var) < 0.08 * var, (full, z2.var(), var)
