@@ -61,7 +61,11 @@ class EdgeGatherPlan:
         self.world = world
 
 
-_UNEVEN_OK = {"nccl": True}     # backends whose all_gather takes unequal segment sizes (cleared on the first failure)
+# Backends on which the unequal-segment all_gather is used.  Off by default even for NCCL: torch issues it as one
+# ncclBroadcast per rank inside a group call, and at 8 ranks those eight small broadcasts measured slower (+0.1 ms per
+# modality) than ONE padded ncclAllGather followed by one index_select; DIFFMM_UNEVEN_ALLGATHER=1 switches it on.
+import os as _os
+_UNEVEN_OK = {"nccl": _os.environ.get("DIFFMM_UNEVEN_ALLGATHER", "0") == "1"}
 
 
 def _backend(group=None) -> str:
@@ -92,17 +96,44 @@ def allgather_edges(items_local: torch.Tensor, indptr: torch.Tensor, n_users: in
             return items_local
         except (RuntimeError, ValueError):       # pragma: no cover - backend without unequal all_gather
             _UNEVEN_OK[be] = False
-    send = torch.zeros(seg, dtype=items_local.dtype, device=items_local.device)
+    return allgather_edges_multi({"_": items_local}, indptr, n_users, group, plan)["_"]
+
+
+def allgather_edges_multi(items: dict, indptr: torch.Tensor, n_users: int, group=None,
+                          plan: Optional[EdgeGatherPlan] = None) -> dict:
+    """The edge lists of ALL modalities in ONE collective: every rank packs its segment of each list into one padded send
+    buffer [M, seg] (padding is never read back), one all_gather_into_tensor, and one index_select per modality compacts
+    the [world, M, seg] result into the CSR-ordered list (the index is precomputed per plan).  3 + M launches per
+    rebuild instead of M x (zero fill + copy + collective + world slice copies)."""
+    world, rk = world_size(group), rank(group)
+    if world == 1:
+        return dict(items)
+    if plan is None or plan.world != world:
+        plan = EdgeGatherPlan(indptr, n_users, world)
+    offs, seg = plan.offs, plan.seg
+    names = list(items)
+    M = len(names)
+    first = items[names[0]]
+    dev, dt = first.device, first.dtype
     s, e = offs[rk]
-    send[: e - s] = items_local[s:e]
-    recv = torch.empty(seg * world, dtype=items_local.dtype, device=items_local.device)
-    td.all_gather_into_tensor(recv, send, group=group)
-    src = getattr(plan, "_unpack_index", None)
-    if src is None or src.device != items_local.device:
-        src = torch.cat([torch.arange(r * seg, r * seg + (e - s), dtype=torch.int64) for r, (s, e) in enumerate(offs)])
-        src = src.to(items_local.device)
-        plan._unpack_index = src
-    return recv.index_select(0, src)
+    send = torch.empty((M, seg), dtype=dt, device=dev)
+    for k, m in enumerate(names):
+        send[k, : e - s].copy_(items[m][s:e])
+    recv = torch.empty((world, M, seg), dtype=dt, device=dev)
+    td.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    key = ("_unpack_index", M)
+    cache = getattr(plan, "_unpack_cache", None)
+    if cache is None:
+        cache = plan._unpack_cache = {}
+    src = cache.get(key)
+    if src is None or src[0].device != dev:
+        src = []
+        for k in range(M):
+            src.append(torch.cat([torch.arange((r * M + k) * seg, (r * M + k) * seg + (b - a), dtype=torch.int64)
+                                  for r, (a, b) in enumerate(offs)]).to(dev))
+        cache[key] = src
+    flat = recv.view(-1)
+    return {m: flat.index_select(0, src[k]) for k, m in enumerate(names)}
 
 
 def allgather_rows(x_local: torch.Tensor, blocks: List[Tuple[int, int]], group=None) -> torch.Tensor:
