@@ -229,7 +229,7 @@ def epoch_seconds(name, seed, precision, epochs=3, cuda_graph=True):
         shutil.rmtree(root, ignore_errors=True)
 
 
-def aux_rooflines(dev, breakdown, U, I, E, n_mod, pk, seed):
+def aux_rooflines(dev, breakdown, U, I, E, n_mod, pk, seed, precision="bf16"):
     """HBM-bound kernels of the path against the measured copy bandwidth: top-k (from the step breakdown) and the
     CSR SpMM at the ifashion-shaped graph of BASELINE.json configs[3] (300k users x 80k items; the shipped
     shapes are L2 resident), each timed with CUDA events on the launching stream."""
@@ -255,22 +255,35 @@ def aux_rooflines(dev, breakdown, U, I, E, n_mod, pk, seed):
     N, D = Ui + Ii, 64
     x = torch.randn((N, D), device=dev)
     y = torch.empty_like(x)
-    for _ in range(3):
-        ops.spmm(adj, x, out=y)
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(10):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.spmm(adj, x, out=y)
-        e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    def _time_product(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
     by = 8.0 * adj.nnz + 8.0 * (N + 1) + 2.0 * N * D * 4
+    table = ops.spmm_table_bf16(adj, x)
+    ms_fp32 = _time_product(lambda: ops.spmm(adj, x, out=y))
+    ms_b16 = _time_product(lambda: ops.spmm_norm_bf16(adj, x, out=y, table=None))
+    ms_b16_given = _time_product(lambda: ops.spmm_norm_bf16(adj, table=table, out=y))
+    ms = ms_b16 if precision == "bf16" else ms_fp32
     out["spmm_csr"] = {"bound": "hbm", "bytes_per_launch": by, "avg_launch_ms": ms, "achieved": by / (ms * 1e-3) / 1e9,
                        "peak": pk["hbm"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"],
-                       "shape": f"ifashion-shaped graph: N = {N} nodes, nnz = {adj.nnz}, D = 64 fp32 (working set > L2)"}
+                       "shape": f"ifashion-shaped graph: N = {N} nodes, nnz = {adj.nnz}, D = 64 (working set > L2)",
+                       "entry_point": ("dmm_spmm_table_bf16 + dmm_spmm_norm_bf16 (the propagation product of precision bf16: "
+                                       "table pass included)" if precision == "bf16" else "dmm_spmm_csr (fp32 gather table)"),
+                       "variants_ms": {"fp32_table_dmm_spmm_csr": ms_fp32, "bf16_table_pass_included": ms_b16,
+                                       "bf16_table_given": ms_b16_given},
+                       "note": "bytes_per_launch is the fp32 product's compulsory traffic 8 nnz + 8 (N + 1) + 2 N D 4 (SURVEY 8d) "
+                               "for every variant"}
     for _ in range(2):                      # allocator warm-up: a cudaMalloc between the events would be timed as well
         ops.build_norm_adj(ptr, idx, Ui, Ii)
     torch.cuda.synchronize()
@@ -750,7 +763,7 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_subprocess(args, w)
     if world == 1 and not args.no_aux:
         try:
-            line["aux_rooflines"] = aux_rooflines(dev, breakdown, U, I, E, len(mods), pk, args.seed)
+            line["aux_rooflines"] = aux_rooflines(dev, breakdown, U, I, E, len(mods), pk, args.seed, args.precision)
         except Exception as e:
             line["aux_rooflines"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_epoch and args.workload in ("tiktok", "baby", "sports"):
@@ -786,8 +799,10 @@ def propagation_bench(dev, world, rank, seed, timed):
     y = torch.empty_like(x)
     k = 10
     full_ms = timed(lambda: ops.spmm(adj, x, out=y), k, warm=3) / k
+    full_b16_ms = timed(lambda: ops.spmm_norm_bf16(adj, x, out=y), k, warm=3) / k
     out = {"shape": f"ifashion-shaped graph: N = {N} nodes, nnz = {adj.nnz}, D = 64 fp32", "n_gpus": world,
-           "full_product_ms": full_ms, "bytes_per_product": 8.0 * adj.nnz + 8.0 * (N + 1) + 2.0 * N * D * 4}
+           "full_product_ms": full_ms, "full_product_bf16_ms": full_b16_ms,
+           "bytes_per_product": 8.0 * adj.nnz + 8.0 * (N + 1) + 2.0 * N * D * 4}
     if world > 1:
         part = ddist.PropPartition(Ui, Ii, td.group.WORLD)
 
@@ -804,6 +819,12 @@ def propagation_bench(dev, world, rank, seed, timed):
         ag.set_partition(part)
         got = ag.spmm(adj, x)
         ag.set_partition(None)
+        ag.set_partition(part)
+        ag.set_spmm_precision("bf16")
+        part_b16_ms = timed(lambda: ag.spmm(adj, x), k, warm=3) / k
+        ag.set_spmm_precision("bf16x3")
+        ag.set_partition(None)
+        out["partitioned_product_bf16_ms"] = part_b16_ms
         out.update({"local_row_blocks_ms": local_ms, "allgather_ms": gather_ms, "partitioned_product_ms": part_ms,
                     "allgather_bytes_per_rank": float(N * D * 4) * (world - 1) / world,
                     "allgather_GBps_per_rank": float(N * D * 4) * (world - 1) / world / (gather_ms * 1e-3) / 1e9,

@@ -25,7 +25,7 @@ from torch.optim.adam import Adam
 from torch.optim.lr_scheduler import CosineAnnealingLR
 
 from . import ops, rng
-from .autograd import joint_losses, linear_tn, spmm
+from .autograd import joint_losses, linear_tn, spmm, spmm_cat
 from .Conf import Config, load_config
 from .DataHandler import DataHandler
 from .Model import Denoise, GaussianDiffusion, Model, _as_csr
@@ -365,11 +365,17 @@ class Coach:
         reg_loss = l2_reg_loss(cfg.train.reg, [self.model.u_embs, self.model.i_embs], self.device)
 
         # cross-layer CL (Main.py:315-330)
-        joint_embs = torch.cat([self.model.u_embs, self.model.i_embs], dim=0)
         all_embs = []
-        all_embs_cl = joint_embs
+        all_embs_cl = None
+        joint_embs = None
         for k in range(3):
-            joint_embs = spmm(biadj, joint_embs)
+            if k == 0:
+                # A . [u ; i] is the very product gcn_MM computed on the same operands (Model.py:110-114): taken from there
+                # when the adjacency is the same object, else computed from the two blocks (no concatenation pass)
+                same = gcn_output.base_product is not None and _as_csr(self.handler.torchBiAdj) is biadj
+                joint_embs = gcn_output.base_product if same else spmm_cat(biadj, self.model.u_embs, self.model.i_embs, cfg.base.precision)
+            else:
+                joint_embs = spmm(biadj, joint_embs, cfg.base.precision)
             random_noise = rng.rand_like(joint_embs)
             joint_embs = _SignNoise.apply(joint_embs, random_noise, cfg.hyper.noise_degree)
             all_embs.append(joint_embs)

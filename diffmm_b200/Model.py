@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import ops, rng
-from .autograd import check_precision, linear_tn, packed_weight, spmm
+from .autograd import check_precision, linear_tn, packed_weight, spmm, spmm_cat
 from .Utils.Utils import *  # noqa: F401,F403  (the reference star-imports its losses here, Model.py:7)
 from .Utils.Utils import l2_reg_loss
 
@@ -58,6 +58,7 @@ class GCNOutput:
     i_audio_embs: Optional[Tensor] = None
     # not in the reference: the un-split [N, 64] node tables (final, then one per modality) for the fused loss call
     final_embs: Optional[Tensor] = None
+    base_product: Optional[Tensor] = None      # A . [u_embs ; i_embs]: also layer 0 of the cross-layer CL (Main.py:319)
     modal_embs: Optional[list] = None
 
 
@@ -123,21 +124,23 @@ class Model(nn.Module):
             feats.append(self.getAudioFeats())
             madj.append(_as_csr(audio_adj))
 
-        zs = [spmm(a, torch.cat([self.u_embs, F.normalize(f)])) for a, f in zip(madj, feats)]   # :89-93,104-105
-        y = spmm(A, torch.cat([self.u_embs, self.i_embs]))        # :110-114,122-123 (identical products, once)
+        prec = getattr(self.config.base, "precision", "bf16")
+        zs = [spmm_cat(a, self.u_embs, F.normalize(f), prec) for a, f in zip(madj, feats)]     # :89-93,104-105
+        y = spmm_cat(A, self.u_embs, self.i_embs, prec)           # :110-114,122-123 (identical products, once)
         modal_embs = None
         for m, z in enumerate(zs):                                 # :116-119,125-127
             aware = y + lam * z
             modal_embs = weight[m] * aware if modal_embs is None else modal_embs + weight[m] * aware
         # :129-131 — ``final_embs = modal_embs`` aliases, so both in-place adds hit the same tensor:
         # final = (m0 + A m0) + residual_weight * (m0 + A m0)
-        t = modal_embs + spmm(A, modal_embs)
+        t = modal_embs + spmm(A, modal_embs, prec)
         final_embs = t + self.config.hyper.residual_weight * t
 
         out = GCNOutput(final_embs[:user], final_embs[user:], zs[0][:user], zs[0][user:], zs[1][:user], zs[1][user:])
         if self.audio_embedding is not None:
             out.u_audio_embs, out.i_audio_embs = zs[2][:user], zs[2][user:]
         out.final_embs, out.modal_embs = final_embs, zs
+        out.base_product = y
         return out
 
 

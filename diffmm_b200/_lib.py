@@ -81,6 +81,9 @@ PROTOTYPES = {
                                c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "dmm_spmm_csr_bf16x": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp,
                                      c_i64, c_vp, c_i64, c_vp]),
+    "dmm_spmm_table_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "dmm_spmm_norm_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                     c_vp, c_i64, c_vp]),
     "dmm_sign_noise_": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "dmm_bpr_fwd_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -97,7 +100,7 @@ PROTOTYPES = {
                                     c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dmm_diff_loss_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_vp, c_vp, c_vp,
                                     c_i64, c_vp, c_vp]),
-    "dmm_hidden_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64,
+    "dmm_hidden_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64,
                                  c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dmm_transpose_bf16": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "dmm_colsum": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),

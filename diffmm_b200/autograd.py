@@ -171,17 +171,40 @@ def linear_tn(x, weight, bias=None, act: int = 0, precision: str = "bf16", const
     return LinearTN.apply(x, weight, bias, act, check_precision(precision), const_input)
 
 
+_SPMM_PRECISION = "bf16x3"     # propagation products: "bf16" = bf16 gather table (separable adjacencies), else fp32
+
+
+def set_spmm_precision(precision: str) -> None:
+    """Precision of the propagation products of this process (Coach sets it from ``base.precision``): "bf16" rounds the
+    gathered operand to bf16 once per product (dmm_spmm_table_bf16 + dmm_spmm_norm_bf16: half the bytes through the L2,
+    no value stream), "bf16x3" keeps the fp32 gather table (dmm_spmm_csr).  DIFFMM_SPMM_FP32=1 forces fp32."""
+    global _SPMM_PRECISION
+    _SPMM_PRECISION = check_precision(precision)
+
+
+def _spmm_bf16(adj, x, precision=None) -> bool:
+    import os
+    return ((precision or _SPMM_PRECISION) == "bf16" and adj.separable and x.shape[1] == 64 and x.is_cuda and adj.n_nodes < (1 << 25)
+            and os.environ.get("DIFFMM_SPMM_FP32", "0") != "1")
+
+
+def _product(adj, x, out=None, row0=0, row1=None, precision=None):
+    if _spmm_bf16(adj, x, precision):
+        return ops.spmm_norm_bf16(adj, x, out=out, row0=row0, row1=row1)
+    return ops.spmm(adj, x, out=out, row0=row0, row1=row1)
+
+
 class SpMM(torch.autograd.Function):
     """y = A x for the symmetric normalised adjacency; dL/dx = A^T g = A g (same kernel)."""
 
     @staticmethod
-    def forward(ctx, x, adj: ops.CsrAdj):
-        ctx.adj = adj
-        return ops.spmm(adj, _rows(x.detach()))
+    def forward(ctx, x, adj: ops.CsrAdj, precision=None):
+        ctx.adj, ctx.precision = adj, precision
+        return _product(adj, _rows(x.detach()), precision=precision)
 
     @staticmethod
     def backward(ctx, g):
-        return ops.spmm(ctx.adj, _rows(g)), None
+        return _product(ctx.adj, _rows(g), precision=ctx.precision), None, None
 
 
 class PartitionedSpMM(torch.autograd.Function):
@@ -191,18 +214,21 @@ class PartitionedSpMM(torch.autograd.Function):
     backward dL/dx = A g is the same partitioned product: rows of A g on the owning rank + all-gather."""
 
     @staticmethod
-    def _product(adj, x, part):
+    def _product(adj, x, part, precision=None):
         y = torch.empty((adj.n_nodes, x.shape[1]), dtype=torch.float32, device=x.device)
+        if _spmm_bf16(adj, x, precision):
+            table = ops.spmm_table_bf16(adj, x)       # one table for all of this rank's row blocks
+            return part.product_(lambda r0, r1: ops.spmm_norm_bf16(adj, table=table, out=y, row0=r0, row1=r1), y)
         return part.product_(lambda r0, r1: ops.spmm(adj, x, out=y, row0=r0, row1=r1), y)
 
     @staticmethod
-    def forward(ctx, x, adj: ops.CsrAdj, part):
-        ctx.adj, ctx.part = adj, part
-        return PartitionedSpMM._product(adj, _rows(x.detach()), part)
+    def forward(ctx, x, adj: ops.CsrAdj, part, precision=None):
+        ctx.adj, ctx.part, ctx.precision = adj, part, precision
+        return PartitionedSpMM._product(adj, _rows(x.detach()), part, precision)
 
     @staticmethod
     def backward(ctx, g):
-        return PartitionedSpMM._product(ctx.adj, _rows(g), ctx.part), None, None
+        return PartitionedSpMM._product(ctx.adj, _rows(g), ctx.part, ctx.precision), None, None, None
 
 
 _PARTITION = None      # dist.PropPartition of the running trainer (None: single GPU)
@@ -215,11 +241,35 @@ def set_partition(part) -> None:
     _PARTITION = part if (part is not None and part.world > 1) else None
 
 
-def spmm(adj: ops.CsrAdj, x: torch.Tensor) -> torch.Tensor:
+class SpMMCat(torch.autograd.Function):
+    """y = A [xa ; xb] without materialising the concatenation (bf16 propagation: the gather table is built straight from
+    the two blocks, dmm_spmm_table_bf16); the gradient A g is handed back as two views."""
+
+    @staticmethod
+    def forward(ctx, xa, xb, adj: ops.CsrAdj):
+        ctx.adj, ctx.na = adj, xa.shape[0]
+        return ops.spmm_norm_bf16(adj, _rows(xa.detach()), x2=_rows(xb.detach()))
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = _product(ctx.adj, _rows(g), precision="bf16")
+        return gx[:ctx.na], gx[ctx.na:], None
+
+
+def spmm_cat(adj: ops.CsrAdj, xa: torch.Tensor, xb: torch.Tensor, precision=None) -> torch.Tensor:
+    """spmm(adj, torch.cat([xa, xb])) (Model.py:89-93,110-114: user block, item block)."""
+    if _PARTITION is None and xa.shape[1] == 64 and xb.shape[1] == 64 and _spmm_bf16(adj, xa, precision):
+        return SpMMCat.apply(xa, xb, adj)
+    return spmm(adj, torch.cat([xa, xb]), precision)
+
+
+def spmm(adj: ops.CsrAdj, x: torch.Tensor, precision=None) -> torch.Tensor:
+    """A x.  ``precision`` ("bf16" / "bf16x3"; None: the process default of set_spmm_precision) selects the bf16 gather
+    table for separable adjacencies."""
     part = _PARTITION
     if part is not None and adj.n_nodes == part.n_nodes and (adj.n_users == part.n_users or adj.n_users == 0):
-        return PartitionedSpMM.apply(x, adj, part)
-    return SpMM.apply(x, adj)
+        return PartitionedSpMM.apply(x, adj, part, precision)
+    return SpMM.apply(x, adj, precision)
 
 
 class InfoNCEFn(torch.autograd.Function):

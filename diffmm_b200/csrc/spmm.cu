@@ -33,6 +33,7 @@ struct Epi {
   float alpha, beta;
   const float* z;
   int64_t ld_z;
+  const float* rscale;   // optional per-row factor applied with alpha (d_r^-1/2 of the separable normalisation), or null
 };
 
 // ---- D == 64 fast path --------------------------------------------------------------------
@@ -281,7 +282,8 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
 __host__ __device__ inline int64_t plan_desc_word(int64_t cap) { return (3 + 2 * cap + 1) & ~(int64_t)1; }
 
 // descriptor of every chunk c of planned row i: {row, neighbours in the chunk, first entry} (one warp per planned row)
-__global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restrict__ ptr, int64_t cap, int64_t* __restrict__ plan) {
+__global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restrict__ ptr, int64_t cap, int64_t* __restrict__ plan,
+                                                        int2* __restrict__ unit) {
   const int64_t n = plan[0] < cap ? plan[0] : cap;
   const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restric
       const int64_t b = rb + (c - c0) * PLAN_CHUNK;
       const int nn = (int)(re - b < PLAN_CHUNK ? re - b : PLAN_CHUNK);
       desc[c] = make_int4((int)r, nn, (int)(uint32_t)(b & 0xFFFFFFFFll), (int)(b >> 32));
+      unit[c] = make_int2((int)((uint32_t)r | ((uint32_t)nn << 25)), (int)(uint32_t)b);      // the same chunk as a v3 unit
     }
   }
 }
@@ -356,18 +359,20 @@ __global__ void __launch_bounds__(SPMM_THREADS, 4) spmm64_planned_kernel(const i
 // one half warp per row, all loads in flight.  Pass B: the few big rows, one CTA per row: the 16 half warps
 // stride the partials (4 loads in flight each) and one half warp adds the 16 sums in a fixed order.
 constexpr int REDUCE_SMALL = 16;
-__global__ void __launch_bounds__(SPMM_THREADS) spmm64_reduce_kernel(int64_t row0, int64_t row1,
+constexpr int REDUCE_THREADS = 1024;     // pass B: 64 half warps x 8 partial rows in flight per big row (the 1600-chunk row is 4 round trips)
+__global__ void __launch_bounds__(REDUCE_THREADS) spmm64_reduce_kernel(int64_t row0, int64_t row1,
                                                                      const int64_t* __restrict__ plan, int64_t cap,
                                                                      const float* __restrict__ partial, Epi ep,
                                                                      float* __restrict__ y, int64_t ld_y) {
-  __shared__ float4 part[SPMM_THREADS / 16][16];
+  __shared__ float4 part[REDUCE_THREADS / 16][16];
   const int l16 = threadIdx.x & 15, hw = threadIdx.x >> 4;
-  constexpr int NHW = SPMM_THREADS / 16;
+  constexpr int NHW = REDUCE_THREADS / 16;
   const int64_t n_long = plan[0] < cap ? plan[0] : cap;
   const int64_t* long_rows = plan + 2;
   const int64_t* chunk_ptr = plan + 2 + cap;
   auto finish = [&](int64_t r, const float4& sum) {
-    float4 o = make_float4(ep.alpha * sum.x, ep.alpha * sum.y, ep.alpha * sum.z, ep.alpha * sum.w);
+    const float a = ep.rscale ? ep.alpha * __ldg(ep.rscale + r) : ep.alpha;
+    float4 o = make_float4(a * sum.x, a * sum.y, a * sum.z, a * sum.w);
     if (ep.z) {
       const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
       o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
@@ -515,6 +520,253 @@ __global__ void __launch_bounds__(256, 6) spmm64_chunks_lean_kernel(const int32_
   reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
 }
 
+
+// ---- D == 64, v3: degree-sorted units ------------------------------------------------------------------------------
+// What bounded the lean kernels (profiles/r02_prof_spmm_v2.txt): 13 warp instructions per stored entry at IPC 1.4 -- the
+// two half warps of a warp walk rows of DIFFERENT lengths (every loop trip is paid by both), each row pays its own
+// pointer / index / store set-up for ~8 entries, and only 4 gathers per half warp are in flight.  v3 removes all three:
+//   * the plan lists every row of at most 64 entries as a UNIT {row, length, first entry} sorted by length (longest
+//     first: counting sort over 65 bins), so the groups of a warp run the same trip counts, and the chunks of the long
+//     rows (all 64 entries) are units of the same kind: ONE persistent launch + the fixed-order reduce;
+//   * a unit is one 8-byte descriptor away from its indices (no row-pointer round trip) and 8 gathers per group are in
+//     flight;
+//   * bf16 table mode (dmm_spmm_norm_bf16): the adjacency values are separable, val = d_r^-1/2 d_c^-1/2,
+//     so the table is T = bf16(d^-1/2 X) (one streaming pass, dmm_spmm_table_bf16), a row of T is 128 B = 8 lanes x
+//     16 B, an entry costs one LDG.128 + 8 FHADD.BF16 (sm_100's mixed-precision add: fp32 accumulator += bf16 half
+//     register, no unpack) per 8 lanes and no value stream, and Y = alpha d_r^-1/2 sum (+ beta Z) in the epilogue.
+// plan sections behind the chunk descriptors (int64 words): 128 words of int32 header {[0] n_short, [1 + b] running
+// cursor and [80 + b] start of bin b = 64 - length}, int2 unit[max_chunks + n_rows] = {row | length << 25, first entry}
+// (the chunks of the long rows, then the short rows by falling length), float dinv[n_rows].
+constexpr int V3_ROW_BITS = 25;
+constexpr int V3_HDR_WORDS = 128;
+__host__ __device__ inline int64_t plan_v3_word(int64_t nnz) { return plan_desc_word(plan_cap(nnz)) + 2 * plan_max_chunks(nnz); }
+__host__ __device__ inline int64_t plan_v3_dinv_word(int64_t nnz, int64_t n_rows) {
+  return plan_v3_word(nnz) + V3_HDR_WORDS + plan_max_chunks(nnz) + n_rows;
+}
+
+__global__ void __launch_bounds__(1024) v3_hist_kernel(const int64_t* __restrict__ ptr, int64_t n_rows, int32_t* __restrict__ h,
+                                                       float* __restrict__ dinv) {
+  __shared__ int sh[65];
+  if (threadIdx.x < 65) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (r < n_rows) {
+    const int64_t len = ptr[r + 1] - ptr[r];
+    dinv[r] = len > 0 ? (float)(1.0 / sqrt((double)len)) : 0.f;
+    if (len <= PLAN_LONG_ROW) atomicAdd(&sh[PLAN_LONG_ROW - (int)len], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 65 && sh[threadIdx.x]) atomicAdd(&h[1 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void v3_scan_kernel(int32_t* __restrict__ h) {
+  if (threadIdx.x != 0) return;
+  int start = 0;
+  for (int b = 0; b < 65; ++b) {
+    const int c = h[1 + b];
+    h[1 + b] = start;
+    h[80 + b] = start;
+    start += c;
+  }
+  h[0] = start;
+}
+
+__global__ void __launch_bounds__(1024) v3_scatter_kernel(const int64_t* __restrict__ ptr, int64_t n_rows, int32_t* __restrict__ h,
+                                                          int2* __restrict__ unit, const int64_t* __restrict__ n_chunks_ptr,
+                                                          int64_t max_chunks) {
+  __shared__ int cnt[65], base[65];
+  if (threadIdx.x < 65) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unit += n_chunks_ptr[0] < max_chunks ? n_chunks_ptr[0] : max_chunks;      // the short rows follow the chunks
+  const int64_t r = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int bin = -1, rank = 0;
+  int64_t b = 0;
+  if (r < n_rows) {
+    b = ptr[r];
+    const int64_t len = ptr[r + 1] - b;
+    if (len <= PLAN_LONG_ROW) {
+      bin = PLAN_LONG_ROW - (int)len;
+      rank = atomicAdd(&cnt[bin], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 65) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&h[1 + threadIdx.x], cnt[threadIdx.x]) : 0;
+  __syncthreads();
+  if (bin >= 0) unit[base[bin] + rank] = make_int2((int)((uint32_t)r | ((uint32_t)(PLAN_LONG_ROW - bin) << V3_ROW_BITS)), (int)(uint32_t)b);
+}
+
+// acc[0..8) += the 8 bf16 of q (element 2j in the low half of word j)
+__device__ __forceinline__ void add_bf16x8(float (&acc)[8], const uint4& q) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint16_t lo = (uint16_t)(w[j] & 0xFFFFu), hi = (uint16_t)(w[j] >> 16);
+    asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc[2 * j]) : "h"(lo));
+    asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc[2 * j + 1]) : "h"(hi));
+  }
+}
+
+// B16: table rows are 64 bf16 (8 lanes x uint4, ld16 = row stride in 16-byte units), sum of the rows, scaled per row in the
+// epilogue.  fp32: table rows are 64 floats (16 lanes x float4), A's values multiply.
+template <bool B16>
+__global__ void __launch_bounds__(256, B16 ? 4 : 3) spmm64_units_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                                                      const void* __restrict__ tab, uint32_t row_bytes,
+                                                                      const int64_t* __restrict__ plan, int64_t nnz, int64_t row0,
+                                                                      int64_t row1, Epi ep, float* __restrict__ y, int64_t ld_y,
+                                                                      float* __restrict__ partial) {
+  constexpr int G = B16 ? 8 : 16;          // lanes per unit
+  constexpr int GPW = 32 / G;              // units per warp
+  constexpr uint32_t FULL = 0xffffffffu;
+  constexpr uint32_t DEAD = 0xffffffffu;   // descriptor of "no unit" (length 127 does not exist)
+  const int lane = threadIdx.x & 31;
+  const int lg = lane & (G - 1);
+  const int e8 = lg & 7;                   // entry of an 8-entry block this lane fetches (fp32: lanes 8-15 fetch the values)
+  const int stride = (int)gridDim.x * 8 * GPW;
+  const int64_t max_chunks = plan_max_chunks(nnz);
+  const int n_chunks = (int)(plan[1] < max_chunks ? plan[1] : max_chunks);
+  const int64_t v3w = plan_v3_word(nnz);
+  const int n_units = n_chunks + reinterpret_cast<const int32_t*>(plan + v3w)[0];
+  const int2* unit = reinterpret_cast<const int2*>(plan + v3w + V3_HDR_WORDS);
+  const char* tl = reinterpret_cast<const char*>(tab) + lg * 16;
+  const uint32_t r_lo = (uint32_t)row0, r_hi = (uint32_t)row1;       // rows < 2^25
+
+  // Software pipeline over this group's units u, u + stride, ...: while unit k is gathered, the first index block (and the
+  // row scale) of unit k + 1 and the descriptor of unit k + 2 are in flight, so a unit exposes ONE memory round trip (its
+  // gathers) instead of three.  All trip counts are warp-uniform (the units of a warp have equal lengths up to bin
+  // borders): the shuffles use the full mask and only the final stores diverge.
+  auto fetch = [&](int uu) { return uu < n_units ? __ldg(unit + uu) : make_int2((int)DEAD, 0); };
+  auto first_block = [&](const int2& d, int len) -> uint32_t {
+    if (e8 >= len) return 0u;
+    if (!B16 && lg >= 8) return __float_as_uint(__ldcs(val + (uint32_t)d.y + e8));
+    return (uint32_t)__ldcs(idx + (uint32_t)d.y + e8);
+  };
+  auto decode_len = [&](const int2& d) -> int {       // 0 for no unit / a row outside [row0, row1)
+    const uint32_t r = (uint32_t)d.x & ((1u << V3_ROW_BITS) - 1);
+    return ((uint32_t)d.x != DEAD && r >= r_lo && r < r_hi) ? (int)((uint32_t)d.x >> V3_ROW_BITS) : -1;
+  };
+  int u = ((int)blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + lane / G;
+  int2 d_cur = fetch(u), d_nxt = fetch(u + stride);
+  int len_cur = decode_len(d_cur);                     // -1: dead
+  uint32_t my = first_block(d_cur, len_cur);
+  float sc_cur = (len_cur >= 0 && ep.rscale) ? __ldg(ep.rscale + ((uint32_t)d_cur.x & ((1u << V3_ROW_BITS) - 1))) : 1.f;
+  for (; __any_sync(FULL, u < n_units); u += stride) {
+    const int2 d_nn = fetch(u + 2 * stride);
+    const int len_nxt = decode_len(d_nxt);
+    const uint32_t my_nxt = first_block(d_nxt, len_nxt);
+    const float sc_nxt = (len_nxt >= 0 && ep.rscale) ? __ldg(ep.rscale + ((uint32_t)d_nxt.x & ((1u << V3_ROW_BITS) - 1))) : 1.f;
+    const int len = len_cur < 0 ? 0 : len_cur;
+    const uint32_t start = (uint32_t)d_cur.y;
+    const int lenw = __reduce_max_sync(FULL, len);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // fp32 path: acc[0..4)
+#pragma unroll 1
+    for (int base = 0; base < lenw; base += 8) {
+      const int n = len - base;          // this unit's entries left (may be <= 0 in a mixed warp)
+      const int nw = lenw - base;        // the warp's
+      uint32_t my_nb = 0u;               // the next block's (column, value) pairs: in flight behind this block's gathers
+      if (n > 8 && e8 < n - 8)
+        my_nb = (!B16 && lg >= 8) ? __float_as_uint(__ldcs(val + start + base + 8 + e8)) : (uint32_t)__ldcs(idx + start + base + 8 + e8);
+      if constexpr (B16) {
+        uint4 q[8];
+        if (nw >= 8) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t c = __shfl_sync(FULL, my, t, 8);
+            q[t] = __ldg(reinterpret_cast<const uint4*>(tl + (size_t)c * row_bytes));
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < n) add_bf16x8(acc, q[t]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 7; ++t)
+            if (t < nw) {
+              const uint32_t c = __shfl_sync(FULL, my, t, 8);
+              q[t] = __ldg(reinterpret_cast<const uint4*>(tl + (size_t)c * row_bytes));
+            }
+#pragma unroll
+          for (int t = 0; t < 7; ++t)
+            if (t < nw && t < n) add_bf16x8(acc, q[t]);
+        }
+      } else {
+        float4 q[8];
+        float v[8];
+        float4 a4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (nw >= 8) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t c = __shfl_sync(FULL, my, t, 16);
+            v[t] = __uint_as_float(__shfl_sync(FULL, my, 8 + t, 16));
+            q[t] = __ldg(reinterpret_cast<const float4*>(tl + (size_t)c * row_bytes));
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) a4 = fma4(v[t], q[t], a4);      // v = 0 beyond this unit's entries
+        } else {
+#pragma unroll
+          for (int t = 0; t < 7; ++t)
+            if (t < nw) {
+              const uint32_t c = __shfl_sync(FULL, my, t, 16);
+              v[t] = __uint_as_float(__shfl_sync(FULL, my, 8 + t, 16));
+              q[t] = __ldg(reinterpret_cast<const float4*>(tl + (size_t)c * row_bytes));
+            }
+#pragma unroll
+          for (int t = 0; t < 7; ++t)
+            if (t < nw) a4 = fma4(v[t], q[t], a4);
+        }
+        acc[0] = a4.x, acc[1] = a4.y, acc[2] = a4.z, acc[3] = a4.w;
+      }
+      my = my_nb;
+    }
+    if (len_cur >= 0) {
+      const int64_t row = (uint32_t)d_cur.x & ((1u << V3_ROW_BITS) - 1);
+      if constexpr (B16) {
+        float4 o0 = make_float4(acc[0], acc[1], acc[2], acc[3]), o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        if (u < n_chunks) {
+          float4* dst = reinterpret_cast<float4*>(partial + (int64_t)u * 64) + 2 * lg;
+          dst[0] = o0, dst[1] = o1;
+        } else {
+          const float a = ep.alpha * sc_cur;
+          o0 = make_float4(a * o0.x, a * o0.y, a * o0.z, a * o0.w), o1 = make_float4(a * o1.x, a * o1.y, a * o1.z, a * o1.w);
+          if (ep.z) {
+            const float4* zp = reinterpret_cast<const float4*>(ep.z + row * ep.ld_z) + 2 * lg;
+            const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
+            o0 = make_float4(fmaf(ep.beta, z0.x, o0.x), fmaf(ep.beta, z0.y, o0.y), fmaf(ep.beta, z0.z, o0.z), fmaf(ep.beta, z0.w, o0.w));
+            o1 = make_float4(fmaf(ep.beta, z1.x, o1.x), fmaf(ep.beta, z1.y, o1.y), fmaf(ep.beta, z1.z, o1.z), fmaf(ep.beta, z1.w, o1.w));
+          }
+          float4* dst = reinterpret_cast<float4*>(y + row * ld_y) + 2 * lg;
+          __stcs(dst, o0);
+          __stcs(dst + 1, o1);
+        }
+      } else {
+        const float4 a4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (u < n_chunks) {
+          reinterpret_cast<float4*>(partial + (int64_t)u * 64)[lg] = a4;
+        } else {
+          store_row_cs(y, ld_y, row, lg, a4, ep);
+        }
+      }
+    }
+    d_cur = d_nxt, d_nxt = d_nn, len_cur = len_nxt, my = my_nxt, sc_cur = sc_nxt;
+  }
+}
+
+// T[r, :] = bf16(dinv[r] * X[r, :]) with X = [x (rows < n_first) ; x2 (the rest)]: the gather table of dmm_spmm_norm_bf16
+__global__ void __launch_bounds__(256) spmm_table_bf16_kernel(const float* __restrict__ x, int64_t ld_x, int64_t n_first,
+                                                              const float* __restrict__ x2, int64_t ld_x2, int64_t n_rows,
+                                                              const float* __restrict__ dinv, uint4* __restrict__ t) {
+  const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+  if (r >= n_rows) return;
+  const int lg = threadIdx.x & 7;
+  const float* src = r < n_first ? x + r * ld_x : x2 + (r - n_first) * ld_x2;
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * lg), b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * lg + 1);
+  const float s = __ldg(dinv + r);
+  uint4 o;
+  o.x = (uint32_t)dmm_bf16_bits(s * a.x) | ((uint32_t)dmm_bf16_bits(s * a.y) << 16);
+  o.y = (uint32_t)dmm_bf16_bits(s * a.z) | ((uint32_t)dmm_bf16_bits(s * a.w) << 16);
+  o.z = (uint32_t)dmm_bf16_bits(s * b.x) | ((uint32_t)dmm_bf16_bits(s * b.y) << 16);
+  o.w = (uint32_t)dmm_bf16_bits(s * b.z) | ((uint32_t)dmm_bf16_bits(s * b.w) << 16);
+  t[r * 8 + lg] = o;
+}
+
 // ---- generic D (multiple of 4, <= 256): one warp per row, lanes stride the float4 columns ----------
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_generic_kernel(const int64_t* __restrict__ ptr,
                                                                     const int32_t* __restrict__ idx,
@@ -571,14 +823,16 @@ __global__ void __launch_bounds__(256) sign_noise_kernel(float* __restrict__ e, 
 }  // namespace
 
 extern "C" int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz) {
-  (void)n_rows;
-  return (int64_t)sizeof(int64_t) * (4 + 2 * plan_cap(nnz)) + (int64_t)sizeof(int4) * plan_max_chunks(nnz);
+  // long-row list + chunk descriptors, then the v3 sections: header, one unit per row, d^-1/2 per row
+  return (int64_t)sizeof(int64_t) * (plan_v3_dinv_word(nnz, n_rows) + (n_rows + 1) / 2 + 2);
 }
 
 extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
                              int64_t plan_bytes, void* stream) {
   DMM_CHECK_ARG(ctx && adj_ptr && plan, "dmm_spmm_plan: null argument");
   DMM_CHECK_ARG(n_rows > 0 && nnz >= 0, "dmm_spmm_plan: bad sizes");
+  DMM_CHECK_ARG(n_rows < (1LL << V3_ROW_BITS) && nnz < (1LL << 31),
+                "dmm_spmm_plan: at most 2^25 rows and 2^31 entries (call dmm_spmm_csr with plan = NULL beyond that)");
   DMM_CHECK_ARG(plan_bytes >= dmm_spmm_plan_bytes(n_rows, nnz), "dmm_spmm_plan: plan buffer too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cap = plan_cap(nnz);
@@ -587,7 +841,20 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
   DMM_LAUNCH_CHECK();
   plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
   DMM_LAUNCH_CHECK();
-  plan_desc_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
+  // v3: the chunks and the rows of at most PLAN_LONG_ROW entries as units sorted by length, and d^-1/2 per row
+  int64_t* v3 = (int64_t*)plan + plan_v3_word(nnz);
+  int32_t* h = (int32_t*)v3;
+  int2* unit = (int2*)(v3 + V3_HDR_WORDS);
+  float* dinv = (float*)((int64_t*)plan + plan_v3_dinv_word(nnz, n_rows));
+  plan_desc_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(adj_ptr, cap, (int64_t*)plan, unit);
+  DMM_LAUNCH_CHECK();
+  DMM_CUDA(cudaMemsetAsync(h, 0, V3_HDR_WORDS * sizeof(int64_t), st));
+  v3_hist_kernel<<<(unsigned)dmm_ceil_div(n_rows, 1024), 1024, 0, st>>>(adj_ptr, n_rows, h, dinv);
+  DMM_LAUNCH_CHECK();
+  v3_scan_kernel<<<1, 32, 0, st>>>(h);
+  DMM_LAUNCH_CHECK();
+  v3_scatter_kernel<<<(unsigned)dmm_ceil_div(n_rows, 1024), 1024, 0, st>>>(adj_ptr, n_rows, h, unit, (const int64_t*)plan + 1,
+                                                                          plan_max_chunks(nnz));
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
@@ -606,12 +873,59 @@ int launch_lean(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, co
   spmm64_chunks_lean_kernel<B16><<<(unsigned)dmm_ceil_div(max_chunks * 16, 256), 256, 0, st>>>(
       adj_idx, adj_val, row0, row1, xt, ldu, (const int64_t*)plan, cap, (float*)workspace);
   DMM_LAUNCH_CHECK();
-  spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 4), SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+  spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+                                                                       (const float*)workspace, ep, y, ld_y);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+// v3: one persistent launch over the units (chunks of the long rows + length-sorted short rows), then the fixed-order reduce
+template <bool B16>
+int launch_units(dmm_ctx* ctx, const int32_t* adj_idx, const float* adj_val, int64_t row0, int64_t row1, const void* tab,
+                 uint32_t row_bytes, const Epi& ep, float* y, int64_t ld_y, const void* plan, int64_t nnz, void* workspace,
+                 cudaStream_t st) {
+  const int64_t cap = plan_cap(nnz);
+  spmm64_units_kernel<B16><<<(unsigned)(ctx->num_sms * (B16 ? 4 : 3)), 256, 0, st>>>(adj_idx, adj_val, tab, row_bytes, (const int64_t*)plan, nnz,
+                                                                        row0, row1, ep, y, ld_y, (float*)workspace);
+  DMM_LAUNCH_CHECK();
+  spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
                                                                        (const float*)workspace, ep, y, ld_y);
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
 }  // namespace
+
+extern "C" int dmm_spmm_table_bf16(dmm_ctx* ctx, const float* x, int64_t ld_x, int64_t n_first, const float* x2, int64_t ld_x2,
+                                   int64_t n_rows, const void* plan, int64_t nnz, uint16_t* t, void* stream) {
+  DMM_CHECK_ARG(ctx && x && plan && t, "dmm_spmm_table_bf16: null argument");
+  DMM_CHECK_ARG(n_rows > 0 && n_first >= 0 && (n_first >= n_rows || x2), "dmm_spmm_table_bf16: bad row split");
+  DMM_CHECK_ARG(ld_x % 4 == 0 && ld_x >= 64 && (!x2 || (ld_x2 % 4 == 0 && ld_x2 >= 64)),
+                "dmm_spmm_table_bf16: D is 64; leading dimensions must be multiples of 4");
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(x) && al16(x2) && al16(t), "dmm_spmm_table_bf16: X and T must be 16-byte aligned");
+  const float* dinv = (const float*)((const int64_t*)plan + plan_v3_dinv_word(nnz, n_rows));
+  spmm_table_bf16_kernel<<<(unsigned)dmm_ceil_div(n_rows * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ld_x, n_first < n_rows ? n_first : n_rows, x2, ld_x2, n_rows, dinv, (uint4*)t);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+extern "C" int dmm_spmm_norm_bf16(dmm_ctx* ctx, const int32_t* adj_idx, int64_t row0, int64_t row1, int64_t n_rows,
+                                  const uint16_t* t, float alpha, float beta, const float* z, int64_t ld_z, float* y,
+                                  int64_t ld_y, const void* plan, int64_t nnz, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+  DMM_CHECK_ARG(ctx && adj_idx && t && y && plan && workspace, "dmm_spmm_norm_bf16: null argument");
+  DMM_CHECK_ARG(ld_y % 4 == 0 && ld_y >= 64 && (!z || (ld_z % 4 == 0 && ld_z >= 64)),
+                "dmm_spmm_norm_bf16: D is 64; leading dimensions must be multiples of 4");
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(t) && al16(y) && al16(z) && al16(workspace), "dmm_spmm_norm_bf16: T/Y/Z/workspace must be 16-byte aligned");
+  DMM_CHECK_ARG(row0 >= 0 && row1 >= row0 && row1 <= n_rows && nnz < (1LL << 31), "dmm_spmm_norm_bf16: bad row range / nnz");
+  DMM_CHECK_ARG(workspace_bytes >= dmm_spmm_workspace_bytes(nnz, 64), "dmm_spmm_norm_bf16: workspace too small");
+  if (row1 == row0) return DMM_OK;
+  const float* dinv = (const float*)((const int64_t*)plan + plan_v3_dinv_word(nnz, n_rows));
+  const Epi ep{alpha, z ? beta : 0.f, z, ld_z, dinv};
+  return launch_units<true>(ctx, adj_idx, nullptr, row0, row1, t, 128u, ep, y, ld_y, plan, nnz, workspace, (cudaStream_t)stream);
+}
 
 extern "C" int dmm_spmm_csr_bf16x(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
                                   int64_t row0, int64_t row1, const uint16_t* x_bf16, int64_t ld_x, float alpha, float beta,
@@ -661,8 +975,9 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
     } else {
       const int64_t cap = plan_cap(nnz);
       static const bool lean = []() { const char* e = getenv("DMM_SPMM_V2"); return !(e && e[0] == '0'); }();   // A/B switch
-      const int64_t n_nodes_x = 0;
-      (void)n_nodes_x;
+      static const bool v3 = []() { const char* e = getenv("DMM_SPMM_V3"); return !(e && e[0] == '0'); }();       // A/B switch
+      if (v3 && nnz < (1LL << 31) && ld_x < (1LL << 28))
+        return launch_units<false>(ctx, adj_idx, adj_val, row0, row1, x, (uint32_t)(ld_x * 4), ep, y, ld_y, plan, nnz, workspace, st);
       // the lean kernels win once the graph has work for three launches (sports: 36 vs 42 us, ifashion: 230 vs 252 us);
       // below ~0.45 M entries the persistent kernel's two launches are faster (baby: 25 vs 31 us)
       if (lean && nnz >= 450000 && nnz < (1LL << 31) && ld_x % 4 == 0 && ld_x / 4 < (1LL << 20))
@@ -682,7 +997,7 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
       spmm64_planned_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y,
                                                                         ld_y, (const int64_t*)plan, cap, (float*)workspace);
       DMM_LAUNCH_CHECK();
-      spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 4), SPMM_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
+      spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
                                                                            (const float*)workspace, ep, y, ld_y);
     }
   } else {

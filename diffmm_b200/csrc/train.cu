@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(256) diff_loss_bwd_kernel(const double* __rest
 // the operand of the input-gradient contraction, and through a shared-memory transpose dz^T and (cm h)^T, the operands
 // of the two weight-gradient contractions (K = batch).
 __global__ void __launch_bounds__(256) hidden_bwd_kernel(const float* __restrict__ dh, int64_t ld_dh,
+                                                         const float* __restrict__ h_f32, int64_t ld_hf,
                                                          const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo,
                                                          int64_t ld_h, const float* __restrict__ cm, int64_t n_rows, int64_t H,
                                                          float* __restrict__ dz_f32, int64_t ld_dz,
@@ -247,8 +248,15 @@ __global__ void __launch_bounds__(256) hidden_bwd_kernel(const float* __restrict
     const int64_t b = b0 + ty + 8 * i, c = c0 + tx;
     float dz = 0.f, hc = 0.f;
     if (b < n_rows && c < H) {
-      float hv = dmm_bf16_to_f32(h_hi[b * ld_h + c]);
-      if (h_lo) hv += dmm_bf16_to_f32(h_lo[b * ld_h + c]);
+      // tanh' = 1 - h^2 needs h at full precision: for a saturated unit (|h| -> 1) the bf16 rounding of h (2^-9) is as
+      // large as 1 - h^2 itself
+      float hv;
+      if (h_f32) {
+        hv = h_f32[b * ld_hf + c];
+      } else {
+        hv = dmm_bf16_to_f32(h_hi[b * ld_h + c]);
+        if (h_lo) hv += dmm_bf16_to_f32(h_lo[b * ld_h + c]);
+      }
       const float s = cm[b];
       dz = s * dh[b * ld_dh + c] * (1.f - hv * hv);
       hc = s * hv;
@@ -405,16 +413,18 @@ extern "C" int dmm_diff_loss_bwd(dmm_ctx* ctx, const double* g_loss, const float
   return DMM_OK;
 }
 
-extern "C" int dmm_hidden_bwd(dmm_ctx* ctx, const float* dh, int64_t ld_dh, const uint16_t* h_hi, const uint16_t* h_lo,
+extern "C" int dmm_hidden_bwd(dmm_ctx* ctx, const float* dh, int64_t ld_dh, const float* h_f32, int64_t ld_hf,
+                              const uint16_t* h_hi, const uint16_t* h_lo,
                               int64_t ld_h, const float* cm, int64_t n_rows, int64_t H, float* dz_f32, int64_t ld_dz,
                               uint16_t* dz_hi, uint16_t* dz_lo, int64_t ld_dz16, uint16_t* dzt_hi, uint16_t* dzt_lo,
                               uint16_t* hct_hi, uint16_t* hct_lo, int64_t ld_t, void* stream) {
-  DMM_CHECK_ARG(ctx && dh && h_hi && cm && dz_f32 && dz_hi && dzt_hi && hct_hi, "dmm_hidden_bwd: null argument");
-  DMM_CHECK_ARG(H > 0 && ld_dh >= H && ld_h >= H && ld_dz >= H && ld_dz16 >= H && ld_t >= n_rows, "dmm_hidden_bwd: bad shape");
+  DMM_CHECK_ARG(ctx && dh && (h_hi || h_f32) && cm && dz_f32 && dz_hi && dzt_hi && hct_hi, "dmm_hidden_bwd: null argument");
+  DMM_CHECK_ARG(H > 0 && ld_dh >= H && (!h_hi || ld_h >= H) && (!h_f32 || ld_hf >= H) && ld_dz >= H && ld_dz16 >= H && ld_t >= n_rows,
+                "dmm_hidden_bwd: bad shape");
   DMM_CHECK_ARG(!!dz_lo == !!dzt_lo && !!dz_lo == !!hct_lo, "dmm_hidden_bwd: lo parts must be given together");
   if (n_rows <= 0) return DMM_OK;
   dim3 grid((unsigned)dmm_ceil_div(H, 32), (unsigned)dmm_ceil_div(ld_t, 32));
-  hidden_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dh, ld_dh, h_hi, h_lo, ld_h, cm, n_rows, H, dz_f32, ld_dz, dz_hi, dz_lo,
+  hidden_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dh, ld_dh, h_f32, ld_hf, h_hi, h_lo, ld_h, cm, n_rows, H, dz_f32, ld_dz, dz_hi, dz_lo,
                                                            ld_dz16, dzt_hi, dzt_lo, hct_hi, hct_lo, ld_t);
   DMM_LAUNCH_CHECK();
   return DMM_OK;

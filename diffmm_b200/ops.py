@@ -286,6 +286,7 @@ class CsrAdj:
     n_items: int
     plan: Optional[torch.Tensor] = None        # long-row plan of the SpMM (dmm_spmm_plan), built on first use
     workspace: Optional[torch.Tensor] = None   # partial rows of the planned chunks
+    separable: bool = False                    # val[r, c] = d_r^-1/2 d_c^-1/2 with d_r = entries of row r (D^-1/2 (A + I) D^-1/2)
 
     @property
     def n_nodes(self):
@@ -317,10 +318,53 @@ def build_norm_adj(row_ptr: torch.Tensor, items: torch.Tensor, n_users: int, n_i
     val = torch.empty(2 * E + N, dtype=torch.float32, device=dev)
     _lib.call("dmm_build_norm_adj_csr", _ctx(row_ptr), _p(row_ptr), _p(items), n_users, n_items, E, _p(ptr), _p(idx),
               _p(val), _p(ws), ws_bytes, _p(status), _stream())
-    return CsrAdj(ptr, idx, val, n_users, n_items)
+    return CsrAdj(ptr, idx, val, n_users, n_items, separable=True)
 
 
 # ----------------------------------------------------------------------------------------- SpMM
+def _ensure_plan(adj: CsrAdj, device):
+    if adj.plan is None:
+        lib = _lib.load()
+        nnz = int(adj.nnz)
+        adj.plan = torch.empty(int(lib.dmm_spmm_plan_bytes(adj.n_nodes, nnz)), dtype=torch.uint8, device=device)
+        adj.workspace = torch.empty(int(lib.dmm_spmm_workspace_bytes(nnz, 64)), dtype=torch.uint8, device=device)
+        _lib.call("dmm_spmm_plan", _ctx(adj.ptr), _p(adj.ptr), adj.n_nodes, nnz, _p(adj.plan), adj.plan.numel(), _stream())
+
+
+def spmm_table_bf16(adj: CsrAdj, x: torch.Tensor, x2: Optional[torch.Tensor] = None, table: Optional[torch.Tensor] = None):
+    """Gather table of spmm_norm_bf16: T = bf16(d^-1/2 [x ; x2]) [N, 64] (the concatenation is never materialised)."""
+    assert adj.separable, "the bf16 propagation needs val = d_r^-1/2 d_c^-1/2 (build_norm_adj / normalizeAdj adjacencies)"
+    n_first = x.shape[0]
+    assert x.dtype == torch.float32 and x.shape[1] == 64 and n_first + (x2.shape[0] if x2 is not None else 0) == adj.n_nodes
+    assert x2 is None or (x2.dtype == torch.float32 and x2.shape[1] == 64)
+    _ensure_plan(adj, x.device)
+    if table is None:
+        table = torch.empty((adj.n_nodes, 64), dtype=torch.bfloat16, device=x.device)
+    _lib.call("dmm_spmm_table_bf16", _ctx(x), _p(x), _row_major(x, "x"), n_first, _p(x2),
+              _row_major(x2, "x2") if x2 is not None else 0, adj.n_nodes, _p(adj.plan), int(adj.nnz), _p(table), _stream())
+    return table
+
+
+def spmm_norm_bf16(adj: CsrAdj, x: Optional[torch.Tensor] = None, *, x2=None, table=None, alpha=1.0, beta=0.0, z=None, out=None,
+                   row0=0, row1=None):
+    """out[row0:row1] = alpha * A[row0:row1] . [x ; x2] (+ beta * z[row0:row1]) in the single-pass bf16 precision of the
+    propagation: the gathered operand is rounded to bf16 once (T = bf16(d^-1/2 X), built here unless `table` is given),
+    sums, row scaling and output are fp32.  Separable adjacencies only (CsrAdj.separable)."""
+    if table is None:
+        table = spmm_table_bf16(adj, x, x2)
+    else:
+        _ensure_plan(adj, table.device)
+    assert table.dtype == torch.bfloat16 and table.shape == (adj.n_nodes, 64) and table.is_contiguous()
+    if out is None:
+        out = torch.empty((adj.n_nodes, 64), dtype=torch.float32, device=table.device)
+    row1 = adj.n_nodes if row1 is None else row1
+    _lib.call("dmm_spmm_norm_bf16", _ctx(table), _p(adj.idx), int(row0), int(row1), adj.n_nodes, _p(table), float(alpha),
+              float(beta), _p(z), _row_major(z, "z") if z is not None else 0, _p(out), _row_major(out, "out"), _p(adj.plan),
+              int(adj.nnz), _p(adj.workspace), adj.workspace.numel(), _stream())
+    return out
+
+
+# (fp32 gather table: every adjacency)
 def spmm(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None, row0=0, row1=None):
     """out[row0:row1] = alpha * A[row0:row1] . x (+ beta * z[row0:row1]); rows outside the block untouched."""
     assert x.dtype == torch.float32 and x.shape[0] == adj.n_nodes
@@ -474,9 +518,11 @@ def diff_loss_bwd(g_loss, um, ui, stats, t, w_tab, sim_weight, n_cols, cm, dumc_
               _stream())
 
 
-def hidden_bwd(dh, h_hi, h_lo, cm, H, dz, dz_hi, dz_lo, dzt_hi, dzt_lo, hct_hi, hct_lo):
+def hidden_bwd(dh, h_f32, h_hi, h_lo, cm, H, dz, dz_hi, dz_lo, dzt_hi, dzt_lo, hct_hi, hct_lo):
     B = dh.shape[0]
-    _lib.call("dmm_hidden_bwd", _ctx(dh), _p(dh), _row_major(dh, "dh"), _p(h_hi), _p(h_lo), _row_major(h_hi, "h_hi"), _p(cm), B,
+    _lib.call("dmm_hidden_bwd", _ctx(dh), _p(dh), _row_major(dh, "dh"), _p(h_f32),
+              _row_major(h_f32, "h_f32") if h_f32 is not None else 0, _p(h_hi), _p(h_lo),
+              _row_major(h_hi, "h_hi") if h_hi is not None else 0, _p(cm), B,
               int(H), _p(dz), _row_major(dz, "dz"), _p(dz_hi), _p(dz_lo), _row_major(dz_hi, "dz_hi"), _p(dzt_hi), _p(dzt_lo),
               _p(hct_hi), _p(hct_lo), _row_major(dzt_hi, "dzt_hi"), _stream())
 

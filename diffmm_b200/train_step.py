@@ -100,7 +100,9 @@ class DenoiseLossFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         Kp = ops.pad_to(I + d, 64)
         a_hi = torch.empty((B, Kp), **bf)
-        a_lo = torch.empty((B, Kp), **bf) if split else None
+        # the lo part of x_t is kept in single-pass mode too, but only as the RESIDUAL of the gate add (x_t' = x_t + G F^T
+        # is then rounded to bf16 once, like the per-op path's fp32 sum); it is an operand only in bf16x3 mode
+        a_lo = torch.empty((B, Kp), **bf)
         x0_hi = torch.empty((B, ops.pad_to(I, 64)), **bf)
         te_raw = torch.empty((B, d), **f32)
         ops.train_prep(x0, noise, t, tab_a, tab_b, emb_w.detach(), emb_b.detach(), a_hi, a_lo, x0_hi, te_raw)
@@ -110,19 +112,21 @@ class DenoiseLossFn(torch.autograd.Function):
         x0f, ui = xfe[:, :64], xfe[:, 64:]
         # gate: P = x_t F, G = P sigmoid(P Wg^T + bg), x_t' = x_t + G F^T (in place on the operand)
         P = torch.empty((B, 64), **f32)
-        ops.gemm_bf16_tn(a_hi, a_lo, fte_hi[:64], fte_lo[:64] if split else None, B, 64, I, out_f32=P)
+        a_lo_op = a_lo if split else None
+        ops.gemm_bf16_tn(a_hi, a_lo_op, fte_hi[:64], fte_lo[:64] if split else None, B, 64, I, out_f32=P)
         sig = torch.empty((B, 64), **f32)
         g_hi = torch.empty((B, 64), **bf)
         g_lo = torch.empty((B, 64), **bf) if split else None
         ops.gate_fwd(P, gate_w.detach(), gate_b.detach(), sig, g_hi, g_lo)
-        ops.gemm_bf16_tn(g_hi, g_lo, f_hi, f_lo, B, I, 64, alpha=1.0, beta=1.0, res_hi=a_hi[:, :I],
-                         res_lo=a_lo[:, :I] if split else None, out_hi=a_hi[:, :I], out_lo=a_lo[:, :I] if split else None)
+        ops.gemm_bf16_tn(g_hi, g_lo, f_hi, f_lo, B, I, 64, alpha=1.0, beta=1.0, res_hi=a_hi[:, :I], res_lo=a_lo[:, :I],
+                         out_hi=a_hi[:, :I], out_lo=a_lo[:, :I] if split else None)
         # h = tanh([x_t', temb] W1^T + b1)
         (w1_hi, w1_lo), _ = packed_weight_pair(w1, split)
         Hp = ops.pad_to(H, 64)
         h_hi = torch.empty((B, Hp), **bf)
         h_lo = torch.empty((B, Hp), **bf) if split else None
-        ops.gemm_bf16_tn(a_hi, a_lo, w1_hi, w1_lo, B, H, I + d, bias=b1.detach(), act=1, out_hi=h_hi[:, :H],
+        h_f32 = torch.empty((B, ops.pad_to(H, 4)), **f32)[:, :H]      # tanh' of saturated units needs h beyond bf16 (4 MB)
+        ops.gemm_bf16_tn(a_hi, a_lo_op, w1_hi, w1_lo, B, H, I + d, bias=b1.detach(), act=1, out_f32=h_f32, out_hi=h_hi[:, :H],
                          out_lo=h_lo[:, :H] if split else None)
         # diff = h W2^T + b2 - x0
         (w2_hi, w2_lo), _ = packed_weight_pair(w2, split)
@@ -141,7 +145,7 @@ class DenoiseLossFn(torch.autograd.Function):
         ctx.split, ctx.sim_weight, ctx.dims = split, float(sim_weight), (B, I, H, d)
         ctx.tabs = tabs
         ctx.feat_ops = (f_hi, f_lo, fte_hi, fte_lo)
-        ctx.bufs = (a_hi, a_lo, h_hi, h_lo, d_hi, d_lo, diff)
+        ctx.bufs = (a_hi, a_lo_op, h_f32, d_hi, d_lo, diff)
         ctx.save_for_backward(t, P, sig, um, ui, stats, te_raw, w1, w2)
         ctx.mse = mse
         return loss
@@ -152,7 +156,7 @@ class DenoiseLossFn(torch.autograd.Function):
         split = ctx.split
         B, I, H, d = ctx.dims
         f_hi, f_lo, fte_hi, fte_lo = ctx.feat_ops
-        a_hi, a_lo, h_hi, h_lo, d_hi, d_lo, diff = ctx.bufs
+        a_hi, a_lo, h_f32, d_hi, d_lo, diff = ctx.bufs
         _, _, w_tab = ctx.tabs
         dev = t.device
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -177,7 +181,7 @@ class DenoiseLossFn(torch.autograd.Function):
         hct_hi = torch.empty((H, Bp), **bf)
         dz_lo, dzt_lo, hct_lo = (torch.empty((B, Hp), **bf), torch.empty((H, Bp), **bf), torch.empty((H, Bp), **bf)) if split \
             else (None, None, None)
-        ops.hidden_bwd(dh, h_hi, h_lo, cm, H, dz, dz_hi, dz_lo, dzt_hi, dzt_lo, hct_hi, hct_lo)
+        ops.hidden_bwd(dh, h_f32, None, None, cm, H, dz, dz_hi, dz_lo, dzt_hi, dzt_lo, hct_hi, hct_lo)
         dW2 = torch.empty((I, ops.pad_to(H, 4)), **f32)[:, :H]
         ops.gemm_bf16_tn(dT_hi, dT_lo, hct_hi, hct_lo, I, H, B, out_f32=dW2)
         db1 = ops.colsum(dz, None)

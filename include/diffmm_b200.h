@@ -240,9 +240,10 @@ int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, const int32_t* 
  * Replaces torch.sparse.mm (Model.py:90,93,105,111,114,123,130; Main.py:319).
  *
  * Item popularity is heavy tailed, so for D == 64 a `plan` (built once per adjacency by
- * dmm_spmm_plan; device-resident, no host sync) lists the rows with more than 64 neighbours; they
- * are cut into 64-neighbour chunks whose partial rows go through `workspace`
- * (dmm_spmm_workspace_bytes) and are added in a fixed order (deterministic).  plan == NULL keeps the
+ * dmm_spmm_plan; device-resident, no host sync; at most 2^25 rows) lists the rows with more than 64
+ * neighbours; they are cut into 64-neighbour chunks whose partial rows go through `workspace`
+ * (dmm_spmm_workspace_bytes) and are added in a fixed order (deterministic), and lists the other rows
+ * sorted by length, so that the lanes of a warp run equal trip counts.  plan == NULL keeps the
  * one-CTA-per-long-row path.  `nnz` is the number of stored entries of A (sizes the plan).      */
 int64_t dmm_spmm_plan_bytes(int64_t n_rows, int64_t nnz);
 int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_rows, int64_t nnz, void* plan,
@@ -262,6 +263,19 @@ int dmm_spmm_csr_bf16x(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_
                        int64_t row1, const uint16_t* x_bf16, int64_t ld_x, float alpha, float beta, const float* z,
                        int64_t ld_z, float* y, int64_t ld_y, const void* plan, int64_t nnz, void* workspace,
                        int64_t workspace_bytes, void* stream);
+
+/* Propagation in the single-pass "bf16" precision for adjacencies whose values are SEPARABLE, val = d_r^-1/2 d_c^-1/2
+ * with d_r = the number of stored entries of row r (what dmm_build_norm_adj_csr and DataHandler.normalizeAdj produce:
+ * D^-1/2 (A + I) D^-1/2).  dmm_spmm_table_bf16 writes the gather table T = bf16(d^-1/2 X) [n_rows, 64]
+ * (X = [x ; x2] split at row n_first: the reference's torch.cat([u_embs, i_embs]) is never materialised; x2 may be NULL
+ * when n_first >= n_rows) and dmm_spmm_norm_bf16 computes Y[r] = alpha d_r^-1/2 sum_{c in row r} T[c] (+ beta Z[r]): no
+ * value stream, 128-byte rows through the L2, fp32 accumulation (FHADD.BF16).  d^-1/2 comes from the plan (dmm_spmm_plan
+ * of the same adjacency; its row pointers define d).  Same plan / workspace / determinism as dmm_spmm_csr.      */
+int dmm_spmm_table_bf16(dmm_ctx* ctx, const float* x, int64_t ld_x, int64_t n_first, const float* x2, int64_t ld_x2,
+                        int64_t n_rows, const void* plan, int64_t nnz, uint16_t* t, void* stream);
+int dmm_spmm_norm_bf16(dmm_ctx* ctx, const int32_t* adj_idx, int64_t row0, int64_t row1, int64_t n_rows, const uint16_t* t,
+                       float alpha, float beta, const float* z, int64_t ld_z, float* y, int64_t ld_y, const void* plan,
+                       int64_t nnz, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Cross-layer CL perturbation (Main.py:320-321) fused with nothing else:
  * e[r,:] += sign(e[r,:]) * rnd[r,:] / max(||rnd[r,:]||, 1e-12) * noise_degree, in place. */
@@ -358,9 +372,11 @@ int dmm_diff_loss_fwd(dmm_ctx* ctx, const float* diff, int64_t ld_d, int64_t n_r
 int dmm_diff_loss_bwd(dmm_ctx* ctx, const double* g_loss, const float* um, const float* ui, int64_t ld_ui, const float* stats,
                       const int64_t* t, const double* w_tab, float sim_weight, int64_t n_rows, int64_t n_cols, float* cm,
                       uint16_t* dumc_hi, uint16_t* dumc_lo, int64_t ld_dumc, float* d_ui, void* stream);
-/* Hidden layer backward: dz = cm[r] dh (1 - h^2) (h = h_hi + h_lo) as fp32, as bf16 operand [n_rows, ld_dz16], and
- * transposed [H, ld_t] together with (cm h)^T [H, ld_t]: the K = batch operands of the weight-gradient contractions. */
-int dmm_hidden_bwd(dmm_ctx* ctx, const float* dh, int64_t ld_dh, const uint16_t* h_hi, const uint16_t* h_lo, int64_t ld_h,
+/* Hidden layer backward: dz = cm[r] dh (1 - h^2) as fp32, as bf16 operand [n_rows, ld_dz16], and transposed [H, ld_t]
+ * together with (cm h)^T [H, ld_t]: the K = batch operands of the weight-gradient contractions.  h comes from h_f32
+ * (fp32 [n_rows, ld_hf]) when given, else from h_hi (+ h_lo): tanh' of a saturated unit needs more than bf16's 8 bits. */
+int dmm_hidden_bwd(dmm_ctx* ctx, const float* dh, int64_t ld_dh, const float* h_f32, int64_t ld_hf, const uint16_t* h_hi,
+                   const uint16_t* h_lo, int64_t ld_h,
                    const float* cm, int64_t n_rows, int64_t H, float* dz_f32, int64_t ld_dz, uint16_t* dz_hi, uint16_t* dz_lo,
                    int64_t ld_dz16, uint16_t* dzt_hi, uint16_t* dzt_lo, uint16_t* hct_hi, uint16_t* hct_lo, int64_t ld_t,
                    void* stream);

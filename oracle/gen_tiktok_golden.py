@@ -64,6 +64,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tag", default="result")
+    ap.add_argument("--perturb", type=int, default=0,
+                    help="move every initial Denoise weight by -1/0/+1 ulp at random (numpy seed 1000 + M): the chaos-floor "
+                         "ensemble of tools/tiktok_real_ensemble.py on the reference's own arithmetic")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     if args.threads:
@@ -99,13 +102,29 @@ def main():
             return r
 
         coach.trainEpoch, coach.testEpoch = train, test
+        if args.perturb:
+            orig_prepare = coach.prepareModel
+
+            def prepare():
+                orig_prepare()
+                rs = np.random.default_rng(1000 + args.perturb)
+                with torch.no_grad():
+                    dens = [coach.image_denoise_model, coach.text_denoise_model, coach.audio_denoise_model]
+                    for den in dens:
+                        for p in den.parameters():
+                            step = torch.from_numpy(rs.integers(-1, 2, size=tuple(p.shape)).astype(np.int8))
+                            up = torch.nextafter(p, torch.full_like(p, float("inf")))
+                            down = torch.nextafter(p, torch.full_like(p, float("-inf")))
+                            p.copy_(torch.where(step > 0, up, torch.where(step < 0, down, p)))
+
+            coach.prepareModel = prepare
         coach.run()
     finally:
         os.chdir(cwd)
         shutil.rmtree(work, ignore_errors=True)
     with open(os.path.join(OUT, f"{args.tag}.json"), "w") as f:
         json.dump({"conf": "conf/tiktok.toml", "epochs_run": EPOCHS, "epochs": results, "torch": torch.__version__,
-                   "numpy": np.__version__, "threads": torch.get_num_threads(),
+                   "numpy": np.__version__, "threads": torch.get_num_threads(), "perturb": args.perturb,
                    "text_feat": "np.random.default_rng(0).standard_normal((6710, 768)).astype(float32)"}, f, indent=1)
 
 

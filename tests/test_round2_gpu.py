@@ -384,6 +384,76 @@ def test_spmm_lean_kernels_row_ranges_and_bf16_table(ops):
     np.testing.assert_allclose(y16, want16, rtol=2e-5, atol=2e-6)
 
 
+def test_spmm_norm_bf16_exact_on_the_rounded_table(ops):
+    """dmm_spmm_table_bf16 + dmm_spmm_norm_bf16 (separable normalisation, bf16 gather table, units sorted by length):
+      * the table is bf16_rn(d^-1/2 x) exactly (d from the row pointers, [x ; x2] never concatenated);
+      * Y = alpha d_r^-1/2 sum_c T[c] (+ beta Z) against the same sum in float64 on the very table the kernel read
+        (fp32 accumulation: 2e-6 relative), whole product and row blocks, rows with 0 .. 3000 entries;
+      * against the fp32 product it stays within bf16 rounding of the gathered operand (the stated bf16 tolerance)."""
+    from diffmm_b200 import synth
+    U, I = 3000, 800
+    inter = synth.interactions(U, I, seed=5, mean_deg=7.0, heavy_frac=0.03)
+    adj = ops.build_norm_adj(T(inter.indptr), T(inter.indices), U, I)
+    assert adj.separable
+    N = U + I
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((N, 64)).astype(np.float32)
+    xu, xi = T(x[:U]), T(x[U:])
+    ptr, idx, val = adj.ptr.cpu().numpy(), adj.idx.cpu().numpy(), adj.val.cpu().numpy()
+    deg = np.diff(ptr)
+    assert deg.max() > 500 and deg.min() >= 1
+    dinv = (1.0 / np.sqrt(deg.astype(np.float64))).astype(np.float32)
+    table = ops.spmm_table_bf16(adj, xu, xi)
+    want_t = torch.from_numpy(dinv[:, None] * x).bfloat16()
+    assert torch.equal(table.cpu(), want_t)
+    tf = table.float().cpu().numpy().astype(np.float64)
+    rows = np.repeat(np.arange(N), deg)
+    ref = np.zeros((N, 64))
+    np.add.at(ref, rows, tf[idx])
+    ref *= dinv[:, None].astype(np.float64)
+    y = ops.spmm_norm_bf16(adj, xu, x2=xi).cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=3e-6, atol=3e-6 * np.abs(ref).max())
+    out = torch.full((N, 64), float("nan"), device=DEV)
+    for a, b in [(0, 1000), (1000, U), (U, U + 300), (U + 300, N)]:
+        ops.spmm_norm_bf16(adj, table=table, out=out, row0=a, row1=b)
+    assert np.array_equal(out.cpu().numpy(), y)                      # row blocks: same units, same sums, bit for bit
+    z = T(rng.standard_normal((N, 64)).astype(np.float32))
+    y2 = ops.spmm_norm_bf16(adj, T(x), alpha=0.5, beta=2.0, z=z).cpu().numpy()
+    np.testing.assert_allclose(y2, 0.5 * ref + 2.0 * z.cpu().numpy(), rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    full = O.spmm_csr(ptr, idx, val, x)                              # fp32 values, fp32 table
+    assert np.abs(y - full).max() <= 4e-3 * np.abs(full).max()
+    assert np.linalg.norm(y - full) <= 2e-3 * np.linalg.norm(full)
+    # the separability the kernel relies on: val == d_r^-1/2 d_c^-1/2 to fp32 rounding
+    assert np.abs(val - dinv[rows] * dinv[idx]).max() <= 2e-7 * val.max()
+    # deterministic
+    assert np.array_equal(ops.spmm_norm_bf16(adj, table=table).cpu().numpy(), y)
+
+
+def test_spmm_bf16_autograd_path_matches_fp32_within_tolerance(ops):
+    """autograd.spmm under set_spmm_precision("bf16"): value and gradient (A symmetric: the same product on g) within the
+    bf16 tolerance of the fp32 path; non-separable adjacencies keep the fp32 kernel."""
+    from diffmm_b200 import autograd as ag, synth
+    from diffmm_b200.DataHandler import csr_from_torch_sparse
+    U, I = 2000, 600
+    inter = synth.interactions(U, I, seed=2, mean_deg=6.0, heavy_frac=0.02)
+    adj = ops.build_norm_adj(T(inter.indptr), T(inter.indices), U, I)
+    x = torch.randn(U + I, 64, device=DEV)
+    w = torch.randn(U + I, 64, device=DEV)
+    res = {}
+    for prec in ("bf16x3", "bf16"):
+        xx = x.clone().requires_grad_(True)
+        yy = ag.spmm(adj, ag.spmm_cat(adj, xx[:U], xx[U:], prec), prec)
+        (yy * w).sum().backward()
+        res[prec] = (yy.detach(), xx.grad.detach())
+    for a, b in zip(res["bf16"], res["bf16x3"]):
+        assert float((a - b).norm() / b.norm()) <= 3e-3
+        assert float((a - b).abs().max() / b.abs().max()) <= 6e-3
+    assert torch.equal(res["bf16x3"][0], ops.spmm(adj, ops.spmm(adj, x)))          # bf16x3: the fp32 kernel, untouched
+    generic = csr_from_torch_sparse(adj.to_torch_coo())
+    assert not generic.separable
+    assert torch.equal(ag.spmm(generic, x, "bf16"), ops.spmm(generic, x))
+
+
 def test_fused_rng_qsample_values_are_standard_normal_and_counter_based(ops):
     """dmm_csr_qsample_values_rng: (vals - a) / b = n_c / ||n|| for i.i.d. N(0, 1) rows generated in the kernel.  Checked:
     moments of sqrt(I) (vals - a) / b (mean 0, variance 1, kurtosis 3), row norms through the identity

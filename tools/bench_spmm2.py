@@ -36,6 +36,14 @@ def run(U, I, label):
     print(f"{label}:   bf16 table (given)      {ms2*1e3:7.1f} us = {by/ms2/1e6:6.0f} GB/s algorithmic   max err / scale {err:.2e}")
     ms3 = timeit(lambda: ops.spmm_bf16x(adj, x, out=y))
     print(f"{label}:   bf16 table (+ pack pass) {ms3*1e3:7.1f} us = {by/ms3/1e6:6.0f} GB/s algorithmic")
+    table = ops.spmm_table_bf16(adj, x)
+    ms4 = timeit(lambda: ops.spmm_norm_bf16(adj, table=table, out=y))
+    err = float((y - want).abs().max() / want.abs().max())
+    print(f"{label}:   v3 separable bf16 (table given) {ms4*1e3:7.1f} us = {by/ms4/1e6:6.0f} GB/s algorithmic   max err / scale {err:.2e}")
+    ms5 = timeit(lambda: ops.spmm_norm_bf16(adj, x, out=y))
+    print(f"{label}:   v3 separable bf16 (+ table pass) {ms5*1e3:7.1f} us = {by/ms5/1e6:6.0f} GB/s algorithmic")
+    ms6 = timeit(lambda: ops.spmm_table_bf16(adj, x, table=table))
+    print(f"{label}:   table pass alone {ms6*1e3:7.1f} us")
 
 
 run(300000, 80000, "ifashion")
