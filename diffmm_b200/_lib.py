@@ -79,8 +79,6 @@ PROTOTYPES = {
     "dmm_spmm_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "dmm_spmm_csr": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_f32, c_f32,
                                c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
-    "dmm_spmm_csr_bf16x": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp,
-                                     c_i64, c_vp, c_i64, c_vp]),
     "dmm_spmm_table_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "dmm_spmm_norm_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                      c_vp, c_i64, c_vp]),

@@ -4,14 +4,11 @@
 // which coalesces (sorts) the operand on every call before cuSPARSE runs.  The adjacency is
 // symmetric, so the backward pass is the same call on the incoming gradient.
 //
-// Layout: one warp per output row.  For D = 64 a row of X is 256 B = 16 float4: the two half warps
-// gather two neighbours at a time with 128-bit loads (fully coalesced 256 B segments), 4 neighbours
-// per half warp in flight.  Item popularity is heavy tailed (a popular item's row has 10^4..10^5
-// neighbours), so rows longer than PLAN_LONG_ROW are listed once per adjacency in a "plan"
-// (dmm_spmm_plan) and cut into PLAN_CHUNK-neighbour chunks: one warp per chunk writes a partial row,
-// a second small kernel adds the partials of every long row in a fixed order (deterministic, no
-// atomics on Y); the short rows run one half warp per row.  Without a plan, rows longer than LONG_ROW are finished by their CTA alone.
-// HBM-bound: 8*nnz + 8*(N+1) + 2*N*D*4 bytes per product when X is not L2 resident.
+// D = 64 with a plan (the product path): see "v3: degree-sorted units" below -- one persistent launch over equal-length
+// units + a fixed-order reduce of the chunked long rows (deterministic, no atomics on Y); fp32 gather table with A's
+// values, or bf16 gather table with the separable normalisation.  Without a plan: one warp per row, rows longer than
+// LONG_ROW finished by their CTA alone.  Generic D: one warp per row.
+// Compulsory traffic of one fp32 product: 8*nnz + 8*(N+1) + 2*N*D*4 bytes.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -23,11 +20,22 @@ constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 constexpr int LONG_ROW = 1024;
 constexpr int PLAN_LONG_ROW = 64;    // rows with more neighbours go through the plan
 constexpr int PLAN_CHUNK = 64;       // neighbours per chunk of a planned row (one warp each)
+constexpr int REDUCE_SMALL = 16;     // planned rows with more chunks are reduced by a whole CTA (listed in the plan)
+constexpr int V3_HDR_WORDS = 128;    // int32 header of the v3 plan sections; [200] = number of listed big rows
 
 // plan buffer (int64 words): [0] n_long, [1] n_chunks, [2, 2+cap) long row ids, [2+cap, 3+2cap) chunk_ptr,
 // then (16-byte aligned) one descriptor per chunk, int4 {row, neighbours, first entry lo, first entry hi}
 __host__ __device__ inline int64_t plan_cap(int64_t nnz) { return nnz / PLAN_LONG_ROW + 1; }
 __host__ __device__ inline int64_t plan_max_chunks(int64_t nnz) { return nnz / PLAN_CHUNK + plan_cap(nnz) + 1; }
+
+// v3 plan sections behind the chunk descriptors (int64 words): header, int32 big_row[cap] (positions in the long-row list of
+// the rows with more than REDUCE_SMALL chunks), int2 unit[max_chunks + n_rows], float dinv[n_rows]
+__host__ __device__ inline int64_t plan_desc_word(int64_t cap) { return (3 + 2 * cap + 1) & ~(int64_t)1; }
+__host__ __device__ inline int64_t plan_v3_word(int64_t nnz) { return plan_desc_word(plan_cap(nnz)) + 2 * plan_max_chunks(nnz); }
+__host__ __device__ inline int64_t plan_v3_unit_word(int64_t nnz) { return plan_v3_word(nnz) + V3_HDR_WORDS + (plan_cap(nnz) + 1) / 2; }
+__host__ __device__ inline int64_t plan_v3_dinv_word(int64_t nnz, int64_t n_rows) {
+  return plan_v3_unit_word(nnz) + plan_max_chunks(nnz) + n_rows;
+}
 
 struct Epi {
   float alpha, beta;
@@ -133,101 +141,6 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm64_kernel(const int64_t* __r
   }
 }
 
-// Half-warp gather of up to 64 neighbours: the 16 lanes first fetch all column ids / values of the segment
-// with coalesced loads (one round trip), then broadcast them by shuffle and keep BATCH row gathers (256 B each)
-// in flight per half warp.  `hmask` is the shuffle mask of this half warp; the two halves of a warp run
-// independent segments.
-template <int BATCH>
-__device__ __forceinline__ float4 gather64_hw(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                              const float* __restrict__ x, int64_t ld_x, int64_t b, int n, int l16,
-                                              uint32_t hmask, int32_t mc, float mv) {
-  // blocks of 16 neighbours: lane l16 holds (column, value) number l16 of the block.  (mc, mv) is the FIRST block's
-  // pair, fetched by the caller (one row ahead, see hw_first_block); the next block's pair is fetched before this
-  // block's gathers are issued.  Most rows (users: ~7 interactions + the self loop) are a single block, so the
-  // per-row instruction count stays close to the per-neighbour work.
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int32_t* ip = idx + b + l16;
-  const float* vp = val + b + l16;
-#pragma unroll 1
-  for (int base = 0; base < n; base += 16) {     // uniform within the half warp
-    const int cnt = n - base < 16 ? n - base : 16;
-    const int32_t cur_c = mc;
-    const float cur_v = mv;
-    if (base + 16 < n) {
-      mc = base + 16 + l16 < n ? __ldg(ip + base + 16) : 0;
-      mv = base + 16 + l16 < n ? __ldg(vp + base + 16) : 0.f;
-    }
-#pragma unroll 1
-    for (int h = 0; h < cnt; h += BATCH) {
-      float4 xs[BATCH];
-      float vs[BATCH];
-#pragma unroll
-      for (int t = 0; t < BATCH; ++t) {
-        const int32_t c = __shfl_sync(hmask, cur_c, h + t, 16);
-        vs[t] = __shfl_sync(hmask, cur_v, h + t, 16);
-        xs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h + t < cnt) xs[t] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ld_x) + l16);
-      }
-#pragma unroll
-      for (int t = 0; t < BATCH; ++t) acc = fma4(vs[t], xs[t], acc);
-    }
-  }
-  return acc;
-}
-// first block of a segment [b, b + n): lane l16's (column, value) pair
-__device__ __forceinline__ void hw_first_block(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t b,
-                                               int n, int l16, int32_t& mc, float& mv) {
-  mc = l16 < n ? __ldg(idx + b + l16) : 0;
-  mv = l16 < n ? __ldg(val + b + l16) : 0.f;
-}
-
-// ---- short rows of a planned adjacency: one HALF warp per row, rows strided over all resident half warps ----
-// A row is three dependent memory round trips (row pointers -> column ids / values -> gathered rows of X), and at ~14
-// neighbours per row that latency chain, not bandwidth, sets the pace.  The half warp therefore keeps a two-deep
-// software pipeline across its rows: while row i is gathered, the (column, value) block of row i + 1 and the row
-// pointers of row i + 2 are already in flight.
-__device__ __forceinline__ void spmm64_short_rows(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                  const float* __restrict__ val, int64_t row0, int64_t row1,
-                                                  const float* __restrict__ x, int64_t ld_x, const Epi& ep,
-                                                  float* __restrict__ y, int64_t ld_y, int64_t hw_id, int64_t n_hw) {
-  const int l16 = threadIdx.x & 15;
-  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  int64_t r = row0 + hw_id;
-  if (r >= row1) return;
-  auto row_ptr = [&](int64_t rr, int64_t& b, int& n) {
-    b = 0;
-    n = 0;
-    if (rr < row1) {
-      b = __ldg(ptr + rr);
-      const int64_t len = __ldg(ptr + rr + 1) - b;
-      n = len > PLAN_LONG_ROW ? 0 : (int)len;        // long rows belong to the chunk path: nothing to gather here
-      if (len > PLAN_LONG_ROW) b = -1;
-    }
-  };
-  int64_t b0, b1, b2;
-  int n0, n1, n2;
-  row_ptr(r, b0, n0);
-  row_ptr(r + n_hw, b1, n1);
-  int32_t c0, c1;
-  float v0, v1;
-  hw_first_block(idx, val, b0 < 0 ? 0 : b0, n0, l16, c0, v0);
-  for (; r < row1; r += n_hw) {
-    row_ptr(r + 2 * n_hw, b2, n2);
-    hw_first_block(idx, val, b1 < 0 ? 0 : b1, n1, l16, c1, v1);
-    if (b0 >= 0) {
-      const float4 acc = gather64_hw<4>(idx, val, x, ld_x, b0, n0, l16, hmask, c0, v0);
-      float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
-      if (ep.z) {
-        const float4 zz = __ldg(reinterpret_cast<const float4*>(ep.z + r * ep.ld_z) + l16);
-        o = make_float4(fmaf(ep.beta, zz.x, o.x), fmaf(ep.beta, zz.y, o.y), fmaf(ep.beta, zz.z, o.z), fmaf(ep.beta, zz.w, o.w));
-      }
-      reinterpret_cast<float4*>(y + r * ld_y)[l16] = o;
-    }
-    b0 = b1; n0 = n1; c0 = c1; v0 = v1;
-    b1 = b2; n1 = n2;
-  }
-}
-
 // ---- planned long rows ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) plan_collect_kernel(const int64_t* __restrict__ ptr, int64_t n_rows,
                                                            int64_t cap, int64_t* __restrict__ plan) {
@@ -241,7 +154,8 @@ __global__ void __launch_bounds__(256) plan_collect_kernel(const int64_t* __rest
 
 // single block: chunk_ptr = exclusive scan of ceil(nnz_r / PLAN_CHUNK) over the listed rows
 __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restrict__ ptr, int64_t cap,
-                                                         int64_t* __restrict__ plan) {
+                                                         int64_t* __restrict__ plan, int32_t* __restrict__ h,
+                                                         int32_t* __restrict__ big_row) {
   __shared__ int64_t warp_sums[32];
   __shared__ int64_t carry;
   const int64_t n = plan[0] < cap ? plan[0] : cap;
@@ -255,6 +169,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
     if (i < n) {
       const int64_t r = plan[2 + i];
       v = (ptr[r + 1] - ptr[r] + PLAN_CHUNK - 1) / PLAN_CHUNK;
+      if (v > REDUCE_SMALL) big_row[atomicAdd(&h[200], 1)] = (int32_t)i;      // any order: every row is reduced on its own
     }
     int64_t incl = v;
 #pragma unroll
@@ -278,8 +193,6 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int64_t* __restri
   }
 }
 
-// first word of the chunk descriptors inside the plan (16-byte aligned: the plan buffer is, and the offset is even)
-__host__ __device__ inline int64_t plan_desc_word(int64_t cap) { return (3 + 2 * cap + 1) & ~(int64_t)1; }
 
 // descriptor of every chunk c of planned row i: {row, neighbours in the chunk, first entry} (one warp per planned row)
 __global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restrict__ ptr, int64_t cap, int64_t* __restrict__ plan,
@@ -302,69 +215,17 @@ __global__ void __launch_bounds__(256) plan_desc_kernel(const int64_t* __restric
   }
 }
 
-// one half warp per chunk (strided over all resident half warps): partial[c, :] = A[row, chunk] . X
-__device__ __forceinline__ void spmm64_chunks(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                              const float* __restrict__ val, int64_t row0, int64_t row1,
-                                              const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ plan,
-                                              int64_t cap, float* __restrict__ partial, int64_t hw_id, int64_t n_hw) {
-  (void)ptr;
-  const int l16 = threadIdx.x & 15;
-  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  const int64_t n_chunks = plan[1];
-  const int4* desc = reinterpret_cast<const int4*>(plan + plan_desc_word(cap));
-  for (int64_t c = hw_id; c < n_chunks; c += n_hw) {
-    const int4 d = __ldg(desc + c);
-    const int64_t r = d.x;
-    if (r < row0 || r >= row1) continue;
-    const int n = d.y;
-    const int64_t b = (int64_t)(uint32_t)d.z | ((int64_t)d.w << 32);
-    int32_t mc;
-    float mv;
-    hw_first_block(idx, val, b, n, l16, mc, mv);
-    const float4 acc = gather64_hw<8>(idx, val, x, ld_x, b, n, l16, hmask, mc, mv);
-    reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
-  }
-}
-
-// One persistent launch for both kinds of rows of a planned adjacency (grid = SMs x resident CTAs, so every half warp
-// is live from the start and the strided assignment is balanced): each half warp first takes its share of the
-// 64-neighbour chunks of the long rows, then its share of the short rows.  The two kinds write disjoint outputs
-// (partials vs. Y rows), so nothing orders them; only the reduce of the partials follows.
-__global__ void __launch_bounds__(SPMM_THREADS, 4) spmm64_planned_kernel(const int64_t* __restrict__ ptr,
-                                                                         const int32_t* __restrict__ idx,
-                                                                         const float* __restrict__ val, int64_t row0,
-                                                                         int64_t row1, const float* __restrict__ x,
-                                                                         int64_t ld_x, Epi ep, float* __restrict__ y,
-                                                                         int64_t ld_y, const int64_t* __restrict__ plan,
-                                                                         int64_t cap, float* __restrict__ partial) {
-  const int64_t hw_id = (int64_t)blockIdx.x * (SPMM_THREADS / 16) + (threadIdx.x >> 4);
-  const int64_t n_hw = (int64_t)gridDim.x * (SPMM_THREADS / 16);
-  // Small graphs (fewer chunks than half of the resident half warps): the first n_chunks half warps take ONE chunk
-  // each and the others share the short rows, so the two dependent chains run side by side instead of back to back
-  // (the launch is latency bound there).  Otherwise every half warp takes its share of both.
-  const int64_t n_chunks = plan[1];
-  if (2 * n_chunks <= n_hw) {
-    if (hw_id < n_chunks) {
-      spmm64_chunks(ptr, idx, val, row0, row1, x, ld_x, plan, cap, partial, hw_id, n_hw);
-    } else {
-      spmm64_short_rows(ptr, idx, val, row0, row1, x, ld_x, ep, y, ld_y, hw_id - n_chunks, n_hw - n_chunks);
-    }
-    return;
-  }
-  spmm64_chunks(ptr, idx, val, row0, row1, x, ld_x, plan, cap, partial, hw_id, n_hw);
-  spmm64_short_rows(ptr, idx, val, row0, row1, x, ld_x, ep, y, ld_y, hw_id, n_hw);
-}
-
 // Y[row] = epilogue(sum of the row's partials), deterministic.  Pass A: rows with at most REDUCE_SMALL chunks,
 // one half warp per row, all loads in flight.  Pass B: the few big rows, one CTA per row: the 16 half warps
 // stride the partials (4 loads in flight each) and one half warp adds the 16 sums in a fixed order.
-constexpr int REDUCE_SMALL = 16;
 constexpr int REDUCE_THREADS = 1024;     // pass B: 64 half warps x 8 partial rows in flight per big row (the 1600-chunk row is 4 round trips)
 __global__ void __launch_bounds__(REDUCE_THREADS) spmm64_reduce_kernel(int64_t row0, int64_t row1,
                                                                      const int64_t* __restrict__ plan, int64_t cap,
                                                                      const float* __restrict__ partial, Epi ep,
-                                                                     float* __restrict__ y, int64_t ld_y) {
+                                                                     float* __restrict__ y, int64_t ld_y,
+                                                                     const int32_t* __restrict__ v3_hdr) {
   __shared__ float4 part[REDUCE_THREADS / 16][16];
+  const int32_t* big_row = v3_hdr + 2 * V3_HDR_WORDS;
   const int l16 = threadIdx.x & 15, hw = threadIdx.x >> 4;
   constexpr int NHW = REDUCE_THREADS / 16;
   const int64_t n_long = plan[0] < cap ? plan[0] : cap;
@@ -396,11 +257,13 @@ __global__ void __launch_bounds__(REDUCE_THREADS) spmm64_reduce_kernel(int64_t r
     for (int t = 1; t < REDUCE_SMALL; ++t) sum = add4(sum, p[t]);
     finish(r, sum);
   }
-  // pass B
-  for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+  // pass B: the rows listed by the plan as big
+  const int n_big = v3_hdr[200];
+  for (int j = blockIdx.x; j < n_big; j += gridDim.x) {
+    const int64_t i = big_row[j];
     const int64_t r = long_rows[i];
     const int64_t cb = chunk_ptr[i], ce = chunk_ptr[i + 1];
-    if (ce - cb <= REDUCE_SMALL || r < row0 || r >= row1) continue;     // block-uniform
+    if (r < row0 || r >= row1) continue;     // block-uniform
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t c = cb + hw;
     for (; c + 7 * NHW < ce; c += 8 * NHW) {      // 8 partial rows in flight per half warp (the longest row sets the tail)
@@ -423,60 +286,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS) spmm64_reduce_kernel(int64_t r
   }
 }
 
-// ---- D == 64, lean kernels (v2) ---------------------------------------------------------------------------
-// The persistent kernel above hides the row -> ids -> gathers latency chain with a software pipeline and pays for it in
-// instructions: ncu (profiles/r02_prof_spmm_before.txt) counts 22 warp instructions per stored entry, 13 % of them FFMA,
-// the SMs 52 % busy issuing while DRAM and L2 idle at 24 % / 25 %.  Here latency is hidden by OCCUPANCY instead
-// (14-17 instructions per entry; 252 -> 230 us at the ifashion shape.  What bounds it now is per-entry issue + latency, not
-// bytes: an L2-resident graph of a third of the size and a bf16 gather table both run at the same ~43 ns per 1000 entries;
-// a variant that walked 4 rows per half warp as one entry stream, with a quarter of the dependent round trips, measured
-// equal and was dropped):
-// one half warp per short row (or per 64-neighbour chunk of a long row), 32 registers, 64 resident warps per SM, no
-// cross-row pipeline, 32-bit offsets, and no predicates in the gather: the tail of a 16-neighbour block is padded with
-// (column 0, value 0) so every group of four gathers is issued unconditionally (the padding reads hit one hot line).
-// Ids / values / row pointers are streamed with evict-first loads and Y leaves through streaming stores, so the 126 MB
-// L2 keeps X (97 MB at the ifashion shape) instead of thrashing it with write-once / read-once data.
-// one lane's 4 columns of row c of the gather table: fp32 [N, 64] (16 B per lane) or bf16 [N, 64] (8 B per lane: half
-// the bytes through the L2 and a table that fits it)
-template <bool B16>
-__device__ __forceinline__ float4 load_row4(const void* __restrict__ xt, uint32_t ldu, uint32_t c, int l16) {
-  if constexpr (B16) {
-    const uint2 q = __ldg(reinterpret_cast<const uint2*>(xt) + (size_t)(c * ldu + (uint32_t)l16));
-    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u), __uint_as_float(q.y << 16),
-                       __uint_as_float(q.y & 0xFFFF0000u));
-  } else {
-    return __ldg(reinterpret_cast<const float4*>(xt) + (size_t)(c * ldu + (uint32_t)l16));
-  }
-}
-
-template <bool B16>
-__device__ __forceinline__ float4 gather64_lean(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                                const void* __restrict__ x4, uint32_t ld4, uint32_t b, int n, int l16,
-                                                uint32_t hmask) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int base = 0; base < n; base += 16) {
-    const int cnt = n - base < 16 ? n - base : 16;
-    const bool in = l16 < cnt;
-    const uint32_t my_c = in ? (uint32_t)__ldcs(idx + b + base + l16) : 0u;
-    const float my_v = in ? __ldcs(val + b + base + l16) : 0.f;
-#pragma unroll 1
-    for (int h = 0; h < cnt; h += 4) {
-      float4 xs[4];
-      float vs[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint32_t c = __shfl_sync(hmask, my_c, h + t, 16);
-        vs[t] = __shfl_sync(hmask, my_v, h + t, 16);
-        xs[t] = load_row4<B16>(x4, ld4, c, l16);
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) acc = fma4(vs[t], xs[t], acc);
-    }
-  }
-  return acc;
-}
-
+// streaming store of one finished row (fp32 path: 16 lanes x float4)
 __device__ __forceinline__ void store_row_cs(float* __restrict__ y, int64_t ld_y, int64_t r, int l16, const float4& acc,
                                              const Epi& ep) {
   float4 o = make_float4(ep.alpha * acc.x, ep.alpha * acc.y, ep.alpha * acc.z, ep.alpha * acc.w);
@@ -486,40 +296,6 @@ __device__ __forceinline__ void store_row_cs(float* __restrict__ y, int64_t ld_y
   }
   __stcs(reinterpret_cast<float4*>(y + r * ld_y) + l16, o);
 }
-
-// one half warp per row of [row0, row1); rows longer than PLAN_LONG_ROW belong to the chunk kernel
-template <bool B16>
-__global__ void __launch_bounds__(256, 6) spmm64_rows_lean_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                                  const float* __restrict__ val, int64_t row0, int64_t row1,
-                                                                  const void* __restrict__ x4, uint32_t ld4, Epi ep,
-                                                                  float* __restrict__ y, int64_t ld_y) {
-  const int64_t r = row0 + (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4);
-  if (r >= row1) return;
-  const int l16 = threadIdx.x & 15;
-  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  const int64_t b = __ldcs(ptr + r);
-  const int64_t len = __ldcs(ptr + r + 1) - b;
-  if (len > PLAN_LONG_ROW) return;
-  const float4 acc = gather64_lean<B16>(idx, val, x4, ld4, (uint32_t)b, (int)len, l16, hmask);
-  store_row_cs(y, ld_y, r, l16, acc, ep);
-}
-
-// one half warp per 64-neighbour chunk of the planned (long) rows: partial[c, :] = A[row, chunk] . X
-template <bool B16>
-__global__ void __launch_bounds__(256, 6) spmm64_chunks_lean_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val,
-                                                                    int64_t row0, int64_t row1, const void* __restrict__ x4,
-                                                                    uint32_t ld4, const int64_t* __restrict__ plan, int64_t cap,
-                                                                    float* __restrict__ partial) {
-  const int64_t c = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
-  if (c >= plan[1]) return;
-  const int l16 = threadIdx.x & 15;
-  const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);
-  const int4 d = __ldg(reinterpret_cast<const int4*>(plan + plan_desc_word(cap)) + c);
-  if (d.x < row0 || d.x >= row1) return;
-  const float4 acc = gather64_lean<B16>(idx, val, x4, ld4, (uint32_t)d.z, d.y, l16, hmask);
-  reinterpret_cast<float4*>(partial + c * 64)[l16] = acc;
-}
-
 
 // ---- D == 64, v3: degree-sorted units ------------------------------------------------------------------------------
 // What bounded the lean kernels (profiles/r02_prof_spmm_v2.txt): 13 warp instructions per stored entry at IPC 1.4 -- the
@@ -538,11 +314,6 @@ __global__ void __launch_bounds__(256, 6) spmm64_chunks_lean_kernel(const int32_
 // cursor and [80 + b] start of bin b = 64 - length}, int2 unit[max_chunks + n_rows] = {row | length << 25, first entry}
 // (the chunks of the long rows, then the short rows by falling length), float dinv[n_rows].
 constexpr int V3_ROW_BITS = 25;
-constexpr int V3_HDR_WORDS = 128;
-__host__ __device__ inline int64_t plan_v3_word(int64_t nnz) { return plan_desc_word(plan_cap(nnz)) + 2 * plan_max_chunks(nnz); }
-__host__ __device__ inline int64_t plan_v3_dinv_word(int64_t nnz, int64_t n_rows) {
-  return plan_v3_word(nnz) + V3_HDR_WORDS + plan_max_chunks(nnz) + n_rows;
-}
 
 __global__ void __launch_bounds__(1024) v3_hist_kernel(const int64_t* __restrict__ ptr, int64_t n_rows, int32_t* __restrict__ h,
                                                        float* __restrict__ dinv) {
@@ -626,7 +397,7 @@ __global__ void __launch_bounds__(256, B16 ? 4 : 3) spmm64_units_kernel(const in
   const int n_chunks = (int)(plan[1] < max_chunks ? plan[1] : max_chunks);
   const int64_t v3w = plan_v3_word(nnz);
   const int n_units = n_chunks + reinterpret_cast<const int32_t*>(plan + v3w)[0];
-  const int2* unit = reinterpret_cast<const int2*>(plan + v3w + V3_HDR_WORDS);
+  const int2* unit = reinterpret_cast<const int2*>(plan + plan_v3_unit_word(nnz));
   const char* tl = reinterpret_cast<const char*>(tab) + lg * 16;
   const uint32_t r_lo = (uint32_t)row0, r_hi = (uint32_t)row1;       // rows < 2^25
 
@@ -837,18 +608,18 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cap = plan_cap(nnz);
   DMM_CUDA(cudaMemsetAsync(plan, 0, 2 * sizeof(int64_t), st));
-  plan_collect_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(adj_ptr, n_rows, cap, (int64_t*)plan);
-  DMM_LAUNCH_CHECK();
-  plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan);
-  DMM_LAUNCH_CHECK();
-  // v3: the chunks and the rows of at most PLAN_LONG_ROW entries as units sorted by length, and d^-1/2 per row
   int64_t* v3 = (int64_t*)plan + plan_v3_word(nnz);
   int32_t* h = (int32_t*)v3;
-  int2* unit = (int2*)(v3 + V3_HDR_WORDS);
+  DMM_CUDA(cudaMemsetAsync(h, 0, V3_HDR_WORDS * sizeof(int64_t), st));
+  plan_collect_kernel<<<(unsigned)dmm_ceil_div(n_rows, 256), 256, 0, st>>>(adj_ptr, n_rows, cap, (int64_t*)plan);
+  DMM_LAUNCH_CHECK();
+  plan_scan_kernel<<<1, 1024, 0, st>>>(adj_ptr, cap, (int64_t*)plan, h, (int32_t*)(v3 + V3_HDR_WORDS));
+  DMM_LAUNCH_CHECK();
+  // v3: the chunks and the rows of at most PLAN_LONG_ROW entries as units sorted by length, and d^-1/2 per row
+  int2* unit = (int2*)((int64_t*)plan + plan_v3_unit_word(nnz));
   float* dinv = (float*)((int64_t*)plan + plan_v3_dinv_word(nnz, n_rows));
   plan_desc_kernel<<<(unsigned)(ctx->num_sms * 4), 256, 0, st>>>(adj_ptr, cap, (int64_t*)plan, unit);
   DMM_LAUNCH_CHECK();
-  DMM_CUDA(cudaMemsetAsync(h, 0, V3_HDR_WORDS * sizeof(int64_t), st));
   v3_hist_kernel<<<(unsigned)dmm_ceil_div(n_rows, 1024), 1024, 0, st>>>(adj_ptr, n_rows, h, dinv);
   DMM_LAUNCH_CHECK();
   v3_scan_kernel<<<1, 32, 0, st>>>(h);
@@ -860,25 +631,6 @@ extern "C" int dmm_spmm_plan(dmm_ctx* ctx, const int64_t* adj_ptr, int64_t n_row
 }
 
 namespace {
-// lean path: short rows (one per half warp), chunks of the long rows, fixed-order reduce
-template <bool B16>
-int launch_lean(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val, int64_t row0, int64_t row1,
-                const void* xt, uint32_t ldu, const Epi& ep, float* y, int64_t ld_y, const void* plan, int64_t nnz,
-                void* workspace, cudaStream_t st) {
-  const int64_t cap = plan_cap(nnz);
-  spmm64_rows_lean_kernel<B16><<<(unsigned)dmm_ceil_div((row1 - row0) * 16, 256), 256, 0, st>>>(adj_ptr, adj_idx, adj_val, row0,
-                                                                                               row1, xt, ldu, ep, y, ld_y);
-  DMM_LAUNCH_CHECK();
-  const int64_t max_chunks = plan_max_chunks(nnz);
-  spmm64_chunks_lean_kernel<B16><<<(unsigned)dmm_ceil_div(max_chunks * 16, 256), 256, 0, st>>>(
-      adj_idx, adj_val, row0, row1, xt, ldu, (const int64_t*)plan, cap, (float*)workspace);
-  DMM_LAUNCH_CHECK();
-  spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
-                                                                       (const float*)workspace, ep, y, ld_y);
-  DMM_LAUNCH_CHECK();
-  return DMM_OK;
-}
-
 // v3: one persistent launch over the units (chunks of the long rows + length-sorted short rows), then the fixed-order reduce
 template <bool B16>
 int launch_units(dmm_ctx* ctx, const int32_t* adj_idx, const float* adj_val, int64_t row0, int64_t row1, const void* tab,
@@ -889,7 +641,8 @@ int launch_units(dmm_ctx* ctx, const int32_t* adj_idx, const float* adj_val, int
                                                                         row0, row1, ep, y, ld_y, (float*)workspace);
   DMM_LAUNCH_CHECK();
   spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
-                                                                       (const float*)workspace, ep, y, ld_y);
+                                                                       (const float*)workspace, ep, y, ld_y,
+                                                                       (const int32_t*)((const int64_t*)plan + plan_v3_word(nnz)));
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }
@@ -927,24 +680,6 @@ extern "C" int dmm_spmm_norm_bf16(dmm_ctx* ctx, const int32_t* adj_idx, int64_t 
   return launch_units<true>(ctx, adj_idx, nullptr, row0, row1, t, 128u, ep, y, ld_y, plan, nnz, workspace, (cudaStream_t)stream);
 }
 
-extern "C" int dmm_spmm_csr_bf16x(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val,
-                                  int64_t row0, int64_t row1, const uint16_t* x_bf16, int64_t ld_x, float alpha, float beta,
-                                  const float* z, int64_t ld_z, float* y, int64_t ld_y, const void* plan, int64_t nnz,
-                                  void* workspace, int64_t workspace_bytes, void* stream) {
-  DMM_CHECK_ARG(ctx && adj_ptr && adj_idx && adj_val && x_bf16 && y && plan && workspace, "dmm_spmm_csr_bf16x: null argument");
-  DMM_CHECK_ARG(ld_x % 4 == 0 && ld_x >= 64 && ld_x / 4 < (1LL << 20) && ld_y % 4 == 0 && ld_y >= 64 &&
-                    (!z || (ld_z % 4 == 0 && ld_z >= 64)),
-                "dmm_spmm_csr_bf16x: D is 64; leading dimensions must be multiples of 4");
-  DMM_CHECK_ARG((reinterpret_cast<uintptr_t>(x_bf16) & 7u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
-                "dmm_spmm_csr_bf16x: X must be 8-byte and Y 16-byte aligned");
-  DMM_CHECK_ARG(row0 >= 0 && row1 >= row0 && nnz < (1LL << 31), "dmm_spmm_csr_bf16x: bad row range / nnz");
-  DMM_CHECK_ARG(workspace_bytes >= dmm_spmm_workspace_bytes(nnz, 64), "dmm_spmm_csr_bf16x: workspace too small");
-  if (row1 == row0) return DMM_OK;
-  const Epi ep{alpha, z ? beta : 0.f, z, ld_z};
-  return launch_lean<true>(ctx, adj_ptr, adj_idx, adj_val, row0, row1, x_bf16, (uint32_t)(ld_x / 4), ep, y, ld_y, plan, nnz,
-                           workspace, (cudaStream_t)stream);
-}
-
 extern "C" int64_t dmm_spmm_workspace_bytes(int64_t nnz, int64_t D) {
   if (D != 64) return 0;
   // chunks <= nnz / PLAN_CHUNK + (#planned rows <= nnz / PLAN_LONG_ROW + 1)
@@ -973,32 +708,8 @@ extern "C" int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t*
     if (!planned) {
       spmm64_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y, ld_y, 0);
     } else {
-      const int64_t cap = plan_cap(nnz);
-      static const bool lean = []() { const char* e = getenv("DMM_SPMM_V2"); return !(e && e[0] == '0'); }();   // A/B switch
-      static const bool v3 = []() { const char* e = getenv("DMM_SPMM_V3"); return !(e && e[0] == '0'); }();       // A/B switch
-      if (v3 && nnz < (1LL << 31) && ld_x < (1LL << 28))
-        return launch_units<false>(ctx, adj_idx, adj_val, row0, row1, x, (uint32_t)(ld_x * 4), ep, y, ld_y, plan, nnz, workspace, st);
-      // the lean kernels win once the graph has work for three launches (sports: 36 vs 42 us, ifashion: 230 vs 252 us);
-      // below ~0.45 M entries the persistent kernel's two launches are faster (baby: 25 vs 31 us)
-      if (lean && nnz >= 450000 && nnz < (1LL << 31) && ld_x % 4 == 0 && ld_x / 4 < (1LL << 20))
-        return launch_lean<false>(ctx, adj_ptr, adj_idx, adj_val, row0, row1, x, (uint32_t)(ld_x / 4), ep, y, ld_y, plan, nnz,
-                                  workspace, st);
-      static std::atomic<int> resident_cache{0};   // CTAs of the persistent kernel per SM (same for every sm_100 device)
-      int resident = resident_cache.load(std::memory_order_relaxed);
-      if (resident == 0) {
-        DMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, spmm64_planned_kernel, SPMM_THREADS, 0));
-        if (resident < 1) resident = 1;
-        resident_cache.store(resident, std::memory_order_relaxed);
-      }
-      int64_t blocks = (int64_t)ctx->num_sms * resident;
-      const int64_t useful = dmm_ceil_div((row1 - row0) + nnz / PLAN_CHUNK, SPMM_THREADS / 16);   // small graphs: fewer CTAs
-      if (blocks > useful) blocks = useful;
-      if (blocks < 1) blocks = 1;
-      spmm64_planned_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, ep, y,
-                                                                        ld_y, (const int64_t*)plan, cap, (float*)workspace);
-      DMM_LAUNCH_CHECK();
-      spmm64_reduce_kernel<<<(unsigned)(ctx->num_sms * 2), REDUCE_THREADS, 0, st>>>(row0, row1, (const int64_t*)plan, cap,
-                                                                           (const float*)workspace, ep, y, ld_y);
+      DMM_CHECK_ARG(nnz < (1LL << 31) && ld_x < (1LL << 28), "dmm_spmm_csr: a planned product needs nnz < 2^31 and ld_x < 2^28");
+      return launch_units<false>(ctx, adj_idx, adj_val, row0, row1, x, (uint32_t)(ld_x * 4), ep, y, ld_y, plan, nnz, workspace, st);
     }
   } else {
     spmm_generic_kernel<<<grid, SPMM_THREADS, 0, st>>>(adj_ptr, adj_idx, adj_val, row0, row1, x, ld_x, (int)(D / 4), ep, y, ld_y);

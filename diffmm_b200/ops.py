@@ -373,36 +373,12 @@ def spmm(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None,
         out = torch.empty((adj.n_nodes, D), dtype=torch.float32, device=x.device)
     row1 = adj.n_nodes if row1 is None else row1
     nnz = int(adj.nnz)
-    if D == 64 and adj.plan is None:
-        lib = _lib.load()
-        adj.plan = torch.empty(int(lib.dmm_spmm_plan_bytes(adj.n_nodes, nnz)), dtype=torch.uint8, device=x.device)
-        adj.workspace = torch.empty(int(lib.dmm_spmm_workspace_bytes(nnz, D)), dtype=torch.uint8, device=x.device)
-        _lib.call("dmm_spmm_plan", _ctx(x), _p(adj.ptr), adj.n_nodes, nnz, _p(adj.plan), adj.plan.numel(), _stream())
+    if D == 64:
+        _ensure_plan(adj, x.device)
     plan, ws = (adj.plan, adj.workspace) if D == 64 else (None, None)
     _lib.call("dmm_spmm_csr", _ctx(x), _p(adj.ptr), _p(adj.idx), _p(adj.val), int(row0), int(row1), _p(x),
               _row_major(x, "x"), D, float(alpha), float(beta), _p(z), _row_major(z, "z") if z is not None else 0,
               _p(out), _row_major(out, "out"), _p(plan), nnz, _p(ws), ws.numel() if ws is not None else 0, _stream())
-    return out
-
-
-def spmm_bf16x(adj: CsrAdj, x: torch.Tensor, *, alpha=1.0, beta=0.0, z=None, out=None, row0=0, row1=None, x16=None):
-    """spmm with the gather table rounded to bf16 (one dmm_pack_bf16 pass over x unless `x16` is given): half the bytes
-    through the L2, fp32 accumulation and output.  D = 64."""
-    assert x.dtype == torch.float32 and x.shape == (adj.n_nodes, 64)
-    if out is None:
-        out = torch.empty((adj.n_nodes, 64), dtype=torch.float32, device=x.device)
-    row1 = adj.n_nodes if row1 is None else row1
-    nnz = int(adj.nnz)
-    if adj.plan is None:
-        lib = _lib.load()
-        adj.plan = torch.empty(int(lib.dmm_spmm_plan_bytes(adj.n_nodes, nnz)), dtype=torch.uint8, device=x.device)
-        adj.workspace = torch.empty(int(lib.dmm_spmm_workspace_bytes(nnz, 64)), dtype=torch.uint8, device=x.device)
-        _lib.call("dmm_spmm_plan", _ctx(x), _p(adj.ptr), adj.n_nodes, nnz, _p(adj.plan), adj.plan.numel(), _stream())
-    if x16 is None:
-        x16, _ = pack_bf16(x, ld_dst=64, split=False)
-    _lib.call("dmm_spmm_csr_bf16x", _ctx(x), _p(adj.ptr), _p(adj.idx), _p(adj.val), int(row0), int(row1), _p(x16),
-              _row_major(x16, "x16"), float(alpha), float(beta), _p(z), _row_major(z, "z") if z is not None else 0, _p(out),
-              _row_major(out, "out"), _p(adj.plan), nnz, _p(adj.workspace), adj.workspace.numel(), _stream())
     return out
 
 

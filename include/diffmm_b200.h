@@ -255,15 +255,6 @@ int dmm_spmm_csr(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, c
                  float* y, int64_t ld_y, const void* plan, int64_t nnz, void* workspace,
                  int64_t workspace_bytes, void* stream);
 
-/* Same product with the GATHER TABLE given in bf16 (x_bf16 [N, ld_x], D = 64, e.g. from dmm_pack_bf16): rows travel
- * through the L2 at 128 instead of 256 bytes and a 380 k-node table (48 MB) stays L2 resident; accumulation, values and
- * output stay fp32.  The single-pass "bf16" precision of the propagation (rel ~2^-9 on the gathered operand); needs the
- * plan and the workspace of dmm_spmm_csr.                                                                    */
-int dmm_spmm_csr_bf16x(dmm_ctx* ctx, const int64_t* adj_ptr, const int32_t* adj_idx, const float* adj_val, int64_t row0,
-                       int64_t row1, const uint16_t* x_bf16, int64_t ld_x, float alpha, float beta, const float* z,
-                       int64_t ld_z, float* y, int64_t ld_y, const void* plan, int64_t nnz, void* workspace,
-                       int64_t workspace_bytes, void* stream);
-
 /* Propagation in the single-pass "bf16" precision for adjacencies whose values are SEPARABLE, val = d_r^-1/2 d_c^-1/2
  * with d_r = the number of stored entries of row r (what dmm_build_norm_adj_csr and DataHandler.normalizeAdj produce:
  * D^-1/2 (A + I) D^-1/2).  dmm_spmm_table_bf16 writes the gather table T = bf16(d^-1/2 X) [n_rows, 64]

@@ -137,6 +137,7 @@ def test_tiktok_real_bf16_ensemble_mean(tmp_path, monkeypatch):
     ensemble, one epoch each.  Every member: smooth losses within 0.5 % and ranking metrics within 3.5 sd of the reference
     ensemble; the ensemble MEAN of Recall@20 / NDCG@20 within 3 standard errors of the reference ensemble mean."""
     stats = _reference_ensemble()
+    monkeypatch.setenv("DIFFMM_SPMM_BF16_MIN_NNZ", "0")      # the bf16 propagation table too (by default only from 1 M entries)
     members = 6
     hists = [_run(tmp_path, monkeypatch, "bf16", 1, member=m) for m in range(members)]
     for m, h in enumerate(hists):
