@@ -65,6 +65,9 @@ PROTOTYPES = {
                                c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "dmm_gemm_bf16_tn": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
                                    C.POINTER(GemmEpilogue), c_vp]),
+    "dmm_gemm_splitk_workspace_bytes": (c_i64, [c_vp, c_i64, c_i64, c_i64]),
+    "dmm_gemm_bf16_tn_splitk": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                          c_vp, c_i64, c_vp]),
     "dmm_gemm_f32_tn": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp]),
     "dmm_topk_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "dmm_topk_edges": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,

@@ -55,6 +55,9 @@ struct GemmParams {
   // grid); the tiles of the last, partly filled wave are cut into `split` column slices of `sub_bn`
   // columns each so that the tail keeps (almost) every SM busy for 1/split of a tile time.
   int full_items, total_items, split, sub_bn;
+  // split-K (single-pass bf16, fp32 partial outputs only): work item w covers the k blocks [ks * kb_per, (ks + 1) * kb_per)
+  // of tile w / ksplit with ks = w % ksplit, and writes its partial product to rows ks * ks_rows + [0, M) of out_f32
+  int ksplit, kb_per, ks_rows;
   int n_pass;
   int pass_a[3];  // 0 = hi, 1 = lo
   int pass_b[3];
@@ -225,6 +228,8 @@ struct WorkItem {
   int m_blk;   // row block
   int col0;    // first output column
   int bn;      // columns of this item (BN, or sub_bn for a tail slice)
+  int kb0, kb1;  // k blocks of this item (split-K; otherwise all of them)
+  int ks;        // split index
 };
 // n fastest: the CTAs running together cover every column block of a few row blocks, so each A tile is
 // fetched from HBM once and re-read from L2 by its neighbours
@@ -258,6 +263,17 @@ __device__ __forceinline__ float epi_tanh(float x) {
 template <int BN>
 __device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
   WorkItem it;
+  it.ks = 0, it.kb0 = 0, it.kb1 = p.num_k_blocks;
+  if (p.ksplit > 1) {
+    it.ks = w % p.ksplit;
+    w /= p.ksplit;
+    it.kb0 = it.ks * p.kb_per;
+    it.kb1 = min(it.kb0 + p.kb_per, p.num_k_blocks);
+    it.m_blk = w / p.num_n_blocks;
+    it.col0 = (w % p.num_n_blocks) * BN;
+    it.bn = BN;
+    return it;
+  }
   if (w < p.full_items) {
     it.m_blk = w / p.num_n_blocks;
     it.col0 = (w % p.num_n_blocks) * BN;
@@ -714,7 +730,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, const CUt
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tm_o32, fbuf_s + (uint32_t)(j * 4096), n0, row0);
+          tma_store_2d(tm_o32, fbuf_s + (uint32_t)(j * 4096), n0, row0 + wi.ks * p.ks_rows);
           bulk_commit();
         }
       }
@@ -833,7 +849,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
-  const int k_iters = p.n_pass * p.num_k_blocks;
   // items whose first column lies beyond N (slices of a ragged last column block) are skipped by all roles
 
   if (warp == 0) {
@@ -851,7 +866,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap* ma = p.pass_a[ps] ? &tm_a_lo : &tm_a_hi;
           const CUtensorMap* mb = p.pass_b[ps] ? (sub ? &tm_bs_lo : &tm_b_lo) : (sub ? &tm_bs_hi : &tm_b_hi);
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             if (PAIR) {
@@ -888,6 +903,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const int k_iters = p.n_pass * (wi.kb1 - wi.kb0);
         for (int j = 0; j < k_iters; ++j) {
           mbar_wait(full_bar(stage), phase, 3);
           tcgen05_fence_after();
@@ -1015,13 +1031,13 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   // work items are tiles of (BLOCK_M * CTAS) rows; one persistent CTA (or CTA pair) per SM (or TPC)
   const int m_items = (int)dmm_ceil_div(p.M, (int64_t)BLOCK_M * C::CTAS);
   p.num_m_blocks = m_items;
-  const int tiles = m_items * p.num_n_blocks;
+  const int tiles = m_items * p.num_n_blocks * p.ksplit;      // split-K: every tile is ksplit work items
   const int slots = ctx->num_sms / C::CTAS;
   const int grid = tiles < slots ? tiles : slots;
   // tail wave: when the last wave would fill at most half of the grid, cut its tiles into column slices
   const int rem = tiles % grid;
   p.split = 1;
-  if (rem > 0 && tiles > grid) {
+  if (rem > 0 && tiles > grid && p.ksplit == 1) {
     while (p.split * 2 <= BN / 64 && rem * p.split * 2 <= grid) p.split *= 2;
   }
   p.sub_bn = BN / p.split;
@@ -1061,7 +1077,9 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
     p.off_bar = p.off_bias + bias_bytes;
     smem_bytes = p.off_bar + BAR_BYTES + 1024;
     if (p.ep.residual && (rc = make_epi_map(ctx, &m_res, p.ep.residual, true, p.M, p.N, p.ep.ld_res))) return rc;
-    if (p.ep.out_f32 && (rc = make_epi_map(ctx, &m_o32, p.ep.out_f32, true, p.M, p.N, p.ep.ld_out))) return rc;
+    // split-K: the partial products are slabs of ks_rows rows, one per split
+    const int64_t o32_rows = p.ksplit > 1 ? (int64_t)p.ksplit * p.ks_rows : (int64_t)p.M;
+    if (p.ep.out_f32 && (rc = make_epi_map(ctx, &m_o32, p.ep.out_f32, true, o32_rows, p.N, p.ep.ld_out))) return rc;
     if (p.ep.out_hi && (rc = make_epi_map(ctx, &m_o16, p.ep.out_hi, false, p.M, p.N, p.ep.ld_out16))) return rc;
   } else {
     p.nbuf = 1;
@@ -1106,11 +1124,107 @@ int launch(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
   return DMM_OK;
 }
 
+// fixed-order sum of the split-K partial slabs -> fp32 and / or bf16 hi (+ lo) operand copies
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int ksplit, int64_t slab, int64_t ld_p,
+                                                            int64_t M, int64_t N, float* __restrict__ out_f32, int64_t ld_out,
+                                                            uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                                            int64_t ld16) {
+  const int64_t n4 = (N + 3) >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * n4) return;
+  const int64_t r = i / n4, c = (i % n4) * 4;
+  float4 acc = __ldcs(reinterpret_cast<const float4*>(part + r * ld_p + c));
+  for (int s = 1; s < ksplit; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(part + s * slab + r * ld_p + c));
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (c + e >= N) break;
+    if (out_f32) out_f32[r * ld_out + c + e] = v[e];
+    if (out_hi) {
+      uint16_t hi, lo;
+      dmm_split_bf16(v[e], hi, lo);
+      out_hi[r * ld16 + c + e] = hi;
+      if (out_lo) out_lo[r * ld16 + c + e] = lo;
+    }
+  }
+}
+
+int run_gemm(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+             int64_t ldb, int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, int ksplit, int ks_rows, void* stream);
+
 }  // namespace
 
 extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda,
                                 const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb, int64_t M, int64_t N,
                                 int64_t K, const dmm_gemm_epilogue* ep, void* stream) {
+  return run_gemm(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, 1, 0, stream);
+}
+
+// Split-K for contractions with few output tiles and a long K (P = W1x W2 of the hidden-space chain: 1024 x 1024 x I is 16
+// pair tiles on 74 pair slots): each tile's k blocks are divided over up to 8 work items whose fp32 partial products go to
+// slabs of the workspace; a second small launch adds the slabs in a fixed order (deterministic) and writes the fp32 result
+// and / or its bf16 operand copies.  Falls back to the plain contraction when the tiles already fill the machine.
+static int splitk_factor(const dmm_ctx* ctx, int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = dmm_ceil_div(M, 2 * BLOCK_M) * dmm_ceil_div(N, 256);
+  const int64_t slots = ctx->num_sms / 2;
+  const int64_t kblocks = dmm_ceil_div(K, BLOCK_K);
+  int64_t ks = slots / (tiles > 0 ? tiles : 1);
+  if (ks > 8) ks = 8;
+  if (ks > kblocks / 8) ks = kblocks / 8;          // at least 8 k blocks (512 columns of K) per work item
+  if (ks < 2 || N <= 128) return 1;
+  const int64_t per = dmm_ceil_div(kblocks, ks);
+  return (int)dmm_ceil_div(kblocks, per);          // no empty split
+}
+
+extern "C" int64_t dmm_gemm_splitk_workspace_bytes(dmm_ctx* ctx, int64_t M, int64_t N, int64_t K) {
+  if (!ctx) return 0;
+  const int ks = splitk_factor(ctx, M, N, K);
+  if (ks <= 1) return 0;
+  const int64_t rows = dmm_ceil_div(M, 2 * BLOCK_M) * 2 * BLOCK_M, ld = (N + 3) & ~(int64_t)3;
+  return (int64_t)ks * rows * ld * (int64_t)sizeof(float);
+}
+
+extern "C" int dmm_gemm_bf16_tn_splitk(dmm_ctx* ctx, const uint16_t* a_hi, int64_t lda, const uint16_t* b_hi, int64_t ldb,
+                                       int64_t M, int64_t N, int64_t K, float* out_f32, int64_t ld_out, uint16_t* out_hi,
+                                       uint16_t* out_lo, int64_t ld_out16, void* workspace, int64_t workspace_bytes,
+                                       void* stream) {
+  DMM_CHECK_ARG(ctx && a_hi && b_hi && (out_f32 || out_hi), "dmm_gemm_bf16_tn_splitk: null argument");
+  DMM_CHECK_ARG(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "dmm_gemm_bf16_tn_splitk: bad shape");
+  DMM_CHECK_ARG(!out_f32 || ld_out >= N, "dmm_gemm_bf16_tn_splitk: ld_out must be >= N");
+  DMM_CHECK_ARG(!out_hi || ld_out16 >= N, "dmm_gemm_bf16_tn_splitk: ld_out16 must be >= N");
+  DMM_CHECK_ARG(!out_lo || out_hi, "dmm_gemm_bf16_tn_splitk: out_lo requires out_hi");
+  const int ks = splitk_factor(ctx, M, N, K);
+  if (ks <= 1) {
+    // plain contraction; the bf16 lo part needs the fp32 result, which the split path has anyway
+    DMM_CHECK_ARG(!out_lo || out_f32, "dmm_gemm_bf16_tn_splitk: out_lo without out_f32 needs a split (shape does not split)");
+    dmm_gemm_epilogue ep = {};
+    ep.alpha = 1.f;
+    ep.out_f32 = out_f32, ep.ld_out = ld_out, ep.out_hi = out_hi, ep.out_lo = out_lo, ep.ld_out16 = ld_out16;
+    return run_gemm(ctx, a_hi, nullptr, lda, b_hi, nullptr, ldb, M, N, K, &ep, 1, 0, stream);
+  }
+  DMM_CHECK_ARG(workspace && workspace_bytes >= dmm_gemm_splitk_workspace_bytes(ctx, M, N, K) &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0,
+                "dmm_gemm_bf16_tn_splitk: workspace of dmm_gemm_splitk_workspace_bytes bytes (16-byte aligned) required");
+  const int64_t rows = dmm_ceil_div(M, 2 * BLOCK_M) * 2 * BLOCK_M, ld = (N + 3) & ~(int64_t)3;
+  dmm_gemm_epilogue ep = {};
+  ep.alpha = 1.f;
+  ep.out_f32 = (float*)workspace;
+  ep.ld_out = ld;
+  int rc = run_gemm(ctx, a_hi, nullptr, lda, b_hi, nullptr, ldb, M, N, K, &ep, ks, (int)rows, stream);
+  if (rc) return rc;
+  const int64_t work = M * ((N + 3) >> 2);
+  splitk_reduce_kernel<<<(unsigned)dmm_ceil_div(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)workspace, ks, rows * ld, ld, M, N, out_f32, ld_out, out_hi, out_lo, ld_out16);
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+namespace {
+int run_gemm(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+             int64_t ldb, int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, int ksplit, int ks_rows, void* stream) {
   DMM_CHECK_ARG(ctx && a_hi && b_hi && ep, "dmm_gemm_bf16_tn: null argument");
   DMM_CHECK_ARG(ctx->encode_tiled, "dmm_gemm_bf16_tn: cuTensorMapEncodeTiled unavailable");
   DMM_CHECK_ARG(M > 0 && N > 0 && K > 0, "dmm_gemm_bf16_tn: empty problem M=%lld N=%lld K=%lld", (long long)M,
@@ -1143,6 +1257,9 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
   p.K = (int)K;
   p.num_m_blocks = (int)dmm_ceil_div(M, BLOCK_M);
   p.num_k_blocks = (int)dmm_ceil_div(K, BLOCK_K);
+  p.ksplit = ksplit > 1 ? ksplit : 1;
+  p.kb_per = (int)dmm_ceil_div(p.num_k_blocks, p.ksplit);
+  p.ks_rows = ks_rows;
   p.n_pass = 0;
   // small correction passes first, the dominant hi.hi product last
   if (a_lo) { p.pass_a[p.n_pass] = 1; p.pass_b[p.n_pass] = 0; ++p.n_pass; }
@@ -1177,11 +1294,18 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
     bn = force_bn;
     pair = force_bn == 256 && force_pair;
   }
+  if (p.ksplit > 1) {
+    bn = 256;
+    pair = true;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // TMA epilogue (residual prefetch ring + bulk tensor stores) for the single-pass bf16 configurations;
   // DMM_GEMM_TEPI=0 keeps the register-staged epilogue (A/B switch for measurements)
   static const bool tepi_ok = []() { const char* e = getenv("DMM_GEMM_TEPI"); return !(e && e[0] == '0'); }();
-  const bool tepi = tepi_ok && !a_lo && !b_lo && !ep->res_hi && !ep->res_lo && !ep->out_lo && (ep->out_f32 || ep->out_hi);
+  const bool tepi = (tepi_ok || p.ksplit > 1) && !a_lo && !b_lo && !ep->res_hi && !ep->res_lo && !ep->out_lo &&
+                    (ep->out_f32 || ep->out_hi);
+  DMM_CHECK_ARG(p.ksplit == 1 || (tepi && ep->out_f32 && !ep->out_hi && !ep->residual && !ep->bias && !ep->cmax && ep->act == 0),
+                "dmm_gemm_bf16_tn: split-K writes plain fp32 partial products");
   switch (bn) {
     case 64: return launch<64, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
     case 128: return launch<128, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
@@ -1190,3 +1314,4 @@ extern "C" int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16
                   : launch<256, false>(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, p, tepi, st);
   }
 }
+}  // namespace

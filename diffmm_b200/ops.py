@@ -233,6 +233,17 @@ def gemm_bf16_tn(a_hi, a_lo, b_hi, b_lo, M, N, K, *, bias=None, act=0, alpha=1.0
               _row_major(b_hi, "b_hi"), int(M), int(N), int(K), C.byref(ep), _stream())
 
 
+def gemm_bf16_tn_splitk(a_hi, b_hi, M, N, K, *, out_f32=None, out_hi=None, out_lo=None):
+    """C = A . B^T (single-pass bf16, no epilogue terms) with the k blocks of every tile divided over several work items
+    when the output has few tiles and K is long (dmm_gemm_bf16_tn_splitk); plain contraction otherwise."""
+    ctx = _ctx(a_hi)
+    ws_bytes = int(_lib.load().dmm_gemm_splitk_workspace_bytes(ctx, int(M), int(N), int(K)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a_hi.device) if ws_bytes > 0 else None
+    _lib.call("dmm_gemm_bf16_tn_splitk", ctx, _p(a_hi), _row_major(a_hi, "a_hi"), _p(b_hi), _row_major(b_hi, "b_hi"), int(M),
+              int(N), int(K), _p(out_f32), _row_major(out_f32, "out_f32") if out_f32 is not None else 0, _p(out_hi), _p(out_lo),
+              _row_major(out_hi, "out_hi") if out_hi is not None else 0, _p(ws), ws_bytes, _stream())
+
+
 def gemm_f32_tn(a, b, M, N, K, *, bias=None, act=0, alpha=1.0, beta=0.0, residual=None, out_f32=None,
                 out_hi=None, out_lo=None, res_pre_act=False, post_bias=None, post_act=0):
     ep = _epilogue(bias, act, alpha, beta, residual, out_f32, out_hi, out_lo, None, None, res_pre_act, post_bias, post_act)

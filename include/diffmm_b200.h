@@ -184,6 +184,16 @@ int dmm_gemm_bf16_tn(dmm_ctx* ctx, const uint16_t* a_hi, const uint16_t* a_lo, i
                      const uint16_t* b_hi, const uint16_t* b_lo, int64_t ldb,
                      int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, void* stream);
 
+/* Split-K form for contractions with few output tiles and a long K (P = W1[:, :I] . W2 of the hidden-space chain,
+ * [H, H] over I items: 16 pair tiles on 74 tile slots): C = A[M,K] . B[N,K]^T, single-pass bf16, no epilogue terms.  The k
+ * blocks of every tile are divided over up to 8 work items of the same persistent launch; their fp32 partial products go to
+ * slabs of `workspace` (dmm_gemm_splitk_workspace_bytes; 0 when the shape does not split) and a second launch adds the slabs
+ * in a fixed order (deterministic) into out_f32 and / or the bf16 operand copies out_hi (+ out_lo = bf16(c - hi)).      */
+int64_t dmm_gemm_splitk_workspace_bytes(dmm_ctx* ctx, int64_t M, int64_t N, int64_t K);
+int dmm_gemm_bf16_tn_splitk(dmm_ctx* ctx, const uint16_t* a_hi, int64_t lda, const uint16_t* b_hi, int64_t ldb,
+                            int64_t M, int64_t N, int64_t K, float* out_f32, int64_t ld_out, uint16_t* out_hi,
+                            uint16_t* out_lo, int64_t ld_out16, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Same contract on the fp32 CUDA-core pipe from fp32 operands (verification mode; no tensor cores). */
 int dmm_gemm_f32_tn(dmm_ctx* ctx, const float* a, int64_t lda, const float* b, int64_t ldb,
                     int64_t M, int64_t N, int64_t K, const dmm_gemm_epilogue* ep, void* stream);

@@ -175,6 +175,47 @@ def test_tcgen05_k_chunked_pre_activation_residual(ops):
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=5e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 7050), (1024, 1024, 18357), (300, 520, 4100), (256, 256, 70000), (128, 64, 4096),
+                                   (19445, 1024, 1024)])
+def test_tcgen05_splitk(ops, M, N, K):
+    """dmm_gemm_bf16_tn_splitk: fp32 result and its bf16 hi / lo copies against float64 on the bf16-rounded operands (exact
+    products; only the fp32 summation order differs), against the plain contraction, and deterministic.  The last two
+    shapes do not split (narrow N / tiles fill the machine): the entry point must fall back to the plain contraction."""
+    rng = np.random.default_rng(M + N + K)
+    a = _bf16_round(rng.standard_normal((M, K)).astype(np.float32) / np.sqrt(K))
+    b = _bf16_round(rng.standard_normal((N, K)).astype(np.float32))
+    ld = (K + 63) // 64 * 64
+    a_d = torch.zeros((M, ld), dtype=torch.bfloat16, device=DEV)
+    b_d = torch.zeros((N, ld), dtype=torch.bfloat16, device=DEV)
+    a_d[:, :K] = T(a).bfloat16()
+    b_d[:, :K] = T(b).bfloat16()
+    want = a.astype(np.float64) @ b.astype(np.float64).T
+    ldn = (N + 63) // 64 * 64
+    out = torch.full((M, (N + 3) // 4 * 4), float("nan"), device=DEV)
+    hi = torch.zeros((M, ldn), dtype=torch.bfloat16, device=DEV)
+    lo = torch.zeros((M, ldn), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16_tn_splitk(a_d[:, :K], b_d[:, :K], M, N, K, out_f32=out[:, :N], out_hi=hi[:, :N], out_lo=lo[:, :N])
+    got = out[:, :N].cpu().numpy()
+    atol = 2e-5 * max(1.0, np.sqrt(K / 7050))        # test_tcgen05's tolerance (values of order 1), grown with sqrt(K)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=atol)
+    plain = torch.empty_like(out)
+    ops.gemm_bf16_tn(a_d[:, :K], None, b_d[:, :K], None, M, N, K, out_f32=plain[:, :N])
+    # the plain contraction accumulates K products in ONE fp32 chain of the tensor pipe (its error grows faster than the
+    # split sums'): a looser bound, it is not the subject here
+    np.testing.assert_allclose(plain[:, :N].cpu().numpy(), want, rtol=1e-5, atol=6 * atol)
+    # operand copies: hi = bf16_rn(c), lo = bf16_rn(c - hi), exactly, of the fp32 result the call returned
+    g = out[:, :N]
+    assert torch.equal(hi[:, :N], g.bfloat16())
+    assert torch.equal(lo[:, :N], (g - g.bfloat16().float()).bfloat16())
+    out2 = torch.empty_like(out)
+    ops.gemm_bf16_tn_splitk(a_d[:, :K], b_d[:, :K], M, N, K, out_f32=out2[:, :N])
+    assert torch.equal(out2[:, :N], out[:, :N])
+    # bf16 copy only (the rebuild's call)
+    hi2 = torch.zeros_like(hi)
+    ops.gemm_bf16_tn_splitk(a_d[:, :K], b_d[:, :K], M, N, K, out_hi=hi2[:, :N])
+    assert torch.equal(hi2[:, :N], hi[:, :N])
+
+
 def test_tcgen05_no_epilogue_extras(ops):
     rng = np.random.default_rng(9)
     M, N, K = 256, 512, 192

@@ -39,3 +39,14 @@ W2t = (torch.randn((H, ops.pad_to(I, 64)), device=DEV, generator=g) / 80).to(tor
 Pf = torch.empty((H, H), device=DEV)
 ms = timeit(lambda: ops.gemm_bf16_tn(W1, None, W2t, None, H, H, I, out_f32=Pf))
 print(f"P = W1x W2  {H}x{H}x{I}: {ms*1e3:.1f} us  {2.0*H*H*I/ms/1e9:.0f} TFLOP/s")
+Ph = torch.zeros((H, H), dtype=torch.bfloat16, device=DEV)
+ms = timeit(lambda: ops.gemm_bf16_tn_splitk(W1[:, :I], W2t[:, :I], H, H, I, out_hi=Ph))
+print(f"P split-K   {H}x{H}x{I}: {ms*1e3:.1f} us  {2.0*H*H*I/ms/1e9:.0f} TFLOP/s (contraction + slab reduce, bf16 operand out)")
+ms = timeit(lambda: ops.gemm_bf16_tn(W1[:, :I], None, W2t[:, :I], None, H, H, I, out_hi=Ph))
+print(f"P plain     {H}x{H}x{I}: {ms*1e3:.1f} us  (bf16 operand out)")
+for I2 in (18357, 500000):
+    A = (torch.randn((H, ops.pad_to(I2, 64)), device=DEV, generator=g) / 80).to(torch.bfloat16)
+    B = (torch.randn((H, ops.pad_to(I2, 64)), device=DEV, generator=g) / 80).to(torch.bfloat16)
+    ms = timeit(lambda: ops.gemm_bf16_tn_splitk(A[:, :I2], B[:, :I2], H, H, I2, out_hi=Ph), n=5)
+    ms0 = timeit(lambda: ops.gemm_bf16_tn(A[:, :I2], None, B[:, :I2], None, H, H, I2, out_hi=Ph), n=5)
+    print(f"P I={I2}: split-K {ms*1e3:.1f} us ({2.0*H*H*I2/ms/1e9:.0f} TFLOP/s)  plain {ms0*1e3:.1f} us ({2.0*H*H*I2/ms0/1e9:.0f} TFLOP/s)")
