@@ -65,7 +65,7 @@ UNIT = "users/s"
 KERNELS_PER_CALL = {   # hand-written kernels launched per C-ABI call (CUB's sort kernels are not counted)
     "dmm_pack_bf16": 1, "dmm_csr_rows_to_dense": 1, "dmm_time_embedding": 1, "dmm_q_sample": 1, "dmm_gemm_bf16_tn": 1,
     "dmm_gemm_f32_tn": 1, "dmm_topk_edges": 1, "dmm_topk_edges_pruned": 2, "dmm_csr_qsample_values": 1,
-    "dmm_build_norm_adj_csr": 4, "dmm_sign_noise_": 1,
+    "dmm_build_norm_adj_csr": 3, "dmm_sign_noise_": 1,
     "dmm_bpr_fwd_bwd": 2, "dmm_infonce_fwd": 3, "dmm_infonce_bwd": 3, "dmm_scatter_add_rows": 1,
     "dmm_spmm_csr": 2, "dmm_spmm_plan": 6, "dmm_spmm_table_bf16": 1, "dmm_spmm_norm_bf16": 2, "dmm_gemm_bf16_tn_splitk": 2,
 }
@@ -552,7 +552,11 @@ def run_ours(args):
         orig_gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, **kw)
         e1.record()
         passes = 1 + (a_lo is not None) + (b_lo is not None)
-        gemm_events.append((2.0 * M * N * K, e0, e1, (M, N, K, passes)))
+        # compulsory HBM bytes of the call: operands once, every epilogue tensor once
+        nbytes = 2.0 * M * K * (1 + (a_lo is not None)) + 2.0 * N * K * (1 + (b_lo is not None))
+        nbytes += 4.0 * M * N * ((kw.get("residual") is not None) + (kw.get("out_f32") is not None))
+        nbytes += 2.0 * M * N * sum(kw.get(k) is not None for k in ("out_hi", "out_lo", "res_hi", "res_lo"))
+        gemm_events.append((2.0 * M * N * K, e0, e1, (M, N, K, passes), nbytes))
     timed_gemm.on = False
     ops.gemm_bf16_tn = timed_gemm
     rebuild.ops.gemm_bf16_tn = timed_gemm
@@ -565,7 +569,9 @@ def run_ours(args):
         e0.record()
         orig_splitk(a_hi, b_hi, M, N, K, **kw)
         e1.record()
-        gemm_events.append((2.0 * M * N * K, e0, e1, (M, N, K, "1+splitK")))
+        nbytes = 2.0 * M * K + 2.0 * N * K + 4.0 * M * N * (kw.get("out_f32") is not None) + 2.0 * M * N * (
+            (kw.get("out_hi") is not None) + (kw.get("out_lo") is not None))
+        gemm_events.append((2.0 * M * N * K, e0, e1, (M, N, K, "1+splitK"), nbytes))
     ops.gemm_bf16_tn_splitk = timed_splitk
     rebuild.ops.gemm_bf16_tn_splitk = timed_splitk
 
@@ -589,17 +595,27 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in counts.items())
 
+    pk = peaks()
+
     def gemm_stats(events):
-        tot_ms = sum(a.elapsed_time(b) for _, a, b, _ in events)
-        flops = sum(f for f, _, _, _ in events)
+        tot_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in events)
+        flops = sum(f for f, _, _, _, _ in events)
         shapes = {}
-        for f, a, b, shape in events:
-            d = shapes.setdefault("x".join(map(str, shape[:3])) + f"/p{shape[3]}", [0, 0.0, 0.0])
+        for f, a, b, shape, nb in events:
+            d = shapes.setdefault("x".join(map(str, shape[:3])) + f"/p{shape[3]}", [0, 0.0, 0.0, 0.0])
             d[0] += 1
             d[1] += a.elapsed_time(b)
             d[2] += f
-        shapes = {k: {"launches": v[0], "avg_ms": v[1] / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12} for k, v in shapes.items()}
-        return tot_ms, flops, shapes
+            d[3] += nb
+        out = {}
+        for k, v in shapes.items():
+            tf, gbs = v[2] / (v[1] * 1e-3) / 1e12, v[3] / (v[1] * 1e-3) / 1e9
+            # the roofline that bounds the shape: tensor pipe above the ridge (peak FLOP/s / peak B/s), HBM below it
+            intensity, ridge = v[2] / max(v[3], 1.0), pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9)
+            out[k] = {"launches": v[0], "avg_ms": v[1] / v[0], "tflops": tf, "compulsory_GBps": gbs,
+                      "flop_per_byte": intensity, "bound": "tensor" if intensity >= ridge else "hbm",
+                      "frac_of_its_bound": tf / pk["tf_burst"] if intensity >= ridge else gbs / pk["hbm"]}
+        return tot_ms, flops, out
 
     # The modalities run as concurrent pipelines on two streams (rebuild.rebuild_edges), so an event pair around a
     # contraction inside the timed region also spans whatever the other stream ran meanwhile.  The kernel's own launch
@@ -707,14 +723,15 @@ def run_ours(args):
             td.destroy_process_group()
         return
 
-    pk = peaks()
     # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json),
     # averaged over this run's launch mix; null when a shape has no capture
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["gemm_bf16_tn_kernel"]
         tot, cnt = 0.0, 0
-        for _, _, _, shape in gemm_events:
+        for _, _, _, shape, _ in gemm_events:
+            if shape[3] == "1+splitK":      # captured as the plain launch only: left out of the average
+                continue
             ent = tr.get("x".join(map(str, shape[:3])))
             if ent is None or shape[3] != 1:
                 tot, cnt = 0.0, 0
@@ -744,6 +761,9 @@ def run_ours(args):
                      "peak_source": f"{pk['source']} bf16_tflops (burst: the timed region is tens of ms at full clocks); "
                                     f"sustained {pk['tf_sustained']}",
                      "frac_of_sustained": achieved / pk["tf_sustained"], "by_shape_MxNxK": by_shape,
+                     "frac_of_binding_roofline_time_weighted": (
+                         sum(v["frac_of_its_bound"] * v["avg_ms"] * v["launches"] for v in by_shape.values()) /
+                         max(sum(v["avg_ms"] * v["launches"] for v in by_shape.values()), 1e-9)),
                      "algorithmic_flops_per_launch": gemm_flops / n_gemm,
                      "measured_in": f"second pass of the same {args.steps} steps with the modality pipelines serialised on one "
                                     f"stream ({serial_ms / args.steps:.3f} ms/step); in the timed region they overlap on "

@@ -7,7 +7,7 @@
 //   1. expand user ids per edge; stable LSD radix sort of (item, user) pairs by item gives R^T with
 //      users ascending inside every item row  (CUB DeviceRadixSort: CCCL library plumbing, the only
 //      non-hand-written device code of the library; candidate for a hand-written counting sort);
-//   2. item row offsets from the boundaries of the sorted list (no atomics, no scan);
+//   2. item row offsets from the boundaries of the sorted list (no atomics, no scan) and d^-1/2 per node, one kernel;
 //   3. one thread per stored entry writes [self loop | neighbours] rows in ascending column order with
 //      val = (d_r^-1/2 * 1) * d_c^-1/2 evaluated in fp64 and rounded to fp32 like the reference.
 // HBM-bound: ~8E bytes in, 8(2E+N) + 8(N+1) bytes out.
@@ -20,7 +20,7 @@ namespace {
 __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __restrict__ row_ptr, int64_t n_users,
                                                            int32_t* __restrict__ edge_user,
                                                            const int32_t* __restrict__ items, int64_t n_items,
-                                                           int32_t* __restrict__ bad, int32_t* __restrict__ status) {
+                                                           int32_t* __restrict__ status) {
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= n_users) return;
@@ -28,35 +28,38 @@ __global__ void __launch_bounds__(256) expand_users_kernel(const int64_t* __rest
   for (int64_t j = b + lane; j < e; j += 32) {
     edge_user[j] = (int32_t)u;
     const int32_t it = items[j];
-    if (it < 0 || it >= n_items) {
-      atomicExch(bad, 1);
-      if (status) atomicOr(status, 2);
-    }
+    if ((it < 0 || it >= n_items) && status) atomicOr(status, 2);
   }
 }
 
-// Item row offsets from the item-sorted edge list: item_ptr[it] = first position whose item is >= it
-// (lower bound by binary search, one thread per item; no atomics: a popular item would serialise 10^5 of them).
-__global__ void __launch_bounds__(256) item_offsets_kernel(const int32_t* __restrict__ items_sorted, int64_t n_edges,
-                                                           int64_t n_items, int64_t* __restrict__ item_ptr) {
-  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (it > n_items) return;
+// One thread per node: item row offsets from the item-sorted edge list -- item_ptr[it] = first position whose item is >= it
+// (lower bound by binary search; no atomics: a popular item would serialise 10^5 of them) -- and d^-1/2 per node in fp64
+// (degree counts the self loop), computed once per node instead of per entry.
+__device__ __forceinline__ int64_t lower_bound_item(const int32_t* __restrict__ items_sorted, int64_t n_edges, int64_t it) {
   int64_t lo = 0, hi = n_edges;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if ((int64_t)__ldg(items_sorted + mid) < it) lo = mid + 1; else hi = mid;
   }
-  item_ptr[it] = lo;
+  return lo;
 }
-
-// d^-1/2 per node in fp64 (degree counts the self loop), computed once per node instead of per entry
-__global__ void __launch_bounds__(256) node_dinv_kernel(const int64_t* __restrict__ row_ptr,
-                                                        const int64_t* __restrict__ item_ptr, int64_t n_users,
-                                                        int64_t n_items, double* __restrict__ dinv) {
+__global__ void __launch_bounds__(256) offsets_dinv_kernel(const int64_t* __restrict__ row_ptr,
+                                                           const int32_t* __restrict__ items_sorted, int64_t n_users,
+                                                           int64_t n_items, int64_t n_edges, int64_t* __restrict__ item_ptr,
+                                                           double* __restrict__ dinv) {
   const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n_users + n_items) return;
-  const int64_t deg = node < n_users ? row_ptr[node + 1] - row_ptr[node] + 1
-                                     : item_ptr[node - n_users + 1] - item_ptr[node - n_users] + 1;
+  int64_t deg;
+  if (node < n_users) {
+    deg = row_ptr[node + 1] - row_ptr[node] + 1;
+  } else {
+    const int64_t it = node - n_users;
+    const int64_t b = lower_bound_item(items_sorted, n_edges, it);
+    const int64_t e = it + 1 < n_items ? lower_bound_item(items_sorted, n_edges, it + 1) : n_edges;
+    item_ptr[it] = b;
+    if (it + 1 == n_items) item_ptr[n_items] = n_edges;
+    deg = e - b + 1;
+  }
   dinv[node] = deg > 0 ? 1.0 / sqrt((double)deg) : 0.0;
 }
 
@@ -159,10 +162,8 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
   DMM_CHECK_ARG((size_t)workspace_bytes > fixed, "dmm_build_norm_adj_csr: workspace too small");
   w.cub_bytes = (size_t)workspace_bytes - fixed;
 
-  int32_t* bad = w.item_count + n_items;
-  DMM_CUDA(cudaMemsetAsync(bad, 0, 4, st));
   expand_users_kernel<<<(unsigned)dmm_ceil_div(n_users * 32, 256), 256, 0, st>>>(row_ptr, n_users, w.edge_user, items, n_items,
-                                                                                bad, status);
+                                                                                status);
   DMM_LAUNCH_CHECK();
   if (n_edges > 0) {
     int end_bit = 1;
@@ -177,10 +178,9 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
     DMM_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, need, items, w.items_sorted, w.edge_user, w.users_by_item,
                                              (int)n_edges, 0, end_bit, st));
   }
-  item_offsets_kernel<<<(unsigned)dmm_ceil_div(n_items + 1, 256), 256, 0, st>>>(w.items_sorted, n_edges, n_items, w.item_ptr);
-  DMM_LAUNCH_CHECK();
   const int64_t N = n_users + n_items;
-  node_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.item_ptr, n_users, n_items, w.dinv);
+  offsets_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.items_sorted, n_users, n_items, n_edges, w.item_ptr,
+                                                                     w.dinv);
   DMM_LAUNCH_CHECK();
   const int64_t work = n_edges > N ? n_edges : N;
   fill_adj_kernel<<<(unsigned)dmm_ceil_div(work, 256), 256, 0, st>>>(row_ptr, items, w.edge_user, w.item_ptr, w.items_sorted,

@@ -2,8 +2,10 @@
 against golden vectors produced by the unmodified reference and against the numpy oracle.
 
 Tolerances (written here, per north_star): "bf16x3" (split-bf16, fp32-faithful) rel 1e-4 of the tensor
-scale on forward values and 1e-3 on gradients; "bf16" rel 2e-2 of the tensor scale.  Index work
-(top-k, adjacency structure) is bit-exact given identical scores."""
+scale on forward values and 1e-3 on gradients; "bf16" rel 7e-3 of the tensor scale on forward values (measured
+worst case: 5.2e-3, the five-step reverse chain -- every operand of every step rounded to 8 mantissa bits; the
+full-size measurement of tests/test_precision_fullsize_gpu.py gives 3.9e-3 .. 4.6e-3) and 2e-2 on gradients.  Index
+work (top-k, adjacency structure) is bit-exact given identical scores."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +16,7 @@ from oracle import diffmm_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 U, I, H, D = 40, 120, 32, 64
-TOL = {"bf16x3": 2e-4, "bf16": 2e-2}
+TOL = {"bf16x3": 1e-4, "bf16": 7e-3}
 
 
 def T(a, dtype=None):
@@ -95,7 +97,7 @@ def test_training_losses_value_and_grads(precision):
     assert losses.dtype == torch.float64 and losses.shape == (g["x0"].shape[0],)
     close(losses, g["losses"], TOL[precision] * (1 if precision == "bf16x3" else 5), "loss rows")
     losses.mean().backward()
-    gt = 1e-3 if precision == "bf16x3" else 1e-1
+    gt = 1e-3 if precision == "bf16x3" else 2e-2
     got = {"w1": den.in_layers[0].weight.grad, "b1": den.in_layers[0].bias.grad, "w2": den.out_layers[0].weight.grad,
            "b2": den.out_layers[0].bias.grad, "emb_w": den.emb_layer.weight.grad, "emb_b": den.emb_layer.bias.grad,
            "gate_w": den.gate_layer.weight.grad, "gate_b": den.gate_layer.bias.grad}
