@@ -47,20 +47,23 @@ __global__ void __launch_bounds__(256) offsets_dinv_kernel(const int64_t* __rest
                                                            const int32_t* __restrict__ items_sorted, int64_t n_users,
                                                            int64_t n_items, int64_t n_edges, int64_t* __restrict__ item_ptr,
                                                            double* __restrict__ dinv) {
-  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= n_users + n_items) return;
-  int64_t deg;
-  if (node < n_users) {
-    deg = row_ptr[node + 1] - row_ptr[node] + 1;
-  } else {
-    const int64_t it = node - n_users;
-    const int64_t b = lower_bound_item(items_sorted, n_edges, it);
-    const int64_t e = it + 1 < n_items ? lower_bound_item(items_sorted, n_edges, it + 1) : n_edges;
-    item_ptr[it] = b;
-    if (it + 1 == n_items) item_ptr[n_items] = n_edges;
-    deg = e - b + 1;
+  // blocks [0, user_blocks): one thread per user; the others: 255 items per block + one halo search, so that every thread
+  // runs ONE binary search (17 dependent loads) and reads its row end from its neighbour
+  __shared__ int64_t lb[256];
+  const int64_t user_blocks = (n_users + 255) / 256;
+  if ((int64_t)blockIdx.x < user_blocks) {
+    const int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (u < n_users) dinv[u] = 1.0 / sqrt((double)(row_ptr[u + 1] - row_ptr[u] + 1));
+    return;
   }
-  dinv[node] = deg > 0 ? 1.0 / sqrt((double)deg) : 0.0;
+  const int64_t it = ((int64_t)blockIdx.x - user_blocks) * 255 + threadIdx.x;      // threadIdx.x == 255: halo
+  lb[threadIdx.x] = it < n_items ? lower_bound_item(items_sorted, n_edges, it) : n_edges;
+  __syncthreads();
+  if (threadIdx.x == 255 || it >= n_items) return;
+  const int64_t b = lb[threadIdx.x], e = lb[threadIdx.x + 1];
+  item_ptr[it] = b;
+  if (it + 1 == n_items) item_ptr[n_items] = n_edges;
+  dinv[n_users + it] = 1.0 / sqrt((double)(e - b + 1));
 }
 
 // Entry-parallel fill (no per-row walks, so popular items with thousands of users cost the same per
@@ -179,8 +182,8 @@ extern "C" int dmm_build_norm_adj_csr(dmm_ctx* ctx, const int64_t* row_ptr, cons
                                              (int)n_edges, 0, end_bit, st));
   }
   const int64_t N = n_users + n_items;
-  offsets_dinv_kernel<<<(unsigned)dmm_ceil_div(N, 256), 256, 0, st>>>(row_ptr, w.items_sorted, n_users, n_items, n_edges, w.item_ptr,
-                                                                     w.dinv);
+  offsets_dinv_kernel<<<(unsigned)(dmm_ceil_div(n_users, 256) + dmm_ceil_div(n_items, 255)), 256, 0, st>>>(
+      row_ptr, w.items_sorted, n_users, n_items, n_edges, w.item_ptr, w.dinv);
   DMM_LAUNCH_CHECK();
   const int64_t work = n_edges > N ? n_edges : N;
   fill_adj_kernel<<<(unsigned)dmm_ceil_div(work, 256), 256, 0, st>>>(row_ptr, items, w.edge_user, w.item_ptr, w.items_sorted,
