@@ -54,6 +54,8 @@ PROTOTYPES = {
     "dmm_time_bias": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "dmm_csr_gather_act": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, C.c_int,
                                      c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmm_csr_gather_act_split": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64,
+                                           c_vp, C.c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "dmm_csr_qsample_values_rng": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_f32, c_f32, c_vp, C.c_int,
                                              c_vp]),
     "dmm_csr_qsample_values": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),

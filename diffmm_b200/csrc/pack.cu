@@ -386,6 +386,199 @@ __global__ void __launch_bounds__(256) csr_gather_act_kernel(const int64_t* __re
   }
 }
 
+// ------------------------------------------------------------------ first layer on CSR rows, rows scheduled by length
+// What bounded the kernel above at the baby shape (ncu): 790 warp instructions per (row, slice) warp for a median row of
+// 4-5 entries -- index arithmetic, item ids, shuffles, predicates and the bias / tanh / pack tail paid once per 256
+// columns -- at 40 % occupancy.  Here ONE warp owns a whole short row: the item ids and entry values are loaded and
+// broadcast once per entry, every entry issues NS independent 16-byte gathers per lane (all NS 256-column slices; two
+// entries in flight), and the per-row overhead is paid once.  The rows of more than `threshold` entries (1 % of the users,
+// 40 % of the entries) would be chains of hundreds of dependent gather rounds for a single warp, so they keep one warp per
+// (row, slice): `order` lists them first (dmm_rows_long_first), `n_long_p` is their number (device scalar), and the first
+// `long_blocks` CTAs of the same launch take them -- they start first and overlap the short rows.  The sums run over the
+// entries in stored order in both roles: bit-identical to csr_gather_act_kernel.
+template <bool LO, bool WT>
+__device__ __forceinline__ void gather_tail(float (&acc)[8], const int64_t r, const int64_t c0, const float* __restrict__ bias,
+                                            const int act, const int64_t n_out, uint16_t* __restrict__ h_hi,
+                                            uint16_t* __restrict__ h_lo, const int64_t ld_h, float* __restrict__ z_f32,
+                                            const int64_t ld_z) {
+  if (c0 >= n_out) return;
+  const bool full = c0 + 8 <= n_out;
+  if (z_f32) {
+    if (full) {
+      *reinterpret_cast<float4*>(z_f32 + r * ld_z + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(z_f32 + r * ld_z + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      for (int j = 0; j < 8 && c0 + j < n_out; ++j) z_f32[r * ld_z + c0 + j] = acc[j];
+    }
+  }
+  if (bias) {
+    if (full && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+      acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+      acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (c0 + j < n_out) ? bias[c0 + j] : 0.f;
+    }
+  }
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+    if (act == 1) {
+      x0 = 1.f - __fdividef(2.f, __expf(2.f * x0) + 1.f);
+      x1 = 1.f - __fdividef(2.f, __expf(2.f * x1) + 1.f);
+    }
+    if constexpr (LO) {
+      uint16_t a0, a1, l0, l1;
+      dmm_split_bf16(x0, a0, l0);
+      dmm_split_bf16(x1, a1, l1);
+      ph[j] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+      pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    } else {
+      ph[j] = (uint32_t)dmm_bf16_bits(x0) | ((uint32_t)dmm_bf16_bits(x1) << 16);
+      pl[j] = 0u;
+    }
+  }
+  if (full) {
+    *reinterpret_cast<uint4*>(h_hi + r * ld_h + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (LO && h_lo) *reinterpret_cast<uint4*>(h_lo + r * ld_h + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  } else {
+    for (int j = 0; j < 8 && c0 + j < n_out; ++j) {
+      h_hi[r * ld_h + c0 + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
+      if (LO && h_lo) h_lo[r * ld_h + c0 + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+    }
+  }
+}
+
+template <bool WT>
+__device__ __forceinline__ void gather_add(float (&acc)[8], const uint4& q, const float w) {
+  const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (WT) {      // sparse rows with values (a q_sample'd start): x[c] * W^T[c, :]
+      acc[2 * j] = fmaf(w, __uint_as_float(wv[j] << 16), acc[2 * j]);
+      acc[2 * j + 1] = fmaf(w, __uint_as_float(wv[j] & 0xFFFF0000u), acc[2 * j + 1]);
+    } else {
+      acc[2 * j] += __uint_as_float(wv[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+    }
+  }
+}
+
+template <bool LO, bool WT, int NS>
+__global__ void __launch_bounds__(256, 4) csr_gather_act_split_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ vals,
+    const int64_t* __restrict__ row_ids, const int32_t* __restrict__ order, const int32_t* __restrict__ n_long_p,
+    const int long_blocks, const int64_t max_long, int64_t row0, int64_t n_rows, int64_t n_cols,
+    const uint16_t* __restrict__ wt_hi, const uint16_t* __restrict__ wt_lo, int64_t ld_w, const float* __restrict__ bias, int act,
+    int64_t n_out, uint16_t* __restrict__ h_hi, uint16_t* __restrict__ h_lo, int64_t ld_h, float* __restrict__ z_f32,
+    int64_t ld_z) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int64_t n_long = (int64_t)__ldg(n_long_p);
+  if (n_long > max_long) n_long = max_long;      // rows beyond the caller's bound take the short-row role (correct, slow)
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  if ((int)blockIdx.x < long_blocks) {
+    // ---- long rows: one warp per (row, 256-column slice), 8 (LO: 4) entries in flight
+    const int64_t wg = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t slot = wg / NS;
+    if (slot >= n_long) return;
+    const int64_t r = (int64_t)__ldg(order + slot);
+    const int64_t c0 = (wg % NS) * 256 + 8 * lane;
+    const bool col_ok = c0 < n_out;
+    const int64_t u = row_ids ? row_ids[r] : row0 + r;
+    const int64_t b = indptr[u], e = indptr[u + 1];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    constexpr int G = LO ? 4 : 8;
+    for (int64_t k = b; k < e; k += 32) {
+      int32_t mine = (k + lane < e) ? indices[k + lane] : -1;
+      if (mine >= n_cols) mine = -1;
+      float my_w = 1.f;
+      if constexpr (WT) my_w = (k + lane < e) ? vals[k + lane] : 0.f;
+      const int cnt = (int)((e - k) < 32 ? (e - k) : 32);
+      for (int j = 0; j < cnt; j += G) {
+        int32_t c[G];
+        float w[G];
+        uint4 qh[G], ql[LO ? G : 1];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+          w[t] = WT ? __shfl_sync(0xffffffffu, my_w, (j + t) & 31) : 1.f;
+        }
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          const bool ok = col_ok && j + t < cnt && c[t] >= 0;
+          qh[t] = ok ? *reinterpret_cast<const uint4*>(wt_hi + (int64_t)c[t] * ld_w + c0) : zero;
+          if constexpr (LO) ql[t] = ok ? *reinterpret_cast<const uint4*>(wt_lo + (int64_t)c[t] * ld_w + c0) : zero;
+        }
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          gather_add<WT>(acc, qh[t], w[t]);
+          if constexpr (LO) gather_add<WT>(acc, ql[t], w[t]);
+        }
+      }
+    }
+    gather_tail<LO, WT>(acc, r, c0, bias, act, n_out, h_hi, h_lo, ld_h, z_f32, ld_z);
+    return;
+  }
+  // ---- short rows: one warp per row, all NS slices; 2 (LO: 1) entries x NS gathers in flight
+  const int64_t s = (int64_t)((int)blockIdx.x - long_blocks) * 8 + warp;
+  if (s >= n_rows - n_long) return;
+  const int64_t r = (int64_t)__ldg(order + n_long + s);
+  const int64_t u = row_ids ? row_ids[r] : row0 + r;
+  const int64_t b = indptr[u], e = indptr[u + 1];
+  const int64_t cl = 8 * lane;                    // this lane's first column inside every slice
+  float acc[NS][8];
+#pragma unroll
+  for (int q = 0; q < NS; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+  constexpr int G = LO ? 1 : 2;
+  for (int64_t k = b; k < e; k += 32) {
+    int32_t mine = (k + lane < e) ? indices[k + lane] : -1;
+    if (mine >= n_cols) mine = -1;
+    float my_w = 1.f;
+    if constexpr (WT) my_w = (k + lane < e) ? vals[k + lane] : 0.f;
+    const int cnt = (int)((e - k) < 32 ? (e - k) : 32);
+    for (int j = 0; j < cnt; j += G) {
+      int32_t c[G];
+      float w[G];
+      uint4 qh[G][NS], ql[LO ? G : 1][LO ? NS : 1];
+#pragma unroll
+      for (int t = 0; t < G; ++t) {
+        c[t] = __shfl_sync(0xffffffffu, mine, (j + t) & 31);
+        w[t] = WT ? __shfl_sync(0xffffffffu, my_w, (j + t) & 31) : 1.f;
+      }
+#pragma unroll
+      for (int t = 0; t < G; ++t) {
+        const bool ok = j + t < cnt && c[t] >= 0;
+        const uint16_t* ph = wt_hi + (int64_t)(ok ? c[t] : 0) * ld_w + cl;
+        const uint16_t* pl = LO ? wt_lo + (int64_t)(ok ? c[t] : 0) * ld_w + cl : nullptr;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+          const bool okq = ok && q * 256 + cl < n_out;
+          qh[t][q] = okq ? *reinterpret_cast<const uint4*>(ph + q * 256) : zero;
+          if constexpr (LO) ql[t][q] = okq ? *reinterpret_cast<const uint4*>(pl + q * 256) : zero;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < G; ++t) {
+        if (t > 0 && j + t >= cnt) break;        // warp-uniform: the padded slot of an odd row length adds zeros
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+          gather_add<WT>(acc[q], qh[t][q], w[t]);
+          if constexpr (LO) gather_add<WT>(acc[q], ql[t][q], w[t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) gather_tail<LO, WT>(acc[q], r, q * 256 + cl, bias, act, n_out, h_hi, h_lo, ld_h, z_f32, ld_z);
+}
+
 // ------------------------------------------------------------------ q_sample on binary CSR rows
 // Default-noise q_sample (Model.py:324-341) of a BINARY row keeps the row's sparsity: noise = sign(x0) * normalize(n)
 // vanishes wherever x0 does, so x_t = a x0 + b noise has the value a + b n_c / max(||n||_2, 1e-12) at the row's items
@@ -885,6 +1078,59 @@ extern "C" int dmm_csr_gather_act(dmm_ctx* ctx, const int64_t* indptr, const int
     else csr_gather_act_kernel<false, false><<<grid, 256, 0, st>>>(DMM_GATHER_ARGS);
   }
 #undef DMM_GATHER_ARGS
+  DMM_LAUNCH_CHECK();
+  return DMM_OK;
+}
+
+template <bool LO, bool WT>
+static void launch_gather_split(int ns, unsigned grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices,
+                                const float* vals, const int64_t* row_ids, const int32_t* order, const int32_t* n_long,
+                                int long_blocks, int64_t max_long, int64_t row0, int64_t n_rows, int64_t n_cols,
+                                const uint16_t* wt_hi, const uint16_t* wt_lo, int64_t ld_w, const float* bias, int act,
+                                int64_t n_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z) {
+#define DMM_GS_ARGS indptr, indices, vals, row_ids, order, n_long, long_blocks, max_long, row0, n_rows, n_cols, wt_hi, wt_lo, ld_w, \
+                    bias, act, n_out, h_hi, h_lo, ld_h, z_f32, ld_z
+  if (ns == 1) csr_gather_act_split_kernel<LO, WT, 1><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
+  else if (ns == 2) csr_gather_act_split_kernel<LO, WT, 2><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
+  else csr_gather_act_split_kernel<LO, WT, 4><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
+#undef DMM_GS_ARGS
+}
+
+extern "C" int dmm_csr_gather_act_split(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const float* vals,
+                                        const int64_t* row_ids, const int32_t* order, const int32_t* n_long,
+                                        int64_t max_long, int64_t row0, int64_t n_rows, int64_t n_cols,
+                                        const uint16_t* wt_hi, const uint16_t* wt_lo, int64_t ld_w, const float* bias,
+                                        int act, int64_t n_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h,
+                                        float* z_f32, int64_t ld_z, void* stream) {
+  DMM_CHECK_ARG(ctx && indptr && indices && wt_hi && h_hi && order && n_long, "dmm_csr_gather_act_split: null argument");
+  DMM_CHECK_ARG(n_rows >= 0 && n_cols > 0 && n_out > 0 && max_long >= 0, "dmm_csr_gather_act_split: bad shape");
+  DMM_CHECK_ARG(n_out <= 1024, "dmm_csr_gather_act_split: at most 1024 output columns (got %lld); use dmm_csr_gather_act",
+                (long long)n_out);
+  DMM_CHECK_ARG(ld_w % 8 == 0 && ld_h % 8 == 0 && ld_w >= dmm_ceil_div(n_out, 8) * 8 && ld_h >= n_out,
+                "dmm_csr_gather_act_split: ld_w / ld_h must be multiples of 8 covering n_out (got %lld, %lld)", (long long)ld_w,
+                (long long)ld_h);
+  DMM_CHECK_ARG(act == 0 || act == 1, "dmm_csr_gather_act_split: unknown activation %d", act);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  DMM_CHECK_ARG(al16(wt_hi) && al16(wt_lo) && al16(h_hi) && al16(h_lo) && al16(z_f32),
+                "dmm_csr_gather_act_split: buffers must be 16-byte aligned");
+  DMM_CHECK_ARG(!z_f32 || (ld_z >= n_out && ld_z % 4 == 0), "dmm_csr_gather_act_split: ld_z must be >= n_out and a multiple of 4");
+  if (n_rows == 0) return DMM_OK;
+  const int slices = (int)dmm_ceil_div(n_out, 256);
+  const int ns = slices <= 1 ? 1 : (slices == 2 ? 2 : 4);
+  if (max_long > n_rows) max_long = n_rows;
+  const int64_t long_blocks = dmm_ceil_div(max_long * ns, 8);
+  const int64_t blocks = long_blocks + dmm_ceil_div(n_rows, 8);
+  DMM_CHECK_ARG(blocks < (1LL << 31), "dmm_csr_gather_act_split: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+#define DMM_GS_CALL(LO, WT) launch_gather_split<LO, WT>(ns, (unsigned)blocks, st, indptr, indices, vals, row_ids, order, n_long, \
+                              (int)long_blocks, max_long, row0, n_rows, n_cols, wt_hi, wt_lo, ld_w, bias, act, n_out, h_hi, h_lo, \
+                              ld_h, z_f32, ld_z)
+  if (wt_lo) {
+    if (vals) DMM_GS_CALL(true, true); else DMM_GS_CALL(true, false);
+  } else {
+    if (vals) DMM_GS_CALL(false, true); else DMM_GS_CALL(false, false);
+  }
+#undef DMM_GS_CALL
   DMM_LAUNCH_CHECK();
   return DMM_OK;
 }

@@ -6,6 +6,7 @@ calls exactly one C-ABI entry point on the current stream.  No arithmetic happen
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -118,6 +119,9 @@ def time_bias(emb_w, emb_b, weight, col0, bias, t0, n_t=1, out=None):
     return out
 
 
+_GATHER_SPLIT = os.environ.get("DIFFMM_GATHER_SPLIT", "1") != "0"
+
+
 def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_out, h_hi, h_lo, *, row_ids=None, row0=0,
                    z_f32=None, order=None, vals=None):
     """h = act(bias + sum of the rows of W^T selected by each binary CSR row) -> bf16 hi (+ lo); z_f32 (optional)
@@ -126,6 +130,15 @@ def csr_gather_act(indptr, indices, n_rows, n_cols, wt_hi, wt_lo, bias, act, n_o
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     assert order is None or (order.dtype == torch.int32 and order.numel() == n_rows)
     assert vals is None or (vals.dtype == torch.float32 and vals.numel() == indices.numel())
+    counters = getattr(order, "_dmm_counters", None) if order is not None else None
+    if counters is not None and n_out <= 1024 and _GATHER_SPLIT:
+        # rows divided by length inside one launch (order / counters from rows_long_first): bit-identical results
+        max_long = indices.numel() // (order._dmm_threshold + 1)
+        _lib.call("dmm_csr_gather_act_split", _ctx(indptr), _p(indptr), _p(indices), _p(vals), _p(row_ids), _p(order),
+                  _p(counters), int(max_long), int(row0), int(n_rows), int(n_cols), _p(wt_hi), _p(wt_lo),
+                  _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo), _row_major(h_hi, "h_hi"),
+                  _p(z_f32), _row_major(z_f32, "z_f32") if z_f32 is not None else 0, _stream())
+        return
     _lib.call("dmm_csr_gather_act", _ctx(indptr), _p(indptr), _p(indices), _p(vals), _p(row_ids), _p(order), int(row0), int(n_rows),
               int(n_cols),
               _p(wt_hi), _p(wt_lo), _row_major(wt_hi, "wt_hi"), _p(bias), int(act), int(n_out), _p(h_hi), _p(h_lo),
@@ -159,6 +172,8 @@ def rows_long_first(indptr, row0, n_rows, threshold=32):
     counters = torch.empty(2, dtype=torch.int32, device=indptr.device)
     _lib.call("dmm_rows_long_first", _ctx(indptr), _p(indptr), int(row0), int(n_rows), int(threshold), _p(order), _p(counters),
               _stream())
+    # counters[0] = number of long rows (device scalar): csr_gather_act divides the launch by it
+    order._dmm_counters, order._dmm_threshold = counters, int(threshold)
     return order
 
 

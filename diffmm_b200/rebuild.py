@@ -448,8 +448,7 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     if out_items is None:
         out_items = {m: torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E] for m in denoise_models}
     mods = list(denoise_models.items())
-    orders = {b0: longest_rows_first(indptr, b0, min(b0 + block_rows, r1) - b0) for b0 in range(r0, r1, block_rows)} \
-        if sampling_step == 0 else {}
+    orders = {b0: longest_rows_first(indptr, b0, min(b0 + block_rows, r1) - b0) for b0 in range(r0, r1, block_rows)}
     n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(mods))
     streams = []
     if n_streams > 1 and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():

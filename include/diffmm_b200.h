@@ -118,6 +118,19 @@ int dmm_csr_qsample_values_rng(dmm_ctx* ctx, const int64_t* indptr, const int32_
                                int64_t row0, int64_t n_rows, int64_t n_cols, const int64_t* seed, float coef_a,
                                float coef_b, float* vals, int full_rows, void* stream);
 
+/* dmm_csr_gather_act with the rows divided by length inside one launch.  `order` and `n_long` come from
+ * dmm_rows_long_first (order: the rows of more than `threshold` entries first; n_long = its counters[0], a DEVICE scalar:
+ * how many they are; no host sync) and max_long is any host-side upper bound of *n_long (e.g. nnz / (threshold + 1)).
+ * The long rows take one warp per (row, 256-column slice) like dmm_csr_gather_act, every other row ONE warp for all its
+ * columns (item ids and values broadcast once per entry, ceil(n_out / 256) independent gathers per entry and lane, the
+ * per-row overhead paid once).  n_out <= 1024.  Results are bit-identical to dmm_csr_gather_act (same order of
+ * summation).  Model.py:212 on the CSR rows, like dmm_csr_gather_act.                                        */
+int dmm_csr_gather_act_split(dmm_ctx* ctx, const int64_t* indptr, const int32_t* indices, const float* vals,
+                             const int64_t* row_ids, const int32_t* order, const int32_t* n_long, int64_t max_long,
+                             int64_t row0, int64_t n_rows, int64_t n_cols, const uint16_t* wt_hi, const uint16_t* wt_lo,
+                             int64_t ld_w, const float* bias, int act, int64_t n_out, uint16_t* h_hi, uint16_t* h_lo,
+                             int64_t ld_h, float* z_f32, int64_t ld_z, void* stream);
+
 /* Scheduling order for dmm_csr_gather_act: order[] (int32 [n_rows]) becomes a permutation of 0..n_rows-1 with every
  * row of the block [row0, row0 + n_rows) that has more than `threshold` entries in front (arbitrary order among
  * equals; `counters` is 2 int32 of device scratch).  No host sync.                                         */

@@ -121,6 +121,31 @@ def test_tcgen05_tma_epilogue_hidden_step(ops, M, N, K, pad):
         assert (h[:, n8:].float() == 7.0).all()
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (4100, 1000, 520), (19445, 1024, 1024)])
+def test_tcgen05_tma_epilogue_last_hidden_step(ops, M, N, K):
+    """The last hidden-space step of the chain: the fp32 state is only read (residual), the one output is the bf16
+    operand h = tanh(alpha (acc + bias) + beta z + post_bias); z must come back untouched."""
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    pbias = (rng.standard_normal(N) * 0.3).astype(np.float32)
+    z0 = rng.standard_normal((M, N)).astype(np.float32)
+    a_hi, _ = ops.pack_bf16(T(a), split=False)
+    b_hi, _ = ops.pack_bf16(T(b), split=False)
+    ldn = ops.pad_to(N, 8)
+    z = torch.zeros((M, ldn), device=DEV)
+    z[:, :N] = T(z0)
+    h = torch.full((M, ldn), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16_tn(a_hi, None, b_hi, None, M, N, K, bias=T(bias), alpha=0.75, beta=0.5, residual=z[:, :N],
+                     out_hi=h[:, :N], post_bias=T(pbias), post_act=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(z[:, :N].cpu().numpy(), z0)
+    v = _ref(_bf16_round(a), _bf16_round(b), bias, 0, 0.75, 0.5, z0)
+    want_h = np.tanh(v.astype(np.float64) + pbias)
+    np.testing.assert_allclose(h[:, :N].float().cpu().numpy(), want_h, rtol=2 ** -8, atol=2e-3)   # MUFU tanh + bf16
+
+
 @pytest.mark.parametrize("M,N,K", [(200, 300, 210), (77, 40, 50), (2000, 2500, 136), (4100, 1024, 512)])
 def test_tcgen05_tma_epilogue_single_outputs(ops, M, N, K):
     """TMA epilogue with one output kind: tanh -> bf16 operand only (dense first layer), and fp32 only with a

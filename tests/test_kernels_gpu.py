@@ -313,6 +313,47 @@ def test_csr_gather_act_vs_dense_and_scheduling_order(ops, n_out):
         assert torch.equal(h1, h0) and torch.equal(z1[:, :n_out], z0[:, :n_out])
 
 
+@pytest.mark.parametrize("split,weighted", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("n_out", [1024, 516, 260, 96])
+def test_csr_gather_act_rows_divided_by_length_is_bit_identical(ops, n_out, split, weighted):
+    """dmm_csr_gather_act_split (one warp per short row over all its columns, one warp per (row, slice) for the long rows,
+    one launch) against dmm_csr_gather_act: same bits in h (hi, lo), z and the untouched padding -- binary and weighted
+    rows, single-pass and split-bf16 weights, a row subset selected through row_ids, ragged last 8-column piece."""
+    rng = np.random.default_rng(n_out + 2 * split + weighted)
+    U, I = 700, 1200
+    deg = rng.integers(0, 14, U)
+    deg[[0, 13, 300, 699]] = [33, 640, 32, 257]              # around the threshold of 32 and far beyond it
+    indptr = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(I, d, replace=False)) for d in deg]).astype(np.int32)
+    vals = T(rng.standard_normal(len(indices)).astype(np.float32)) if weighted else None
+    w = (rng.standard_normal((n_out, I)) * 0.05).astype(np.float32)
+    bias = T((rng.standard_normal(n_out) * 0.1).astype(np.float32))
+    wt_hi, wt_lo = ops.pack_bf16(T(w), transpose=True, split=split)
+    ld = ops.pad_to(n_out, 8)
+    row0, n_rows = 100, 550                                    # a block of the users
+    d_ptr, d_idx = T(indptr), T(indices)
+    order = ops.rows_long_first(d_ptr, row0, n_rows, 32)
+    assert int(order._dmm_counters[0]) == int((deg[row0:row0 + n_rows] > 32).sum())
+    plain = order.clone()                                      # same permutation without the counters: the per-slice kernel
+
+    def run(o):
+        h = torch.full((n_rows, ld), 3.0, dtype=torch.bfloat16, device=DEV)
+        hl = torch.full((n_rows, ld), 5.0, dtype=torch.bfloat16, device=DEV) if split else None
+        z = torch.full((n_rows, ld), float("nan"), device=DEV)
+        ops.csr_gather_act(d_ptr, d_idx, n_rows, I, wt_hi, wt_lo, bias, 1, n_out, h[:, :n_out],
+                           hl[:, :n_out] if split else None, row0=row0, z_f32=z[:, :n_out], order=o, vals=vals)
+        return h, hl, z
+
+    h0, l0, z0 = run(plain)
+    h1, l1, z1 = run(order)
+    assert torch.equal(h1.view(torch.int16), h0.view(torch.int16))
+    assert torch.equal(z1[:, :n_out], z0[:, :n_out]) and torch.isnan(z1[:, n_out:]).all()
+    if split:
+        assert torch.equal(l1.view(torch.int16), l0.view(torch.int16))
+    assert not torch.isnan(z1[:, :n_out]).any()
+
+
 # ------------------------------------------------------------------------------------------- staging kernels
 def test_pack_bf16_split_and_transpose(ops):
     rng = np.random.default_rng(1)
