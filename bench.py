@@ -330,13 +330,14 @@ def reference_rebuild_step(ref, diff, dens, x_rows, deg, sampling_step):
     return time.perf_counter() - t0, edges
 
 
-def load_reference_arm(w, seed, hyper):
-    """Unmodified reference modules from oracle/_ref (never /root/reference at run time), forced onto the CPU, with
-    Denoise weights drawn exactly like the GPU arm's (same seed, same construction order)."""
+def load_reference_arm(w, seed, hyper, force_cpu=True):
+    """Unmodified reference modules from oracle/_ref (never /root/reference at run time), forced onto the CPU (or left on
+    their own ``cuda:0`` path: force_cpu=False), with Denoise weights drawn exactly like the GPU arm's (same seed, same
+    construction order)."""
     import torch
     os.environ["DIFFMM_REFERENCE_ROOT"] = REF_DIR
     from oracle import ref_shim
-    ref = ref_shim.load_reference(force_cpu=True)
+    ref = ref_shim.load_reference(force_cpu=force_cpu)
     cfg = ref_shim.make_config(ref, "tiktok" if len(w["modalities"]) == 3 else "sports")
     cfg.base.denoise_dim = f"[{w['hidden']}]"
     cfg.hyper.steps = hyper["steps"]
@@ -370,14 +371,25 @@ def run_reference(args):
     ptr, idx = inter.indptr, inter.indices
     deg = np.diff(ptr)[:n_sample]
     kind = "reference"
+    on_gpu = args.ref_device == "cuda"
+    if on_gpu and not (os.path.isfile(os.path.join(REF_DIR, "Model.py")) and torch.cuda.is_available()):
+        emit({"impl": "reference", "unavailable": "stock-torch GPU leg needs oracle/_ref and a GPU"})
+        return
     if os.path.isfile(os.path.join(REF_DIR, "Model.py")):
-        ref, diff, dens = load_reference_arm(w, args.seed, hyper)
+        ref, diff, dens = load_reference_arm(w, args.seed, hyper, force_cpu=not on_gpu)
         x = torch.zeros((n_sample, w["items"]), dtype=torch.float32)
         for u in range(n_sample):
             x[u, torch.from_numpy(idx[ptr[u]:ptr[u + 1]].astype(np.int64))] = 1.0
+        if on_gpu:
+            # the reference's own device path (Main.py:60-77 moves the models with .cuda(), DataHandler the rows): stock
+            # torch kernels (cuBLAS fp32 GEMMs, torch.topk per user, one int(tensor) device->host sync per emitted edge)
+            x = x.cuda()
+            dens = {m: d.cuda() for m, d in dens.items()}
+            kind = "reference-on-gpu"
 
         def step(n):
-            return reference_rebuild_step(ref, diff, dens, x[:n], deg, hyper["sampling_step"])
+            dt, e = reference_rebuild_step(ref, diff, dens, x[:n], deg, hyper["sampling_step"])
+            return dt, e
     else:   # oracle/_ref not built on this machine: numpy restatement of the same path (oracle/diffmm_oracle.py)
         kind = "port"
         _, _, _, dens_t = build_workload(args.workload, "cpu", args.seed, "bf16", 1, hyper)
@@ -396,8 +408,10 @@ def run_reference(args):
     val = users / total
     sample = (f"first {n_sample} of {w['users']} users x {len(w['modalities'])} modalities per step, {args.steps} steps, "
               f"{total:.1f} s; " + ("unmodified reference modules (oracle/_ref: GaussianDiffusion.generate_view + the "
-                                    "Main.py:224-230 per-user torch.topk loop) on torch-CPU" if kind == "reference" else
+                                    "Main.py:224-230 per-user torch.topk loop) on torch-CPU" if kind.startswith("reference") else
                                     "numpy port (oracle/diffmm_oracle.py)") + f", same seed-{args.seed} weights as the GPU arm")
+    if on_gpu:
+        sample = sample.replace("on torch-CPU", "on cuda:0 through stock torch (the reference's own .cuda() path)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -422,6 +436,26 @@ def cpu_baseline_subprocess(args, w):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         ref_line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         return ref_line["cpu_baseline"]
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def stock_torch_gpu_subprocess(args, w):
+    """SURVEY 8(d) "stock library" comparison: the UNMODIFIED reference's rebuild phase on the same B200 through stock
+    torch (its own .cuda() path), on a bounded sample of the same workload, in its own process."""
+    import subprocess
+    n = max(64, int(2048 * min(1.0, 7050.0 / w["items"])))
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-device", "cuda", "--workload", args.workload,
+           "--seed", str(args.seed), "--steps", "1", "--warmup", "1", "--ref-sample", str(n)]
+    if args.sampling_step is not None:
+        cmd += ["--sampling-step", str(args.sampling_step)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        ref_line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        if "unavailable" in ref_line:
+            return {"unavailable": ref_line["unavailable"]}
+        cb = ref_line["cpu_baseline"]
+        return {"value": cb["value"], "unit": cb["unit"], "kind": cb["kind"], "sample": cb["sample"]}
     except Exception as e:
         return {"error": repr(e)[:300]}
 
@@ -615,6 +649,21 @@ def run_ours(args):
             out[k] = {"launches": v[0], "avg_ms": v[1] / v[0], "tflops": tf, "compulsory_GBps": gbs,
                       "flop_per_byte": intensity, "bound": "tensor" if intensity >= ridge else "hbm",
                       "frac_of_its_bound": tf / pk["tf_burst"] if intensity >= ridge else gbs / pk["hbm"]}
+            # Third bound, the one that binds the 256 x 256 pair tiles in practice (tools/gemm_l2_model.py):
+            # bytes a CTA pulls through the L2 per tile (its 128 rows of A + its 128-row half of B per k-block, and its
+            # 128 x 256 part of the epilogue tensors) against the measured L2 slice throughput of the chip
+            # (B300_MICROARCH "LTS throughput cap" ~6300 B/clk), in waves of 74 pair tiles.
+            Ms, Ns, Ks = (int(t) for t in k.split("/")[0].split("x"))
+            if Ms >= 256 and Ns > 256 and "splitK" not in k:
+                passes = int(k.split("/p")[1][0])
+                ep_b = max(v[3] / v[0] - (Ms + Ns) * Ks * 2.0 * (2 if passes > 1 else 1), 0.0) / (Ms * Ns)
+                tiles = -(-Ms // 256) * -(-Ns // 256)
+                full_w, rem = divmod(tiles, 74)
+                waves = full_w + (max(rem / 74.0, 0.25) if rem else 0.0)
+                cta_bytes = 2 * 128 * Ks * 2.0 * passes + 128 * 256 * ep_b
+                l2_ms = waves * cta_bytes / (6300.0 / 148) / (1.965e9) * 1e3
+                out[k].update({"l2_bytes_per_cta_tile": cta_bytes, "l2_bound_ms": l2_ms,
+                               "measured_over_l2_bound": (v[1] / v[0]) / l2_ms})
         return tot_ms, flops, out
 
     # The modalities run as concurrent pipelines on two streams (rebuild.rebuild_edges), so an event pair around a
@@ -793,6 +842,7 @@ def run_ours(args):
         line["propagation"] = prop
     if world == 1 and not args.no_cpu_baseline:          # reported on rank 0 at N = 1 only (a bounded host-core sample)
         line["cpu_baseline"] = cpu_baseline_subprocess(args, w)
+        line["stock_torch_gpu"] = stock_torch_gpu_subprocess(args, w)
     if world == 1 and not args.no_aux:
         try:
             line["aux_rooflines"] = aux_rooflines(dev, breakdown, U, I, E, len(mods), pk, args.seed, args.precision)
@@ -876,6 +926,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="users of the cpu_baseline sample (scaled down with the row width)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="users per step of the reference (CPU) arm")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: cpu = the driver's reference arm (host cores); cuda = the same unmodified reference "
+                         "through stock torch on the GPU (the stock_torch_gpu leg of the main line)")
     ap.add_argument("--sampling-step", type=int, default=None,
                     help="override the workload's conf/*.toml hyper.sampling_step (0 = rebuild from the binary rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
