@@ -709,7 +709,10 @@ __global__ void __launch_bounds__(256) csr_qsample_values_rng_kernel(const int64
 // exactly the reference's joint distribution of the outputs (Model.py:337-341), O(k) work per row.
 // chi^2(nu) = 2 Gamma(nu / 2) by Marsaglia-Tsang (exact rejection sampler, acceptance > 99.9 % at nu ~ 7000); nu <= 64:
 // the sum of nu explicit normals.  One warp per row.
-__device__ __forceinline__ float chi2_sample(uint32_t nu, uint32_t row_lo, uint32_t row_hi, uint2 key) {
+// `first`: the Philox block of attempt 0 when the caller already drew it (in lockstep with the support normals of the
+// other lanes); the variate is the same either way.
+__device__ __forceinline__ float chi2_sample(uint32_t nu, uint32_t row_lo, uint32_t row_hi, uint2 key,
+                                             const uint4* first = nullptr) {
   if (nu == 0u) return 0.f;
   if (nu <= 64u) {
     float s = 0.f;
@@ -727,7 +730,7 @@ __device__ __forceinline__ float chi2_sample(uint32_t nu, uint32_t row_lo, uint3
   const float c = rsqrtf(9.0f * d);
   float v = 1.f;
   for (uint32_t attempt = 0; attempt < 64u; ++attempt) {
-    const uint4 u4 = philox4x32_10(make_uint4(attempt, row_lo, row_hi, 1u), key);
+    const uint4 u4 = (attempt == 0u && first) ? *first : philox4x32_10(make_uint4(attempt, row_lo, row_hi, 1u), key);
     const float x = normal4(u4).x;
     const float t = fmaf(c, x, 1.0f);
     if (t <= 0.f) continue;
@@ -755,10 +758,29 @@ __global__ void __launch_bounds__(256) csr_qsample_values_chi2_kernel(const int6
   const uint64_t sd = (uint64_t)seed[0];
   const uint2 key = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
   const uint32_t row_lo = (uint32_t)u, row_hi = (uint32_t)((uint64_t)u >> 32);
+  auto pick = [](const float4& n, int w) -> float { return w == 0 ? n.x : (w == 1 ? n.y : (w == 2 ? n.z : n.w)); };
+  if (e - b < 32) {
+    // Short row (99 % of them): one entry per lane, ONE Philox + Box-Muller round for the whole row.  Lane 31 has no
+    // entry: it draws attempt 0 of the chi-square variate in the same instructions (counter stream 1 instead of 0), and
+    // every lane keeps its normal for the value pass.  Same Philox elements, same arithmetic, same values as the general
+    // path below.
+    const bool has = b + lane < e;
+    const int32_t c = has ? indices[b + lane] : -1;
+    const bool ok = c >= 0 && c < n_cols;
+    const uint32_t valid = (uint32_t)__popc(__ballot_sync(0xffffffffu, ok));
+    const uint4 ctr = lane == 31 ? make_uint4(0u, row_lo, row_hi, 1u) : make_uint4((uint32_t)(ok ? c >> 2 : 0), row_lo, row_hi, 0u);
+    const uint4 blk = philox4x32_10(ctr, key);
+    const float nv = ok ? pick(normal4(blk), c & 3) : 0.f;
+    const float ss = dmm_warp_sum(ok ? fmaf(nv, nv, 0.f) : 0.f);
+    float rest = 0.f;
+    if (lane == 31) rest = chi2_sample((uint32_t)(n_cols - (int64_t)valid), row_lo, row_hi, key, &blk);
+    rest = __shfl_sync(0xffffffffu, rest, 31);
+    const float inv = 1.f / fmaxf(sqrtf(ss + rest), 1e-12f);
+    if (has) vals[b + lane] = __fadd_rn(coef_a, __fmul_rn(coef_b, __fmul_rn(nv, inv)));
+    return;
+  }
   auto normal_at = [&](int32_t c) -> float {
-    const float4 n = normal4(philox4x32_10(make_uint4((uint32_t)(c >> 2), row_lo, row_hi, 0u), key));
-    const int w = c & 3;
-    return w == 0 ? n.x : (w == 1 ? n.y : (w == 2 ? n.z : n.w));
+    return pick(normal4(philox4x32_10(make_uint4((uint32_t)(c >> 2), row_lo, row_hi, 0u), key)), c & 3);
   };
   float ss = 0.f;
   uint32_t valid = 0;

@@ -511,3 +511,31 @@ def test_qsample_values_follow_the_exact_beta_law(ops, n_cols):
         z2 = vals.cpu().numpy().astype(np.float64) ** 2
         assert abs(z2.mean() - mean) < 5.0 * np.sqrt(var / U), (full, z2.mean(), mean)
         assert abs(z2.var() - var) < 0.08 * var, (full, z2.var(), var)
+
+
+@pytest.mark.parametrize("n_cols", [50, 7050])
+def test_qsample_values_short_row_path_equals_general_path(ops, n_cols):
+    """Rows of fewer than 32 entries take the one-round path of the sufficient-statistics generator (one entry per lane, the
+    chi-square draw in lockstep on the free lane).  The values are a pure function of (seed, row, column, support size):
+    the same rows padded to >= 32 entries with out-of-range columns (ignored by contract) go through the general path and
+    must give the same bits."""
+    rng = np.random.default_rng(n_cols + 1)
+    U = 3000
+    deg = rng.integers(0, 32, U)
+    deg[:4] = [0, 1, 31, 30]
+    rows = [np.sort(rng.choice(n_cols, d, replace=False)).astype(np.int32) for d in deg]
+    ptr_a = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum(deg, out=ptr_a[1:])
+    idx_a = np.concatenate(rows) if ptr_a[-1] else np.zeros(0, dtype=np.int32)
+    padded = [np.concatenate([r, np.full(40 - len(r), n_cols, dtype=np.int32)]) if len(r) else r for r in rows]
+    ptr_b = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in padded], out=ptr_b[1:])
+    idx_b = np.concatenate(padded)
+    seed = torch.tensor([1234567], dtype=torch.int64, device=DEV)
+    va = torch.zeros(len(idx_a), dtype=torch.float32, device=DEV)
+    vb = torch.zeros(len(idx_b), dtype=torch.float32, device=DEV)
+    ops.csr_qsample_values_rng(T(ptr_a), T(idx_a), U, n_cols, seed, 0.25, 0.75, va, full_rows=False)
+    ops.csr_qsample_values_rng(T(ptr_b), T(idx_b), U, n_cols, seed, 0.25, 0.75, vb, full_rows=False)
+    keep = torch.from_numpy(idx_b < n_cols).to(DEV)
+    assert torch.equal(va, vb[keep])
+    assert float((va - 0.25).abs().max()) > 0.0
