@@ -501,9 +501,9 @@ class RebuildJob:
             dn._dmm_hidden_ops = None
         U, I, SS = self.users_total, self.I, self.hyper["sampling_step"]
         if self.world > 1:
-            items = rebuild.rebuild_edges(self.diff, self.dens, ip, ix, U, I, SS, self.precision, row_range=(self.r0, self.r1))
             full = {}
-            adjs = rebuild.gather_and_build(items, ip, U, I, None, self.plan, full_items=full)
+            adjs = rebuild.rebuild_sharded(self.diff, self.dens, ip, ix, U, I, SS, self.precision, (self.r0, self.r1),
+                                           group=None, plan=self.plan, full_items=full)
             return adjs, full
         res = {}
         rebuild.rebuild_edges(self.diff, self.dens, ip, ix, U, I, SS, self.precision, row_range=(self.r0, self.r1),

@@ -411,10 +411,16 @@ def longest_rows_first(indptr: torch.Tensor, row0: int, n_rows: int) -> torch.Te
 _SIDE_STREAMS: Dict[Tuple[int, int], list] = {}
 
 
-def _side_streams(dev: torch.device, n: int):
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+def _side_streams(dev: torch.device, n: int, staggered: bool = False):
+    """n side streams of the device.  staggered: falling priorities (stream 0 highest), so the pipeline on stream 0 gets
+    the SMs first and finishes first while the later ones fill its gaps -- its tail (collective, adjacency build) then
+    overlaps the pipelines still running."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n, staggered)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        if staggered:
+            _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev, priority=-(n - 1 - i)) for i in range(n)]
+        else:
+            _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
     return _SIDE_STREAMS[key]
 
 
@@ -422,7 +428,8 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
                   n_users: int, n_items: int, sampling_step: int = 0, precision: Optional[str] = None,
                   row_range: Optional[Tuple[int, int]] = None, block_rows: Optional[int] = None,
                   out_items: Optional[Dict[str, torch.Tensor]] = None, per_modality=None,
-                  per_modality_out: Optional[dict] = None, status: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                  per_modality_out: Optional[dict] = None, status: Optional[torch.Tensor] = None,
+                  staggered: bool = False) -> Dict[str, torch.Tensor]:
     """Top-k item ids per modality for users in ``row_range`` (default all), written at the train-CSR
     offsets (k_u = deg(u), Main.py:215-216,226).  Returns {modality: int32 [E]} (only this range filled).
 
@@ -451,8 +458,9 @@ def rebuild_edges(diff, denoise_models: Dict[str, torch.nn.Module], indptr: torc
     orders = {b0: longest_rows_first(indptr, b0, min(b0 + block_rows, r1) - b0) for b0 in range(r0, r1, block_rows)}
     n_streams = min(int(os.environ.get("DIFFMM_STREAMS", "2")), len(mods))
     streams = []
+    staggered = staggered or os.environ.get("DIFFMM_STAGGER_ALL") == "1"      # experiment switch: priorities without a tail
     if n_streams > 1 and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
-        streams = _side_streams(dev, n_streams)
+        streams = _side_streams(dev, n_streams, staggered)
         main = torch.cuda.current_stream(dev)
         fork = torch.cuda.Event()
         fork.record(main)
@@ -502,9 +510,35 @@ def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: 
                       per_modality_out=adjs, status=status)
         return {m: adjs[m] for m in denoise_models}
     row_range = ddist.shard_rows(n_users, ddist.world_size(group), ddist.rank(group), indptr)
-    items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                          row_range=row_range, block_rows=block_rows, status=status)
-    return gather_and_build(items, indptr, n_users, n_items, group, plan, status=status)
+    return rebuild_sharded(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision, row_range,
+                           group=group, plan=plan, block_rows=block_rows, status=status)
+
+
+def rebuild_sharded(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision, row_range, *,
+                    group=None, plan=None, block_rows=None, status=None, full_items: Optional[dict] = None):
+    """User-sharded rebuild of one rank: chain + top-k on ``row_range``, the edge lists of all ranks, the whole-graph
+    adjacencies.  Default: equal-priority modality pipelines, join, ONE all-gather for all modalities, then the builds on
+    the side streams.  DIFFMM_STAGGER=1 (experiment, measured SLOWER: 1.458 vs 1.412 ms per step at 2 GPUs): the pipelines
+    run on side streams of falling priority and each one continues into its own all-gather and adjacency build, so that
+    the first modality's exchange would overlap the chains still running (collectives in modality order on every rank)."""
+    from . import dist as ddist
+    if os.environ.get("DIFFMM_STAGGER", "0") != "1" or len(denoise_models) < 2:
+        items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
+                              row_range=row_range, block_rows=block_rows, status=status)
+        return gather_and_build(items, indptr, n_users, n_items, group, plan, full_items=full_items, status=status)
+    if plan is None or plan.world != ddist.world_size(group):
+        plan = ddist.EdgeGatherPlan(indptr, n_users, ddist.world_size(group))
+
+    def tail(local_items):
+        full = ddist.allgather_edges(local_items, indptr, n_users, group, plan)
+        return ops.build_norm_adj(indptr, full, n_users, n_items, status=status), full
+
+    res: dict = {}
+    rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision, row_range=row_range,
+                  block_rows=block_rows, status=status, per_modality=tail, per_modality_out=res, staggered=True)
+    if full_items is not None:
+        full_items.update({m: r[1] for m, r in res.items()})
+    return {m: res[m][0] for m in denoise_models}
 
 
 def gather_and_build(items: Dict[str, torch.Tensor], indptr: torch.Tensor, n_users: int, n_items: int, group=None,
