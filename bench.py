@@ -491,7 +491,7 @@ class RebuildJob:
         self.d_indices_e2e = torch.zeros_like(self.d_indices)          # only the rank's slice is ever uploaded into it
         self.h_edges = {m: torch.empty(self.e1 - self.e0, dtype=torch.int32).pin_memory() for m in self.mods}
 
-    def step(self, ip, ix):
+    def step(self, ip, ix, edges_to_host=False):
         import torch  # noqa: F401
         from diffmm_b200 import autograd as _ag, ops, rebuild
         # everything that depends on the Denoise weights is rebuilt inside the step, as after an epoch of training:
@@ -506,8 +506,20 @@ class RebuildJob:
                                            group=None, plan=self.plan, full_items=full)
             return adjs, full
         res = {}
+        if edges_to_host:
+            # end-to-end leg: every modality's edge list leaves for its pinned host buffer from inside its own pipeline, as
+            # soon as its top-k has emitted it (the per_modality hook of the public API runs on the pipeline's stream), so
+            # the copy overlaps the adjacency build instead of following the join
+            host = iter(self.h_edges.values())
+
+            def tail(v):
+                next(host).copy_(v[self.e0:self.e1], non_blocking=True)
+                return ops.build_norm_adj(ip, v, U, I), v
+        else:
+            def tail(v):
+                return ops.build_norm_adj(ip, v, U, I), v
         rebuild.rebuild_edges(self.diff, self.dens, ip, ix, U, I, SS, self.precision, row_range=(self.r0, self.r1),
-                              per_modality=lambda v: (ops.build_norm_adj(ip, v, U, I), v), per_modality_out=res)
+                              per_modality=tail, per_modality_out=res)
         return {m: r[0] for m, r in res.items()}, {m: r[1] for m, r in res.items()}
 
     def step_device(self):
@@ -518,6 +530,9 @@ class RebuildJob:
         from pinned host memory, the rank's slice of every rebuilt edge list goes back to pinned host memory."""
         ip = self.h_indptr.to(self.dev, non_blocking=True)
         self.d_indices_e2e[self.e0:self.e1].copy_(self.h_indices_local, non_blocking=True)
+        if self.world == 1:
+            adjs, items = self.step(ip, self.d_indices_e2e, edges_to_host=True)
+            return adjs
         adjs, items = self.step(ip, self.d_indices_e2e)
         for m, v in items.items():
             self.h_edges[m].copy_(v[self.e0:self.e1], non_blocking=True)
