@@ -502,8 +502,14 @@ class RebuildJob:
         U, I, SS = self.users_total, self.I, self.hyper["sampling_step"]
         if self.world > 1:
             full = {}
+            hook = None
+            if edges_to_host:     # the rank's slice of every edge list leaves from inside the modality's pipeline
+                host = iter(self.h_edges.values())
+
+                def hook(v):
+                    next(host).copy_(v[self.e0:self.e1], non_blocking=True)
             adjs = rebuild.rebuild_sharded(self.diff, self.dens, ip, ix, U, I, SS, self.precision, (self.r0, self.r1),
-                                           group=None, plan=self.plan, full_items=full)
+                                           group=None, plan=self.plan, full_items=full, local_hook=hook)
             return adjs, full
         res = {}
         if edges_to_host:
@@ -530,12 +536,7 @@ class RebuildJob:
         from pinned host memory, the rank's slice of every rebuilt edge list goes back to pinned host memory."""
         ip = self.h_indptr.to(self.dev, non_blocking=True)
         self.d_indices_e2e[self.e0:self.e1].copy_(self.h_indices_local, non_blocking=True)
-        if self.world == 1:
-            adjs, items = self.step(ip, self.d_indices_e2e, edges_to_host=True)
-            return adjs
-        adjs, items = self.step(ip, self.d_indices_e2e)
-        for m, v in items.items():
-            self.h_edges[m].copy_(v[self.e0:self.e1], non_blocking=True)
+        adjs, items = self.step(ip, self.d_indices_e2e, edges_to_host=True)
         return adjs
 
     def h2d_bytes(self):

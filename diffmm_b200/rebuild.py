@@ -515,21 +515,27 @@ def rebuild_modal_adj(diff, denoise_models: Dict[str, torch.nn.Module], indptr: 
 
 
 def rebuild_sharded(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision, row_range, *,
-                    group=None, plan=None, block_rows=None, status=None, full_items: Optional[dict] = None):
+                    group=None, plan=None, block_rows=None, status=None, full_items: Optional[dict] = None,
+                    local_hook=None):
     """User-sharded rebuild of one rank: chain + top-k on ``row_range``, the edge lists of all ranks, the whole-graph
     adjacencies.  Default: equal-priority modality pipelines, join, ONE all-gather for all modalities, then the builds on
     the side streams.  DIFFMM_STAGGER=1 (experiment, measured SLOWER: 1.458 vs 1.412 ms per step at 2 GPUs): the pipelines
     run on side streams of falling priority and each one continues into its own all-gather and adjacency build, so that
-    the first modality's exchange would overlap the chains still running (collectives in modality order on every rank)."""
+    the first modality's exchange would overlap the chains still running (collectives in modality order on every rank).
+    local_hook(items_m) (optional) runs inside every modality's pipeline once its local edge list is complete (e.g. a copy
+    of the rank's slice to pinned host memory that overlaps the exchange)."""
     from . import dist as ddist
     if os.environ.get("DIFFMM_STAGGER", "0") != "1" or len(denoise_models) < 2:
         items = rebuild_edges(diff, denoise_models, indptr, indices, n_users, n_items, sampling_step, precision,
-                              row_range=row_range, block_rows=block_rows, status=status)
+                              row_range=row_range, block_rows=block_rows, status=status, per_modality=local_hook,
+                              per_modality_out={} if local_hook is not None else None)
         return gather_and_build(items, indptr, n_users, n_items, group, plan, full_items=full_items, status=status)
     if plan is None or plan.world != ddist.world_size(group):
         plan = ddist.EdgeGatherPlan(indptr, n_users, ddist.world_size(group))
 
     def tail(local_items):
+        if local_hook is not None:
+            local_hook(local_items)
         full = ddist.allgather_edges(local_items, indptr, n_users, group, plan)
         return ops.build_norm_adj(indptr, full, n_users, n_items, status=status), full
 
