@@ -466,8 +466,9 @@ __device__ __forceinline__ void gather_add(float (&acc)[8], const uint4& q, cons
   }
 }
 
+constexpr int GS_WARPS = 4;   // warps per CTA of the row-divided gather: 128 threads x 64 registers fit next to a resident contraction CTA
 template <bool LO, bool WT, int NS>
-__global__ void __launch_bounds__(256, 4) csr_gather_act_split_kernel(
+__global__ void __launch_bounds__(32 * GS_WARPS, 32 / GS_WARPS) csr_gather_act_split_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ vals,
     const int64_t* __restrict__ row_ids, const int32_t* __restrict__ order, const int32_t* __restrict__ n_long_p,
     const int long_blocks, const int64_t max_long, int64_t row0, int64_t n_rows, int64_t n_cols,
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(256, 4) csr_gather_act_split_kernel(
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   if ((int)blockIdx.x < long_blocks) {
     // ---- long rows: one warp per (row, 256-column slice), 8 (LO: 4) entries in flight
-    const int64_t wg = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t wg = (int64_t)blockIdx.x * GS_WARPS + warp;
     const int64_t slot = wg / NS;
     if (slot >= n_long) return;
     const int64_t r = (int64_t)__ldg(order + slot);
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(256, 4) csr_gather_act_split_kernel(
     return;
   }
   // ---- short rows: one warp per row, all NS slices; 2 (LO: 1) entries x NS gathers in flight
-  const int64_t s = (int64_t)((int)blockIdx.x - long_blocks) * 8 + warp;
+  const int64_t s = (int64_t)((int)blockIdx.x - long_blocks) * GS_WARPS + warp;
   if (s >= n_rows - n_long) return;
   const int64_t r = (int64_t)__ldg(order + n_long + s);
   const int64_t u = row_ids ? row_ids[r] : row0 + r;
@@ -1112,9 +1113,9 @@ static void launch_gather_split(int ns, unsigned grid, cudaStream_t st, const in
                                 int64_t n_out, uint16_t* h_hi, uint16_t* h_lo, int64_t ld_h, float* z_f32, int64_t ld_z) {
 #define DMM_GS_ARGS indptr, indices, vals, row_ids, order, n_long, long_blocks, max_long, row0, n_rows, n_cols, wt_hi, wt_lo, ld_w, \
                     bias, act, n_out, h_hi, h_lo, ld_h, z_f32, ld_z
-  if (ns == 1) csr_gather_act_split_kernel<LO, WT, 1><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
-  else if (ns == 2) csr_gather_act_split_kernel<LO, WT, 2><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
-  else csr_gather_act_split_kernel<LO, WT, 4><<<grid, 256, 0, st>>>(DMM_GS_ARGS);
+  if (ns == 1) csr_gather_act_split_kernel<LO, WT, 1><<<grid, 32 * GS_WARPS, 0, st>>>(DMM_GS_ARGS);
+  else if (ns == 2) csr_gather_act_split_kernel<LO, WT, 2><<<grid, 32 * GS_WARPS, 0, st>>>(DMM_GS_ARGS);
+  else csr_gather_act_split_kernel<LO, WT, 4><<<grid, 32 * GS_WARPS, 0, st>>>(DMM_GS_ARGS);
 #undef DMM_GS_ARGS
 }
 
@@ -1140,8 +1141,8 @@ extern "C" int dmm_csr_gather_act_split(dmm_ctx* ctx, const int64_t* indptr, con
   const int slices = (int)dmm_ceil_div(n_out, 256);
   const int ns = slices <= 1 ? 1 : (slices == 2 ? 2 : 4);
   if (max_long > n_rows) max_long = n_rows;
-  const int64_t long_blocks = dmm_ceil_div(max_long * ns, 8);
-  const int64_t blocks = long_blocks + dmm_ceil_div(n_rows, 8);
+  const int64_t long_blocks = dmm_ceil_div(max_long * ns, GS_WARPS);
+  const int64_t blocks = long_blocks + dmm_ceil_div(n_rows, GS_WARPS);
   DMM_CHECK_ARG(blocks < (1LL << 31), "dmm_csr_gather_act_split: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
 #define DMM_GS_CALL(LO, WT) launch_gather_split<LO, WT>(ns, (unsigned)blocks, st, indptr, indices, vals, row_ids, order, n_long, \
