@@ -14,6 +14,7 @@ unchanged.  What runs underneath:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -23,7 +24,8 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import ops, rng
-from .autograd import check_precision, linear_tn, packed_weight, spmm, spmm_cat
+from .autograd import (check_precision, linear_tn, modal_mix, packed_weight, row_normalize, spmm, spmm_axpy,
+                       spmm_cat)
 from .Utils.Utils import *  # noqa: F401,F403  (the reference star-imports its losses here, Model.py:7)
 from .Utils.Utils import l2_reg_loss
 
@@ -125,16 +127,24 @@ class Model(nn.Module):
             madj.append(_as_csr(audio_adj))
 
         prec = getattr(self.config.base, "precision", "bf16")
-        zs = [spmm_cat(a, self.u_embs, F.normalize(f), prec) for a, f in zip(madj, feats)]     # :89-93,104-105
+        # the element-wise glue between the products runs as fused launches (csrc/prop.cu: F.normalize, the modality mix,
+        # the residual tail in the SpMM epilogue) on the GPU; DIFFMM_FUSED_PROP=0 keeps the per-op ATen expressions
+        fused = self.u_embs.is_cuda and self.u_embs.shape[1] == 64 and os.environ.get("DIFFMM_FUSED_PROP", "1") != "0"
+        norm = row_normalize if fused else F.normalize
+        zs = [spmm_cat(a, self.u_embs, norm(f), prec) for a, f in zip(madj, feats)]            # :89-93,104-105
         y = spmm_cat(A, self.u_embs, self.i_embs, prec)           # :110-114,122-123 (identical products, once)
-        modal_embs = None
-        for m, z in enumerate(zs):                                 # :116-119,125-127
-            aware = y + lam * z
-            modal_embs = weight[m] * aware if modal_embs is None else modal_embs + weight[m] * aware
-        # :129-131 — ``final_embs = modal_embs`` aliases, so both in-place adds hit the same tensor:
-        # final = (m0 + A m0) + residual_weight * (m0 + A m0)
-        t = modal_embs + spmm(A, modal_embs, prec)
-        final_embs = t + self.config.hyper.residual_weight * t
+        if fused:
+            modal_embs = modal_mix(weight, lam, y, zs)             # :116-119,125-127
+            # :129-131 — ``final_embs = modal_embs`` aliases, so both in-place adds hit the same tensor:
+            # final = (m0 + A m0) + residual_weight * (m0 + A m0) = (1 + residual_weight) (A m0 + m0)
+            final_embs = spmm_axpy(A, modal_embs, 1.0 + self.config.hyper.residual_weight, prec)
+        else:
+            modal_embs = None
+            for m, z in enumerate(zs):
+                aware = y + lam * z
+                modal_embs = weight[m] * aware if modal_embs is None else modal_embs + weight[m] * aware
+            t = modal_embs + spmm(A, modal_embs, prec)
+            final_embs = t + self.config.hyper.residual_weight * t
 
         out = GCNOutput(final_embs[:user], final_embs[user:], zs[0][:user], zs[0][user:], zs[1][:user], zs[1][user:])
         if self.audio_embedding is not None:

@@ -278,6 +278,74 @@ def spmm(adj: ops.CsrAdj, x: torch.Tensor, precision=None) -> torch.Tensor:
     return SpMM.apply(x, adj, precision)
 
 
+class SpMMAxpy(torch.autograd.Function):
+    """y = c (A x + x) in one launch (the SpMM epilogue adds the scaled operand): the tail of Model.gcn_MM,
+    final = (m0 + A m0) + residual_weight (m0 + A m0) with c = 1 + residual_weight (Model.py:129-131).  A is symmetric:
+    dL/dx = c (A g + g), the same call on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, adj: ops.CsrAdj, c: float):
+        ctx.adj, ctx.c = adj, float(c)
+        xd = _rows(x.detach())
+        return ops.spmm(adj, xd, alpha=ctx.c, beta=ctx.c, z=xd)
+
+    @staticmethod
+    def backward(ctx, g):
+        gd = _rows(g)
+        return ops.spmm(ctx.adj, gd, alpha=ctx.c, beta=ctx.c, z=gd), None, None
+
+
+def spmm_axpy(adj: ops.CsrAdj, x: torch.Tensor, c: float, precision=None) -> torch.Tensor:
+    """c (A x + x); fused only on the exact fp32 product of one GPU (otherwise the plain composition)."""
+    if _PARTITION is None and x.is_cuda and x.shape[1] == 64 and not _spmm_bf16(adj, x, precision):
+        return SpMMAxpy.apply(x, adj, c)
+    return c * (x + spmm(adj, x, precision))
+
+
+class RowNormalize(torch.autograd.Function):
+    """F.normalize(x) (dim 1, eps 1e-12) with a one-launch forward and a one-launch backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = ops.rownorm_fwd(_rows(x.detach()))
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, inv = ctx.saved_tensors
+        return ops.rownorm_bwd(y, inv, _rows(g))
+
+
+def row_normalize(x: torch.Tensor) -> torch.Tensor:
+    return RowNormalize.apply(x) if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 else \
+        torch.nn.functional.normalize(x)
+
+
+class ModalMix(torch.autograd.Function):
+    """sum_m w[m] (y + lam z_m) (Model.py:116-119,125-127) with one launch forward and one backward (+ a fixed-order sum
+    of the per-CTA partials for d/dw)."""
+
+    @staticmethod
+    def forward(ctx, w, lam: float, y, *zs):
+        yd = y.detach().contiguous()
+        zd = [z.detach().contiguous() for z in zs]
+        wd = w.detach().contiguous()
+        ctx.lam = float(lam)
+        ctx.save_for_backward(wd, yd, *zd)
+        return ops.modal_mix_fwd(yd, zd, wd, ctx.lam)
+
+    @staticmethod
+    def backward(ctx, g):
+        wd, yd, *zd = ctx.saved_tensors
+        gy, gzs, gw = ops.modal_mix_bwd(g.contiguous(), yd, zd, wd, ctx.lam)
+        return (gw, None, gy, *gzs)
+
+
+def modal_mix(w: torch.Tensor, lam: float, y: torch.Tensor, zs) -> torch.Tensor:
+    return ModalMix.apply(w, lam, y, *zs)
+
+
 class InfoNCEFn(torch.autograd.Function):
     """-mean_b log softmax_b(<n1_b, n2_.>/T)_b on gathered, L2-normalised rows (Utils/Utils.py:57-75).
 

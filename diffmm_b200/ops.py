@@ -423,6 +423,57 @@ def sign_noise_(e: torch.Tensor, rnd: torch.Tensor, noise_degree: float):
     return e
 
 
+# ----------------------------------------------------------------------------------------- gcn_MM glue
+def rownorm_fwd(x: torch.Tensor, eps: float = 1e-12):
+    """F.normalize(x) per row (Model.py:89-93): returns (y, inv); inv < 0 flags a row clamped at eps."""
+    assert x.dtype == torch.float32 and x.dim() == 2
+    y = torch.empty((x.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _lib.call("dmm_rownorm_fwd", _ctx(x), _p(x), _row_major(x, "x"), x.shape[0], x.shape[1], float(eps), _p(y), y.shape[1], _p(inv),
+              _stream())
+    return y, inv
+
+
+def rownorm_bwd(y: torch.Tensor, inv: torch.Tensor, g: torch.Tensor):
+    gx = torch.empty_like(y)
+    _lib.call("dmm_rownorm_bwd", _ctx(y), _p(y), _row_major(y, "y"), _p(inv), _p(g), _row_major(g, "g"), y.shape[0], y.shape[1],
+              _p(gx), gx.shape[1], _stream())
+    return gx
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def _dense(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_contiguous() or t.dtype != torch.float32:
+        raise _lib.DiffMMError(f"{name}: dense contiguous fp32 tensor expected")
+    return t
+
+
+def modal_mix_fwd(y: torch.Tensor, zs, w: torch.Tensor, lam: float):
+    """sum_m w[m] (y + lam zs[m]) (Model.py:116-119,125-127); w: device fp32 [M]."""
+    y = _dense(y, "y")
+    zs = [_dense(z, "z") for z in zs]
+    out = torch.empty_like(y)
+    arr = _ptr_array(zs)
+    _lib.call("dmm_modal_mix_fwd", _ctx(y), _p(y), arr, _p(w), len(zs), float(lam), y.numel(), _p(out), _stream())
+    return out
+
+
+def modal_mix_bwd(g: torch.Tensor, y: torch.Tensor, zs, w: torch.Tensor, lam: float, need_gz=True):
+    """Returns (gy, [gz_m], gw [M]) of modal_mix_fwd; gw from per-CTA partial sums added in a fixed order."""
+    g = _dense(g, "g")
+    M = len(zs)
+    gy = torch.empty_like(y)
+    gzs = [torch.empty_like(y) if need_gz else None for _ in range(M)]
+    rows = (y.numel() // 4 + 255) // 256
+    partial = torch.empty((rows, M), dtype=torch.float32, device=y.device)
+    az, agz = _ptr_array(zs), _ptr_array(gzs)
+    _lib.call("dmm_modal_mix_bwd", _ctx(y), _p(g), _p(y), az, _p(w), M, float(lam), y.numel(), _p(gy), agz, _p(partial), _stream())
+    return gy, gzs, partial.sum(0)
+
+
 # ----------------------------------------------------------------------------------------- losses
 def bpr_fwd_bwd(u_emb, i_emb, users, pos, neg, grad_scale=1.0, want_grad=True):
     B, D = users.numel(), u_emb.shape[1]

@@ -296,6 +296,25 @@ int dmm_spmm_norm_bf16(dmm_ctx* ctx, const int32_t* adj_idx, int64_t row0, int64
 int dmm_sign_noise_(dmm_ctx* ctx, float* e, int64_t ld_e, const float* rnd, int64_t ld_r,
                     int64_t n_rows, int64_t D, float noise_degree, void* stream);
 
+/* ---- element-wise glue of Model.gcn_MM between its SpMM products (Model.py:60-134), forward and backward ----------
+ * F.normalize of the projected modality features (Model.py:89-93,104-105): y[r,:] = x[r,:] / max(||x[r,:]||_2, eps);
+ * inv[r] = +-1 / max(||x||, eps), negative when the row was clamped at eps (flag for the backward).
+ * Backward: gx = (g - y (y . g)) |inv| for an unclamped row, g |inv| for a clamped one.                             */
+int dmm_rownorm_fwd(dmm_ctx* ctx, const float* x, int64_t ld_x, int64_t n_rows, int64_t D, float eps, float* y, int64_t ld_y,
+                    float* inv, void* stream);
+int dmm_rownorm_bwd(dmm_ctx* ctx, const float* y, int64_t ld_y, const float* inv, const float* g, int64_t ld_g, int64_t n_rows,
+                    int64_t D, float* gx, int64_t ld_gx, void* stream);
+/* The modality mix (Model.py:116-119,125-127): out = sum_m w[m] (y + lam z[m]) over dense fp32 arrays of n_elems elements
+ * (multiple of 4, 16-byte aligned), w = softmax(modal_weight) on the DEVICE (no host sync), 1 <= n_modal <= 4, evaluated
+ * in the reference's order of operations.  Backward: gy = sum_m w[m] g, gz[m] = lam w[m] g (gz[m] may be NULL), and
+ * partial[b, m] = sum over CTA b of g . (y + lam z[m]) for b < dmm_modal_mix_partial_rows(n_elems): the caller adds the
+ * rows in a fixed order to get d/dw[m] (deterministic, no atomics).                                               */
+int dmm_modal_mix_fwd(dmm_ctx* ctx, const float* y, const float* const* z, const float* w, int32_t n_modal, float lam,
+                      int64_t n_elems, float* out, void* stream);
+int64_t dmm_modal_mix_partial_rows(int64_t n_elems);
+int dmm_modal_mix_bwd(dmm_ctx* ctx, const float* g, const float* y, const float* const* z, const float* w, int32_t n_modal,
+                      float lam, int64_t n_elems, float* gy, float* const* gz, float* partial, void* stream);
+
 /* ---- fused losses ---------------------------------------------------------------------------
  * BPR (Utils/Utils.py:78-98): loss = mean_b -log(1e-5 + sigmoid(u.p - u.n)) over gathered rows
  * users[b] of U_emb and pos[b]/neg[b] of I_emb; also writes d(loss)/d(rows) scaled by
