@@ -295,10 +295,33 @@ class SpMMAxpy(torch.autograd.Function):
         return ops.spmm(ctx.adj, gd, alpha=ctx.c, beta=ctx.c, z=gd), None, None
 
 
+class PartitionedSpMMAxpy(torch.autograd.Function):
+    """SpMMAxpy with the rows partitioned over the ranks (dist.PropPartition): the same epilogue on every rank's row blocks
+    (bit-identical to the single-GPU launch), then the in-place all-gather; backward = the same call on the gradient."""
+
+    @staticmethod
+    def _product(adj, x, part, c):
+        y = torch.empty((adj.n_nodes, x.shape[1]), dtype=torch.float32, device=x.device)
+        return part.product_(lambda r0, r1: ops.spmm(adj, x, alpha=c, beta=c, z=x, out=y, row0=r0, row1=r1), y)
+
+    @staticmethod
+    def forward(ctx, x, adj: ops.CsrAdj, part, c: float):
+        ctx.adj, ctx.part, ctx.c = adj, part, float(c)
+        return PartitionedSpMMAxpy._product(adj, _rows(x.detach()), part, ctx.c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return PartitionedSpMMAxpy._product(ctx.adj, _rows(g), ctx.part, ctx.c), None, None, None
+
+
 def spmm_axpy(adj: ops.CsrAdj, x: torch.Tensor, c: float, precision=None) -> torch.Tensor:
-    """c (A x + x); fused only on the exact fp32 product of one GPU (otherwise the plain composition)."""
-    if _PARTITION is None and x.is_cuda and x.shape[1] == 64 and not _spmm_bf16(adj, x, precision):
-        return SpMMAxpy.apply(x, adj, c)
+    """c (A x + x); fused on the exact fp32 product (one GPU or row-partitioned), otherwise the plain composition."""
+    if x.is_cuda and x.shape[1] == 64 and not _spmm_bf16(adj, x, precision):
+        part = _PARTITION
+        if part is None:
+            return SpMMAxpy.apply(x, adj, c)
+        if adj.n_nodes == part.n_nodes and (adj.n_users == part.n_users or adj.n_users == 0):
+            return PartitionedSpMMAxpy.apply(x, adj, part, c)
     return c * (x + spmm(adj, x, precision))
 
 
