@@ -122,15 +122,15 @@ class Coach:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach()).cuda(self.device)
         # graph replay needs the optimiser state (step counter) on the device: capturable Adam, same update rule
         # DIFFMM_FUSED_ADAM=1 (opt-in, graph mode only): torch's fused implementation of Adam (one multi-tensor kernel, one
-        # pass over p / g / m / v instead of the four to five of foreach): epoch 0.233 -> 0.185 s at baby, but on the real
-        # TikTok run its epoch losses sit 0.4-0.5 % off the foreach trajectory that tracks the reference within 0.1 %
+        # pass over p / g / m / v instead of the four to five of foreach): epoch 0.21 -> 0.185 s at baby, but on the real
+        # TikTok run its epoch losses sit 0.4-0.5 % off the trajectory of the unfused update, which tracks the reference within 0.1 %
         # (tools/tiktok_real_default_mode.py, profiles/r02_tiktok_real_default_mode.txt), so it is not the default
-        fused_adam = os.environ.get("DIFFMM_FUSED_ADAM", "0") == "1"
+        fused_adam = os.environ.get("DIFFMM_FUSED_ADAM", "0") == "1"     # None (not False) keeps torch's foreach default
         if self._use_graph():
             # device-resident step counter and learning rate: one captured graph serves every epoch (the scheduler
             # updates a tensor lr in place)
             self.opt = Adam(self.model.parameters(), lr=torch.tensor(float(self.config.train.lr), device=self.device),
-                            weight_decay=0, capturable=True, fused=fused_adam)
+                            weight_decay=0, capturable=True, fused=True if fused_adam else None)
         else:
             self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
         self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
@@ -142,7 +142,7 @@ class Coach:
             # graph mode: phase 1 is replayed from a CUDA graph as well (device-resident step counter and lr)
             if self._use_graph():
                 return Adam(params, lr=torch.tensor(float(self.config.train.lr), device=self.device), weight_decay=0,
-                            capturable=True, fused=fused_adam)
+                            capturable=True, fused=True if fused_adam else None)
             return Adam(params, lr=self.config.train.lr, weight_decay=0)
 
         self.image_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
