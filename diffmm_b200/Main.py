@@ -28,6 +28,7 @@ from . import ops, rng
 from .autograd import joint_losses, linear_tn, spmm, spmm_cat
 from .Conf import Config, load_config
 from .DataHandler import DataHandler
+from .optim import FusedStepAdam
 from .Model import Denoise, GaussianDiffusion, Model, _as_csr
 from .rebuild import rebuild_modal_adj
 from .Utils.Log import Log
@@ -120,17 +121,25 @@ class Coach:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach(), h.audio_feats.detach()).cuda(self.device)
         else:
             self.model = Model(self.config, h.image_feats.detach(), h.text_feats.detach()).cuda(self.device)
-        # graph replay needs the optimiser state (step counter) on the device: capturable Adam, same update rule
-        # DIFFMM_FUSED_ADAM=1 (opt-in, graph mode only): torch's fused implementation of Adam (one multi-tensor kernel, one
-        # pass over p / g / m / v instead of the four to five of foreach): epoch 0.21 -> 0.185 s at baby, but on the real
-        # TikTok run its epoch losses sit 0.4-0.5 % off the trajectory of the unfused update, which tracks the reference within 0.1 %
-        # (tools/tiktok_real_default_mode.py, profiles/r02_tiktok_real_default_mode.txt), so it is not the default
-        fused_adam = os.environ.get("DIFFMM_FUSED_ADAM", "0") == "1"     # None (not False) keeps torch's foreach default
+        # graph replay needs the optimiser state (step counter) on the device: capturable Adam, same update rule.
+        # Graph mode: Adam with the one-launch update of csrc/optim.cu (optim.FusedStepAdam: torch's optimiser object, state
+        # and scheduler interplay; the step is ONE pass over p / g / m / v evaluating the operation sequence of torch's
+        # capturable foreach implementation -- bit-identical, tests/test_optim_gpu.py).  DIFFMM_ADAM=foreach: torch's foreach
+        # implementation (fourteen passes); DIFFMM_ADAM=torch_fused: torch's own fused kernel (fast, but its epoch losses sit
+        # 0.4-0.5 % off on the real TikTok run, profiles/r02_tiktok_real_default_mode.txt: not used)
+        adam_impl = os.environ.get("DIFFMM_ADAM", "dmm")
+        if adam_impl not in ("dmm", "foreach", "torch_fused"):
+            raise ValueError(f"DIFFMM_ADAM must be dmm, foreach or torch_fused, got {adam_impl!r}")
+
+        def graph_adam(params):
+            lr = torch.tensor(float(self.config.train.lr), device=self.device)
+            if adam_impl == "dmm":
+                return FusedStepAdam(params, lr=lr, weight_decay=0, capturable=True)
+            return Adam(params, lr=lr, weight_decay=0, capturable=True, fused=True if adam_impl == "torch_fused" else None)
         if self._use_graph():
             # device-resident step counter and learning rate: one captured graph serves every epoch (the scheduler
             # updates a tensor lr in place)
-            self.opt = Adam(self.model.parameters(), lr=torch.tensor(float(self.config.train.lr), device=self.device),
-                            weight_decay=0, capturable=True, fused=True if fused_adam else None)
+            self.opt = graph_adam(self.model.parameters())
         else:
             self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
         self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
@@ -141,8 +150,7 @@ class Coach:
         def denoise_adam(params):
             # graph mode: phase 1 is replayed from a CUDA graph as well (device-resident step counter and lr)
             if self._use_graph():
-                return Adam(params, lr=torch.tensor(float(self.config.train.lr), device=self.device), weight_decay=0,
-                            capturable=True, fused=True if fused_adam else None)
+                return graph_adam(params)
             return Adam(params, lr=self.config.train.lr, weight_decay=0)
 
         self.image_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)

@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -Xptxas -v -I"${HERE}/../../include")
 mkdir -p "${HERE}/obj"
 pids=()
-for f in capi gemm_tcgen05 gemm_simt pack topk adj spmm prop loss eval train; do
+for f in capi gemm_tcgen05 gemm_simt pack topk adj spmm prop optim loss eval train; do
   src="${HERE}/${f}.cu"; obj="${HERE}/obj/${f}.o"
   if [[ ! -f "$obj" || "$src" -nt "$obj" || "${HERE}/common.cuh" -nt "$obj" || "${HERE}/../../include/diffmm_b200.h" -nt "$obj" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" > "${HERE}/obj/${f}.log" 2>&1 || { cat "${HERE}/obj/${f}.log"; exit 1; } ) &

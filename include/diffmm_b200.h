@@ -315,6 +315,15 @@ int64_t dmm_modal_mix_partial_rows(int64_t n_elems);
 int dmm_modal_mix_bwd(dmm_ctx* ctx, const float* g, const float* y, const float* const* z, const float* w, int32_t n_modal,
                       float lam, int64_t n_elems, float* gy, float* const* gz, float* partial, void* stream);
 
+/* ---- optimiser step (Main.py:92-110,189-192,375-377) ------------------------------------------------
+ * One launch for the Adam update of ALL tensors of an optimiser (weight_decay 0, no amsgrad): p, g, m, v read once, p, m, v
+ * written once, the operation sequence of torch.optim.Adam's capturable foreach implementation evaluated in its own order
+ * (bit-identical update).  `step` (already incremented) and `lr` are fp32 DEVICE scalars: capturable in a CUDA graph.
+ * params / grads / exp_avg / exp_avg_sq: host arrays of n_tensors device pointers (dense fp32), numel their lengths.     */
+int dmm_adam_step(dmm_ctx* ctx, int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, const float* step, const float* lr, double beta1,
+                  double beta2, double eps, void* stream);
+
 /* ---- fused losses ---------------------------------------------------------------------------
  * BPR (Utils/Utils.py:78-98): loss = mean_b -log(1e-5 + sigmoid(u.p - u.n)) over gathered rows
  * users[b] of U_emb and pos[b]/neg[b] of I_emb; also writes d(loss)/d(rows) scaled by

@@ -1,7 +1,7 @@
 """Real-TikTok three-epoch runs (tests/golden/tiktok_real, conf/tiktok.toml) in the DEFAULT mode of the trainer -- device
 generator, phases 1 and 3 replayed from CUDA graphs, bf16 -- next to the reference's 14-run ensemble: the parity tests gate
 the seed-exact CPU-RNG / eager mode, this shows that the mode users actually run lands in the same distribution.
-    python tools/tiktok_real_default_mode.py [seeds]         DIFFMM_FUSED_ADAM=0/1 selects torch's Adam implementation"""
+    python tools/tiktok_real_default_mode.py [repetitions]         DIFFMM_ADAM=dmm|foreach|torch_fused selects the Adam implementation"""
 import glob
 import json
 import os
@@ -42,7 +42,7 @@ for s in range(n_seeds):
     coach.run()
     assert coach._use_graph()
     runs.append([(r["test"]["Recall"], r["test"]["NDCG"], r["train"]["Loss"]) for r in coach.history])
-    print(f"seed {cfg.base.seed} adam={'fused' if os.environ.get('DIFFMM_FUSED_ADAM', '1') != '0' else 'foreach'}: " + " | ".join(
+    print(f"seed {cfg.base.seed} adam={os.environ.get('DIFFMM_ADAM', 'dmm')}: " + " | ".join(
         f"R@20 {a:.5f} N@20 {b:.5f} Loss {c:.4f}" for a, b, c in runs[-1]), flush=True)
     del coach, h
     torch.cuda.empty_cache()
