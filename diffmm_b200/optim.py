@@ -29,6 +29,7 @@ class FusedStepAdam(Adam):
         check = getattr(self, "_accelerator_graph_capture_health_check", None) or getattr(self, "_cuda_graph_capture_health_check", None)
         if check is not None:
             check()
+        work = []
         for group in self.param_groups:
             params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps = [], [], [], [], [], []
             self._init_group(group, params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps)
@@ -36,8 +37,10 @@ class FusedStepAdam(Adam):
                 continue
             ok = all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.dtype == torch.float32 and not g.is_sparse
                      for p, g in zip(params, grads))
-            if not ok:
+            if not ok:                                          # nothing has been touched yet: the parent takes the whole step
                 return super().step(closure)
+            work.append((group, params, grads, exp_avgs, exp_avg_sqs, steps))
+        for group, params, grads, exp_avgs, exp_avg_sqs, steps in work:
             grads = [g if g.is_contiguous() else g.contiguous() for g in grads]
             torch._foreach_add_(steps, 1)                       # every parameter keeps its own (equal) step counter
             n = len(params)
