@@ -187,3 +187,24 @@ def test_reference_arm_and_gpu_arm_draw_identical_denoise_weights(monkeypatch):
         for k in so:
             assert torch.equal(so[k], sr[k]), (m, k)
     assert torch.equal(diff_o.posterior_mean_coef1.cpu(), diff_r.posterior_mean_coef1.cpu())
+
+
+def test_fused_step_adam_falls_back_to_torch_on_unsupported_configurations():
+    """optim.FusedStepAdam only takes the one-launch path for the graph-mode configuration (CUDA fp32 parameters, capturable,
+    tensor lr, no weight decay); everything else -- here CPU parameters -- is torch's own step, bit for bit."""
+    import torch
+    from torch.optim.adam import Adam
+    from diffmm_b200.optim import FusedStepAdam
+    torch.manual_seed(0)
+    a = [torch.randn(7, 3, requires_grad=True), torch.randn(5, requires_grad=True)]
+    b = [t.detach().clone().requires_grad_(True) for t in a]
+    oa, ob = FusedStepAdam(a, lr=1e-2, weight_decay=0.1), Adam(b, lr=1e-2, weight_decay=0.1)
+    for _ in range(5):
+        for x, y in zip(a, b):
+            g = torch.randn_like(x)
+            x.grad, y.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert oa.state_dict()["param_groups"][0]["lr"] == ob.state_dict()["param_groups"][0]["lr"]
