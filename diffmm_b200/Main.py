@@ -136,12 +136,19 @@ class Coach:
             if adam_impl == "dmm":
                 return FusedStepAdam(params, lr=lr, weight_decay=0, capturable=True)
             return Adam(params, lr=lr, weight_decay=0, capturable=True, fused=True if adam_impl == "torch_fused" else None)
+
+        def eager_adam(params):
+            # eager mode (python-float lr, host-side step counters): the one-launch step reproduces torch's non-capturable
+            # foreach sequence bit for bit as well
+            if adam_impl == "dmm" and os.environ.get("DIFFMM_ADAM_EAGER", "0") == "1":
+                return FusedStepAdam(params, lr=self.config.train.lr, weight_decay=0)
+            return Adam(params, lr=self.config.train.lr, weight_decay=0, fused=True if adam_impl == "torch_fused" else None)
         if self._use_graph():
             # device-resident step counter and learning rate: one captured graph serves every epoch (the scheduler
             # updates a tensor lr in place)
             self.opt = graph_adam(self.model.parameters())
         else:
-            self.opt = Adam(self.model.parameters(), lr=self.config.train.lr, weight_decay=0)
+            self.opt = eager_adam(self.model.parameters())
         self.model_scheduler = CosineAnnealingLR(self.opt, T_max=self.config.train.epoch, eta_min=1e-4)
         self.diffusion_model = GaussianDiffusion(self.config).cuda(self.device)
 
@@ -151,7 +158,7 @@ class Coach:
             # graph mode: phase 1 is replayed from a CUDA graph as well (device-resident step counter and lr)
             if self._use_graph():
                 return graph_adam(params)
-            return Adam(params, lr=self.config.train.lr, weight_decay=0)
+            return eager_adam(params)
 
         self.image_denoise_model = Denoise(in_dims, out_dims, self.config).cuda(self.device)
         self.image_denoise_opt = denoise_adam(self.image_denoise_model.parameters())

@@ -90,6 +90,8 @@ PROTOTYPES = {
     "dmm_sign_noise_": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "dmm_adam_step": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double, C.c_double,
                                 c_vp]),
+    "dmm_adam_step_host": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     C.c_double, c_vp]),
     "dmm_rownorm_fwd": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_vp]),
     "dmm_rownorm_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "dmm_modal_mix_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int32, c_f32, c_i64, c_vp, c_vp]),

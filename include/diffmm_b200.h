@@ -324,6 +324,13 @@ int dmm_adam_step(dmm_ctx* ctx, int32_t n_tensors, float* const* params, const f
                   float* const* exp_avg_sq, const int64_t* numel, const float* step, const float* lr, double beta1,
                   double beta2, double eps, void* stream);
 
+/* Same launch for torch's NON-capturable foreach sequence (eager trainer): step_size = -lr / (1 - beta1^t) and
+ * bias_correction2_sqrt = sqrt(1 - beta2^t) are the python doubles of torch.optim.adam._multi_tensor_adam, cast to fp32
+ * where torch's kernels cast them; p = p + step_size (m / ((sqrt(v) / bc2_sqrt) + eps)).                              */
+int dmm_adam_step_host(dmm_ctx* ctx, int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, double step_size, double bias_correction2_sqrt,
+                       double beta1, double beta2, double eps, void* stream);
+
 /* ---- fused losses ---------------------------------------------------------------------------
  * BPR (Utils/Utils.py:78-98): loss = mean_b -log(1e-5 + sigmoid(u.p - u.n)) over gathered rows
  * users[b] of U_emb and pos[b]/neg[b] of I_emb; also writes d(loss)/d(rows) scaled by

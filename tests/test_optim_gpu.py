@@ -78,3 +78,27 @@ def test_fused_step_adam_replays_from_a_cuda_graph():
     torch.cuda.synchronize()
     for x, y in zip(pa, pb):
         assert torch.equal(x, y)
+
+
+def test_fused_step_adam_eager_mode_is_bit_identical_to_torch_foreach():
+    """The eager trainer's configuration: python-float lr (rewritten by the scheduler), step counters on the host."""
+    from diffmm_b200.optim import FusedStepAdam
+    pa, pb = _params(4), _params(4)
+    oa = FusedStepAdam(pa, lr=1e-3, weight_decay=0)
+    ob = Adam(pb, lr=1e-3, weight_decay=0, foreach=True)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for it in range(40):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, device=DEV, generator=g) * (10.0 ** ((it % 7) - 4))
+            if it % 5 == 0:
+                gr[..., ::3] = 0.0
+            x.grad, y.grad = gr.clone(), gr.clone()
+        if it == 20:
+            oa.param_groups[0]["lr"] = ob.param_groups[0]["lr"] = 4.321e-4
+        oa.step()
+        ob.step()
+        for k, (x, y) in enumerate(zip(pa, pb)):
+            assert torch.equal(x, y), (it, k, float((x - y).abs().max()))
+            sa, sb = oa.state[x], ob.state[y]
+            assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"]), (it, k)
+            assert float(sa["step"]) == float(sb["step"])
