@@ -125,8 +125,8 @@ class Coach:
         # Graph mode: Adam with the one-launch update of csrc/optim.cu (optim.FusedStepAdam: torch's optimiser object, state
         # and scheduler interplay; the step is ONE pass over p / g / m / v evaluating the operation sequence of torch's
         # capturable foreach implementation -- bit-identical, tests/test_optim_gpu.py).  DIFFMM_ADAM=foreach: torch's foreach
-        # implementation (fourteen passes); DIFFMM_ADAM=torch_fused: torch's own fused kernel (fast, but its epoch losses sit
-        # 0.4-0.5 % off on the real TikTok run, profiles/r02_tiktok_real_default_mode.txt: not used)
+        # implementation (fourteen passes); DIFFMM_ADAM=torch_fused: torch's own fused kernel (not validated against the
+        # parity runs)
         adam_impl = os.environ.get("DIFFMM_ADAM", "dmm")
         if adam_impl not in ("dmm", "foreach", "torch_fused"):
             raise ValueError(f"DIFFMM_ADAM must be dmm, foreach or torch_fused, got {adam_impl!r}")
@@ -140,7 +140,7 @@ class Coach:
         def eager_adam(params):
             # eager mode (python-float lr, host-side step counters): the one-launch step reproduces torch's non-capturable
             # foreach sequence bit for bit as well
-            if adam_impl == "dmm" and os.environ.get("DIFFMM_ADAM_EAGER", "0") == "1":
+            if adam_impl == "dmm":
                 return FusedStepAdam(params, lr=self.config.train.lr, weight_decay=0)
             return Adam(params, lr=self.config.train.lr, weight_decay=0, fused=True if adam_impl == "torch_fused" else None)
         if self._use_graph():

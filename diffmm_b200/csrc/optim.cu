@@ -6,8 +6,7 @@
 // This kernel reads p, g, m, v once and writes p, m, v once -- 28 bytes per weight -- and evaluates EXACTLY the operation
 // sequence of torch.optim.adam._multi_tensor_adam (capturable branch, weight_decay = 0, amsgrad = False, maximize = False)
 // in fp32, operation for operation (same roundings, same fused multiply-adds the ATen kernels contract to), so the update is
-// bit-identical to the stock optimiser's (tests/test_optim_gpu.py); torch's own `fused=True` implementation is NOT (its
-// epoch losses sit 0.4-0.5 % off on the real TikTok run), which is why it is not used.
+// bit-identical to the stock optimiser's (tests/test_optim_gpu.py: 40 steps, eager and under CUDA-graph replay).
 //   m   = m + w1 (g - m)                         w1 = float(1 - beta1)            (_foreach_lerp_)
 //   v   = v * beta2;  v = v + w2 (g g)           w2 = float(1 - beta2)            (_foreach_mul_, _foreach_addcmul_)
 //   ss  = 1 / ((beta1^t - 1) / lr)               = -lr / (1 - beta1^t)            (_foreach_pow, sub_, div_, reciprocal_)
